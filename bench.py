@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: RTFx (audio-seconds transcribed per second), Zipformer-68M RNN-T,
+modified_beam_search beam 4, batch of 256 VAD-like segments per GPU (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle stand-in), rank 0 only
+
+One step = one pass of the hot path (fbank -> encoder -> decoder/joiner/beam search) over one batch of
+synthetic segments. `value` is measured with the PCM already resident in HBM (CUDA events on the engine's
+stream, max over ranks); `e2e` goes through the recognizer surface (create_stream / accept_waveform /
+decode_streams) with host buffers, host<->device copies inside the timed region. Multi-GPU: utterance
+sharding, one process per GPU, no collective on the data path (weak scaling: 256 segments per rank).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--segments", type=int, default=256)
+    ap.add_argument("--model", default="zipformer-68m")
+    ap.add_argument("--beam", type=int, default=4)
+    ap.add_argument("--precision", default=os.environ.get("B200ASR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--cpu-sample", type=int, default=6, help="segments in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def model_dir(name: str, seed: int) -> dict:
+    from sherpa_vietnamese_asr_b200 import weights
+    d = os.path.join(tempfile.gettempdir(), f"b200asr_models_{os.getuid()}", f"{name}-{seed}-r{os.environ.get('LOCAL_RANK', '0')}")
+    cfg = weights.CONFIGS[name]()
+    return cfg, weights.write_model_dir(d, cfg, seed)
+
+
+def workload(args, rank: int):
+    from sherpa_vietnamese_asr_b200 import synth
+    durs = synth.c2_durations(args.segments, 256 + 1000 * rank)
+    return [synth.speech_like(int(round(d * 16000)), (256 + rank) * 100003 + i) for i, d in enumerate(durs)]
+
+
+def encoder_flops(cfg, T: int) -> float:
+    """2*MACs of SURVEY App. B.5 for one segment with T fbank frames."""
+    if T < 9:
+        return 0.0
+    T1 = (T - 7) // 2
+    t2 = (T - 5) // 2 + 1
+    macs = (T - 2) * 80 * 72 + t2 * 39 * 32 * 72 + T1 * 19 * 128 * 288 + T1 * 19 * (128 * 49 + 2 * 128 * 384) + T1 * 2432 * cfg.encoder_dim[0]
+    for L, ds, D, F, H, k in zip(cfg.num_encoder_layers, cfg.downsampling_factor, cfg.encoder_dim, cfg.feedforward_dim,
+                                 cfg.num_heads, cfg.cnn_module_kernel):
+        Tk = (T1 + ds - 1) // ds
+        h = 3 * D // 4
+        per = (D * 68 * H + 32 * H * Tk + 4 * H * (2 * Tk - 1) + 2 * D * (3 * F // 4 + F + 5 * F // 4) + (D * 3 * h + h * D + h * Tk)
+               + 2 * (2 * D * 12 * H + 12 * H * Tk) + 2 * (2 * D * D + D * k + D * D))
+        macs += L * Tk * per
+    Tp = (T1 + 1) // 2
+    macs += Tp * max(cfg.encoder_dim) * cfg.joiner_dim
+    return 2.0 * macs
+
+
+def cpu_reference_pass(cfg, paths, audios, beam, threads):
+    """The reference CPU path restated (oracle): NumPy fbank + PyTorch-CPU fp32 encoder/decoder/joiner driving the
+    restated `_ort_beam_search`, batch 1 per segment as core/asr_engine.py:1045-1047 does. Returns seconds."""
+    import torch
+
+    from oracle import fbank_ref, search_ref, zipformer_ref
+    from sherpa_vietnamese_asr_b200 import weights
+    torch.set_num_threads(threads)
+    tensors = {}
+    for part in ("encoder", "decoder", "joiner"):
+        tensors.update(weights.load_container(paths[part])[1])
+    rec = zipformer_ref.make_recognizer(tensors, cfg, max_active_paths=beam)
+    t0 = time.perf_counter()
+    ntok = 0
+    for a in audios:
+        feats = fbank_ref.fbank(a, np.float32)
+        rec["dec_cache"].clear()
+        ntok += len(search_ref.modified_beam_search(rec, feats, beam)[0])
+    return time.perf_counter() - t0, ntok
+
+
+def physical_cores() -> int:
+    try:
+        import psutil
+        return psutil.cpu_count(logical=False) or os.cpu_count() or 1
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from sherpa_vietnamese_asr_b200 import weights  # noqa: F401
+    cfg, paths = model_dir(args.model, 68 if "68" in args.model else 30)
+    audios = workload(args, 0)[: args.cpu_sample]
+    audio_s = sum(len(a) for a in audios) / 16000.0
+    cores = min(physical_cores(), 32)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_pass(cfg, paths, audios[:1], args.beam, cores)
+    times = []
+    for _ in range(args.steps):
+        dt, _ = cpu_reference_pass(cfg, paths, audios, args.beam, cores)
+        times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    val = audio_s / (ms / 1000.0)
+    line = {"impl": "reference", "metric": "RTFx (audio-s/s) Zipformer-68M batch ASR", "value": val, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2: {args.model} modified_beam_search beam {args.beam}, bounded sample = first "
+                                   f"{len(audios)} of {args.segments} VAD-like segments ({audio_s:.1f} audio-s), batch 1 per segment"},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": f"first {len(audios)} segments of C2 ({audio_s:.1f} audio-s) per step"},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from sherpa_vietnamese_asr_b200.recognizer import OfflineRecognizer
+    seed = 68 if "68" in args.model else 30
+    cfg, paths = model_dir(args.model, seed)
+    rec = OfflineRecognizer.from_transducer(encoder=paths["encoder"], decoder=paths["decoder"], joiner=paths["joiner"],
+                                            tokens=paths["tokens"], decoding_method="modified_beam_search",
+                                            max_active_paths=args.beam, device_id=local_rank, precision=args.precision)
+    audios = workload(args, rank)
+    audio_s = sum(len(a) for a in audios) / 16000.0
+    pcm_bytes = sum(len(a) for a in audios) * 4
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident: PCM staged in HBM once
+    h = rec.stage_batch(audios)
+    for _ in range(args.warmup):
+        ntok = rec.run_staged(h)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, launches, stage = 0.0, 0, {"fbank_ms": 0.0, "encoder_ms": 0.0, "search_ms": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ntok = rec.run_staged(h)
+        tm = rec.last_timings()
+        dev_ms += tm["total_ms"]
+        launches += tm["launches"]
+        for k in stage:
+            stage[k] += tm[k]
+    barrier()
+    wall_ms = 1000.0 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    ms_dev = dev_ms / args.steps
+
+    # ---------------- end to end through the recognizer surface (host buffers)
+    def e2e_step():
+        ss = []
+        for a in audios:
+            s = rec.create_stream()
+            s.accept_waveform(16000, a)
+            ss.append(s)
+        rec.decode_streams(ss)
+        return ss
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ss = e2e_step()
+    barrier()
+    e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
+    d2h_bytes = int(sum(len(s.result.token_ids) for s in ss) * (4 + 4 + 4 + 16) + 4 * len(ss))
+
+    # ---------------- dominant kernel (GEMM) timed live with CUDA events around every launch
+    rec.set_profiling(True)
+    rec.run_staged(h)
+    gs = rec.last_gemm_stats()
+    tm_prof = rec.last_timings()
+    rec.set_profiling(False)
+    rec.release_batch(h)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_dev, e2e_ms, wall_ms / args.steps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, e2e_ms, wall_step = [float(x) for x in t.tolist()]
+        a = torch.tensor([audio_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        total_audio = float(a.item())
+    else:
+        total_audio, wall_step = audio_s, wall_ms / args.steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    ach = (gs["flops"] / (gs["ms"] * 1e-3)) / 1e12 if gs["ms"] > 0 else None
+    enc_fl = sum(encoder_flops(cfg, (len(a) + 80) // 160) for a in audios)
+    line = {
+        "metric": "RTFx (audio-s/s) Zipformer-68M batch ASR", "value": total_audio / (ms_dev * 1e-3), "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": f"C2: {args.model} random-init, modified_beam_search beam {args.beam}, {args.segments} VAD-like "
+                               f"segments/GPU clip(lognormal(ln 9 s, 0.7), 1, 30) = {audio_s:.0f} audio-s/GPU; "
+                               f"utterance-sharded, no collective",
+                   "l2": f"inputs larger than L2 ({pcm_bytes / 1e6:.0f} MB PCM, multi-GB activations per step)",
+                   "precision": args.precision, "wall_ms_per_step": wall_step,
+                   "stage_ms": {k: v / args.steps for k, v in stage.items()},
+                   "encoder_algorithmic_tflop_per_step": enc_fl / 1e12},
+        "clocks": clocks,
+        "e2e": {"value": total_audio / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": pcm_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm (all Linear layers of the encoder)", "achieved": ach, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": None, "peak_source": peak_src,
+                     "gemm_ms_per_step": gs["ms"], "gemm_launches_per_step": gs["launches"],
+                     "gemm_share_of_step": gs["ms"] / tm_prof["total_ms"] if tm_prof["total_ms"] else None},
+    }
+    if not args.no_cpu_baseline:
+        cores = min(physical_cores(), 32)
+        sample = audios[: args.cpu_sample]
+        dt, _ = cpu_reference_pass(cfg, paths, sample, args.beam, cores)
+        sa = sum(len(a) for a in sample) / 16000.0
+        line["cpu_baseline"] = {"value": sa / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": f"first {len(sample)} segments of C2 ({sa:.1f} audio-s), oracle = reference CPU path restated "
+                                          f"(sherpa-onnx/onnxruntime unavailable offline)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

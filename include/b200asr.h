@@ -1,0 +1,173 @@
+/* b200asr.h — C-ABI of libb200asr.so: the B200-native offline Zipformer RNN-T transcription path.
+ *
+ * Every entry point replaces one call the reference makes into a third-party CPU library; names mirror
+ * sherpa-onnx's C API as bound by the reference's vendored wrapper
+ *   /root/reference offline_pwa/static/vendor/sherpa-onnx-wasm/sherpa-onnx-asr.js
+ * and the Python surface used at
+ *   /root/reference streaming_asr.py:224-243,285,308-312,355-359,408-409
+ *   /root/reference core/audio_analyzer.py:333-367, web_service/audio_quality.py:177-209,268-292
+ * plus raw stage entry points that stand where core/asr_engine.py calls kaldi-native-fbank and
+ * onnxruntime (core/asr_engine.py:698-721,1045-1056,1084-1093) and runs `_ort_beam_search` (:1023-1153).
+ *
+ * Plain C: pointers and sizes only, no exceptions cross the boundary. Functions returning int return
+ * 0 on success, non-zero on failure; B200AsrGetLastError() gives the thread-local message.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200ASR_H_
+#define B200ASR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ASR_API __attribute__((visibility("default")))
+
+/* ---- config PODs (layout follows SherpaOnnxOfflineRecognizerConfig as the wrapper packs it,
+ *      sherpa-onnx-asr.js:1678-1782: feat, model, decoding method, max active paths, hotwords) ---- */
+typedef struct B200AsrFeatureConfig {
+  int32_t sample_rate;   /* 16000 (core/asr_engine.py:706) */
+  int32_t feature_dim;   /* 80    (core/asr_engine.py:710) */
+} B200AsrFeatureConfig;
+
+typedef struct B200AsrOfflineTransducerModelConfig {
+  const char *encoder;   /* `.b200w` container holding encoder.* tensors (stands for encoder-*.onnx) */
+  const char *decoder;   /* container with decoder.*  */
+  const char *joiner;    /* container with joiner.*   */
+} B200AsrOfflineTransducerModelConfig;
+
+typedef struct B200AsrOfflineModelConfig {
+  B200AsrOfflineTransducerModelConfig transducer;
+  const char *tokens;        /* tokens.txt: "<piece> <id>" per line (core/asr_engine.py:981-987) */
+  int32_t num_threads;       /* accepted for source compatibility; ignored */
+  int32_t debug;
+  const char *provider;      /* must be "cuda" or "" ; anything else is an error (no CPU provider) */
+  const char *model_type;
+  const char *modeling_unit; /* "bpe" | "cjkchar" | "token_id" */
+  const char *bpe_vocab;
+} B200AsrOfflineModelConfig;
+
+typedef struct B200AsrOfflineRecognizerConfig {
+  B200AsrFeatureConfig feat_config;
+  B200AsrOfflineModelConfig model_config;
+  const char *decoding_method; /* "greedy_search" | "modified_beam_search" */
+  int32_t max_active_paths;    /* beam; reference default 8 (core/asr_engine.py:903), sherpa default 4 */
+  const char *hotwords_file;   /* optional; lines of space separated token ids [" :score"] when
+                                  modeling_unit == "token_id"; text phrases are tokenised by the host
+                                  binding and passed through B200AsrSetHotwordsTokenIds */
+  float hotwords_score;        /* default boost 1.5 (core/config.py:405-412) */
+  float blank_penalty;
+  int32_t device_id;           /* CUDA device ordinal */
+  int32_t precision;           /* 0 = FP32 (bit-exact token mode), 1 = BF16 tensor-core mode */
+} B200AsrOfflineRecognizerConfig;
+
+typedef struct B200AsrOfflineRecognizer B200AsrOfflineRecognizer;
+typedef struct B200AsrOfflineStream B200AsrOfflineStream;
+
+/* Result of one stream (SherpaOnnxOfflineRecognizerResult + the per-token statistics the reference
+ * derives from the emitted logits rows, core/asr_engine.py:1159-1181). Library-owned. */
+typedef struct B200AsrOfflineRecognizerResult {
+  const char *text;            /* pieces joined, U+2581 -> space, stripped */
+  const char *json;            /* {"text","tokens","timestamps","ys_log_probs","lang","emotion","event"} */
+  const char *const *tokens;   /* count piece strings */
+  const int32_t *token_ids;    /* count */
+  const float *timestamps;     /* seconds, frame * duration / T' (core/asr_engine.py:1237) */
+  const int32_t *frames;       /* encoder frame index per token */
+  const float *ys_log_probs;   /* per-token log-prob (core/asr_engine.py:1121) */
+  const float *tsallis;        /* normalised Tsallis entropy (alpha = 1/3), unrounded */
+  const float *margin;         /* top1 - top2 probability */
+  const float *entropy;        /* Shannon entropy / ln V */
+  const float *top1;           /* top-1 probability */
+  int32_t count;
+  int32_t num_frames;          /* T' */
+  float duration;              /* seconds of audio in the stream */
+} B200AsrOfflineRecognizerResult;
+
+/* ---- recognizer surface ---- */
+/* SherpaOnnxCreateOfflineRecognizer (sherpa-onnx-asr.js:1843-1851); OfflineRecognizer.from_transducer
+ * (streaming_asr.py:243). Strings are borrowed for the call only. NULL on failure. */
+B200ASR_API const B200AsrOfflineRecognizer *B200AsrCreateOfflineRecognizer(const B200AsrOfflineRecognizerConfig *config);
+/* SherpaOnnxDestroyOfflineRecognizer (sherpa-onnx-asr.js:1859-1862) */
+B200ASR_API void B200AsrDestroyOfflineRecognizer(const B200AsrOfflineRecognizer *r);
+/* SherpaOnnxOfflineRecognizerSetConfig (sherpa-onnx-asr.js:1853-1857): decoding method, beam, hotword score */
+B200ASR_API int32_t B200AsrOfflineRecognizerSetConfig(const B200AsrOfflineRecognizer *r, const B200AsrOfflineRecognizerConfig *config);
+/* Hotword phrases as token ids (what build_context_graph produces after SentencePiece,
+ * core/hotword_context.py:222-259): phrase p = tokens[offsets[p] .. offsets[p+1]). n_phrases == 0 clears. */
+B200ASR_API int32_t B200AsrSetHotwordsTokenIds(const B200AsrOfflineRecognizer *r, const int32_t *tokens,
+                                               const int32_t *offsets, const float *scores, int32_t n_phrases);
+/* SherpaOnnxCreateOfflineStream (sherpa-onnx-asr.js:1864-1867; streaming_asr.py:308) */
+B200ASR_API const B200AsrOfflineStream *B200AsrCreateOfflineStream(const B200AsrOfflineRecognizer *r);
+B200ASR_API void B200AsrDestroyOfflineStream(const B200AsrOfflineStream *s);
+/* SherpaOnnxAcceptWaveformOffline (sherpa-onnx-asr.js:1798-1806; streaming_asr.py:285,312,355): copies the
+ * samples ([-1,1] floats) and appends on repeated calls. */
+B200ASR_API void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n);
+/* SherpaOnnxDecodeOfflineStream (sherpa-onnx-asr.js:1869-1871; streaming_asr.py:358,408) */
+B200ASR_API int32_t B200AsrDecodeOfflineStream(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *s);
+/* SherpaOnnxDecodeMultipleOfflineStreams (upstream C API; Python decode_streams): the batch entry point.
+ * Ragged batch, per-utterance unpadded semantics. Returns after results are on the host. */
+B200ASR_API int32_t B200AsrDecodeMultipleOfflineStreams(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *const *ss, int32_t n);
+/* SherpaOnnxGetOfflineStreamResult / ...AsJson (sherpa-onnx-asr.js:1873-1880). The struct stays valid until
+ * the stream is decoded again or destroyed; B200AsrDestroyOfflineRecognizerResult is a no-op kept for
+ * source compatibility; the JSON string is malloc'ed and must be released with ...ResultJson. */
+B200ASR_API const B200AsrOfflineRecognizerResult *B200AsrGetOfflineStreamResult(const B200AsrOfflineStream *s);
+B200ASR_API void B200AsrDestroyOfflineRecognizerResult(const B200AsrOfflineRecognizerResult *r);
+B200ASR_API const char *B200AsrGetOfflineStreamResultAsJson(const B200AsrOfflineStream *s);
+B200ASR_API void B200AsrDestroyOfflineStreamResultJson(const char *s);
+
+B200ASR_API const char *B200AsrGetLastError(void);
+B200ASR_API const char *B200AsrVersion(void);
+B200ASR_API int32_t B200AsrVocabSize(const B200AsrOfflineRecognizer *r);
+B200ASR_API int32_t B200AsrEncoderOutDim(const B200AsrOfflineRecognizer *r);
+
+/* ---- raw stage entry points (host pointers; used by parity tests, ncu and the asr_engine-style sessions) ---- */
+/* compute_fbank_ort (core/asr_engine.py:698-721): samples[n] -> out[T*80], T = (n+80)/160. `out` may be NULL
+ * to query T. Returns T or <0. */
+B200ASR_API int32_t B200AsrFbank(const B200AsrOfflineRecognizer *r, const float *samples, int32_t n, float *out);
+/* Ragged batch variant: utterance u = samples[sample_offsets[u] .. sample_offsets[u+1]); features packed,
+ * frame_offsets[n_utts+1] written. */
+B200ASR_API int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const float *samples, const int64_t *sample_offsets,
+                                      int32_t n_utts, float *out, int64_t *frame_offsets);
+/* enc_sess.run (core/asr_engine.py:1045-1049): packed features [sum T, 80] with x_lens[n] ->
+ * packed encoder_out [sum T', 512], out_lens[n]. `out` may be NULL to query lengths only. */
+B200ASR_API int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, const int32_t *x_lens,
+                                   int32_t n_utts, float *out, int32_t *out_lens);
+/* Debug tap: after B200AsrEncoder on ONE utterance, copies an intermediate ("embed", "stack0".."stack5") into
+ * out (rows*dim floats); returns rows, writes dim. */
+B200ASR_API int32_t B200AsrEncoderTap(const B200AsrOfflineRecognizer *r, const char *name, float *out, int32_t *dim);
+/* dec_sess.run (core/asr_engine.py:1055,1085): y[m*2] (already max(0,.)) -> out[m*512] */
+B200ASR_API int32_t B200AsrDecoder(const B200AsrOfflineRecognizer *r, const int64_t *y, int32_t m, float *out);
+/* joi_sess.run (core/asr_engine.py:1092): enc[m*512], dec[m*512] -> logits[m*V] */
+B200ASR_API int32_t B200AsrJoiner(const B200AsrOfflineRecognizer *r, const float *enc, const float *dec, int32_t m, float *logits);
+/* _ort_beam_search from encoder_out on (core/asr_engine.py:1051-1153), batch of n utterances with packed
+ * enc_out and lens; method 0 = greedy, 1 = modified beam search. Results are returned per utterance into
+ * caller arrays of capacity max_tokens each: tokens, frames, tok_logprobs, stats[4] (tsallis, margin,
+ * entropy, top1); n_tokens[n]. */
+B200ASR_API int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const float *enc_out, const int32_t *lens, int32_t n_utts,
+                                      int32_t method, int32_t beam, int32_t max_tokens, int32_t *tokens, int32_t *frames,
+                                      float *tok_logprobs, float *stats, int32_t *n_tokens);
+/* ContextGraph.forward_one_step / finalize on the flattened automaton the device uses
+ * (core/hotword_context.py:139-184): returns the score delta, writes the next state id. */
+B200ASR_API double B200AsrContextForwardOneStep(const B200AsrOfflineRecognizer *r, int32_t state, int32_t token, int32_t *next_state);
+B200ASR_API double B200AsrContextFinalize(const B200AsrOfflineRecognizer *r, int32_t state);
+B200ASR_API int32_t B200AsrContextNumNodes(const B200AsrOfflineRecognizer *r);
+
+/* ---- device-resident benchmarking hooks (inputs staged once, timed region touches HBM only) ---- */
+/* Stages a ragged batch of PCM in HBM; returns a handle (>=0). */
+B200ASR_API int32_t B200AsrStageBatch(const B200AsrOfflineRecognizer *r, const float *samples, const int64_t *sample_offsets, int32_t n_utts);
+/* Runs fbank -> encoder -> search on a staged batch entirely on the device; token counts per utterance are
+ * copied back (n_tokens may be NULL). */
+B200ASR_API int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle, int32_t *n_tokens);
+B200ASR_API int32_t B200AsrReleaseBatch(const B200AsrOfflineRecognizer *r, int32_t handle);
+/* Per-stage device times (ms, CUDA events on the engine's stream) of the last decode / staged run:
+ * out[0]=fbank, [1]=encoder, [2]=search, [3]=total, [4]=H2D, [5]=D2H; and kernel launch count. */
+B200ASR_API int32_t B200AsrLastTimings(const B200AsrOfflineRecognizer *r, float *out6, int64_t *n_launches);
+/* Dominant-kernel timing: accumulated device time (ms) and FLOPs of all GEMM launches in the last run. */
+B200ASR_API int32_t B200AsrLastGemmStats(const B200AsrOfflineRecognizer *r, double *ms, double *flops, int64_t *launches);
+/* Enables per-GEMM CUDA-event timing (costs a little launch overhead); 0/1. */
+B200ASR_API int32_t B200AsrSetProfiling(const B200AsrOfflineRecognizer *r, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ASR_H_ */

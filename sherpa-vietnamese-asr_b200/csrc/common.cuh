@@ -1,0 +1,140 @@
+// Shared declarations for libb200asr.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace b200asr {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      throw ::b200asr::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                                 __FILE__ + ":" + std::to_string(__LINE__));                          \
+  } while (0)
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+// Global launch counter (host side) so bench.py can report `gpu_launches`.
+extern long long g_launches;
+inline void count_launch(int n = 1) { g_launches += n; }
+
+enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2 };
+
+// ---------------------------------------------------------------- fbank (fbank.cu)
+struct FbankTables {
+  float *window;     // [400] povey
+  float *twiddle;    // [512] interleaved cos,sin for k=0..255 of exp(-2*pi*i*k/512)
+  int *mel_start;    // [80] first fft bin with non-zero weight
+  int *mel_count;    // [80]
+  int *mel_off;      // [80] offset into mel_w
+  float *mel_w;      // packed weights
+};
+void fbank_tables_create(FbankTables *t);
+void fbank_tables_destroy(FbankTables *t);
+// samples: packed PCM, sample_off[n+1], frame_off[n+1]; out [total_frames, 80]
+void launch_fbank(const FbankTables &t, const float *samples, const long long *sample_off, const long long *frame_off,
+                  int n_utts, int max_frames, float *out, cudaStream_t st);
+
+// ---------------------------------------------------------------- GEMM (gemm.cu / gemm_tc.cu)
+// C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ R[M,N] if R). Row strides lda / ldc / ldr in elements.
+struct GemmArgs {
+  const float *A; int lda;
+  const float *W;            // [N,K] row-major (ldw = K)
+  const float *bias;         // [N] or null
+  const float *R; int ldr;   // residual or null
+  float *C; int ldc;
+  int M, N, K;
+  int act;
+};
+void launch_gemm_fp32(const GemmArgs &g, cudaStream_t st);
+
+// ---------------------------------------------------------------- encoder kernels (encoder.cu)
+struct RaggedDesc {     // per-rate description of the packed batch, all device pointers
+  const int *len;       // [n] frames per utterance at this rate
+  const int *off;       // [n+1] row offsets
+  int n;                // utterances
+  int total;            // total rows
+  int max_len;
+};
+
+void launch_embed_conv0(const float *feats, const int *T, const long long *foff, const long long *ooff, int n, int max_T,
+                        const float *w, const float *b, float *out, cudaStream_t st);
+void launch_embed_conv1(const float *in, const int *T, const long long *ioff, const long long *ooff, int n, int max_t2,
+                        const float *w, const float *b, float *out, cudaStream_t st);
+void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,
+                        const float *w, const float *b, float *out, cudaStream_t st);
+void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st);
+void launch_biasnorm(const float *x, int M, int D, const float *bias, const float *log_scale, float *out, cudaStream_t st);
+// out = orig + (biasnorm(x) - orig) * bypass
+void launch_biasnorm_bypass(const float *x, const float *orig, int M, int D, const float *bias, const float *log_scale,
+                            const float *bypass, float *out, cudaStream_t st);
+void launch_bypass(const float *x, const float *orig, long long M, int D, const float *scale, float *out, cudaStream_t st);
+void launch_convert_channels(const float *in, int Cin, float *out, int Cout, long long M, cudaStream_t st);
+void launch_downsample(const float *in, const RaggedDesc &rin, const RaggedDesc &rout, int C, int ds, const float *bias,
+                       float *out, cudaStream_t st);
+void launch_upsample_combine(const float *y, const RaggedDesc &rlow, const float *orig, const RaggedDesc &rfull, int C, int ds,
+                             const float *scale, float *out, cudaStream_t st);
+struct ConcatPiece { const float *src; int ld; int c0; int c1; };
+void launch_concat_downsample2(const ConcatPiece *pieces, int n_pieces, const RaggedDesc &rin, const RaggedDesc &rout, int C,
+                               const float *bias, float *out, cudaStream_t st);
+void launch_pos_emb(float *pe, int max_len, int pos_dim, cudaStream_t st);  // [2*max_len-1, pos_dim]
+// attention weights: proj [M, H*(2*qd+pd)], pos [2*max_len-1, H*pd] -> A packed per utterance: H*len*len at aoff[n]
+void launch_attn_weights(const float *proj, int ldp, const float *pos, const RaggedDesc &r, const long long *aoff, int H, int qd,
+                         int pd, float *A, cudaStream_t st);
+// out[i, c] = (sum_j A[h(c)][i][j] * V[j,c]) (* Y[i,c]);  V = X (* tanh(S) if S). head = c / dv_per_head (0 if single_head)
+void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &r, const float *X, int ldx, const float *S, int lds,
+                       const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st);
+// conv module middle: h [M, 2D] -> out [M, D] = SwooshR(dwconv_k(x * sigmoid(s)) + b)
+void launch_glu_dwconv(const float *h, const RaggedDesc &r, int D, int k, const float *w, const float *b, float *out, cudaStream_t st);
+
+// ---------------------------------------------------------------- search kernels (search.cu)
+struct ContextGraphDev {   // flattened Aho-Corasick automaton (BFS order; node 0 = root)
+  int n_nodes = 0;
+  int *edge_start = nullptr;   // [n_nodes+1]
+  int *edge_token = nullptr;   // sorted by token within a node
+  int *edge_child = nullptr;
+  int *fail = nullptr;         // [n_nodes]
+  int *token = nullptr;        // [n_nodes] (-1 root)
+  int *is_end = nullptr;
+  int *output = nullptr;       // node id or -1
+  double *token_score = nullptr, *node_score = nullptr, *output_score = nullptr;
+};
+
+struct SearchModel {
+  const float *emb;        // [V, dd]
+  const float *conv_w;     // [dd, 4, ctx]
+  const float *dec_proj_w; // [jd, dd]
+  const float *dec_proj_b;
+  const float *join_w;     // [V, jd]
+  const float *join_b;
+  int V, dd, jd;
+  int blank_id, unk_id;
+};
+
+struct SearchState;   // opaque, search.cu
+SearchState *search_state_create();
+void search_state_destroy(SearchState *s);
+// Runs the whole search for a batch. enc [sum T', jd] packed with enc_off; results to device arrays then host.
+struct SearchResultHost {
+  int n_utts;
+  int max_tokens;
+  int *n_tokens;      // [n]
+  int *tokens;        // [n, max_tokens]
+  int *frames;
+  float *tok_lp;
+  float *stats;       // [n, max_tokens, 4]
+};
+void run_search(SearchState *s, const SearchModel &m, const ContextGraphDev *g, const float *enc, const int *h_lens, int n_utts,
+                int method, int beam, float blank_penalty, SearchResultHost *out, cudaStream_t st);
+void launch_decoder_rows(const SearchModel &m, const long long *y, int rows, float *out, cudaStream_t st);
+void launch_joiner_rows(const SearchModel &m, const float *enc, const float *dec, int rows, float *tmp, float *logits,
+                        cudaStream_t st);
+
+}  // namespace b200asr

@@ -1,0 +1,615 @@
+// CUDA-core kernels of the Zipformer2 encoder (everything that is not a dense Linear):
+// Conv2dSubsampling front-end, BiasNorm, Bypass, SimpleDownsample/Upsample, relative-position attention
+// weights, attention application, and the convolution module's GLU + depthwise conv + SwooshR.
+// The reference runs this arithmetic inside the encoder ONNX graph (/root/reference core/asr_engine.py:1045-1049);
+// the architecture statement followed here is SURVEY.md Appendix B (icefall Zipformer2, inference only).
+//
+// Batch layout: ragged, packed. Every activation is [rows, C] row-major fp32 where rows = sum over utterances
+// of that utterance's own frame count at the stack's rate; per-utterance lengths/offsets (RaggedDesc) make
+// every time-dependent op stop at each utterance's own end (App. B.6), which is what the reference's batch-1
+// execution computes.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200asr {
+
+namespace {
+
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float swoosh_r(float v) { return softplus_f(v - 1.0f) - 0.08f * v - 0.313261687f; }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------ Conv2dSubsampling (App. B.2)
+// conv0: [T,80] -> [(T-2),80,8] channels-last, k3, pad (0,1), SwooshR.   w: [3][3][8] (kh,kw,co)
+__global__ void embed_conv0_kernel(const float *__restrict__ feats, const int *__restrict__ T, const long long *__restrict__ foff,
+                                   const long long *__restrict__ ooff, const float *__restrict__ w, const float *__restrict__ b,
+                                   float *__restrict__ out) {
+  const int u = blockIdx.y;
+  const int To = T[u] - 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (To <= 0 || idx >= To * 80) return;
+  const int t = idx / 80, f = idx % 80;
+  const float *x = feats + foff[u] * 80;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = __ldg(b + c);
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ff = f + kw - 1;
+      const float v = (ff >= 0 && ff < 80) ? __ldg(x + (long long)(t + kh) * 80 + ff) : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, __ldg(w + (kh * 3 + kw) * 8 + c), acc[c]);
+    }
+  float *o = out + ((ooff[u] + t) * 80 + f) * 8;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = swoosh_r(acc[c]);
+}
+
+// conv1: [(T-2),80,8] -> [t2,39,32], k3 stride 2, SwooshR.   w: [3][3][8][32]
+__global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restrict__ in, const int *__restrict__ T,
+                                                          const long long *__restrict__ ioff, const long long *__restrict__ ooff,
+                                                          const float *__restrict__ w, const float *__restrict__ b,
+                                                          float *__restrict__ out) {
+  __shared__ float sw[72 * 32];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 72 * 32; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const int u = blockIdx.y;
+  const int Tu = T[u];
+  const int t2 = Tu >= 5 ? (Tu - 5) / 2 + 1 : 0;
+  // thread -> (pixel, group of 8 output channels)
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pix = idx >> 2, cg = (idx & 3) * 8;
+  if (pix >= t2 * 39) return;
+  const int t = pix / 39, f = pix % 39;
+  const float *x = in + ioff[u] * 80 * 8;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = sb[cg + c];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const float *px = x + ((long long)(2 * t + kh) * 80 + (2 * f + kw)) * 8;
+      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(px));
+      const float4 v1 = __ldg(reinterpret_cast<const float4 *>(px + 4));
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        const float *wr = sw + ((kh * 3 + kw) * 8 + ci) * 32 + cg;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v[ci], wr[c], acc[c]);
+      }
+    }
+  float *o = out + ((ooff[u] + t) * 39 + f) * 32 + cg;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = swoosh_r(acc[c]);
+}
+
+// conv2: [t2,39,32] -> [T1,19,128], k3 stride (1,2), SwooshR.  w: [3][3][32][128]
+// CTA = 4 output time rows of one utterance; the 6x39x32 input patch sits in shared memory; thread = one
+// output channel x half of the 19 frequency positions.
+constexpr int kC2Rows = 4;
+__global__ void __launch_bounds__(256) embed_conv2_kernel(const float *__restrict__ in, const int *__restrict__ T,
+                                                          const long long *__restrict__ ioff, const int *__restrict__ ooff,
+                                                          const float *__restrict__ w, const float *__restrict__ b,
+                                                          float *__restrict__ out) {
+  __shared__ __align__(16) float patch[(kC2Rows + 2) * 39 * 32];
+  const int u = blockIdx.y;
+  const int Tu = T[u];
+  const int T1 = (Tu - 7) / 2;
+  const int t0 = blockIdx.x * kC2Rows;
+  if (Tu < 9 || t0 >= T1) return;
+  const int t2 = (Tu - 5) / 2 + 1;
+  const float *x = in + ioff[u] * 39 * 32;
+  const int rows = min(kC2Rows + 2, t2 - t0);
+  for (int i = threadIdx.x; i < (kC2Rows + 2) * 39 * 32 / 4; i += blockDim.x) {
+    const int r = i / (39 * 32 / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < rows) v = __ldg(reinterpret_cast<const float4 *>(x + (long long)t0 * 39 * 32) + i);
+    reinterpret_cast<float4 *>(patch)[i] = v;
+  }
+  __syncthreads();
+  const int co = threadIdx.x & 127, fh = threadIdx.x >> 7;  // fh 0: f 0..9, fh 1: f 10..18
+  const int fbeg = fh * 10, fcnt = fh ? 9 : 10;
+  float acc[kC2Rows][10];
+#pragma unroll
+  for (int r = 0; r < kC2Rows; ++r)
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc[r][j] = 0.f;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw)
+      for (int ci = 0; ci < 32; ++ci) {
+        const float wv = __ldg(w + ((kh * 3 + kw) * 32 + ci) * 128 + co);
+#pragma unroll
+        for (int r = 0; r < kC2Rows; ++r) {
+          const float *pr = patch + ((r + kh) * 39 + kw) * 32 + ci;
+#pragma unroll
+          for (int j = 0; j < 10; ++j)
+            if (j < fcnt) acc[r][j] = fmaf(wv, pr[(2 * (fbeg + j)) * 32], acc[r][j]);
+        }
+      }
+  const float bias = __ldg(b + co);
+#pragma unroll
+  for (int r = 0; r < kC2Rows; ++r) {
+    const int t = t0 + r;
+    if (t >= T1) break;
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+      if (j < fcnt) out[((long long)(ooff[u] + t) * 19 + fbeg + j) * 128 + co] = swoosh_r(acc[r][j] + bias);
+  }
+}
+
+// ConvNeXt depthwise 7x7 over (time, freq) of [T1,19,128], zero padded at each utterance's own edges. w: [7][7][128]
+__global__ void embed_dw7_kernel(const float *__restrict__ in, const int *__restrict__ len, const int *__restrict__ off,
+                                 const float *__restrict__ w, const float *__restrict__ b, float *__restrict__ out) {
+  const int u = blockIdx.y;
+  const int T1 = len[u];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T1 * 19 * 128) return;
+  const int c = idx & 127;
+  const int f = (int)((idx >> 7) % 19), t = (int)((idx >> 7) / 19);
+  const float *x = in + (long long)off[u] * 19 * 128;
+  float acc = __ldg(b + c);
+#pragma unroll
+  for (int dt = 0; dt < 7; ++dt) {
+    const int tt = t + dt - 3;
+    if (tt < 0 || tt >= T1) continue;
+#pragma unroll
+    for (int df = 0; df < 7; ++df) {
+      const int ff = f + df - 3;
+      if (ff < 0 || ff >= 19) continue;
+      acc = fmaf(__ldg(w + (dt * 7 + df) * 128 + c), __ldg(x + ((long long)tt * 19 + ff) * 128 + c), acc);
+    }
+  }
+  out[((long long)off[u] * 19) * 128 + idx] = acc;
+}
+
+// ------------------------------------------------------------------ BiasNorm / Bypass
+// one warp per row: x * (mean((x-bias)^2))^-0.5 * exp(log_scale); optional bypass against `orig`
+__global__ void biasnorm_kernel(const float *__restrict__ x, const float *__restrict__ orig, int M, int D,
+                                const float *__restrict__ bias, const float *__restrict__ log_scale,
+                                const float *__restrict__ bypass, float *__restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float *xr = x + (long long)row * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float d = xr[c] - __ldg(bias + c);
+    ss = fmaf(d, d, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float scale = (1.0f / sqrtf(ss / (float)D)) * expf(__ldg(log_scale));
+  float *orow = out + (long long)row * D;
+  if (orig) {
+    const float *og = orig + (long long)row * D;
+    for (int c = lane; c < D; c += 32) {
+      const float o0 = og[c];
+      orow[c] = o0 + (xr[c] * scale - o0) * __ldg(bypass + c);
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) orow[c] = xr[c] * scale;
+  }
+}
+
+__global__ void bypass_kernel(const float *__restrict__ x, const float *__restrict__ orig, long long total, int D,
+                              const float *__restrict__ scale, float *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float o0 = orig[i];
+  out[i] = o0 + (x[i] - o0) * __ldg(scale + (int)(i % D));
+}
+
+__global__ void convert_channels_kernel(const float *__restrict__ in, int Cin, float *__restrict__ out, int Cout, long long M) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * Cout) return;
+  const long long m = i / Cout;
+  const int c = (int)(i % Cout);
+  out[i] = c < Cin ? in[m * Cin + c] : 0.f;
+}
+
+// ------------------------------------------------------------------ SimpleDownsample / SimpleUpsample (App. B.3)
+__global__ void downsample_kernel(const float *__restrict__ in, const int *__restrict__ len_in, const int *__restrict__ off_in,
+                                  const int *__restrict__ len_out, const int *__restrict__ off_out, int C, int ds,
+                                  const float *__restrict__ bias, float *__restrict__ out) {
+  const int u = blockIdx.y;
+  const int Lo = len_out[u], Li = len_in[u];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Lo * C) return;
+  const int t = (int)(idx / C), c = (int)(idx % C);
+  // softmax over the ds bias entries
+  float mx = -INFINITY;
+  for (int k = 0; k < ds; ++k) mx = fmaxf(mx, __ldg(bias + k));
+  float den = 0.f;
+  for (int k = 0; k < ds; ++k) den += expf(__ldg(bias + k) - mx);
+  const float *x = in + (long long)off_in[u] * C;
+  float acc = 0.f;
+  for (int k = 0; k < ds; ++k) {
+    const int ti = min(t * ds + k, Li - 1);   // right-pad by repeating the utterance's own last frame
+    acc += x[(long long)ti * C + c] * (expf(__ldg(bias + k) - mx) / den);
+  }
+  out[((long long)off_out[u] + t) * C + c] = acc;
+}
+
+__global__ void upsample_combine_kernel(const float *__restrict__ y, const int *__restrict__ off_low, const float *__restrict__ orig,
+                                        const int *__restrict__ len_full, const int *__restrict__ off_full, int C, int ds,
+                                        const float *__restrict__ scale, float *__restrict__ out) {
+  const int u = blockIdx.y;
+  const int L = len_full[u];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)L * C) return;
+  const int t = (int)(idx / C), c = (int)(idx % C);
+  const long long o = ((long long)off_full[u] + t) * C + c;
+  const float o0 = orig[o];
+  const float v = y[((long long)off_low[u] + t / ds) * C + c];
+  out[o] = o0 + (v - o0) * __ldg(scale + c);
+}
+
+struct ConcatArgs {
+  const float *src[4];
+  int ld[4], c0[4], c1[4];
+  int n;
+};
+__global__ void concat_downsample2_kernel(ConcatArgs a, const int *__restrict__ len_in, const int *__restrict__ off_in,
+                                          const int *__restrict__ len_out, const int *__restrict__ off_out, int C,
+                                          const float *__restrict__ bias, float *__restrict__ out) {
+  const int u = blockIdx.y;
+  const int Lo = len_out[u], Li = len_in[u];
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Lo * C) return;
+  const int t = (int)(idx / C), c = (int)(idx % C);
+  const float b0 = __ldg(bias), b1 = __ldg(bias + 1);
+  const float mx = fmaxf(b0, b1);
+  const float e0 = expf(b0 - mx), e1 = expf(b1 - mx);
+  const float den = e0 + e1;
+  const float *src = nullptr;
+  int ld = 0;
+  for (int p = 0; p < a.n; ++p)
+    if (c >= a.c0[p] && c < a.c1[p]) { src = a.src[p]; ld = a.ld[p]; }
+  const long long r0 = (long long)off_in[u] + min(2 * t, Li - 1);
+  const long long r1 = (long long)off_in[u] + min(2 * t + 1, Li - 1);
+  float acc = 0.f;
+  acc += src[r0 * ld + c] * (e0 / den);
+  acc += src[r1 * ld + c] * (e1 / den);
+  out[((long long)off_out[u] + t) * C + c] = acc;
+}
+
+// ------------------------------------------------------------------ CompactRelPositionalEncoding
+__global__ void pos_emb_kernel(float *__restrict__ pe, int L, int pos_dim) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = pos_dim / 2;
+  if (idx >= (2 * L - 1) * half) return;
+  const int r = idx / half, j = idx % half;
+  const float x = (float)(r - (L - 1));
+  const float cl = (float)sqrt((double)pos_dim);
+  const float sgn = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+  const float xc = cl * sgn * (logf(fabsf(x) + cl) - (float)log(sqrt((double)pos_dim)));
+  const float length_scale = (float)((double)pos_dim / (2.0 * M_PI));
+  const float th = atanf(xc / length_scale);
+  const float fr = (float)(j + 1);
+  pe[(long long)r * pos_dim + 2 * j] = cosf(th * fr);
+  pe[(long long)r * pos_dim + 2 * j + 1] = (2 * j + 1 == pos_dim - 1) ? 1.0f : sinf(th * fr);
+}
+
+// ------------------------------------------------------------------ attention weights (scores + rel-pos + softmax)
+// CTA = (query tile of 16 rows, head, utterance). Scores for the 16 rows against all keys live in shared
+// memory; softmax per row by a warp; normalised weights written once to HBM: A[u][h][i][j].
+constexpr int kAttRows = 16;
+template <int QD, int PD>
+__global__ void __launch_bounds__(256) attn_weights_kernel(const float *__restrict__ proj, int ldp, const float *__restrict__ pos,
+                                                           int ldpos, const int *__restrict__ len, const int *__restrict__ off,
+                                                           const long long *__restrict__ aoff, int H, int Lmax,
+                                                           float *__restrict__ A) {
+  extern __shared__ float smem[];
+  const int u = blockIdx.z, h = blockIdx.y;
+  const int Tk = len[u];
+  const int i0 = blockIdx.x * kAttRows;
+  if (i0 >= Tk) return;
+  float *sq = smem;                       // [16][QD]
+  float *sp = sq + kAttRows * QD;         // [16][PD]
+  float *sc = sp + kAttRows * PD;         // [16][Tk]
+  const float *base = proj + (long long)off[u] * ldp;
+  const int nrow = min(kAttRows, Tk - i0);
+  for (int i = threadIdx.x; i < kAttRows * QD; i += blockDim.x) {
+    const int r = i / QD, d = i % QD;
+    sq[i] = r < nrow ? base[(long long)(i0 + r) * ldp + h * QD + d] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kAttRows * PD; i += blockDim.x) {
+    const int r = i / PD, d = i % PD;
+    sp[i] = r < nrow ? base[(long long)(i0 + r) * ldp + 2 * H * QD + h * PD + d] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
+    float kv[QD];
+    const float4 *kr = reinterpret_cast<const float4 *>(base + (long long)j * ldp + H * QD + h * QD);
+#pragma unroll
+    for (int d = 0; d < QD / 4; ++d) {
+      const float4 v = __ldg(kr + d);
+      kv[4 * d] = v.x; kv[4 * d + 1] = v.y; kv[4 * d + 2] = v.z; kv[4 * d + 3] = v.w;
+    }
+#pragma unroll 4
+    for (int r = 0; r < kAttRows; ++r) {
+      if (r >= nrow) break;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < QD; ++d) s = fmaf(sq[r * QD + d], kv[d], s);
+      // relative position term: pos row for offset (j - i) is (j - i) + (Lmax - 1)
+      const int pr = j - (i0 + r) + (Lmax - 1);
+      const float *pp = pos + (long long)pr * ldpos + h * PD;
+      float ps = 0.f;
+#pragma unroll
+      for (int d = 0; d < PD; ++d) ps = fmaf(sp[r * PD + d], __ldg(pp + d), ps);
+      sc[r * Tk + j] = s + ps;
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *Abase = A + aoff[u] + (long long)h * Tk * Tk;
+  for (int r = warp; r < nrow; r += (blockDim.x >> 5)) {
+    float *row = sc + r * Tk;
+    float mx = -INFINITY;
+    for (int j = lane; j < Tk; j += 32) mx = fmaxf(mx, row[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float e = expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float *orow = Abase + (long long)(i0 + r) * Tk;
+    for (int j = lane; j < Tk; j += 32) orow[j] = row[j] / sum;
+  }
+}
+
+// ------------------------------------------------------------------ attention application: out = (A_h * V) (* Y)
+// CTA = 64 query rows x CT columns of one utterance; loops over keys in chunks of 32 through shared memory.
+template <int CT, int TR, int TC>
+__global__ void __launch_bounds__(256) attn_apply_kernel(const float *__restrict__ A, const long long *__restrict__ aoff,
+                                                         const int *__restrict__ len, const int *__restrict__ off,
+                                                         const float *__restrict__ X, int ldx, const float *__restrict__ S, int lds,
+                                                         const float *__restrict__ Y, int ldy, int C, int single_head,
+                                                         float *__restrict__ out, int ldo) {
+  constexpr int KC = 32;
+  __shared__ float As[64][KC + 1];
+  __shared__ float Vs[KC][CT];
+  const int u = blockIdx.z;
+  const int Tk = len[u];
+  const int i0 = blockIdx.x * 64;
+  if (i0 >= Tk) return;
+  const int ctile = blockIdx.y;                 // column tile (== head when !single_head)
+  const int c0 = ctile * CT;
+  const int head = single_head ? 0 : ctile;
+  const float *Ah = A + aoff[u] + (long long)head * Tk * Tk;
+  const long long rbase = off[u];
+  constexpr int NCG = CT / TC;                  // column groups
+  const int cg = threadIdx.x % NCG, rg = threadIdx.x / NCG;   // rg in [0, 64/TR)
+  float acc[TR][TC];
+#pragma unroll
+  for (int a = 0; a < TR; ++a)
+#pragma unroll
+    for (int b = 0; b < TC; ++b) acc[a][b] = 0.f;
+  for (int j0 = 0; j0 < Tk; j0 += KC) {
+    for (int i = threadIdx.x; i < 64 * KC; i += blockDim.x) {
+      const int r = i / KC, jj = i % KC;
+      const int gi = i0 + r, gj = j0 + jj;
+      As[r][jj] = (gi < Tk && gj < Tk) ? Ah[(long long)gi * Tk + gj] : 0.f;
+    }
+    for (int i = threadIdx.x; i < KC * CT; i += blockDim.x) {
+      const int jj = i / CT, c = i % CT;
+      const int gj = j0 + jj, gc = c0 + c;
+      float v = 0.f;
+      if (gj < Tk && gc < C) {
+        v = X[(rbase + gj) * ldx + gc];
+        if (S) v *= tanhf(S[(rbase + gj) * lds + gc]);
+      }
+      Vs[jj][c] = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int jj = 0; jj < KC; ++jj) {
+      float a[TR], v[TC];
+#pragma unroll
+      for (int x = 0; x < TR; ++x) a[x] = As[rg * TR + x][jj];
+#pragma unroll
+      for (int y = 0; y < TC; ++y) v[y] = Vs[jj][cg * TC + y];
+#pragma unroll
+      for (int x = 0; x < TR; ++x)
+#pragma unroll
+        for (int y = 0; y < TC; ++y) acc[x][y] = fmaf(a[x], v[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < TR; ++x) {
+    const int gi = i0 + rg * TR + x;
+    if (gi >= Tk) continue;
+#pragma unroll
+    for (int y = 0; y < TC; ++y) {
+      const int gc = c0 + cg * TC + y;
+      if (gc >= C) continue;
+      float v = acc[x][y];
+      if (Y) v *= Y[(rbase + gi) * ldy + gc];
+      out[(rbase + gi) * ldo + gc] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ conv module: GLU -> depthwise conv -> SwooshR
+// CTA = 32 frames x 64 channels of one utterance; GLU values (with k-1 halo, zero outside the utterance) in smem.
+constexpr int kDwT = 32, kDwC = 64, kDwMaxK = 31;
+__global__ void __launch_bounds__(256) glu_dwconv_kernel(const float *__restrict__ h, const int *__restrict__ len,
+                                                         const int *__restrict__ off, int D, int k, const float *__restrict__ w,
+                                                         const float *__restrict__ b, float *__restrict__ out) {
+  __shared__ float g[(kDwT + kDwMaxK - 1)][kDwC];
+  const int u = blockIdx.z;
+  const int L = len[u];
+  const int t0 = blockIdx.x * kDwT;
+  if (t0 >= L) return;
+  const int c0 = blockIdx.y * kDwC;
+  const int pad = k / 2;
+  const long long rbase = off[u];
+  const int rows = kDwT + k - 1;
+  for (int i = threadIdx.x; i < rows * kDwC; i += blockDim.x) {
+    const int r = i / kDwC, c = i % kDwC;
+    const int t = t0 - pad + r, gc = c0 + c;
+    float v = 0.f;
+    if (t >= 0 && t < L && gc < D) {
+      const float *row = h + (rbase + t) * (2LL * D);
+      v = row[gc] * sigmoid_f(row[D + gc]);
+    }
+    g[r][c] = v;
+  }
+  __syncthreads();
+  const int c = threadIdx.x % kDwC, tq = threadIdx.x / kDwC;  // 4 groups x 8 frames
+  const int gc = c0 + c;
+  if (gc >= D) return;
+  float wr[kDwMaxK];
+#pragma unroll
+  for (int j = 0; j < kDwMaxK; ++j) wr[j] = j < k ? __ldg(w + j * D + gc) : 0.f;
+  const float bias = __ldg(b + gc);
+#pragma unroll
+  for (int f = 0; f < 8; ++f) {
+    const int tl = tq * 8 + f;
+    const int t = t0 + tl;
+    if (t >= L) break;
+    float acc = bias;
+#pragma unroll
+    for (int j = 0; j < kDwMaxK; ++j)
+      if (j < k) acc = fmaf(wr[j], g[tl + j][c], acc);
+    out[(rbase + t) * D + gc] = swoosh_r(acc);
+  }
+}
+
+inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+// ====================================================================== launchers
+void launch_embed_conv0(const float *feats, const int *T, const long long *foff, const long long *ooff, int n, int max_T,
+                        const float *w, const float *b, float *out, cudaStream_t st) {
+  if (max_T <= 2) return;
+  dim3 grid(cdiv((long long)(max_T - 2) * 80, 256), n);
+  embed_conv0_kernel<<<grid, 256, 0, st>>>(feats, T, foff, ooff, w, b, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_embed_conv1(const float *in, const int *T, const long long *ioff, const long long *ooff, int n, int max_t2,
+                        const float *w, const float *b, float *out, cudaStream_t st) {
+  if (max_t2 <= 0) return;
+  dim3 grid(cdiv((long long)max_t2 * 39 * 4, 256), n);
+  embed_conv1_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, w, b, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,
+                        const float *w, const float *b, float *out, cudaStream_t st) {
+  if (max_T1 <= 0) return;
+  dim3 grid(cdiv(max_T1, kC2Rows), n);
+  embed_conv2_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, w, b, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st) {
+  if (r.total <= 0) return;
+  dim3 grid(cdiv((long long)r.max_len * 19 * 128, 256), r.n);
+  embed_dw7_kernel<<<grid, 256, 0, st>>>(in, r.len, r.off, w, b, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_biasnorm(const float *x, int M, int D, const float *bias, const float *log_scale, float *out, cudaStream_t st) {
+  if (M <= 0) return;
+  biasnorm_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, nullptr, M, D, bias, log_scale, nullptr, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_biasnorm_bypass(const float *x, const float *orig, int M, int D, const float *bias, const float *log_scale,
+                            const float *bypass, float *out, cudaStream_t st) {
+  if (M <= 0) return;
+  biasnorm_kernel<<<cdiv(M, 8), 256, 0, st>>>(x, orig, M, D, bias, log_scale, bypass, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_bypass(const float *x, const float *orig, long long M, int D, const float *scale, float *out, cudaStream_t st) {
+  if (M <= 0) return;
+  bypass_kernel<<<cdiv(M * D, 256), 256, 0, st>>>(x, orig, M * D, D, scale, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_convert_channels(const float *in, int Cin, float *out, int Cout, long long M, cudaStream_t st) {
+  if (M <= 0) return;
+  convert_channels_kernel<<<cdiv(M * Cout, 256), 256, 0, st>>>(in, Cin, out, Cout, M);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_downsample(const float *in, const RaggedDesc &rin, const RaggedDesc &rout, int C, int ds, const float *bias,
+                       float *out, cudaStream_t st) {
+  if (rout.total <= 0) return;
+  dim3 grid(cdiv((long long)rout.max_len * C, 256), rout.n);
+  downsample_kernel<<<grid, 256, 0, st>>>(in, rin.len, rin.off, rout.len, rout.off, C, ds, bias, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_upsample_combine(const float *y, const RaggedDesc &rlow, const float *orig, const RaggedDesc &rfull, int C, int ds,
+                             const float *scale, float *out, cudaStream_t st) {
+  if (rfull.total <= 0) return;
+  dim3 grid(cdiv((long long)rfull.max_len * C, 256), rfull.n);
+  upsample_combine_kernel<<<grid, 256, 0, st>>>(y, rlow.off, orig, rfull.len, rfull.off, C, ds, scale, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_concat_downsample2(const ConcatPiece *pieces, int n_pieces, const RaggedDesc &rin, const RaggedDesc &rout, int C,
+                               const float *bias, float *out, cudaStream_t st) {
+  if (rout.total <= 0) return;
+  ConcatArgs a{};
+  a.n = n_pieces;
+  for (int i = 0; i < n_pieces && i < 4; ++i) {
+    a.src[i] = pieces[i].src; a.ld[i] = pieces[i].ld; a.c0[i] = pieces[i].c0; a.c1[i] = pieces[i].c1;
+  }
+  dim3 grid(cdiv((long long)rout.max_len * C, 256), rout.n);
+  concat_downsample2_kernel<<<grid, 256, 0, st>>>(a, rin.len, rin.off, rout.len, rout.off, C, bias, out);
+  count_launch(); KERNEL_CHECK();
+}
+void launch_pos_emb(float *pe, int max_len, int pos_dim, cudaStream_t st) {
+  if (max_len <= 0) return;
+  pos_emb_kernel<<<cdiv((long long)(2 * max_len - 1) * (pos_dim / 2), 256), 256, 0, st>>>(pe, max_len, pos_dim);
+  count_launch(); KERNEL_CHECK();
+}
+
+void launch_attn_weights(const float *proj, int ldp, const float *pos, const RaggedDesc &r, const long long *aoff, int H, int qd,
+                         int pd, float *A, cudaStream_t st) {
+  if (r.total <= 0) return;
+  if (qd != 32 || pd != 4) throw CudaError("attn_weights: only query_head_dim=32, pos_head_dim=4 are built");
+  const size_t smem = (size_t)(kAttRows * (qd + pd) + (size_t)kAttRows * r.max_len) * sizeof(float);
+  if (smem > 227 * 1024) throw CudaError("attn_weights: segment too long for one pass (max ~3400 frames at the stack rate)");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(attn_weights_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(r.max_len, kAttRows), H, r.n);
+  attn_weights_kernel<32, 4><<<grid, 256, smem, st>>>(proj, ldp, pos, H * pd, r.len, r.off, aoff, H, r.max_len, A);
+  count_launch(); KERNEL_CHECK();
+}
+
+void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &r, const float *X, int ldx, const float *S, int lds,
+                       const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st) {
+  if (r.total <= 0) return;
+  if (single_head) {
+    dim3 grid(cdiv(r.max_len, 64), cdiv(C, 64), r.n);
+    attn_apply_kernel<64, 4, 4><<<grid, 256, 0, st>>>(A, aoff, r.len, r.off, X, ldx, S, lds, Y, ldy, C, 1, out, ldo);
+  } else {
+    if (dv_per_head != 12) throw CudaError("attn_apply: only value_head_dim=12 is built");
+    dim3 grid(cdiv(r.max_len, 64), C / 12, r.n);
+    attn_apply_kernel<12, 1, 3><<<grid, 256, 0, st>>>(A, aoff, r.len, r.off, X, ldx, S, lds, Y, ldy, C, 0, out, ldo);
+  }
+  count_launch(); KERNEL_CHECK();
+}
+
+void launch_glu_dwconv(const float *h, const RaggedDesc &r, int D, int k, const float *w, const float *b, float *out, cudaStream_t st) {
+  if (r.total <= 0) return;
+  if (k > kDwMaxK) throw CudaError("glu_dwconv: kernel size > 31 not built");
+  dim3 grid(cdiv(r.max_len, kDwT), cdiv(D, kDwC), r.n);
+  glu_dwconv_kernel<<<grid, 256, 0, st>>>(h, r.len, r.off, D, k, w, b, out);
+  count_launch(); KERNEL_CHECK();
+}
+
+}  // namespace b200asr

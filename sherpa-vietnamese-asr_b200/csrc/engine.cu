@@ -1,0 +1,1165 @@
+// Engine: weight container loading, workspace management, the fbank -> encoder -> search pipeline over a
+// ragged batch, and the C-ABI declared in include/b200asr.h.
+// The pipeline stands where the reference runs compute_fbank_ort + `_ort_beam_search` per chunk
+// (/root/reference core/asr_engine.py:1209-1253, chunk loop :2326-2397); the encoder schedule follows
+// SURVEY.md Appendix B (icefall Zipformer2 inference graph).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/b200asr.h"
+#include "common.cuh"
+#include "context_graph.h"
+
+namespace b200asr {
+
+void launch_gemm_tc(const GemmArgs &g, cudaStream_t st);   // gemm_tc.cu (BF16 tcgen05 path)
+bool gemm_tc_available();
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------ growable device buffer
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  template <typename T>
+  T *get(size_t n) {
+    const size_t need = n * sizeof(T);
+    if (need > cap) {
+      if (p) CUDA_CHECK(cudaFree(p));
+      p = nullptr;
+      cap = need + need / 8 + 256;
+      CUDA_CHECK(cudaMalloc(&p, cap));
+    }
+    return reinterpret_cast<T *>(p);
+  }
+  template <typename T>
+  T *ptr() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Tensor {
+  std::vector<int> shape;
+  std::vector<float> host;
+  float *dev = nullptr;
+  size_t numel() const { size_t n = 1; for (int d : shape) n *= (size_t)d; return n; }
+};
+
+std::vector<int> parse_int_list(const std::string &s) {
+  std::vector<int> v;
+  std::stringstream ss(s);
+  std::string tok;
+  while (std::getline(ss, tok, ',')) if (!tok.empty()) v.push_back(atoi(tok.c_str()));
+  return v;
+}
+
+struct LayerW {
+  const float *attn_in_w, *attn_in_b, *pos_w;
+  const float *ff_in_w[3], *ff_in_b[3], *ff_out_w[3], *ff_out_b[3];
+  int ff_dim[3];
+  const float *nl_in_w, *nl_in_b, *nl_out_w, *nl_out_b;
+  const float *sa_in_w[2], *sa_in_b[2], *sa_out_w[2], *sa_out_b[2];
+  const float *cv_in_w[2], *cv_in_b[2], *cv_dw_w[2], *cv_dw_b[2], *cv_out_w[2], *cv_out_b[2];
+  const float *norm_bias, *norm_log_scale, *bypass, *bypass_mid;
+};
+
+struct StackW {
+  int L, ds, D, F, H, k;
+  const float *ds_bias = nullptr, *combiner = nullptr;
+  std::vector<LayerW> layers;
+};
+
+struct Timings { float fbank = 0, encoder = 0, search = 0, total = 0, h2d = 0, d2h = 0; };
+
+}  // namespace
+
+struct Stream;
+
+struct Engine {
+  // config
+  std::map<std::string, std::string> cfg;
+  std::vector<int> num_layers, ds_factor, enc_dim, ff_dim, num_heads, cnn_kernel;
+  int qd = 32, pd = 4, vd = 12, pos_dim = 48, feat_dim = 80, dec_dim = 512, join_dim = 512, ctx_size = 2, V = 2000;
+  int blank_id = 0, unk_id = 2, out_dim = 512;
+  int device = 0, precision = 0;
+  std::string decoding_method = "greedy_search";
+  int max_active_paths = 4;
+  float hotwords_score = 1.5f, blank_penalty = 0.f;
+  std::vector<std::string> id2token;
+
+  std::map<std::string, Tensor> tensors;
+  std::vector<StackW> stacks;
+  // embed weights (re-laid out)
+  float *w_conv0 = nullptr, *w_conv1 = nullptr, *w_conv2 = nullptr, *w_dw7 = nullptr, *w_out = nullptr;
+  std::vector<float *> owned;   // extra device allocations to free
+
+  FbankTables fb{};
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[8]{};
+  SearchState *search = nullptr;
+  SearchModel sm{};
+  ContextGraphHost cg_host;
+  ContextGraphDev cg_dev;
+  bool has_graph = false;
+  std::mutex mu;
+  Timings tm;
+  long long launches_last = 0;
+  bool profiling = false;
+  double gemm_ms = 0, gemm_flops = 0;
+  long long gemm_launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+  size_t gemm_ev_used = 0;
+
+  // workspaces
+  DevBuf b_pcm, b_soff, b_foff, b_feats;
+  DevBuf b_T, b_c0off, b_c1off, b_len[4], b_off[4], b_aoff;
+  DevBuf b_c0, b_c1, b_c2, b_dw, b_pw1, b_cn, b_x0, b_xc, b_sin, b_w1, b_proj, b_hid, b_A, b_pe, b_pp, b_cat, b_enc;
+  DevBuf b_stack[6];
+  DevBuf b_tmp;
+  // host-side batch description of the last encoder run
+  std::vector<int> h_T, h_T1, h_Tp;
+  std::vector<std::vector<int>> h_len = std::vector<std::vector<int>>(4), h_off = std::vector<std::vector<int>>(4);
+  int last_n = 0;
+  // staged batches for device-resident benchmarking
+  struct Staged { float *pcm = nullptr; long long *soff = nullptr; std::vector<long long> h_soff; int n = 0; };
+  std::map<int, Staged> staged;
+  int next_handle = 0;
+
+  ~Engine();
+  void load(const B200AsrOfflineRecognizerConfig *c);
+  void load_container(const std::string &path, const std::string &prefix);
+  const float *W(const std::string &name, std::vector<int> expect = {});
+  float *upload(const std::vector<float> &h);
+  void gemm(const float *A, int lda, const float *Wt, const float *bias, const float *R, int ldr, float *C, int ldc, int M, int N,
+            int K, int act);
+  void set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n);
+  // pipeline pieces (device pointers)
+  void run_fbank(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n, float **d_feats,
+                 std::vector<int> *T);
+  void run_encoder(const float *d_feats, const std::vector<int> &T, float **d_enc, std::vector<int> *Tp);
+  void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax);
+  void decode(Stream *const *ss, int n);
+  void decode_pcm_device(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n,
+                         SearchResultHost *res, std::vector<int> *Tp);
+  void collect_gemm_times();
+};
+
+struct Stream {
+  Engine *eng;
+  std::vector<float> samples;
+  // result storage
+  B200AsrOfflineRecognizerResult res{};
+  std::string text, json;
+  std::vector<std::string> tok_str;
+  std::vector<const char *> tok_ptr;
+  std::vector<int32_t> token_ids, frames;
+  std::vector<float> timestamps, lps, tsallis, margin, entropy, top1;
+  bool decoded = false;
+};
+
+Engine::~Engine() {
+  for (auto &kv : tensors) if (kv.second.dev) cudaFree(kv.second.dev);
+  for (float *p : owned) cudaFree(p);
+  if (fb.window) fbank_tables_destroy(&fb);
+  if (search) search_state_destroy(search);
+  for (auto &e : ev) if (e) cudaEventDestroy(e);
+  for (auto &p : gemm_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto &kv : staged) { cudaFree(kv.second.pcm); cudaFree(kv.second.soff); }
+  int *ptrs[] = {cg_dev.edge_start, cg_dev.edge_token, cg_dev.edge_child, cg_dev.fail, cg_dev.token, cg_dev.is_end, cg_dev.output};
+  for (int *p : ptrs) if (p) cudaFree(p);
+  double *dp[] = {cg_dev.token_score, cg_dev.node_score, cg_dev.output_score};
+  for (double *p : dp) if (p) cudaFree(p);
+  if (st) cudaStreamDestroy(st);
+}
+
+void Engine::load_container(const std::string &path, const std::string &prefix) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot open weight container: " + path);
+  std::string first;
+  std::getline(f, first);
+  char magic[32];
+  int ver = 0;
+  long long hb = 0;
+  if (sscanf(first.c_str(), "%31s %d %lld", magic, &ver, &hb) != 3 || std::string(magic) != "B200ASRW")
+    throw std::runtime_error(path + ": not a B200ASRW container");
+  f.seekg(0);
+  std::string header((size_t)hb, '\0');
+  f.read(&header[0], hb);
+  std::stringstream hs(header);
+  std::string line;
+  std::getline(hs, line);
+  struct Ent { std::string name; std::vector<int> shape; long long off, nbytes; };
+  std::vector<Ent> ents;
+  while (std::getline(hs, line)) {
+    std::stringstream ls(line);
+    std::string kind;
+    ls >> kind;
+    if (kind == "end" || kind.empty() || kind[0] == '\0') break;
+    if (kind == "config") {
+      std::string k, v;
+      ls >> k >> v;
+      if (!cfg.count(k)) cfg[k] = v;
+      else if (cfg[k] != v && k != "name") throw std::runtime_error("containers disagree on config " + k);
+    } else if (kind == "tensor") {
+      Ent e;
+      std::string dt;
+      int nd;
+      ls >> e.name >> dt >> nd;
+      e.shape.resize(nd);
+      for (int i = 0; i < nd; ++i) ls >> e.shape[i];
+      ls >> e.off >> e.nbytes;
+      if (dt != "f32") throw std::runtime_error("unsupported dtype in container: " + dt);
+      if (e.name.compare(0, prefix.size(), prefix) == 0) ents.push_back(e);
+    }
+  }
+  for (auto &e : ents) {
+    Tensor t;
+    t.shape = e.shape;
+    t.host.resize((size_t)e.nbytes / 4);
+    f.seekg(hb + e.off);
+    f.read(reinterpret_cast<char *>(t.host.data()), e.nbytes);
+    if (!f) throw std::runtime_error(path + ": truncated tensor " + e.name);
+    if (t.numel() * 4 != (size_t)e.nbytes) throw std::runtime_error(path + ": shape/bytes mismatch for " + e.name);
+    CUDA_CHECK(cudaMalloc(&t.dev, std::max<size_t>(e.nbytes, 16)));
+    CUDA_CHECK(cudaMemcpy(t.dev, t.host.data(), e.nbytes, cudaMemcpyHostToDevice));
+    tensors[e.name] = std::move(t);
+  }
+  if (ents.empty()) throw std::runtime_error(path + ": holds no '" + prefix + "*' tensors");
+}
+
+const float *Engine::W(const std::string &name, std::vector<int> expect) {
+  auto it = tensors.find(name);
+  if (it == tensors.end()) throw std::runtime_error("missing tensor: " + name);
+  if (!expect.empty() && it->second.shape != expect) {
+    std::string s = "tensor " + name + " has shape [";
+    for (int d : it->second.shape) s += std::to_string(d) + ",";
+    s += "] expected [";
+    for (int d : expect) s += std::to_string(d) + ",";
+    throw std::runtime_error(s + "]");
+  }
+  return it->second.dev;
+}
+
+float *Engine::upload(const std::vector<float> &h) {
+  float *d;
+  CUDA_CHECK(cudaMalloc(&d, h.size() * sizeof(float)));
+  CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  owned.push_back(d);
+  return d;
+}
+
+void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
+  const auto &mc = c->model_config;
+  auto str = [](const char *s) { return std::string(s ? s : ""); };
+  const std::string prov = str(mc.provider);
+  if (!prov.empty() && prov != "cuda" && prov != "b200")
+    throw std::runtime_error("provider '" + prov + "' is not available: this library has only the CUDA (sm_100a) path");
+  if (c->feat_config.sample_rate != 0 && c->feat_config.sample_rate != 16000)
+    throw std::runtime_error("only 16 kHz input is supported (core/asr_engine.py:706)");
+  if (c->feat_config.feature_dim != 0 && c->feat_config.feature_dim != 80)
+    throw std::runtime_error("only 80-bin fbank is supported (core/asr_engine.py:710)");
+  device = c->device_id;
+  precision = c->precision;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    throw std::runtime_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libb200asr has no CPU fallback)");
+  if (device < 0 || device >= ndev) throw std::runtime_error("device_id out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) throw std::runtime_error("libb200asr is built for sm_100a only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
+
+  load_container(str(mc.transducer.encoder), "encoder.");
+  load_container(str(mc.transducer.decoder), "decoder.");
+  load_container(str(mc.transducer.joiner), "joiner.");
+  auto geti = [&](const char *k) { if (!cfg.count(k)) throw std::runtime_error(std::string("container lacks config ") + k); return atoi(cfg[k].c_str()); };
+  num_layers = parse_int_list(cfg["num_encoder_layers"]);
+  ds_factor = parse_int_list(cfg["downsampling_factor"]);
+  enc_dim = parse_int_list(cfg["encoder_dim"]);
+  ff_dim = parse_int_list(cfg["feedforward_dim"]);
+  num_heads = parse_int_list(cfg["num_heads"]);
+  cnn_kernel = parse_int_list(cfg["cnn_module_kernel"]);
+  qd = geti("query_head_dim"); pd = geti("pos_head_dim"); vd = geti("value_head_dim"); pos_dim = geti("pos_dim");
+  feat_dim = geti("feature_dim"); dec_dim = geti("decoder_dim"); join_dim = geti("joiner_dim"); ctx_size = geti("context_size");
+  V = geti("vocab_size"); blank_id = geti("blank_id"); unk_id = geti("unk_id");
+  const size_t ns = num_layers.size();
+  if (ns == 0 || ns > 6 || ds_factor.size() != ns || enc_dim.size() != ns || ff_dim.size() != ns || num_heads.size() != ns ||
+      cnn_kernel.size() != ns)
+    throw std::runtime_error("inconsistent stack configuration in container");
+  if (ctx_size != 2) throw std::runtime_error("only context_size=2 is built");
+  if (feat_dim != 80) throw std::runtime_error("only feature_dim=80 is built");
+  out_dim = *std::max_element(enc_dim.begin(), enc_dim.end());
+
+  // ---- embed weights, re-laid out channels-last
+  {
+    const auto &w0 = tensors.at("encoder.embed.conv0.weight").host;   // [8,1,3,3] -> [3][3][8]
+    W("encoder.embed.conv0.weight", {8, 1, 3, 3});
+    std::vector<float> t(72);
+    for (int co = 0; co < 8; ++co) for (int k = 0; k < 9; ++k) t[k * 8 + co] = w0[co * 9 + k];
+    w_conv0 = upload(t);
+    const auto &w1 = tensors.at("encoder.embed.conv1.weight").host;   // [32,8,3,3] -> [3][3][8][32]
+    W("encoder.embed.conv1.weight", {32, 8, 3, 3});
+    t.assign(72 * 32, 0.f);
+    for (int co = 0; co < 32; ++co) for (int ci = 0; ci < 8; ++ci) for (int k = 0; k < 9; ++k)
+      t[(k * 8 + ci) * 32 + co] = w1[(co * 8 + ci) * 9 + k];
+    w_conv1 = upload(t);
+    const auto &w2 = tensors.at("encoder.embed.conv2.weight").host;   // [128,32,3,3] -> [3][3][32][128]
+    W("encoder.embed.conv2.weight", {128, 32, 3, 3});
+    t.assign(288 * 128, 0.f);
+    for (int co = 0; co < 128; ++co) for (int ci = 0; ci < 32; ++ci) for (int k = 0; k < 9; ++k)
+      t[(k * 32 + ci) * 128 + co] = w2[(co * 32 + ci) * 9 + k];
+    w_conv2 = upload(t);
+    const auto &wd = tensors.at("encoder.embed.convnext.dw.weight").host;  // [128,1,7,7] -> [7][7][128]
+    W("encoder.embed.convnext.dw.weight", {128, 1, 7, 7});
+    t.assign(49 * 128, 0.f);
+    for (int c2 = 0; c2 < 128; ++c2) for (int k = 0; k < 49; ++k) t[k * 128 + c2] = wd[c2 * 49 + k];
+    w_dw7 = upload(t);
+    const int D0 = enc_dim[0];
+    const auto &wo = tensors.at("encoder.embed.out.weight").host;     // [D0, c*19+f] -> [D0, f*128+c]
+    W("encoder.embed.out.weight", {D0, 128 * 19});
+    t.assign((size_t)D0 * 2432, 0.f);
+    for (int o = 0; o < D0; ++o) for (int c2 = 0; c2 < 128; ++c2) for (int f = 0; f < 19; ++f)
+      t[(size_t)o * 2432 + f * 128 + c2] = wo[(size_t)o * 2432 + c2 * 19 + f];
+    w_out = upload(t);
+  }
+  // ---- stacks
+  stacks.resize(ns);
+  for (size_t i = 0; i < ns; ++i) {
+    StackW &s = stacks[i];
+    s.L = num_layers[i]; s.ds = ds_factor[i]; s.D = enc_dim[i]; s.F = ff_dim[i]; s.H = num_heads[i]; s.k = cnn_kernel[i];
+    const std::string sp = "encoder.stack" + std::to_string(i) + ".";
+    if (s.ds > 1) {
+      s.ds_bias = W(sp + "downsample.bias", {s.ds});
+      s.combiner = W(sp + "out_combiner.scale", {s.D});
+    }
+    const int D = s.D, H = s.H, h = (3 * D) / 4;
+    for (int l = 0; l < s.L; ++l) {
+      const std::string p = sp + "layer" + std::to_string(l) + ".";
+      LayerW w{};
+      w.attn_in_w = W(p + "attn_w.in_proj.weight", {H * (2 * qd + pd), D});
+      w.attn_in_b = W(p + "attn_w.in_proj.bias", {H * (2 * qd + pd)});
+      w.pos_w = W(p + "attn_w.linear_pos.weight", {H * pd, pos_dim});
+      const int fd[3] = {(s.F * 3) / 4, s.F, (s.F * 5) / 4};
+      for (int j = 0; j < 3; ++j) {
+        const std::string q = p + "ff" + std::to_string(j + 1) + ".";
+        w.ff_dim[j] = fd[j];
+        w.ff_in_w[j] = W(q + "in.weight", {fd[j], D}); w.ff_in_b[j] = W(q + "in.bias", {fd[j]});
+        w.ff_out_w[j] = W(q + "out.weight", {D, fd[j]}); w.ff_out_b[j] = W(q + "out.bias", {D});
+      }
+      w.nl_in_w = W(p + "nonlin.in.weight", {3 * h, D}); w.nl_in_b = W(p + "nonlin.in.bias", {3 * h});
+      w.nl_out_w = W(p + "nonlin.out.weight", {D, h}); w.nl_out_b = W(p + "nonlin.out.bias", {D});
+      for (int j = 0; j < 2; ++j) {
+        const std::string a = p + "attn" + std::to_string(j + 1) + ".";
+        w.sa_in_w[j] = W(a + "in.weight", {H * vd, D}); w.sa_in_b[j] = W(a + "in.bias", {H * vd});
+        w.sa_out_w[j] = W(a + "out.weight", {D, H * vd}); w.sa_out_b[j] = W(a + "out.bias", {D});
+        const std::string cname = p + "conv" + std::to_string(j + 1) + ".";
+        w.cv_in_w[j] = W(cname + "in.weight", {2 * D, D}); w.cv_in_b[j] = W(cname + "in.bias", {2 * D});
+        W(cname + "dw.weight", {D, 1, s.k});
+        const auto &dw = tensors.at(cname + "dw.weight").host;       // [D,1,k] -> [k][D]
+        std::vector<float> t((size_t)s.k * D);
+        for (int c2 = 0; c2 < D; ++c2) for (int j2 = 0; j2 < s.k; ++j2) t[(size_t)j2 * D + c2] = dw[(size_t)c2 * s.k + j2];
+        w.cv_dw_w[j] = upload(t);
+        w.cv_dw_b[j] = W(cname + "dw.bias", {D});
+        w.cv_out_w[j] = W(cname + "out.weight", {D, D}); w.cv_out_b[j] = W(cname + "out.bias", {D});
+      }
+      w.norm_bias = W(p + "norm.bias", {D}); w.norm_log_scale = W(p + "norm.log_scale", {1});
+      w.bypass = W(p + "bypass.scale", {D}); w.bypass_mid = W(p + "bypass_mid.scale", {D});
+      s.layers.push_back(w);
+    }
+  }
+  W("encoder.downsample_output.bias", {2});
+  W("encoder.encoder_proj.weight", {join_dim, out_dim});
+  // ---- decoder / joiner
+  sm.emb = W("decoder.embedding.weight", {V, dec_dim});
+  sm.conv_w = W("decoder.conv.weight", {dec_dim, 4, ctx_size});
+  sm.dec_proj_w = W("decoder.decoder_proj.weight", {join_dim, dec_dim});
+  sm.dec_proj_b = W("decoder.decoder_proj.bias", {join_dim});
+  sm.join_w = W("joiner.output_linear.weight", {V, join_dim});
+  sm.join_b = W("joiner.output_linear.bias", {V});
+  sm.V = V; sm.dd = dec_dim; sm.jd = join_dim; sm.blank_id = blank_id; sm.unk_id = unk_id;
+
+  // tokens
+  const std::string tp = str(mc.tokens);
+  id2token.assign(V, "");
+  if (!tp.empty()) {
+    std::ifstream tf(tp);
+    if (!tf) throw std::runtime_error("cannot open tokens file: " + tp);
+    std::string ln;
+    while (std::getline(tf, ln)) {
+      const size_t sp2 = ln.find_last_of(" \t");
+      if (sp2 == std::string::npos) continue;
+      const int id = atoi(ln.c_str() + sp2 + 1);
+      std::string sym = ln.substr(0, sp2);
+      while (!sym.empty() && (sym.back() == ' ' || sym.back() == '\t')) sym.pop_back();
+      if (id >= 0 && id < V) id2token[id] = sym;
+    }
+  }
+  decoding_method = str(c->decoding_method).empty() ? "greedy_search" : str(c->decoding_method);
+  if (decoding_method != "greedy_search" && decoding_method != "modified_beam_search")
+    throw std::runtime_error("unsupported decoding_method: " + decoding_method);
+  max_active_paths = c->max_active_paths > 0 ? c->max_active_paths : 4;
+  if (max_active_paths > 16) throw std::runtime_error("max_active_paths > 16 is not built");
+  hotwords_score = c->hotwords_score > 0 ? c->hotwords_score : 1.5f;
+  blank_penalty = c->blank_penalty;
+  fbank_tables_create(&fb);
+  search = search_state_create();
+  if (precision == 1 && !gemm_tc_available()) throw std::runtime_error("BF16 tensor-core GEMM path unavailable in this build");
+
+  // hotwords file with token ids (modeling_unit token_id); text units are tokenised by the host binding
+  const std::string hw = str(c->hotwords_file), mu_ = str(mc.modeling_unit);
+  if (!hw.empty() && mu_ == "token_id") {
+    std::ifstream hf(hw);
+    if (!hf) throw std::runtime_error("cannot open hotwords file: " + hw);
+    std::vector<int32_t> toks, offs{0};
+    std::vector<float> scs;
+    std::string ln;
+    while (std::getline(hf, ln)) {
+      if (ln.empty() || ln[0] == '#') continue;
+      float sc = hotwords_score;
+      const size_t colon = ln.rfind(':');
+      if (colon != std::string::npos) { sc = (float)atof(ln.c_str() + colon + 1); ln = ln.substr(0, colon); }
+      std::stringstream ls(ln);
+      int id, cnt = 0;
+      while (ls >> id) { toks.push_back(id); ++cnt; }
+      if (cnt == 0) continue;
+      offs.push_back((int32_t)toks.size());
+      scs.push_back(sc);
+    }
+    set_graph(toks.data(), offs.data(), scs.data(), (int)scs.size());
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void Engine::set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n) {
+  int *ptrs[] = {cg_dev.edge_start, cg_dev.edge_token, cg_dev.edge_child, cg_dev.fail, cg_dev.token, cg_dev.is_end, cg_dev.output};
+  for (int *p : ptrs) if (p) cudaFree(p);
+  double *dp[] = {cg_dev.token_score, cg_dev.node_score, cg_dev.output_score};
+  for (double *p : dp) if (p) cudaFree(p);
+  cg_dev = ContextGraphDev{};
+  has_graph = false;
+  cg_host = ContextGraphHost{};
+  if (n <= 0) return;
+  for (int p = 0; p < n; ++p)
+    for (int j = offsets[p]; j < offsets[p + 1]; ++j)
+      if (tokens[j] < 0 || tokens[j] >= V) throw std::runtime_error("hotword token id out of range");
+  cg_host.build(tokens, offsets, scores, n);
+  const int N = cg_host.n_nodes();
+  if (N <= 1) return;
+  auto up_i = [&](const std::vector<int> &v) { int *d; CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(int)));
+    CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); return d; };
+  auto up_d = [&](const std::vector<double> &v) { double *d; CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(double)));
+    CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice)); return d; };
+  cg_dev.n_nodes = N;
+  cg_dev.edge_start = up_i(cg_host.edge_start); cg_dev.edge_token = up_i(cg_host.edge_token);
+  cg_dev.edge_child = up_i(cg_host.edge_child); cg_dev.fail = up_i(cg_host.fail); cg_dev.token = up_i(cg_host.token);
+  cg_dev.is_end = up_i(cg_host.is_end); cg_dev.output = up_i(cg_host.output);
+  cg_dev.token_score = up_d(cg_host.token_score); cg_dev.node_score = up_d(cg_host.node_score);
+  cg_dev.output_score = up_d(cg_host.output_score);
+  has_graph = true;
+}
+
+void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, const float *R, int ldr, float *C, int ldc, int M,
+                  int N, int K, int act) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.W = Wt; g.bias = bias; g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.act = act;
+  if (M <= 0) return;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (profiling) {
+    if (gemm_ev_used >= gemm_events.size()) {
+      cudaEvent_t a, b;
+      CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+      gemm_events.emplace_back(a, b);
+    }
+    e0 = gemm_events[gemm_ev_used].first; e1 = gemm_events[gemm_ev_used].second;
+    ++gemm_ev_used;
+    CUDA_CHECK(cudaEventRecord(e0, st));
+  }
+  if (precision == 1) launch_gemm_tc(g, st); else launch_gemm_fp32(g, st);
+  if (profiling) CUDA_CHECK(cudaEventRecord(e1, st));
+  gemm_flops += 2.0 * (double)M * (double)N * (double)K;
+  ++gemm_launches;
+}
+
+void Engine::collect_gemm_times() {
+  gemm_ms = 0;
+  for (size_t i = 0; i < gemm_ev_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, gemm_events[i].first, gemm_events[i].second) == cudaSuccess) gemm_ms += ms;
+  }
+  gemm_ev_used = 0;
+}
+
+// ------------------------------------------------------------------ fbank
+void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n, float **d_feats,
+                       std::vector<int> *T) {
+  std::vector<long long> foff(n + 1, 0);
+  T->assign(n, 0);
+  int maxT = 0;
+  for (int u = 0; u < n; ++u) {
+    const long long ns = h_soff[u + 1] - h_soff[u];
+    (*T)[u] = (int)((ns + 80) / 160);
+    foff[u + 1] = foff[u] + (*T)[u];
+    maxT = std::max(maxT, (*T)[u]);
+  }
+  long long *d_foff = b_foff.get<long long>(n + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_foff, foff.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  float *feats = b_feats.get<float>((size_t)std::max<long long>(foff[n], 1) * 80);
+  launch_fbank(fb, d_pcm, d_soff, d_foff, n, maxT, feats, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));   // foff is a local; keep it alive until the copy is done
+  *d_feats = feats;
+}
+
+// ------------------------------------------------------------------ encoder
+void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax) {
+  const int D = s.D, H = s.H, h = (3 * D) / 4;
+  const int pw = H * (2 * qd + pd);
+  int maxw = std::max({pw, 3 * h, 2 * D, w.ff_dim[2], H * vd});
+  float *proj = b_proj.get<float>((size_t)M * maxw);
+  float *hid = b_hid.get<float>((size_t)M * std::max({h, D, H * vd}));
+  float *w1 = b_w1.get<float>((size_t)M * D);
+  float *A = b_A.ptr<float>();
+  float *pp = b_pp.get<float>((size_t)(2 * Lmax - 1) * H * pd);
+  // attention weights (computed once per layer from the layer input)
+  gemm(src, D, w.attn_in_w, w.attn_in_b, nullptr, 0, proj, pw, M, pw, D, ACT_NONE);
+  gemm(b_pe.ptr<float>(), pos_dim, w.pos_w, nullptr, nullptr, 0, pp, H * pd, 2 * Lmax - 1, H * pd, pos_dim, ACT_NONE);
+  launch_attn_weights(proj, pw, pp, r, aoff, H, qd, pd, A, st);
+  // feed_forward1
+  gemm(src, D, w.ff_in_w[0], w.ff_in_b[0], nullptr, 0, proj, w.ff_dim[0], M, w.ff_dim[0], D, ACT_SWOOSH_L);
+  gemm(proj, w.ff_dim[0], w.ff_out_w[0], w.ff_out_b[0], src, D, w1, D, M, D, w.ff_dim[0], ACT_NONE);
+  // nonlin attention (head 0)
+  gemm(w1, D, w.nl_in_w, w.nl_in_b, nullptr, 0, proj, 3 * h, M, 3 * h, D, ACT_NONE);
+  launch_attn_apply(A, aoff, r, proj + h, 3 * h, proj, 3 * h, proj + 2 * h, 3 * h, h, 0, 1, hid, h, st);
+  gemm(hid, h, w.nl_out_w, w.nl_out_b, w1, D, w1, D, M, D, h, ACT_NONE);
+  for (int j = 0; j < 2; ++j) {
+    // self attention j
+    gemm(w1, D, w.sa_in_w[j], w.sa_in_b[j], nullptr, 0, proj, H * vd, M, H * vd, D, ACT_NONE);
+    launch_attn_apply(A, aoff, r, proj, H * vd, nullptr, 0, nullptr, 0, H * vd, vd, 0, hid, H * vd, st);
+    gemm(hid, H * vd, w.sa_out_w[j], w.sa_out_b[j], w1, D, w1, D, M, D, H * vd, ACT_NONE);
+    // conv module j
+    gemm(w1, D, w.cv_in_w[j], w.cv_in_b[j], nullptr, 0, proj, 2 * D, M, 2 * D, D, ACT_NONE);
+    launch_glu_dwconv(proj, r, D, s.k, w.cv_dw_w[j], w.cv_dw_b[j], hid, st);
+    gemm(hid, D, w.cv_out_w[j], w.cv_out_b[j], w1, D, w1, D, M, D, D, ACT_NONE);
+    // feed forward 2 / 3
+    const int f = w.ff_dim[j + 1];
+    gemm(w1, D, w.ff_in_w[j + 1], w.ff_in_b[j + 1], nullptr, 0, proj, f, M, f, D, ACT_SWOOSH_L);
+    gemm(proj, f, w.ff_out_w[j + 1], w.ff_out_b[j + 1], w1, D, w1, D, M, D, f, ACT_NONE);
+    if (j == 0) launch_bypass(w1, src, M, D, w.bypass_mid, w1, st);
+  }
+  launch_biasnorm_bypass(w1, src, M, D, w.norm_bias, w.norm_log_scale, w.bypass, src, st);
+}
+
+void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float **d_enc, std::vector<int> *Tp) {
+  const int n = (int)T.size();
+  last_n = n;
+  h_T = T;
+  h_T1.assign(n, 0);
+  std::vector<long long> foff(n + 1, 0), c0off(n + 1, 0), c1off(n + 1, 0);
+  int maxT = 0, maxt2 = 0;
+  for (int u = 0; u < n; ++u) {
+    const int t = T[u];
+    h_T1[u] = t >= 9 ? (t - 7) / 2 : 0;
+    const int t2 = t >= 9 ? (t - 5) / 2 + 1 : 0;
+    foff[u + 1] = foff[u] + t;
+    c0off[u + 1] = c0off[u] + (t >= 9 ? t - 2 : 0);
+    c1off[u + 1] = c1off[u] + t2;
+    if (t >= 9) { maxT = std::max(maxT, t); maxt2 = std::max(maxt2, t2); }
+  }
+  const int rates[4] = {1, 2, 4, 8};
+  int Mr[4], Lr[4];
+  for (int q = 0; q < 4; ++q) {
+    h_len[q].assign(n, 0); h_off[q].assign(n + 1, 0);
+    Lr[q] = 0;
+    for (int u = 0; u < n; ++u) {
+      h_len[q][u] = (h_T1[u] + rates[q] - 1) / rates[q];
+      h_off[q][u + 1] = h_off[q][u] + h_len[q][u];
+      Lr[q] = std::max(Lr[q], h_len[q][u]);
+    }
+    Mr[q] = h_off[q][n];
+  }
+  Tp->assign(h_len[1].begin(), h_len[1].end());   // T' = (T1+1)//2
+  h_Tp = *Tp;
+  const int M1 = Mr[0];
+  // upload descriptors
+  int *d_T = b_T.get<int>(n);
+  std::vector<int> Tclamped(n);
+  for (int u = 0; u < n; ++u) Tclamped[u] = T[u] >= 9 ? T[u] : 0;
+  CUDA_CHECK(cudaMemcpyAsync(d_T, Tclamped.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+  long long *d_foff = b_foff.get<long long>(n + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_foff, foff.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  long long *d_c0off = b_c0off.get<long long>(n + 1), *d_c1off = b_c1off.get<long long>(n + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_c0off, c0off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(d_c1off, c1off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  RaggedDesc rd[4];
+  for (int q = 0; q < 4; ++q) {
+    int *dl = b_len[q].get<int>(n), *dof = b_off[q].get<int>(n + 1);
+    CUDA_CHECK(cudaMemcpyAsync(dl, h_len[q].data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(dof, h_off[q].data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    rd[q] = RaggedDesc{dl, dof, n, Mr[q], Lr[q]};
+  }
+  // attention-weight offsets per stack and the max A size
+  const size_t ns = stacks.size();
+  std::vector<std::vector<long long>> aoffs(ns, std::vector<long long>(n + 1, 0));
+  long long maxA = 1;
+  auto rate_idx = [](int ds) { return ds == 1 ? 0 : ds == 2 ? 1 : ds == 4 ? 2 : 3; };
+  for (size_t i = 0; i < ns; ++i) {
+    const int q = rate_idx(stacks[i].ds);
+    for (int u = 0; u < n; ++u)
+      aoffs[i][u + 1] = aoffs[i][u] + (long long)stacks[i].H * h_len[q][u] * h_len[q][u];
+    maxA = std::max(maxA, aoffs[i][n]);
+  }
+  long long *d_aoff = b_aoff.get<long long>(ns * (n + 1));
+  for (size_t i = 0; i < ns; ++i)
+    CUDA_CHECK(cudaMemcpyAsync(d_aoff + i * (n + 1), aoffs[i].data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  b_A.get<float>((size_t)maxA);
+  float *enc = b_enc.get<float>((size_t)std::max(Mr[1], 1) * join_dim);
+  *d_enc = enc;
+  if (M1 <= 0) { CUDA_CHECK(cudaStreamSynchronize(st)); return; }
+
+  // ---- Conv2dSubsampling
+  const int D0 = enc_dim[0];
+  float *c0 = b_c0.get<float>((size_t)c0off[n] * 640);
+  float *c1 = b_c1.get<float>((size_t)c1off[n] * 39 * 32);
+  float *c2 = b_c2.get<float>((size_t)M1 * 2432);
+  float *dw = b_dw.get<float>((size_t)M1 * 2432);
+  float *pw1 = b_pw1.get<float>((size_t)M1 * 19 * 384);
+  float *cn = b_cn.get<float>((size_t)M1 * 2432);
+  float *x0 = b_x0.get<float>((size_t)M1 * D0);
+  launch_embed_conv0(d_feats, d_T, d_foff, d_c0off, n, maxT, w_conv0, W("encoder.embed.conv0.bias"), c0, st);
+  launch_embed_conv1(c0, d_T, d_c0off, d_c1off, n, maxt2, w_conv1, W("encoder.embed.conv1.bias"), c1, st);
+  launch_embed_conv2(c1, d_T, d_c1off, rd[0].off, n, Lr[0], w_conv2, W("encoder.embed.conv2.bias"), c2, st);
+  launch_embed_dw7(c2, rd[0], w_dw7, W("encoder.embed.convnext.dw.bias"), dw, st);
+  gemm(dw, 128, W("encoder.embed.convnext.pw1.weight"), W("encoder.embed.convnext.pw1.bias"), nullptr, 0, pw1, 384, M1 * 19, 384, 128,
+       ACT_SWOOSH_L);
+  gemm(pw1, 384, W("encoder.embed.convnext.pw2.weight"), W("encoder.embed.convnext.pw2.bias"), c2, 128, cn, 128, M1 * 19, 128, 384,
+       ACT_NONE);
+  gemm(cn, 2432, w_out, W("encoder.embed.out.bias"), nullptr, 0, dw, D0, M1, D0, 2432, ACT_NONE);   // dw reused as scratch
+  launch_biasnorm(dw, M1, D0, W("encoder.embed.out_norm.bias"), W("encoder.embed.out_norm.log_scale"), x0, st);
+
+  // ---- stacks
+  const float *x = x0;
+  int xC = D0;
+  for (size_t i = 0; i < ns; ++i) {
+    const StackW &s = stacks[i];
+    const int q = rate_idx(s.ds);
+    const int D = s.D;
+    float *outb = b_stack[i].get<float>((size_t)M1 * D);
+    const long long *aoff = d_aoff + i * (n + 1);
+    float *pe = b_pe.get<float>((size_t)(2 * Lr[q] - 1) * pos_dim);
+    launch_pos_emb(pe, Lr[q], pos_dim, st);
+    if (s.ds == 1) {
+      launch_convert_channels(x, xC, outb, D, M1, st);
+      for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], outb, rd[0], aoff, M1, Lr[0]);
+    } else {
+      float *xc = b_xc.get<float>((size_t)M1 * D);
+      launch_convert_channels(x, xC, xc, D, M1, st);
+      float *sin_ = b_sin.get<float>((size_t)Mr[q] * D);
+      launch_downsample(xc, rd[0], rd[q], D, s.ds, s.ds_bias, sin_, st);
+      for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], sin_, rd[q], aoff, Mr[q], Lr[q]);
+      launch_upsample_combine(sin_, rd[q], xc, rd[0], D, s.ds, s.combiner, outb, st);
+    }
+    x = outb;
+    xC = D;
+  }
+  // ---- full-dim output: each channel range from the latest stack that has it, then downsample(2), encoder_proj
+  std::vector<ConcatPiece> pieces;
+  int curd = enc_dim[ns - 1];
+  pieces.push_back(ConcatPiece{b_stack[ns - 1].ptr<float>(), enc_dim[ns - 1], 0, curd});
+  for (int i = (int)ns - 2; i >= 0; --i) {
+    if (enc_dim[i] > curd) {
+      pieces.push_back(ConcatPiece{b_stack[i].ptr<float>(), enc_dim[i], curd, enc_dim[i]});
+      curd = enc_dim[i];
+    }
+  }
+  if (pieces.size() > 4) throw std::runtime_error("more than 4 output pieces not built");
+  float *cat = b_cat.get<float>((size_t)Mr[1] * out_dim);
+  launch_concat_downsample2(pieces.data(), (int)pieces.size(), rd[0], rd[1], out_dim, W("encoder.downsample_output.bias"), cat, st);
+  gemm(cat, out_dim, W("encoder.encoder_proj.weight"), W("encoder.encoder_proj.bias"), nullptr, 0, enc, join_dim, Mr[1], join_dim,
+       out_dim, ACT_NONE);
+  CUDA_CHECK(cudaStreamSynchronize(st));   // host descriptor vectors are locals
+}
+
+// ------------------------------------------------------------------ full pipeline on device-resident PCM
+void Engine::decode_pcm_device(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n,
+                               SearchResultHost *res, std::vector<int> *Tp) {
+  gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
+  const long long l0 = g_launches;
+  CUDA_CHECK(cudaEventRecord(ev[0], st));
+  float *d_feats = nullptr, *d_enc = nullptr;
+  std::vector<int> T;
+  run_fbank(d_pcm, d_soff, h_soff, n, &d_feats, &T);
+  CUDA_CHECK(cudaEventRecord(ev[1], st));
+  run_encoder(d_feats, T, &d_enc, Tp);
+  CUDA_CHECK(cudaEventRecord(ev[2], st));
+  int max_tokens = 1;
+  for (int v : *Tp) max_tokens = std::max(max_tokens, v);
+  res->n_utts = n;
+  res->max_tokens = max_tokens;
+  const int method = decoding_method == "greedy_search" ? 0 : 1;
+  run_search(search, sm, has_graph ? &cg_dev : nullptr, d_enc, Tp->data(), n, method, max_active_paths, blank_penalty, res, st);
+  CUDA_CHECK(cudaEventRecord(ev[3], st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&tm.fbank, ev[0], ev[1]);
+  cudaEventElapsedTime(&tm.encoder, ev[1], ev[2]);
+  cudaEventElapsedTime(&tm.search, ev[2], ev[3]);
+  cudaEventElapsedTime(&tm.total, ev[0], ev[3]);
+  launches_last = g_launches - l0;
+  if (profiling) collect_gemm_times();
+}
+
+static std::string json_escape(const std::string &s) {
+  std::string o;
+  for (unsigned char c : s) {
+    if (c == '"') o += "\\\"";
+    else if (c == '\\') o += "\\\\";
+    else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o += (char)c;
+  }
+  return o;
+}
+
+void Engine::decode(Stream *const *ss, int n) {
+  if (n <= 0) return;
+  std::lock_guard<std::mutex> lk(mu);
+  CUDA_CHECK(cudaSetDevice(device));
+  // sub-batches bounded by total audio so workspaces stay bounded (about 70 min of audio per pass)
+  const long long kMaxSamples = 4200LL * 16000;
+  int begin = 0;
+  while (begin < n) {
+    int end = begin;
+    long long tot = 0;
+    while (end < n && (end == begin || tot + (long long)ss[end]->samples.size() <= kMaxSamples)) {
+      tot += (long long)ss[end]->samples.size();
+      ++end;
+    }
+    const int nb = end - begin;
+    std::vector<long long> soff(nb + 1, 0);
+    for (int i = 0; i < nb; ++i) soff[i + 1] = soff[i] + (long long)ss[begin + i]->samples.size();
+    float *d_pcm = b_pcm.get<float>((size_t)std::max<long long>(soff[nb], 1));
+    long long *d_soff = b_soff.get<long long>(nb + 1);
+    CUDA_CHECK(cudaEventRecord(ev[4], st));
+    for (int i = 0; i < nb; ++i)
+      if (!ss[begin + i]->samples.empty())
+        CUDA_CHECK(cudaMemcpyAsync(d_pcm + soff[i], ss[begin + i]->samples.data(), ss[begin + i]->samples.size() * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaEventRecord(ev[5], st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
+    // results
+    std::vector<int> Tp;
+    SearchResultHost res{};
+    int cap = 1;
+    for (int i = 0; i < nb; ++i) {
+      const long long ns = soff[i + 1] - soff[i];
+      const int T = (int)((ns + 80) / 160);
+      const int T1 = T >= 9 ? (T - 7) / 2 : 0;
+      cap = std::max(cap, (T1 + 1) / 2);
+    }
+    std::vector<int> ntok(nb), toks((size_t)nb * cap), frm((size_t)nb * cap);
+    std::vector<float> lp((size_t)nb * cap), stt((size_t)nb * cap * 4);
+    res.n_tokens = ntok.data(); res.tokens = toks.data(); res.frames = frm.data(); res.tok_lp = lp.data(); res.stats = stt.data();
+    decode_pcm_device(d_pcm, d_soff, soff, nb, &res, &Tp);
+    for (int i = 0; i < nb; ++i) {
+      Stream *s = ss[begin + i];
+      const int cnt = std::min(ntok[i], res.max_tokens);
+      const float dur = (float)s->samples.size() / 16000.0f;
+      s->token_ids.assign(toks.begin() + (size_t)i * res.max_tokens, toks.begin() + (size_t)i * res.max_tokens + cnt);
+      s->frames.assign(frm.begin() + (size_t)i * res.max_tokens, frm.begin() + (size_t)i * res.max_tokens + cnt);
+      s->lps.assign(lp.begin() + (size_t)i * res.max_tokens, lp.begin() + (size_t)i * res.max_tokens + cnt);
+      s->timestamps.resize(cnt); s->tsallis.resize(cnt); s->margin.resize(cnt); s->entropy.resize(cnt); s->top1.resize(cnt);
+      s->tok_str.resize(cnt); s->tok_ptr.resize(cnt);
+      s->text.clear();
+      for (int j = 0; j < cnt; ++j) {
+        const size_t o = (size_t)i * res.max_tokens + j;
+        s->timestamps[j] = Tp[i] > 0 ? (float)((double)s->frames[j] / (double)Tp[i] * (double)dur) : 0.f;
+        s->tsallis[j] = stt[o * 4]; s->margin[j] = stt[o * 4 + 1]; s->entropy[j] = stt[o * 4 + 2]; s->top1[j] = stt[o * 4 + 3];
+        const int id = s->token_ids[j];
+        s->tok_str[j] = (id >= 0 && id < V) ? id2token[id] : "";
+        s->text += s->tok_str[j];
+      }
+      for (int j = 0; j < cnt; ++j) s->tok_ptr[j] = s->tok_str[j].c_str();
+      // U+2581 -> space, strip
+      std::string txt;
+      for (size_t p = 0; p < s->text.size();) {
+        if (p + 2 < s->text.size() + 0 && (unsigned char)s->text[p] == 0xE2 && (unsigned char)s->text[p + 1] == 0x96 &&
+            (unsigned char)s->text[p + 2] == 0x81) { txt += ' '; p += 3; }
+        else txt += s->text[p++];
+      }
+      size_t a = txt.find_first_not_of(' '), b = txt.find_last_not_of(' ');
+      s->text = (a == std::string::npos) ? "" : txt.substr(a, b - a + 1);
+      std::string js = "{\"lang\": \"\", \"emotion\": \"\", \"event\": \"\", \"text\": \"" + json_escape(s->text) + "\", \"timestamps\": [";
+      char buf[64];
+      for (int j = 0; j < cnt; ++j) { snprintf(buf, sizeof buf, "%s%.3f", j ? ", " : "", s->timestamps[j]); js += buf; }
+      js += "], \"tokens\": [";
+      for (int j = 0; j < cnt; ++j) js += std::string(j ? ", " : "") + "\"" + json_escape(s->tok_str[j]) + "\"";
+      js += "], \"ys_log_probs\": [";
+      for (int j = 0; j < cnt; ++j) { snprintf(buf, sizeof buf, "%s%.6f", j ? ", " : "", s->lps[j]); js += buf; }
+      js += "], \"words\": []}";
+      s->json = js;
+      s->res.text = s->text.c_str(); s->res.json = s->json.c_str(); s->res.tokens = s->tok_ptr.data();
+      s->res.token_ids = s->token_ids.data(); s->res.timestamps = s->timestamps.data(); s->res.frames = s->frames.data();
+      s->res.ys_log_probs = s->lps.data(); s->res.tsallis = s->tsallis.data(); s->res.margin = s->margin.data();
+      s->res.entropy = s->entropy.data(); s->res.top1 = s->top1.data(); s->res.count = cnt; s->res.num_frames = Tp[i];
+      s->res.duration = dur;
+      s->decoded = true;
+    }
+    begin = end;
+  }
+}
+
+}  // namespace b200asr
+
+// ====================================================================== C ABI
+using namespace b200asr;
+
+struct B200AsrOfflineRecognizer { Engine eng; };
+struct B200AsrOfflineStream { Stream s; };
+
+#define API_TRY try {
+#define API_CATCH(ret)                                    \
+  } catch (const std::exception &e) {                     \
+    g_last_error = e.what();                              \
+    return ret;                                           \
+  } catch (...) {                                         \
+    g_last_error = "unknown error";                       \
+    return ret;                                           \
+  }
+
+static Engine *E(const B200AsrOfflineRecognizer *r) {
+  if (!r) throw std::runtime_error("null recognizer");
+  return const_cast<Engine *>(&r->eng);
+}
+
+extern "C" {
+
+const char *B200AsrGetLastError(void) { return g_last_error.c_str(); }
+const char *B200AsrVersion(void) { return "b200asr 0.1.0 (sm_100a)"; }
+
+const B200AsrOfflineRecognizer *B200AsrCreateOfflineRecognizer(const B200AsrOfflineRecognizerConfig *config) {
+  B200AsrOfflineRecognizer *r = nullptr;
+  try {
+    if (!config) throw std::runtime_error("null config");
+    r = new B200AsrOfflineRecognizer();
+    r->eng.load(config);
+    return r;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    delete r;
+    return nullptr;
+  }
+}
+
+void B200AsrDestroyOfflineRecognizer(const B200AsrOfflineRecognizer *r) { delete const_cast<B200AsrOfflineRecognizer *>(r); }
+
+int32_t B200AsrOfflineRecognizerSetConfig(const B200AsrOfflineRecognizer *r, const B200AsrOfflineRecognizerConfig *c) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  const std::string dm = c->decoding_method ? c->decoding_method : "";
+  if (!dm.empty()) {
+    if (dm != "greedy_search" && dm != "modified_beam_search") throw std::runtime_error("unsupported decoding_method: " + dm);
+    e->decoding_method = dm;
+  }
+  if (c->max_active_paths > 0) {
+    if (c->max_active_paths > 16) throw std::runtime_error("max_active_paths > 16 is not built");
+    e->max_active_paths = c->max_active_paths;
+  }
+  if (c->hotwords_score > 0) e->hotwords_score = c->hotwords_score;
+  e->blank_penalty = c->blank_penalty;
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrSetHotwordsTokenIds(const B200AsrOfflineRecognizer *r, const int32_t *tokens, const int32_t *offsets,
+                                   const float *scores, int32_t n) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  e->set_graph(tokens, offsets, scores, n);
+  return 0;
+  API_CATCH(-1)
+}
+
+const B200AsrOfflineStream *B200AsrCreateOfflineStream(const B200AsrOfflineRecognizer *r) {
+  try {
+    auto *s = new B200AsrOfflineStream();
+    s->s.eng = E(r);
+    return s;
+  } catch (const std::exception &e) { g_last_error = e.what(); return nullptr; }
+}
+void B200AsrDestroyOfflineStream(const B200AsrOfflineStream *s) { delete const_cast<B200AsrOfflineStream *>(s); }
+
+void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n) {
+  if (!s || !samples || n <= 0) return;
+  auto *ms = const_cast<B200AsrOfflineStream *>(s);
+  if (sample_rate != 16000) { g_last_error = "accept_waveform: only 16000 Hz is supported (no resampler on the path)"; return; }
+  ms->s.samples.insert(ms->s.samples.end(), samples, samples + n);
+  ms->s.decoded = false;
+}
+
+int32_t B200AsrDecodeMultipleOfflineStreams(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *const *ss, int32_t n) {
+  API_TRY
+  Engine *e = E(r);
+  std::vector<Stream *> v(n);
+  for (int i = 0; i < n; ++i) {
+    if (!ss[i]) throw std::runtime_error("null stream");
+    v[i] = &const_cast<B200AsrOfflineStream *>(ss[i])->s;
+  }
+  e->decode(v.data(), n);
+  return 0;
+  API_CATCH(-1)
+}
+int32_t B200AsrDecodeOfflineStream(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *s) {
+  return B200AsrDecodeMultipleOfflineStreams(r, &s, 1);
+}
+
+const B200AsrOfflineRecognizerResult *B200AsrGetOfflineStreamResult(const B200AsrOfflineStream *s) {
+  if (!s || !s->s.decoded) { g_last_error = "stream has not been decoded"; return nullptr; }
+  return &s->s.res;
+}
+void B200AsrDestroyOfflineRecognizerResult(const B200AsrOfflineRecognizerResult *) {}
+const char *B200AsrGetOfflineStreamResultAsJson(const B200AsrOfflineStream *s) {
+  if (!s || !s->s.decoded) { g_last_error = "stream has not been decoded"; return nullptr; }
+  return strdup(s->s.json.c_str());
+}
+void B200AsrDestroyOfflineStreamResultJson(const char *s) { free(const_cast<char *>(s)); }
+
+int32_t B200AsrVocabSize(const B200AsrOfflineRecognizer *r) { return r ? r->eng.V : -1; }
+int32_t B200AsrEncoderOutDim(const B200AsrOfflineRecognizer *r) { return r ? r->eng.join_dim : -1; }
+
+// ---- raw stage entry points
+int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const float *samples, const int64_t *sample_offsets, int32_t n,
+                          float *out, int64_t *frame_offsets) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  std::vector<long long> soff(n + 1);
+  for (int i = 0; i <= n; ++i) soff[i] = sample_offsets[i] - sample_offsets[0];
+  long long total_frames = 0;
+  std::vector<long long> foff(n + 1, 0);
+  for (int i = 0; i < n; ++i) { foff[i + 1] = foff[i] + (soff[i + 1] - soff[i] + 80) / 160; }
+  total_frames = foff[n];
+  if (frame_offsets) for (int i = 0; i <= n; ++i) frame_offsets[i] = foff[i];
+  if (!out) return (int32_t)total_frames;
+  float *d_pcm = e->b_pcm.get<float>((size_t)std::max<long long>(soff[n], 1));
+  long long *d_soff = e->b_soff.get<long long>(n + 1);
+  CUDA_CHECK(cudaMemcpyAsync(d_pcm, samples + sample_offsets[0], soff[n] * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->st));
+  float *d_feats = nullptr;
+  std::vector<int> T;
+  e->run_fbank(d_pcm, d_soff, soff, n, &d_feats, &T);
+  CUDA_CHECK(cudaMemcpyAsync(out, d_feats, (size_t)total_frames * 80 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  return (int32_t)total_frames;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrFbank(const B200AsrOfflineRecognizer *r, const float *samples, int32_t n, float *out) {
+  const int64_t offs[2] = {0, n};
+  return B200AsrFbankBatch(r, samples, offs, 1, out, nullptr);
+}
+
+int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, const int32_t *x_lens, int32_t n, float *out,
+                       int32_t *out_lens) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  std::vector<int> T(x_lens, x_lens + n);
+  long long tot = 0, totp = 0;
+  for (int i = 0; i < n; ++i) {
+    tot += T[i];
+    const int T1 = T[i] >= 9 ? (T[i] - 7) / 2 : 0;
+    const int tp = (T1 + 1) / 2;
+    if (out_lens) out_lens[i] = tp;
+    totp += tp;
+  }
+  if (!out) return (int32_t)totp;
+  float *d_feats = e->b_feats.get<float>((size_t)std::max<long long>(tot, 1) * 80);
+  CUDA_CHECK(cudaMemcpyAsync(d_feats, feats, (size_t)tot * 80 * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  float *d_enc = nullptr;
+  std::vector<int> Tp;
+  e->gemm_flops = 0; e->gemm_launches = 0; e->gemm_ev_used = 0;
+  e->run_encoder(d_feats, T, &d_enc, &Tp);
+  CUDA_CHECK(cudaMemcpyAsync(out, d_enc, (size_t)totp * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  return (int32_t)totp;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrEncoderTap(const B200AsrOfflineRecognizer *r, const char *name, float *out, int32_t *dim) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  const std::string nm = name ? name : "";
+  const int M1 = e->h_off[0].empty() ? 0 : e->h_off[0].back();
+  const float *src = nullptr;
+  int D = 0;
+  if (nm == "embed") { src = e->b_x0.ptr<float>(); D = e->enc_dim[0]; }
+  else if (nm.compare(0, 5, "stack") == 0) {
+    const int i = atoi(nm.c_str() + 5);
+    if (i < 0 || i >= (int)e->stacks.size()) throw std::runtime_error("no such tap: " + nm);
+    src = e->b_stack[i].ptr<float>(); D = e->enc_dim[i];
+  } else throw std::runtime_error("no such tap: " + nm);
+  if (dim) *dim = D;
+  if (out && M1 > 0) CUDA_CHECK(cudaMemcpy(out, src, (size_t)M1 * D * sizeof(float), cudaMemcpyDeviceToHost));
+  return M1;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrDecoder(const B200AsrOfflineRecognizer *r, const int64_t *y, int32_t m, float *out) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (m <= 0) return 0;
+  for (int i = 0; i < 2 * m; ++i) if (y[i] >= e->V) throw std::runtime_error("decoder: token id out of range");
+  long long *dy = e->b_tmp.get<long long>((size_t)2 * m + (size_t)m * e->join_dim);
+  float *dout = reinterpret_cast<float *>(dy + 2 * m);
+  CUDA_CHECK(cudaMemcpyAsync(dy, y, (size_t)2 * m * sizeof(long long), cudaMemcpyHostToDevice, e->st));
+  launch_decoder_rows(e->sm, dy, m, dout, e->st);
+  CUDA_CHECK(cudaMemcpyAsync(out, dout, (size_t)m * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrJoiner(const B200AsrOfflineRecognizer *r, const float *enc, const float *dec, int32_t m, float *logits) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (m <= 0) return 0;
+  const size_t jd = e->join_dim;
+  float *buf = e->b_tmp.get<float>((size_t)m * (3 * jd + e->V));
+  float *d_enc = buf, *d_dec = buf + m * jd, *d_tmp = buf + 2 * m * jd, *d_lg = buf + 3 * m * jd;
+  CUDA_CHECK(cudaMemcpyAsync(d_enc, enc, m * jd * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  CUDA_CHECK(cudaMemcpyAsync(d_dec, dec, m * jd * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  launch_joiner_rows(e->sm, d_enc, d_dec, m, d_tmp, d_lg, e->st);
+  CUDA_CHECK(cudaMemcpyAsync(logits, d_lg, (size_t)m * e->V * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const float *enc_out, const int32_t *lens, int32_t n, int32_t method,
+                          int32_t beam, int32_t max_tokens, int32_t *tokens, int32_t *frames, float *tok_logprobs, float *stats,
+                          int32_t *n_tokens) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  long long tot = 0;
+  for (int i = 0; i < n; ++i) tot += std::max(lens[i], 0);
+  float *d_enc = e->b_enc.get<float>((size_t)std::max<long long>(tot, 1) * e->join_dim);
+  CUDA_CHECK(cudaMemcpyAsync(d_enc, enc_out, (size_t)tot * e->join_dim * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  SearchResultHost res{};
+  res.n_utts = n; res.max_tokens = max_tokens; res.n_tokens = n_tokens; res.tokens = tokens; res.frames = frames;
+  res.tok_lp = tok_logprobs; res.stats = stats;
+  std::vector<int> l(lens, lens + n);
+  run_search(e->search, e->sm, e->has_graph ? &e->cg_dev : nullptr, d_enc, l.data(), n, method, beam, e->blank_penalty, &res, e->st);
+  return 0;
+  API_CATCH(-1)
+}
+
+double B200AsrContextForwardOneStep(const B200AsrOfflineRecognizer *r, int32_t state, int32_t token, int32_t *next_state) {
+  if (!r || r->eng.cg_host.n_nodes() == 0 || state < 0 || state >= r->eng.cg_host.n_nodes()) { if (next_state) *next_state = 0; return 0.0; }
+  int nxt = 0;
+  const double d = cg_forward_one_step(r->eng.cg_host.view(), state, token, &nxt);
+  if (next_state) *next_state = nxt;
+  return d;
+}
+double B200AsrContextFinalize(const B200AsrOfflineRecognizer *r, int32_t state) {
+  if (!r || r->eng.cg_host.n_nodes() == 0 || state < 0 || state >= r->eng.cg_host.n_nodes()) return 0.0;
+  return cg_finalize(r->eng.cg_host.view(), state);
+}
+int32_t B200AsrContextNumNodes(const B200AsrOfflineRecognizer *r) { return r ? r->eng.cg_host.n_nodes() : 0; }
+
+// ---- device-resident benchmarking hooks
+int32_t B200AsrStageBatch(const B200AsrOfflineRecognizer *r, const float *samples, const int64_t *sample_offsets, int32_t n) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  Engine::Staged sgd;
+  sgd.n = n;
+  sgd.h_soff.resize(n + 1);
+  for (int i = 0; i <= n; ++i) sgd.h_soff[i] = sample_offsets[i] - sample_offsets[0];
+  CUDA_CHECK(cudaMalloc(&sgd.pcm, std::max<long long>(sgd.h_soff[n], 1) * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&sgd.soff, (n + 1) * sizeof(long long)));
+  CUDA_CHECK(cudaMemcpy(sgd.pcm, samples + sample_offsets[0], sgd.h_soff[n] * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(sgd.soff, sgd.h_soff.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+  const int h = e->next_handle++;
+  e->staged[h] = std::move(sgd);
+  return h;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle, int32_t *n_tokens) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  auto it = e->staged.find(handle);
+  if (it == e->staged.end()) throw std::runtime_error("no such staged batch");
+  const Engine::Staged &sgd = it->second;
+  std::vector<int> Tp, ntok(sgd.n);
+  SearchResultHost res{};
+  res.n_tokens = ntok.data();   // token arrays stay on the device; only counts come back
+  e->decode_pcm_device(sgd.pcm, sgd.soff, sgd.h_soff, sgd.n, &res, &Tp);
+  if (n_tokens) memcpy(n_tokens, ntok.data(), sgd.n * sizeof(int));
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrReleaseBatch(const B200AsrOfflineRecognizer *r, int32_t handle) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  auto it = e->staged.find(handle);
+  if (it == e->staged.end()) return -1;
+  cudaFree(it->second.pcm); cudaFree(it->second.soff);
+  e->staged.erase(it);
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrLastTimings(const B200AsrOfflineRecognizer *r, float *out6, int64_t *n_launches) {
+  if (!r) return -1;
+  const Engine &e = r->eng;
+  if (out6) { out6[0] = e.tm.fbank; out6[1] = e.tm.encoder; out6[2] = e.tm.search; out6[3] = e.tm.total; out6[4] = e.tm.h2d; out6[5] = e.tm.d2h; }
+  if (n_launches) *n_launches = e.launches_last;
+  return 0;
+}
+int32_t B200AsrLastGemmStats(const B200AsrOfflineRecognizer *r, double *ms, double *flops, int64_t *launches) {
+  if (!r) return -1;
+  if (ms) *ms = r->eng.gemm_ms;
+  if (flops) *flops = r->eng.gemm_flops;
+  if (launches) *launches = r->eng.gemm_launches;
+  return 0;
+}
+int32_t B200AsrSetProfiling(const B200AsrOfflineRecognizer *r, int32_t on) {
+  if (!r) return -1;
+  const_cast<Engine &>(r->eng).profiling = on != 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+"""GPU parity: every stage of the CUDA path, called through the C-ABI, against the CPU oracle.
+Tolerances (BASELINE.json north_star): fbank 1e-4 abs, encoder/joiner logits 1e-3 relative, token ids exact."""
+import numpy as np
+import pytest
+
+from helpers import make_graph, oracle_recognizer, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_rec(paths, **kw):
+    from sherpa_vietnamese_asr_b200.recognizer import OfflineRecognizer
+    return OfflineRecognizer.from_transducer(encoder=paths["encoder"], decoder=paths["decoder"], joiner=paths["joiner"],
+                                             tokens=paths["tokens"], **kw)
+
+
+@pytest.fixture(scope="module")
+def tiny(model_dirs):
+    cfg, paths, d = model_dirs("zipformer-tiny", 3)
+    return cfg, paths, _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+
+
+@pytest.fixture(scope="module")
+def m30(model_dirs):
+    cfg, paths, d = model_dirs("zipformer-30m", 30)
+    return cfg, paths, _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+
+
+@pytest.mark.parametrize("n", [160000, 48037, 5000, 401, 160, 1])
+def test_fbank_matches_oracle(tiny, n):
+    from oracle import fbank_ref
+    from sherpa_vietnamese_asr_b200 import synth
+    _, _, rec = tiny
+    a = synth.speech_like(n, 11 + n)
+    got = rec.fbank(a)
+    want64 = fbank_ref.fbank(a, np.float64)
+    assert got.shape == want64.shape
+    # 1e-4 absolute where the bin is not sitting on the log floor / in cancellation noise
+    loud = want64 > -9.0
+    assert np.abs(got - want64)[loud].max() <= 1e-4 if loud.any() else True
+    assert np.abs(got - want64).max() <= 5e-3
+
+
+def test_fbank_ragged_batch_equals_single(tiny):
+    from sherpa_vietnamese_asr_b200 import synth
+    _, _, rec = tiny
+    utts = [synth.speech_like(n, 70 + i) for i, n in enumerate([16000, 401, 52345, 80, 31999])]
+    batch = rec.fbank_batch(utts)
+    for u, b in zip(utts, batch):
+        np.testing.assert_array_equal(rec.fbank(u), b)
+
+
+def _encoder_taps_check(cfg, paths, rec, audio, tol):
+    import torch
+    from oracle import fbank_ref, zipformer_ref as zr
+    orec, ocfg, tensors = oracle_recognizer(paths)
+    feats = fbank_ref.fbank(audio, np.float64)
+    W = zr.Weights(tensors)
+    with torch.no_grad():
+        want, inter = zr.encoder(W, ocfg, feats, return_intermediate=True)
+    got = rec.encoder([feats])[0]
+    errs = {}
+    for name, ref in inter.items():
+        tap = rec.encoder_tap(name)
+        assert tap.shape == tuple(ref.shape), name
+        errs[name] = rel_err(tap, ref.numpy())
+    errs["enc_out"] = rel_err(got, want.numpy())
+    print("encoder relative errors:", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():
+        assert v <= tol, (k, v, errs)
+    return feats, got, want.numpy()
+
+
+def test_encoder_tiny_matches_oracle(tiny):
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = tiny
+    _encoder_taps_check(cfg, paths, rec, synth.speech_like(16000 * 4 + 123, 5), 1e-3)
+
+
+@pytest.mark.parametrize("n", [16000 * 10, 1600 * 7 + 5, 1600])
+def test_encoder_30m_matches_oracle(m30, n):
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    _encoder_taps_check(cfg, paths, rec, synth.speech_like(n, 1234), 1e-3)
+
+
+def test_encoder_ragged_batch_equals_single(m30):
+    from oracle import fbank_ref
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    feats = [fbank_ref.fbank(synth.speech_like(n, 40 + i), np.float64) for i, n in enumerate([32000, 16000 * 5 + 77, 9000, 1000, 48123])]
+    batch = rec.encoder(feats)
+    for f, b in zip(feats, batch):
+        single = rec.encoder([f])[0]
+        assert single.shape == b.shape
+        # same kernels, same per-utterance arithmetic: ragged batching must not leak across utterances
+        assert rel_err(b, single) <= 2e-6
+
+
+def test_decoder_joiner_rows(m30):
+    import torch
+    from oracle import zipformer_ref as zr
+    cfg, paths, rec = m30
+    orec, ocfg, tensors = oracle_recognizer(paths)
+    W = zr.Weights(tensors)
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, ocfg.vocab_size, (37, 2))
+    y[0] = (0, 0)
+    with torch.no_grad():
+        want_dec = zr.decoder(W, ocfg, y).numpy()
+        enc = rng.standard_normal((37, ocfg.joiner_dim)).astype(np.float32)
+        want_lg = zr.joiner(W, torch.from_numpy(enc), torch.from_numpy(want_dec)).numpy()
+    got_dec = rec.decoder(y)
+    assert rel_err(got_dec, want_dec) <= 1e-5
+    got_lg = rec.joiner(enc, want_dec)
+    assert rel_err(got_lg, want_lg) <= 1e-5
+
+
+def _search_case(rec, orec, enc_list, beam, method, graph_args=None):
+    from oracle import search_ref as sr
+    V = orec["vocab_size"]
+    if graph_args is not None:
+        rec.set_hotwords_token_ids(*graph_args)
+        orec["context_graph"] = make_graph(*graph_args)
+    else:
+        rec.set_hotwords_token_ids([], [])
+        orec["context_graph"] = None
+    got = rec.beam_search(enc_list, method=method, beam=beam)
+    n_tok = 0
+    for e, (toks, frames, lps, stats) in zip(enc_list, got):
+        orec["dec_cache"].clear()
+        if method == "greedy_search":
+            w_toks, w_frames, w_lps, _, w_emit = sr.greedy_search(orec, None, enc_out=e)
+        else:
+            w_toks, w_frames, w_lps, _, w_emit = sr.modified_beam_search(orec, None, beam, enc_out=e)
+        assert toks == w_toks
+        assert frames == w_frames
+        np.testing.assert_allclose(lps, w_lps, rtol=0, atol=2e-4)
+        for j, lg in enumerate(w_emit):
+            st = sr.token_entropy(lg, V, rounded=False)
+            np.testing.assert_allclose(stats[j], [st["tsallis_norm"], st["margin"], st["entropy_norm"], st["top1_prob"]], atol=2e-4)
+        n_tok += len(toks)
+    return n_tok
+
+
+def _oracle_enc(orec, cfg, audios):
+    import torch
+    from oracle import fbank_ref, zipformer_ref as zr
+    out = []
+    W = orec["enc_sess"].W
+    with torch.no_grad():
+        for a in audios:
+            out.append(zr.encoder(W, cfg, fbank_ref.fbank(a, np.float64)).numpy())
+    return out
+
+
+@pytest.mark.parametrize("method,beam", [("greedy_search", 1), ("modified_beam_search", 4), ("modified_beam_search", 8)])
+def test_search_from_oracle_encoder_out(m30, method, beam):
+    """Search alone: same encoder_out (the oracle's) on both sides, so token ids must be identical."""
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    orec, ocfg, _ = oracle_recognizer(paths, beam=beam)
+    audios = [synth.speech_like(n, 300 + i) for i, n in enumerate([16000 * 6, 16000 * 3 + 11, 16000 * 9, 2000])]
+    encs = _oracle_enc(orec, ocfg, audios)
+    n_tok = _search_case(rec, orec, encs, beam, method)
+    assert n_tok > 10
+
+
+def test_search_with_hotwords(m30):
+    from oracle import search_ref as sr
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    orec, ocfg, _ = oracle_recognizer(paths, beam=4)
+    audios = [synth.speech_like(16000 * 8, 500 + i) for i in range(3)]
+    encs = _oracle_enc(orec, ocfg, audios)
+    planted = []
+    for e in encs:
+        orec["dec_cache"].clear()
+        planted.append(sr.modified_beam_search(orec, None, 4, enc_out=e)[0])
+    seqs, scores = synth.random_hotwords(200, ocfg.vocab_size, 500, planted=planted)
+    base = [sr.modified_beam_search(orec, None, 4, enc_out=e)[0] for e in encs]
+    _search_case(rec, orec, encs, 4, "modified_beam_search", graph_args=(seqs, scores))
+    boosted = [sr.modified_beam_search(orec, None, 4, enc_out=e)[0] for e in encs]
+    print("hotwords changed the decode:", base != boosted)
+    rec.set_hotwords_token_ids([], [])
+
+
+def test_context_graph_matches_oracle(m30):
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    seqs = [[5, 6, 7], [6, 7, 8], [5, 6], [9], [5, 6, 7, 8, 9], [7, 8]]
+    scores = [1.5, 2.0, 1.0, 1.5, 2.5, 1.5]
+    rec.set_hotwords_token_ids(seqs, scores)
+    g = make_graph(seqs, scores)
+    rng = np.random.default_rng(1)
+    st_o, st_d = g.root, 0
+    for _ in range(500):
+        tok = int(rng.integers(4, 11))
+        d_o, st_o = g.forward_one_step(st_o, tok)
+        d_d, st_d = rec.context_forward_one_step(st_d, tok)
+        assert d_o == d_d
+        assert g.finalize(st_o) == rec.context_finalize(st_d)
+    rec.set_hotwords_token_ids([], [])
+
+
+def test_end_to_end_streams_match_oracle(m30):
+    """create_stream / accept_waveform / decode_streams on a ragged batch vs the oracle run utterance by
+    utterance (fbank -> encoder -> modified_beam_search, beam 4)."""
+    from oracle import fbank_ref, search_ref as sr
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    orec, ocfg, _ = oracle_recognizer(paths, beam=4)
+    audios = [synth.speech_like(n, 900 + i) for i, n in enumerate([16000 * 5, 16000 * 2 + 7, 16000 * 8 + 1234, 3000, 100])]
+    streams = []
+    for a in audios:
+        s = rec.create_stream()
+        s.accept_waveform(16000, a[: len(a) // 2])
+        s.accept_waveform(16000, a[len(a) // 2:])
+        streams.append(s)
+    rec.decode_streams(streams)
+    exact = 0
+    for a, s in zip(audios, streams):
+        feats = fbank_ref.fbank(a, np.float64)
+        if feats.shape[0] < 9:
+            assert s.result.token_ids == []
+            exact += 1
+            continue
+        orec["dec_cache"].clear()
+        toks, frames, lps, T, _ = sr.modified_beam_search(orec, feats, 4)
+        assert s.result.num_frames == T
+        assert s.result.token_ids == toks
+        assert s.result.frames == frames
+        np.testing.assert_allclose(s.result.ys_log_probs, lps, atol=5e-3)
+        exact += 1
+    assert exact == len(audios)
