@@ -39,7 +39,8 @@ def speech_like(n_samples: int, seed: int) -> np.ndarray:
         gate[pos:pos + ln] = 0.0
         pos += ln + int(rng.uniform(1.5, 4.0) * SAMPLE_RATE)
     k = 160
-    gate = np.convolve(gate, np.ones(k) / k, mode="same")
+    if n >= k:
+        gate = np.convolve(gate, np.ones(k) / k, mode="same")
     sig *= gate
     peak = np.max(np.abs(sig)) + 1e-9
     sig = sig / peak * 0.6

@@ -33,4 +33,6 @@ def make_graph(seqs, scores):
 def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))

@@ -35,6 +35,8 @@ def test_fbank_matches_oracle(tiny, n):
     got = rec.fbank(a)
     want64 = fbank_ref.fbank(a, np.float64)
     assert got.shape == want64.shape
+    if got.size == 0:
+        return
     # 1e-4 absolute where the bin is not sitting on the log floor / in cancellation noise
     loud = want64 > -9.0
     assert np.abs(got - want64)[loud].max() <= 1e-4 if loud.any() else True
