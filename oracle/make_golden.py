@@ -1,0 +1,215 @@
+"""Regenerates tests/golden/* from the reference's own code. Needs /root/reference (this container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+What is pinned, and by what:
+  search_cases.npz / .json   `_ort_beam_search` from /root/reference core/asr_engine.py:1023-1153 run UNMODIFIED
+                             on duck-typed sessions (oracle decoder/joiner of the seeded zipformer-tiny model)
+                             over seeded random encoder outputs, beams 1/4/8, with and without a ContextGraph
+                             built by the reference's core/hotword_context.py.
+  context_graph.json         ContextGraph.forward_one_step / finalize traces (reference class).
+  entropy.json               `_compute_token_entropy` (:1159-1181) on seeded logits rows.
+  words.json                 `decode_chunk` (:1209-1326) word lists (with precomputed_features + fake encoder).
+  rover.json                 `rover_merge_words` (:1446-1577) on seeded word lists.
+  fbank_5000.npz             torchaudio.compliance.kaldi.fbank (independent Kaldi restatement) on a seeded clip;
+                             kaldi-native-fbank itself is not installable offline.
+"""
+from __future__ import annotations
+
+import copy
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with redirect_stdout(io.StringIO()):
+        import core.asr_engine as ae
+        import core.hotword_context as hc
+    return ae, hc
+
+
+def tiny_model():
+    from oracle import zipformer_ref
+    from sherpa_vietnamese_asr_b200 import weights
+    cfg = weights.zipformer_tiny()
+    W = weights.init_weights(cfg, 3)
+    id2token = {i: t for i, t in enumerate(weights.make_tokens(cfg))}
+    return cfg, W, id2token, zipformer_ref
+
+
+class FixedEncoder:
+    """enc_sess stand-in returning a preset encoder_out (the search does not care where it came from)."""
+
+    def __init__(self, enc_out):
+        self.enc_out = enc_out
+
+    def run(self, _, feeds):
+        return [self.enc_out[None].astype(np.float32), np.array([self.enc_out.shape[0]], dtype=np.int64)]
+
+
+def search_cases(ae, hc):
+    cfg, W, id2token, zr = tiny_model()
+    from sherpa_vietnamese_asr_b200 import synth
+    rng = np.random.default_rng(2024)
+    cases, arrays = [], {}
+    for ci, (T, beam, with_graph) in enumerate([(40, 1, False), (60, 4, False), (60, 8, False), (90, 4, True), (75, 8, True),
+                                                 (3, 4, False), (120, 4, True)]):
+        # smooth-ish random encoder output with enough swing to emit tokens
+        base = rng.standard_normal((T, cfg.joiner_dim)).astype(np.float32)
+        enc = (0.6 * base + 0.4 * np.roll(base, 1, axis=0)) * 1.6
+        rec = zr.make_recognizer(W, cfg, id2token=id2token, max_active_paths=beam)
+        rec["enc_sess"] = FixedEncoder(enc)
+        graph_spec = None
+        if with_graph:
+            plain = ae._ort_beam_search(rec, np.zeros((T * 4 + 9, 80), np.float32), beam)[0]
+            seqs, scores = synth.random_hotwords(60, cfg.vocab_size, 77 + ci, planted=[plain])
+            g = hc.ContextGraph()
+            g.build(seqs, scores)
+            rec["context_graph"] = g
+            rec["dec_cache"] = {}
+            graph_spec = {"seqs": seqs, "scores": scores}
+        toks, frames, lps, Tout, emit = ae._ort_beam_search(rec, np.zeros((T * 4 + 9, 80), np.float32), beam)
+        arrays[f"enc_{ci}"] = enc
+        cases.append({"id": ci, "T": T, "beam": beam, "graph": graph_spec, "tokens": [int(t) for t in toks],
+                      "frames": [int(f) for f in frames], "tok_lp": [float(x) for x in lps], "T_out": int(Tout),
+                      "entropy": [ae._compute_token_entropy(e, cfg.vocab_size) for e in emit]})
+    np.savez_compressed(os.path.join(GOLD, "search_cases.npz"), **arrays)
+    with open(os.path.join(GOLD, "search_cases.json"), "w") as f:
+        json.dump({"model": "zipformer-tiny", "seed": 3, "cases": cases}, f)
+    return cases
+
+
+def context_graph_traces(hc):
+    rng = np.random.default_rng(5)
+    out = []
+    specs = [([[1, 2, 3], [2, 3, 4], [1, 2]], [1.5, 2.0, 1.0]),
+             ([[5, 6, 7], [6, 7, 8], [5, 6], [9], [5, 6, 7, 8, 9], [7, 8]], [1.5, 2.0, 1.0, 1.5, 2.5, 1.5]),
+             ([[3, 3, 3], [3, 3], [3], [4, 3, 3, 5]], [2.0, 1.5, 1.0, 2.5]),
+             ([[7, 8, 9, 10], [8, 9], [9, 10, 11], [], [7, 8]], [1.5, 1.5, 2.0, 1.5, 2.5])]
+    for seqs, scores in specs:
+        g = hc.ContextGraph()
+        g.build(seqs, scores)
+        st = g.root
+        toks = [int(t) for t in rng.integers(1, 13, 300)]
+        deltas, fins = [], []
+        for t in toks:
+            d, st = g.forward_one_step(st, t)
+            deltas.append(float(d))
+            fins.append(float(g.finalize(st)))
+        out.append({"seqs": seqs, "scores": scores, "tokens": toks, "deltas": deltas, "finalize": fins,
+                    "n_phrases": g.n_phrases})
+    with open(os.path.join(GOLD, "context_graph.json"), "w") as f:
+        json.dump(out, f)
+
+
+def entropy_cases(ae):
+    rng = np.random.default_rng(9)
+    out = []
+    for V, scale in [(2000, 4.0), (2000, 0.5), (500, 8.0), (50, 2.0)]:
+        lg = (rng.standard_normal(V) * scale).astype(np.float32)
+        out.append({"V": V, "logits": [float(x) for x in lg], "stats": ae._compute_token_entropy(lg, V)})
+    with open(os.path.join(GOLD, "entropy.json"), "w") as f:
+        json.dump(out, f)
+
+
+def word_cases(ae):
+    cfg, W, id2token, zr = tiny_model()
+    rng = np.random.default_rng(31)
+    out, arrays = [], {}
+    for ci, (T, n_samples, off) in enumerate([(80, 16000 * 13, 0.0), (50, 16000 * 8 + 11, 12.5)]):
+        base = rng.standard_normal((T, cfg.joiner_dim)).astype(np.float32)
+        enc = (0.6 * base + 0.4 * np.roll(base, 1, axis=0)) * 1.6
+        rec = zr.make_recognizer(W, cfg, id2token=id2token, max_active_paths=4)
+        rec["enc_sess"] = FixedEncoder(enc)
+        audio = np.zeros(n_samples, dtype=np.float32)
+        with redirect_stdout(io.StringIO()):
+            words = ae.decode_chunk(rec, audio, off, precomputed_features=np.zeros((T * 4 + 9, 80), np.float32))
+        arrays[f"enc_{ci}"] = enc
+        out.append({"id": ci, "n_samples": n_samples, "time_offset": off, "words": words})
+    np.savez_compressed(os.path.join(GOLD, "words_enc.npz"), **arrays)
+    with open(os.path.join(GOLD, "words.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
+    return out
+
+
+def rover_cases(ae):
+    rng = np.random.default_rng(12)
+    vocab = ["xin", "chào", "các", "bạn", "hôm", "nay", "trời", "đẹp", "quá", "ban", "tổ", "chức", "ký", "kết", "hợp", "đồng"]
+
+    def words(n, t0=0.0):
+        ws, t = [], t0
+        for _ in range(n):
+            d = float(rng.uniform(0.1, 0.4))
+            ws.append({"text": str(rng.choice(vocab)), "start": t, "end": t + d, "prob": float(rng.uniform(0.3, 1.0)),
+                       "margin_min": round(float(rng.uniform(0.0, 1.0)), 4), "tsallis_max": round(float(rng.uniform(0.0, 0.8)), 4)})
+            t += d + float(rng.uniform(0.0, 0.2))
+        return ws
+    out = []
+    ae._hotword_phrases_cache = ["ban tổ chức", "hợp đồng"]
+    for ci in range(6):
+        a = words(int(rng.integers(5, 25)))
+        b = copy.deepcopy(a)
+        # perturb b: substitutions, deletions, insertions
+        for w in b:
+            if rng.random() < 0.25:
+                w["text"] = str(rng.choice(vocab))
+                w["margin_min"] = round(float(rng.uniform(0.0, 1.0)), 4)
+        b = [w for w in b if rng.random() > 0.12]
+        for _ in range(int(rng.integers(0, 3))):
+            k = int(rng.integers(0, len(b) + 1))
+            ins = words(1, t0=b[k - 1]["end"] if k > 0 else 0.0)[0]
+            b.insert(k, ins)
+        ia, ib = copy.deepcopy(a), copy.deepcopy(b)
+        with redirect_stdout(io.StringIO()):
+            merged, dis = ae.rover_merge_words(a, b)
+        out.append({"a": ia, "b": ib, "merged": merged, "disagree": sorted(int(i) for i in dis),
+                    "hotword_phrases": ["ban tổ chức", "hợp đồng"]})
+    with redirect_stdout(io.StringIO()):
+        out.append({"a": [], "b": words(3), "merged": None, "disagree": [], "hotword_phrases": []})
+        out[-1]["merged"] = ae.rover_merge_words([], copy.deepcopy(out[-1]["b"]))[0]
+    ae._hotword_phrases_cache = None
+    with open(os.path.join(GOLD, "rover.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
+
+
+def fbank_case():
+    import torch
+    import torchaudio
+
+    from sherpa_vietnamese_asr_b200 import synth
+    a = synth.speech_like(5000, 4242)
+    ta = torchaudio.compliance.kaldi.fbank(torch.from_numpy(a)[None].double(), num_mel_bins=80, dither=0.0, snip_edges=False,
+                                           window_type="povey", low_freq=20, high_freq=7600, sample_frequency=16000,
+                                           energy_floor=1.0)
+    np.savez_compressed(os.path.join(GOLD, "fbank_5000.npz"), audio=a, feats=ta.numpy().astype(np.float64))
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ae, hc = load_reference()
+    cases = search_cases(ae, hc)
+    print("search cases:", [(c["T"], c["beam"], len(c["tokens"])) for c in cases])
+    context_graph_traces(hc)
+    entropy_cases(ae)
+    w = word_cases(ae)
+    print("word cases:", [len(x["words"]) for x in w])
+    rover_cases(ae)
+    fbank_case()
+    print("golden written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

@@ -249,8 +249,13 @@ class DecoderSession:
         self.W, self.cfg = W, cfg
 
     def run(self, _, feeds):
+        # row by row: BLAS results depend on the batch shape in the last bits, and the reference's memo
+        # (core/asr_engine.py:1072-1088) batches whatever contexts happen to miss; per-row evaluation makes
+        # a context's decoder output a pure function of the context.
+        y = np.asarray(feeds["y"])
         with torch.no_grad():
-            return [decoder(self.W, self.cfg, feeds["y"]).to(torch.float32).numpy()]
+            rows = [decoder(self.W, self.cfg, y[i:i + 1]).to(torch.float32).numpy() for i in range(y.shape[0])]
+        return [np.concatenate(rows, axis=0)]
 
 
 class JoinerSession:
@@ -264,7 +269,8 @@ class JoinerSession:
         with torch.no_grad():
             e = torch.from_numpy(np.ascontiguousarray(feeds["encoder_out"])).to(self.W.dtype)
             d = torch.from_numpy(np.ascontiguousarray(feeds["decoder_out"])).to(self.W.dtype)
-            return [joiner(self.W, e, d).to(torch.float32).numpy()]
+            rows = [joiner(self.W, e[i:i + 1], d[i:i + 1]).to(torch.float32).numpy() for i in range(e.shape[0])]
+            return [np.concatenate(rows, axis=0)]
 
 
 def make_recognizer(tensors: dict, cfg, id2token=None, max_active_paths=4, context_graph=None,
