@@ -146,6 +146,12 @@ B200ASR_API int32_t B200AsrJoiner(const B200AsrOfflineRecognizer *r, const float
 B200ASR_API int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const float *enc_out, const int32_t *lens, int32_t n_utts,
                                       int32_t method, int32_t beam, int32_t max_tokens, int32_t *tokens, int32_t *frames,
                                       float *tok_logprobs, float *stats, int32_t *n_tokens);
+/* One dense Linear as the encoder/joiner graphs run it (onnxruntime MatMul+Add inside enc_sess/joi_sess,
+ * core/asr_engine.py:1047,1092): C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ R). Host pointers; act 0/1/2 = none/SwooshL/
+ * SwooshR; impl 0 = FP32 CUDA-core kernel, 1 = tcgen05 tensor-core kernel. reps > 1 repeats the launch and
+ * writes the mean device time per launch (ms, CUDA events) to *ms_per_launch (may be NULL). */
+B200ASR_API int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const float *W, const float *bias, const float *R,
+                                float *C, int32_t M, int32_t N, int32_t K, int32_t act, int32_t impl, int32_t reps, float *ms_per_launch);
 /* ContextGraph.forward_one_step / finalize on the flattened automaton the device uses
  * (core/hotword_context.py:139-184): returns the score delta, writes the next state id. */
 B200ASR_API double B200AsrContextForwardOneStep(const B200AsrOfflineRecognizer *r, int32_t state, int32_t token, int32_t *next_state);

@@ -71,6 +71,7 @@ SYMBOLS = {
     "B200AsrDecoder": (C.c_int32, [_P, _I64, C.c_int32, _F]),
     "B200AsrJoiner": (C.c_int32, [_P, _F, _F, C.c_int32, _F]),
     "B200AsrBeamSearch": (C.c_int32, [_P, _F, _I32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _I32, _F, _F, _I32]),
+    "B200AsrGemm": (C.c_int32, [_P, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F]),
     "B200AsrContextForwardOneStep": (C.c_double, [_P, C.c_int32, C.c_int32, _I32]),
     "B200AsrContextFinalize": (C.c_double, [_P, C.c_int32]),
     "B200AsrContextNumNodes": (C.c_int32, [_P]),

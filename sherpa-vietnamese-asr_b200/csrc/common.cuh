@@ -121,6 +121,7 @@ struct SearchModel {
 struct SearchState;   // opaque, search.cu
 SearchState *search_state_create();
 void search_state_destroy(SearchState *s);
+void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t));   // joiner GEMM implementation
 // Runs the whole search for a batch. enc [sum T', jd] packed with enc_off; results to device arrays then host.
 struct SearchResultHost {
   int n_utts;

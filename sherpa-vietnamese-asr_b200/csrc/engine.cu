@@ -418,7 +418,10 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   blank_penalty = c->blank_penalty;
   fbank_tables_create(&fb);
   search = search_state_create();
-  if (precision == 1 && !gemm_tc_available()) throw std::runtime_error("BF16 tensor-core GEMM path unavailable in this build");
+  if (precision == 1) {
+    if (!gemm_tc_available()) throw std::runtime_error("tensor-core GEMM path unavailable (cuTensorMapEncodeTiled not found)");
+    search_set_gemm(search, launch_gemm_tc);
+  }
 
   // hotwords file with token ids (modeling_unit token_id); text units are tokenised by the host binding
   const std::string hw = str(c->hotwords_file), mu_ = str(mc.modeling_unit);
@@ -1076,6 +1079,39 @@ int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const float *enc_ou
   res.tok_lp = tok_logprobs; res.stats = stats;
   std::vector<int> l(lens, lens + n);
   run_search(e->search, e->sm, e->has_graph ? &e->cg_dev : nullptr, d_enc, l.data(), n, method, beam, e->blank_penalty, &res, e->st);
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const float *W, const float *bias, const float *R, float *C,
+                    int32_t M, int32_t N, int32_t K, int32_t act, int32_t impl, int32_t reps, float *ms_per_launch) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  const size_t nA = (size_t)M * K, nW = (size_t)N * K, nC = (size_t)M * N;
+  float *buf = e->b_tmp.get<float>(nA + nW + 2 * nC + N + 64);
+  float *dA = buf, *dW = dA + ((nA + 3) & ~size_t(3)), *dC = dW + ((nW + 3) & ~size_t(3)), *dR = dC + ((nC + 3) & ~size_t(3));
+  float *dB = dR + ((nC + 3) & ~size_t(3));
+  CUDA_CHECK(cudaMemcpyAsync(dA, A, nA * 4, cudaMemcpyHostToDevice, e->st));
+  CUDA_CHECK(cudaMemcpyAsync(dW, W, nW * 4, cudaMemcpyHostToDevice, e->st));
+  if (bias) CUDA_CHECK(cudaMemcpyAsync(dB, bias, (size_t)N * 4, cudaMemcpyHostToDevice, e->st));
+  if (R) CUDA_CHECK(cudaMemcpyAsync(dR, R, nC * 4, cudaMemcpyHostToDevice, e->st));
+  GemmArgs g{};
+  g.A = dA; g.lda = K; g.W = dW; g.bias = bias ? dB : nullptr; g.R = R ? dR : nullptr; g.ldr = N; g.C = dC; g.ldc = N;
+  g.M = M; g.N = N; g.K = K; g.act = act;
+  if (reps < 1) reps = 1;
+  if (impl == 1) launch_gemm_tc(g, e->st); else launch_gemm_fp32(g, e->st);   // warm-up / the checked result
+  CUDA_CHECK(cudaEventRecord(e->ev[6], e->st));
+  for (int i = 1; i < reps; ++i) { if (impl == 1) launch_gemm_tc(g, e->st); else launch_gemm_fp32(g, e->st); }
+  CUDA_CHECK(cudaEventRecord(e->ev[7], e->st));
+  CUDA_CHECK(cudaMemcpyAsync(C, dC, nC * 4, cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  if (ms_per_launch) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]);
+    *ms_per_launch = reps > 1 ? ms / (reps - 1) : 0.f;
+  }
   return 0;
   API_CATCH(-1)
 }

@@ -416,6 +416,7 @@ struct SearchState {
 };
 
 SearchState *search_state_create() { return new SearchState(); }
+void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t)) { s->gemm = fn; }
 void search_state_destroy(SearchState *s) {
   if (!s) return;
   cudaFree(s->hyps); cudaFree(s->hyp_count); cudaFree(s->node_count); cudaFree(s->arena); cudaFree(s->dec);

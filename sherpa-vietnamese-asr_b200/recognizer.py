@@ -333,6 +333,23 @@ class OfflineRecognizer:
             raise RuntimeError(_capi.last_error())
         return out
 
+    def gemm(self, A, W, bias=None, R=None, act: int = 0, impl: str = "fp32", reps: int = 1):
+        """One Linear: act(A W^T + bias) (+ R) through the selected kernel. Returns (C, ms_per_launch)."""
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        W = np.ascontiguousarray(W, dtype=np.float32)
+        M, K = A.shape
+        N = W.shape[0]
+        out = np.empty((M, N), dtype=np.float32)
+        b = np.ascontiguousarray(bias, dtype=np.float32) if bias is not None else None
+        Rr = np.ascontiguousarray(R, dtype=np.float32) if R is not None else None
+        ms = C.c_float(0)
+        rc = _capi.lib().B200AsrGemm(self._h, _capi.fptr(A), _capi.fptr(W), _capi.fptr(b) if b is not None else None,
+                                    _capi.fptr(Rr) if Rr is not None else None, _capi.fptr(out), M, N, K, act,
+                                    1 if impl == "tc" else 0, reps, C.byref(ms))
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+        return out, ms.value
+
     def beam_search(self, enc_list, method: str = "modified_beam_search", beam: int = 4):
         """Search from encoder outputs. Returns per utterance (tokens, frames, tok_logprobs, stats[U,4])."""
         lens = np.array([e.shape[0] for e in enc_list], dtype=np.int32)

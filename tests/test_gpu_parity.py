@@ -235,3 +235,68 @@ def test_end_to_end_streams_match_oracle(m30):
         np.testing.assert_allclose(s.result.ys_log_probs, lps, atol=5e-3)
         exact += 1
     assert exact == len(audios)
+
+
+# ----------------------------------------------------------------------------- GEMM kernels
+GEMM_SHAPES = [(1000, 272, 192), (517, 48, 192), (4096, 640, 192), (130, 2000, 512), (777, 192, 2432), (64, 16, 48),
+               (2500, 384, 128), (3000, 512, 512), (129, 130, 36)]
+
+
+@pytest.mark.parametrize("impl", ["fp32", "tc"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_kernels_match_numpy(tiny, impl, M, N, K):
+    """Both GEMM kernels against a float64 product. FP32 CUDA-core kernel: fp32 rounding only. tcgen05 kernel:
+    TF32 operands (10-bit mantissa), FP32 accumulate -> 1e-3 relative to the output scale."""
+    _, _, rec = tiny
+    rng = np.random.default_rng(M * 7 + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    for act in (0, 1, 2):
+        got, _ = rec.gemm(A, W, b, R, act=act, impl=impl)
+        z = A.astype(np.float64) @ W.astype(np.float64).T + b
+        if act == 1:
+            z = np.logaddexp(0, z - 4.0) - 0.08 * z - 0.035
+        elif act == 2:
+            z = np.logaddexp(0, z - 1.0) - 0.08 * z - 0.313261687
+        want = z + R
+        tol = 2e-6 if impl == "fp32" else 1.5e-3
+        assert rel_err(got, want) <= tol, (impl, act, rel_err(got, want))
+    got, _ = rec.gemm(A, W, None, None, act=0, impl=impl)
+    assert rel_err(got, A.astype(np.float64) @ W.astype(np.float64).T) <= (2e-6 if impl == "fp32" else 1.5e-3)
+
+
+def test_tensor_core_mode_end_to_end(model_dirs):
+    """precision='bf16' slot = tensor-core mode (tcgen05, TF32 operands): encoder within 1e-2 relative of the
+    oracle, token edit distance vs the FP32 oracle decode small."""
+    from oracle import fbank_ref, search_ref as sr
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, d = model_dirs("zipformer-30m", 30)
+    rec = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4, precision="bf16")
+    orec, ocfg, _ = oracle_recognizer(paths, beam=4)
+    audios = [synth.speech_like(n, 900 + i) for i, n in enumerate([16000 * 5, 16000 * 8 + 1234, 16000 * 3])]
+    import torch
+    from oracle import zipformer_ref as zr
+    feats = [fbank_ref.fbank(a, np.float64) for a in audios]
+    encs = rec.encoder(feats)
+    tot, dist = 0, 0
+    for f, e in zip(feats, encs):
+        with torch.no_grad():
+            want = zr.encoder(orec["enc_sess"].W, ocfg, f).numpy()
+        err = rel_err(e, want)
+        print("tensor-core encoder rel err", err)
+        assert err <= 2e-2
+    ss = []
+    for a in audios:
+        s = rec.create_stream(); s.accept_waveform(16000, a); ss.append(s)
+    rec.decode_streams(ss)
+    import difflib
+    for f, s in zip(feats, ss):
+        orec["dec_cache"].clear()
+        toks = sr.modified_beam_search(orec, f, 4)[0]
+        sm = difflib.SequenceMatcher(None, toks, s.result.token_ids, autojunk=False)
+        dist += sum(max(i2 - i1, j2 - j1) for tag, i1, i2, j1, j2 in sm.get_opcodes() if tag != "equal")
+        tot += len(toks)
+    print("tensor-core mode token edit distance:", dist, "/", tot)
+    assert dist <= max(2, 0.05 * tot)

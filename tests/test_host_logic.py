@@ -1,0 +1,128 @@
+"""CPU suite for the product's host side: C-ABI surface, hotword parsing/tokenising, token->word merge and
+ROVER (against golden vectors made by the reference), workload generators, sharding."""
+import copy
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import search_ref as sr, zipformer_ref as zr
+from sherpa_vietnamese_asr_b200 import _capi, asr_engine, recognizer, synth, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200asr.h")).read()
+    declared = set(re.findall(r"B200ASR_API[^;]*?\b(B200Asr\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    lib = _capi.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.B200AsrVersion()
+
+
+def test_no_cpu_fallback(tmp_path):
+    """Without a CUDA device the recognizer must fail loudly, never fall back."""
+    import ctypes
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    paths = weights.write_model_dir(str(tmp_path), weights.zipformer_tiny(), 3)
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        recognizer.OfflineRecognizer.from_transducer(encoder=paths["encoder"], decoder=paths["decoder"],
+                                                     joiner=paths["joiner"], tokens=paths["tokens"])
+    cfg = _capi.RecognizerConfig()
+    assert not _capi.lib().B200AsrCreateOfflineRecognizer(ctypes.byref(cfg))
+    assert _capi.last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sherpa-vietnamese-asr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_parse_hotwords_text_matches_reference_rules():
+    txt = "# comment\n\nHà Nội :2.5\nban tổ chức\nA:B\nfoo :x\n  spaced phrase  : 1.0 \n"
+    got = recognizer.parse_hotwords_text(txt, 1.5)
+    assert got == [("HÀ NỘI", 2.5), ("BAN TỔ CHỨC", 1.5), ("A:B", 1.5), ("FOO :X", 1.5), ("SPACED PHRASE", 1.0)]
+
+
+def test_table_tokenizer_roundtrip():
+    cfg = weights.zipformer_tiny()
+    toks = weights.make_tokens(cfg)
+    tt = recognizer._TableTokenizer(toks)
+    word_starts = [t for t in toks[3:] if t.startswith("▁")]
+    phrase = " ".join(t[1:] for t in word_starts[:3])
+    ids = tt.encode(phrase)
+    assert ids and "".join(toks[i] for i in ids).replace("▁", " ").strip() == phrase
+    assert tt.encode("@@@") == []
+
+
+class _Res:
+    pass
+
+
+def _result_from_oracle(cfg, W, id2token, enc):
+    rec = zr.make_recognizer(W, cfg, id2token=id2token, max_active_paths=4)
+    toks, frames, lps, T, emit = sr.modified_beam_search(rec, None, 4, enc_out=enc)
+    r = _Res()
+    r.token_ids, r.frames, r.ys_log_probs, r.num_frames = toks, frames, lps, T
+    st = [sr.token_entropy(e, cfg.vocab_size, rounded=False) for e in emit]
+    r.tsallis = [s["tsallis_norm"] for s in st]
+    r.margin = [s["margin"] for s in st]
+    r.entropy = [s["entropy_norm"] for s in st]
+    r.top1 = [s["top1_prob"] for s in st]
+    return r
+
+
+def test_words_from_result_matches_reference_golden():
+    cfg = weights.zipformer_tiny()
+    W = weights.init_weights(cfg, 3)
+    id2token = {i: t for i, t in enumerate(weights.make_tokens(cfg))}
+    encs = np.load(os.path.join(GOLD, "words_enc.npz"))
+    for c in json.load(open(os.path.join(GOLD, "words.json"), encoding="utf-8")):
+        res = _result_from_oracle(cfg, W, id2token, encs[f"enc_{c['id']}"])
+        words = asr_engine.words_from_result(res, id2token, c["n_samples"], c["time_offset"])
+        assert len(words) == len(c["words"])
+        for got, want in zip(words, c["words"]):
+            assert set(got) == set(want)
+            for k, v in want.items():
+                if isinstance(v, float):
+                    assert got[k] == pytest.approx(v, abs=1e-9), k
+                else:
+                    assert got[k] == v, k
+
+
+def test_product_rover_matches_reference_golden():
+    for c in json.load(open(os.path.join(GOLD, "rover.json"), encoding="utf-8")):
+        merged, dis = asr_engine.rover_merge_words(copy.deepcopy(c["a"]), copy.deepcopy(c["b"]), c["hotword_phrases"])
+        assert json.loads(json.dumps(merged)) == c["merged"]
+        assert sorted(dis) == c["disagree"]
+
+
+def test_synthetic_workloads_are_seeded_and_shaped():
+    a, b = synth.c1_clip(), synth.c1_clip()
+    assert a.shape == (160000,) and a.dtype == np.float32 and np.array_equal(a, b)
+    assert 0.55 <= np.abs(a).max() <= 1.0
+    d = synth.c2_durations()
+    assert d.shape == (256,) and d.min() >= 1.0 and d.max() <= 30.0 and 2400 < d.sum() < 3400
+    seqs, scores = synth.random_hotwords(500, 2000, 500)
+    assert len(seqs) == 500 and all(2 <= len(s) <= 8 for s in seqs) and set(scores) <= {1.5, 2.0, 2.5}
+    assert synth.speech_like(1, 0).shape == (1,)
+
+
+def test_create_recognizer_discovery_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        asr_engine.create_recognizer(str(tmp_path))

@@ -1,0 +1,66 @@
+"""N>1 path on CPU: world_size-2 gloo processes shard the utterances, decode their shard with a stand-in
+decoder, and rank 0 gathers every transcript in the original order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from sherpa_vietnamese_asr_b200 import sharding
+
+
+def test_partition_is_balanced_and_complete():
+    rng = np.random.default_rng(0)
+    n = [int(x) for x in rng.integers(16000, 480000, 257)]
+    for world in (1, 2, 4, 8):
+        shards = sharding.partition_by_duration(n, world)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(len(n)))
+        loads = [sum(n[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(n)
+    batches = sharding.batches_by_length(range(len(n)), n, max_batch_seconds=600.0)
+    assert sorted(i for b in batches for i in b) == list(range(len(n)))
+    assert all(sum(n[i] for i in b) / 16000.0 <= 600.0 + 30.0 for b in batches)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    audios = [np.full(int(n), i, dtype=np.float32) for i, n in enumerate(rng.integers(100, 5000, 23))]
+    seen = []
+
+    def decode(batch):
+        seen.extend(int(a[0]) for a in batch)
+        return [(int(a[0]), len(a), rank) for a in batch]
+    out = sharding.transcribe_sharded(decode, audios, rank, world)
+    q.put((rank, out, seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        rank, out, seen = q.get(timeout=120)
+        got[rank] = (out, seen)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    out0, seen0 = got[0]
+    out1, seen1 = got[1]
+    assert out1 is None
+    assert [o[0] for o in out0] == list(range(23))
+    assert set(seen0).isdisjoint(seen1) and len(seen0) + len(seen1) == 23
+    assert {o[2] for o in out0} == {0, 1}
