@@ -261,10 +261,10 @@ def test_gemm_kernels_match_numpy(tiny, impl, M, N, K):
         elif act == 2:
             z = np.logaddexp(0, z - 1.0) - 0.08 * z - 0.313261687
         want = z + R
-        tol = 2e-6 if impl == "fp32" else 1.5e-3
+        tol = 5e-6 if impl == "fp32" else 1.5e-3
         assert rel_err(got, want) <= tol, (impl, act, rel_err(got, want))
     got, _ = rec.gemm(A, W, None, None, act=0, impl=impl)
-    assert rel_err(got, A.astype(np.float64) @ W.astype(np.float64).T) <= (2e-6 if impl == "fp32" else 1.5e-3)
+    assert rel_err(got, A.astype(np.float64) @ W.astype(np.float64).T) <= (5e-6 if impl == "fp32" else 1.5e-3)
 
 
 def test_tensor_core_mode_end_to_end(model_dirs):
