@@ -59,7 +59,9 @@ typedef struct B200AsrOfflineRecognizerConfig {
   float hotwords_score;        /* default boost 1.5 (core/config.py:405-412) */
   float blank_penalty;
   int32_t device_id;           /* CUDA device ordinal */
-  int32_t precision;           /* 0 = FP32 (bit-exact token mode), 1 = BF16 tensor-core mode */
+  int32_t precision;           /* 0 = FP32 mode (token-exact): tcgen05 with error-compensated 3xTF32 operands;
+                                  1 = tensor-core fast mode: tcgen05, TF32 operands, FP32 accumulate;
+                                  2 = FP32 on CUDA cores (plain FFMA kernels, the cross-check of mode 0) */
 } B200AsrOfflineRecognizerConfig;
 
 typedef struct B200AsrOfflineRecognizer B200AsrOfflineRecognizer;
@@ -148,7 +150,7 @@ B200ASR_API int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const f
                                       float *tok_logprobs, float *stats, int32_t *n_tokens);
 /* One dense Linear as the encoder/joiner graphs run it (onnxruntime MatMul+Add inside enc_sess/joi_sess,
  * core/asr_engine.py:1047,1092): C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ R). Host pointers; act 0/1/2 = none/SwooshL/
- * SwooshR; impl 0 = FP32 CUDA-core kernel, 1 = tcgen05 tensor-core kernel. reps > 1 repeats the launch and
+ * SwooshR; impl 0 = FP32 CUDA-core kernel, 1 = tcgen05 TF32 kernel, 2 = tcgen05 3xTF32 kernel. reps > 1 repeats the launch and
  * writes the mean device time per launch (ms, CUDA events) to *ms_per_launch (may be NULL). */
 B200ASR_API int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const float *W, const float *bias, const float *R,
                                 float *C, int32_t M, int32_t N, int32_t K, int32_t act, int32_t impl, int32_t reps, float *ms_per_launch);

@@ -23,7 +23,8 @@
 
 namespace b200asr {
 
-void launch_gemm_tc(const GemmArgs &g, cudaStream_t st);   // gemm_tc.cu (BF16 tcgen05 path)
+void launch_gemm_tc(const GemmArgs &g, cudaStream_t st);    // gemm_tc.cu: tcgen05, TF32 operands
+void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st);   // gemm_tc.cu: tcgen05, error-compensated 3xTF32 (fp32-grade)
 bool gemm_tc_available();
 
 namespace {
@@ -302,6 +303,7 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
       cnn_kernel.size() != ns)
     throw std::runtime_error("inconsistent stack configuration in container");
   if (ctx_size != 2) throw std::runtime_error("only context_size=2 is built");
+  if ((dec_dim & 3) || (join_dim & 3)) throw std::runtime_error("decoder_dim and joiner_dim must be multiples of 4");
   if (feat_dim != 80) throw std::runtime_error("only feature_dim=80 is built");
   out_dim = *std::max_element(enc_dim.begin(), enc_dim.end());
 
@@ -418,10 +420,9 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   blank_penalty = c->blank_penalty;
   fbank_tables_create(&fb);
   search = search_state_create();
-  if (precision == 1) {
-    if (!gemm_tc_available()) throw std::runtime_error("tensor-core GEMM path unavailable (cuTensorMapEncodeTiled not found)");
-    search_set_gemm(search, launch_gemm_tc);
-  }
+  if (precision < 0 || precision > 2) throw std::runtime_error("precision must be 0 (fp32 via 3xTF32 tcgen05), 1 (tf32 tcgen05) or 2 (fp32 CUDA cores)");
+  if (precision != 2 && !gemm_tc_available()) throw std::runtime_error("tensor-core GEMM path unavailable (cuTensorMapEncodeTiled not found)");
+  search_set_gemm(search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32));
 
   // hotwords file with token ids (modeling_unit token_id); text units are tokenised by the host binding
   const std::string hw = str(c->hotwords_file), mu_ = str(mc.modeling_unit);
@@ -492,7 +493,9 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
     ++gemm_ev_used;
     CUDA_CHECK(cudaEventRecord(e0, st));
   }
-  if (precision == 1) launch_gemm_tc(g, st); else launch_gemm_fp32(g, st);
+  if (precision == 1) launch_gemm_tc(g, st);
+  else if (precision == 0) launch_gemm_tc3(g, st);
+  else launch_gemm_fp32(g, st);
   if (profiling) CUDA_CHECK(cudaEventRecord(e1, st));
   gemm_flops += 2.0 * (double)M * (double)N * (double)K;
   ++gemm_launches;
@@ -1101,9 +1104,10 @@ int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const flo
   g.A = dA; g.lda = K; g.W = dW; g.bias = bias ? dB : nullptr; g.R = R ? dR : nullptr; g.ldr = N; g.C = dC; g.ldc = N;
   g.M = M; g.N = N; g.K = K; g.act = act;
   if (reps < 1) reps = 1;
-  if (impl == 1) launch_gemm_tc(g, e->st); else launch_gemm_fp32(g, e->st);   // warm-up / the checked result
+  auto run = [&]() { if (impl == 1) launch_gemm_tc(g, e->st); else if (impl == 2) launch_gemm_tc3(g, e->st); else launch_gemm_fp32(g, e->st); };
+  run();   // warm-up / the checked result
   CUDA_CHECK(cudaEventRecord(e->ev[6], e->st));
-  for (int i = 1; i < reps; ++i) { if (impl == 1) launch_gemm_tc(g, e->st); else launch_gemm_fp32(g, e->st); }
+  for (int i = 1; i < reps; ++i) run();
   CUDA_CHECK(cudaEventRecord(e->ev[7], e->st));
   CUDA_CHECK(cudaMemcpyAsync(C, dC, nC * 4, cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));

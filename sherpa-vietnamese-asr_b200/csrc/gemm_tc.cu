@@ -117,7 +117,12 @@ struct TcParams {
   int M, N, K, act;
 };
 
-template <int BN>
+// SPLIT3 = error-compensated "3xTF32": every fp32 operand x is split in shared memory into hi = x with the 13 low
+// mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32), and each K step issues
+// A_lo*W_hi + A_hi*W_lo + A_hi*W_hi into the same FP32 TMEM accumulator. The dropped lo*lo term and the TF32
+// rounding of lo are ~2^-21 relative, i.e. the product is fp32-grade while still running on the tensor pipe.
+// This is the FP32 (token-exact) mode; the epilogue warps do the split while the main loop runs.
+template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_w, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -127,9 +132,12 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __gri
   constexpr int kWBytes = BN * TBK * 4;    // 16 or 8 KB
   uint8_t *sA = smem;
   uint8_t *sW = smem + kStages * kABytes;
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sW + kStages * kWBytes);
+  uint8_t *sAlo = sW + kStages * kWBytes;                       // only carved when SPLIT3
+  uint8_t *sWlo = sAlo + (SPLIT3 ? kStages * kABytes : 0);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWlo + (SPLIT3 ? kStages * kWBytes : 0));
   uint64_t *empty_bar = full_bar + kStages;
-  uint64_t *tmem_full_bar = empty_bar + kStages;
+  uint64_t *ready_bar = empty_bar + kStages;                    // split done (SPLIT3)
+  uint64_t *tmem_full_bar = ready_bar + kStages;
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __gri
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -169,14 +177,26 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __gri
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(SPLIT3 ? &ready_bar[s] : &full_bar[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t da = make_smem_desc(smem_u32(sA + s * kABytes));
         const uint64_t dw = make_smem_desc(smem_u32(sW + s * kWBytes));
+        if constexpr (SPLIT3) {
+          const uint64_t dal = make_smem_desc(smem_u32(sAlo + s * kABytes));
+          const uint64_t dwl = make_smem_desc(smem_u32(sWlo + s * kWBytes));
 #pragma unroll
-        for (int k = 0; k < TBK / UMMA_K; ++k) {
-          // advance along K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte units
-          umma_tf32(tmem_base, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < TBK / UMMA_K; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32(tmem_base, dal + o, dw + o, idesc, (kb | k) ? 1u : 0u);   // small terms first
+            umma_tf32(tmem_base, da + o, dwl + o, idesc, 1u);
+            umma_tf32(tmem_base, da + o, dw + o, idesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < TBK / UMMA_K; ++k) {
+            // advance along K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte units
+            umma_tf32(tmem_base, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
       }
@@ -185,6 +205,33 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __gri
   } else {
     // epilogue warps 2..5: TMEM lane quarter = warp % 4
     const int q = warp & 3;
+    if constexpr (SPLIT3) {
+      // operand split while the main loop runs: hi in place, lo into the shadow stage (same swizzled layout)
+      const int t = threadIdx.x - 64;   // 0..127
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        float4 *a4 = reinterpret_cast<float4 *>(sA + s * kABytes), *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
+        float4 *w4 = reinterpret_cast<float4 *>(sW + s * kWBytes), *wl4 = reinterpret_cast<float4 *>(sWlo + s * kWBytes);
+        auto split = [](float4 *hi_p, float4 *lo_p, int i) {
+          const float4 v = hi_p[i];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          hi_p[i] = h;
+          lo_p[i] = l;
+        };
+#pragma unroll 4
+        for (int i = t; i < kABytes / 16; i += 128) split(a4, al4, i);
+#pragma unroll 4
+        for (int i = t; i < kWBytes / 16; i += 128) split(w4, wl4, i);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = m0 + q * 32 + lane;
@@ -253,8 +300,8 @@ void init_once() {
   });
 }
 
-constexpr size_t smem_bytes(int BN) {
-  return 1024 + (size_t)kStages * (TBM * TBK * 4 + BN * TBK * 4) + (2 * kStages + 1) * 8 + 16;
+constexpr size_t smem_bytes(int BN, bool split3) {
+  return 1024 + (size_t)kStages * (TBM * TBK * 4 + BN * TBK * 4) * (split3 ? 2 : 1) + (3 * kStages + 1) * 8 + 16;
 }
 
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
@@ -276,7 +323,7 @@ bool gemm_tc_available() {
   return g_ok;
 }
 
-void launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
+static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   if (g.M <= 0 || g.N <= 0) return;
   init_once();
   if (!g_ok) throw CudaError("tcgen05 GEMM: cuTensorMapEncodeTiled entry point unavailable");
@@ -287,8 +334,10 @@ void launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
   }
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128)));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64)));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128, false)));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64, false)));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128, true)));
+    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64, true)));
     attr_done = true;
   }
   const int BN = g.N > 64 ? 128 : 64;
@@ -297,10 +346,19 @@ void launch_gemm_tc(const GemmArgs &g, cudaStream_t st) {
   make_map(&mw, g.W, g.N, g.K, g.K, BN);
   TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act};
   dim3 grid((g.M + TBM - 1) / TBM, (g.N + BN - 1) / BN);
-  if (BN == 128) gemm_tf32_tcgen05_kernel<128><<<grid, kThreads, smem_bytes(128), st>>>(ma, mw, p);
-  else gemm_tf32_tcgen05_kernel<64><<<grid, kThreads, smem_bytes(64), st>>>(ma, mw, p);
+  if (split3) {
+    if (BN == 128) gemm_tf32_tcgen05_kernel<128, true><<<grid, kThreads, smem_bytes(128, true), st>>>(ma, mw, p);
+    else gemm_tf32_tcgen05_kernel<64, true><<<grid, kThreads, smem_bytes(64, true), st>>>(ma, mw, p);
+  } else {
+    if (BN == 128) gemm_tf32_tcgen05_kernel<128, false><<<grid, kThreads, smem_bytes(128, false), st>>>(ma, mw, p);
+    else gemm_tf32_tcgen05_kernel<64, false><<<grid, kThreads, smem_bytes(64, false), st>>>(ma, mw, p);
+  }
   count_launch();
   KERNEL_CHECK();
 }
+
+void launch_gemm_tc(const GemmArgs &g, cudaStream_t st) { launch_tc_impl(g, st, false); }
+// FP32-grade product on the tensor pipe (error-compensated 3xTF32)
+void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st) { launch_tc_impl(g, st, true); }
 
 }  // namespace b200asr

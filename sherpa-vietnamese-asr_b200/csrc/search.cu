@@ -80,14 +80,33 @@ __device__ void decoder_row(const SearchModel &m, int y0, int y1, float *s_e, fl
     s_e[o] = fmaxf(acc, 0.f);
   }
   __syncthreads();
+  // decoder_proj GEMV: each warp owns 4 output rows at a time, 128-bit loads, up to 16 independent loads in
+  // flight per lane (the weights come from L2; latency, not bandwidth, is what has to be hidden)
   const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < m.jd; j += nw) {
-    const float *wr = m.dec_proj_w + (long long)j * m.dd;
-    float acc = 0.f;
-    for (int o = lane; o < m.dd; o += 32) acc = fmaf(__ldg(wr + o), s_e[o], acc);
+  const int dd4 = m.dd >> 2;
+  const float4 *e4 = reinterpret_cast<const float4 *>(s_e);
+  for (int j0 = warp * 4; j0 < m.jd; j0 += nw * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4 *w4 = reinterpret_cast<const float4 *>(m.dec_proj_w + (long long)j0 * m.dd);
+#pragma unroll 4
+    for (int c = lane; c < dd4; c += 32) {
+      const float4 ev = e4[c];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) out_row[j] = acc + __ldg(m.dec_proj_b + j);
+      for (int r = 0; r < 4; ++r) {
+        const float4 wv = __ldg(w4 + (long long)r * dd4 + c);
+        acc[r] = fmaf(wv.x, ev.x, acc[r]); acc[r] = fmaf(wv.y, ev.y, acc[r]);
+        acc[r] = fmaf(wv.z, ev.z, acc[r]); acc[r] = fmaf(wv.w, ev.w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], sft);
+    }
+    if (lane < 4 && j0 + lane < m.jd) {
+      const float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+      out_row[j0 + lane] = v + __ldg(m.dec_proj_b + j0 + lane);
+    }
   }
   __syncthreads();
 }
@@ -160,6 +179,7 @@ __device__ bool same_chain(const ArenaNode *arena, int a, int b) {
 
 struct NewNode { int arena_idx; int row; };
 
+template <int KB>
 __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m, SearchDev d, ContextGraphView g, int has_graph,
                                                                   int t, int cur, int greedy, float blank_penalty) {
   const int s = blockIdx.x;
@@ -202,19 +222,19 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
 
   // (b) global top-k over count*V candidates; key = (ordered value, ~flat index) so max = value desc, index asc
   const int k = min(d.beam, count * V);
-  unsigned long long loc[kMaxBeam];
+  unsigned long long loc[KB];   // KB >= beam: per-thread candidates, descending
 #pragma unroll
-  for (int i = 0; i < kMaxBeam; ++i) loc[i] = 0ULL;
+  for (int i = 0; i < KB; ++i) loc[i] = 0ULL;
   const int total = count * V;
   for (int idx = tid; idx < total; idx += kSelThreads) {
     const int b = idx / V, v = idx - b * V;
     const float lp = ((lg[idx] - s_mx[b]) - s_lse[b]) + s_prev[b];
     const unsigned long long key = ((unsigned long long)ord_f32(lp) << 32) | (unsigned)(~(unsigned)idx);
-    if (key > loc[kMaxBeam - 1]) {
+    if (key > loc[KB - 1]) {
       // insertion into the descending local list (fully unrolled so it stays in registers)
       unsigned long long carry = key;
 #pragma unroll
-      for (int i = 0; i < kMaxBeam; ++i) {
+      for (int i = 0; i < KB; ++i) {
         if (carry > loc[i]) { const unsigned long long tmp = loc[i]; loc[i] = carry; carry = tmp; }
       }
     }
@@ -223,7 +243,7 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
   for (int round = 0; round < k; ++round) {
     unsigned long long best = 0ULL;
 #pragma unroll
-    for (int i = 0; i < kMaxBeam; ++i) if (i == head) best = loc[i];
+    for (int i = 0; i < KB; ++i) if (i == head) best = loc[i];
     unsigned long long wb = best;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -498,7 +518,9 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
     ga.ldc = m.V; ga.M = n_active * beam; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE;
     S->gemm(ga, st);
-    select_step_kernel<<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    if (beam <= 4) select_step_kernel<4><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    else if (beam <= 8) select_step_kernel<8><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    else select_step_kernel<16><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
     count_launch(2);
   }
   KERNEL_CHECK();

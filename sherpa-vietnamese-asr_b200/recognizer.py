@@ -168,7 +168,7 @@ class OfflineRecognizer:
         cfg.hotwords_score = hotwords_score
         cfg.blank_penalty = blank_penalty
         cfg.device_id = device_id
-        cfg.precision = {"fp32": 0, "bf16": 1}[precision]
+        cfg.precision = {"fp32": 0, "tf32": 1, "bf16": 1, "fp32_simt": 2}[precision]
         self._cfg = cfg
         self._h = _capi.lib().B200AsrCreateOfflineRecognizer(C.byref(cfg))
         if not self._h:
@@ -345,7 +345,7 @@ class OfflineRecognizer:
         ms = C.c_float(0)
         rc = _capi.lib().B200AsrGemm(self._h, _capi.fptr(A), _capi.fptr(W), _capi.fptr(b) if b is not None else None,
                                     _capi.fptr(Rr) if Rr is not None else None, _capi.fptr(out), M, N, K, act,
-                                    1 if impl == "tc" else 0, reps, C.byref(ms))
+                                    {"fp32": 0, "tc": 1, "tc3": 2}[impl], reps, C.byref(ms))
         if rc != 0:
             raise RuntimeError(_capi.last_error())
         return out, ms.value

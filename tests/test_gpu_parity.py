@@ -242,7 +242,7 @@ GEMM_SHAPES = [(1000, 272, 192), (517, 48, 192), (4096, 640, 192), (130, 2000, 5
                (2500, 384, 128), (3000, 512, 512), (129, 130, 36)]
 
 
-@pytest.mark.parametrize("impl", ["fp32", "tc"])
+@pytest.mark.parametrize("impl", ["fp32", "tc", "tc3"])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_kernels_match_numpy(tiny, impl, M, N, K):
     """Both GEMM kernels against a float64 product. FP32 CUDA-core kernel: fp32 rounding only. tcgen05 kernel:
@@ -261,10 +261,10 @@ def test_gemm_kernels_match_numpy(tiny, impl, M, N, K):
         elif act == 2:
             z = np.logaddexp(0, z - 1.0) - 0.08 * z - 0.313261687
         want = z + R
-        tol = 5e-6 if impl == "fp32" else 1.5e-3
+        tol = {"fp32": 5e-6, "tc": 1.5e-3, "tc3": 2e-5}[impl]
         assert rel_err(got, want) <= tol, (impl, act, rel_err(got, want))
     got, _ = rec.gemm(A, W, None, None, act=0, impl=impl)
-    assert rel_err(got, A.astype(np.float64) @ W.astype(np.float64).T) <= (5e-6 if impl == "fp32" else 1.5e-3)
+    assert rel_err(got, A.astype(np.float64) @ W.astype(np.float64).T) <= {"fp32": 5e-6, "tc": 1.5e-3, "tc3": 2e-5}[impl]
 
 
 def test_tensor_core_mode_end_to_end(model_dirs):
