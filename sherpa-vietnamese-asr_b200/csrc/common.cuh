@@ -70,6 +70,8 @@ void launch_embed_conv1(const float *in, const int *T, const long long *ioff, co
                         const float *w, const float *b, float *out, cudaStream_t st);
 void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,
                         const float *w, const float *b, float *out, cudaStream_t st);
+void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,
+                          cudaStream_t st);
 void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st);
 void launch_biasnorm(const float *x, int M, int D, const float *bias, const float *log_scale, float *out, cudaStream_t st);
 // out = orig + (biasnorm(x) - orig) * bypass

@@ -144,29 +144,59 @@ __global__ void __launch_bounds__(256) embed_conv2_kernel(const float *__restric
   }
 }
 
-// ConvNeXt depthwise 7x7 over (time, freq) of [T1,19,128], zero padded at each utterance's own edges. w: [7][7][128]
-__global__ void embed_dw7_kernel(const float *__restrict__ in, const int *__restrict__ len, const int *__restrict__ off,
-                                 const float *__restrict__ w, const float *__restrict__ b, float *__restrict__ out) {
+// conv2 as a GEMM: im2col rows [pixel (t,f)][(kh,kw,ci)] = 9 contiguous 128-byte chunks of the channels-last
+// conv1 output, so both the gather reads and the row writes are fully coalesced; the 288 -> 128 contraction then
+// runs on the tensor pipe (gemm_tc.cu) with bias + SwooshR in its epilogue.
+__global__ void embed_im2col2_kernel(const float *__restrict__ in, const int *__restrict__ T, const long long *__restrict__ ioff,
+                                     const int *__restrict__ ooff, float *__restrict__ out) {
   const int u = blockIdx.y;
+  const int Tu = T[u];
+  const int T1 = Tu >= 9 ? (Tu - 7) / 2 : 0;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of one chunk
+  if (idx >= (long long)T1 * 19 * 72) return;
+  const int q = (int)(idx & 7);            // float4 within the 32-channel chunk
+  const int tap = (int)((idx >> 3) % 9);   // kh*3+kw
+  const long long pix = (idx >> 3) / 9;
+  const int f = (int)(pix % 19), t = (int)(pix / 19);
+  const int kh = tap / 3, kw = tap % 3;
+  const float4 v = __ldg(reinterpret_cast<const float4 *>(in + ((ioff[u] + t + kh) * 39 + (2 * f + kw)) * 32) + q);
+  reinterpret_cast<float4 *>(out + ((long long)ooff[u] * 19 + pix) * 288 + tap * 32)[q] = v;
+}
+
+// ConvNeXt depthwise 7x7 over (time, freq) of [T1,19,128], zero padded at each utterance's own edges. w: [7][7][128]
+// CTA = 8 time rows x 19 freq x 32 channels; the (8+6) x (19+6) x 32 zero-padded patch sits in shared memory;
+// thread = (channel, time row) keeps its 49 taps in registers and slides over frequency.
+constexpr int kDw7Rows = 8, kDw7Ch = 32;
+__global__ void __launch_bounds__(256) embed_dw7_kernel(const float *__restrict__ in, const int *__restrict__ len,
+                                                        const int *__restrict__ off, const float *__restrict__ w,
+                                                        const float *__restrict__ b, float *__restrict__ out) {
+  __shared__ float patch[(kDw7Rows + 6) * 25 * kDw7Ch];
+  const int u = blockIdx.z;
   const int T1 = len[u];
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)T1 * 19 * 128) return;
-  const int c = idx & 127;
-  const int f = (int)((idx >> 7) % 19), t = (int)((idx >> 7) / 19);
+  const int t0 = blockIdx.x * kDw7Rows;
+  if (t0 >= T1) return;
+  const int c0 = blockIdx.y * kDw7Ch;
   const float *x = in + (long long)off[u] * 19 * 128;
-  float acc = __ldg(b + c);
-#pragma unroll
-  for (int dt = 0; dt < 7; ++dt) {
-    const int tt = t + dt - 3;
-    if (tt < 0 || tt >= T1) continue;
-#pragma unroll
-    for (int df = 0; df < 7; ++df) {
-      const int ff = f + df - 3;
-      if (ff < 0 || ff >= 19) continue;
-      acc = fmaf(__ldg(w + (dt * 7 + df) * 128 + c), __ldg(x + ((long long)tt * 19 + ff) * 128 + c), acc);
-    }
+  for (int i = threadIdx.x; i < (kDw7Rows + 6) * 25 * kDw7Ch; i += 256) {
+    const int c = i % kDw7Ch, ff = (i / kDw7Ch) % 25 - 3, tt = t0 + i / (kDw7Ch * 25) - 3;
+    patch[i] = (tt >= 0 && tt < T1 && ff >= 0 && ff < 19) ? __ldg(x + ((long long)tt * 19 + ff) * 128 + c0 + c) : 0.f;
   }
-  out[((long long)off[u] * 19) * 128 + idx] = acc;
+  __syncthreads();
+  const int c = threadIdx.x % kDw7Ch, tr = threadIdx.x / kDw7Ch;
+  if (t0 + tr >= T1) return;
+  float wr[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) wr[k] = __ldg(w + k * 128 + c0 + c);
+  const float bias = __ldg(b + c0 + c);
+  float *o = out + ((long long)off[u] + t0 + tr) * 19 * 128 + c0 + c;
+  for (int f = 0; f < 19; ++f) {
+    float acc = bias;
+#pragma unroll
+    for (int dt = 0; dt < 7; ++dt)
+#pragma unroll
+      for (int df = 0; df < 7; ++df) acc = fmaf(wr[dt * 7 + df], patch[((tr + dt) * 25 + f + df) * kDw7Ch + c], acc);
+    o[f * 128] = acc;
+  }
 }
 
 // ------------------------------------------------------------------ BiasNorm / Bypass
@@ -298,60 +328,91 @@ __global__ void pos_emb_kernel(float *__restrict__ pe, int L, int pos_dim) {
 }
 
 // ------------------------------------------------------------------ attention weights (scores + rel-pos + softmax)
-// CTA = (query tile of 16 rows, head, utterance). Scores for the 16 rows against all keys live in shared
-// memory; softmax per row by a warp; normalised weights written once to HBM: A[u][h][i][j].
-constexpr int kAttRows = 16;
+// CTA = (16 query rows, head, utterance), 256 threads. Keys are processed in tiles of 256: the K tile sits
+// transposed in shared memory ([d][key]) so each thread computes a 4 (rows) x 4 (keys) register tile from two
+// 128-bit shared loads per d; the relative-position term needs only the 7 pos rows (j-i) in [-3, 3] of that tile.
+// All 16 x Tk scores stay in shared memory for the softmax; the normalised weights are written once: A[u][h][i][j].
+constexpr int kAttRows = 16, kAttKeys = 256, kAttKStride = kAttKeys + 4;
 template <int QD, int PD>
 __global__ void __launch_bounds__(256) attn_weights_kernel(const float *__restrict__ proj, int ldp, const float *__restrict__ pos,
                                                            int ldpos, const int *__restrict__ len, const int *__restrict__ off,
                                                            const long long *__restrict__ aoff, int H, int Lmax,
                                                            float *__restrict__ A) {
-  extern __shared__ float smem[];
+  static_assert(QD == 32 && PD == 4, "tile mapping assumes 32/4");
+  extern __shared__ __align__(16) float smem[];
   const int u = blockIdx.z, h = blockIdx.y;
   const int Tk = len[u];
   const int i0 = blockIdx.x * kAttRows;
   if (i0 >= Tk) return;
-  float *sq = smem;                       // [16][QD]
-  float *sp = sq + kAttRows * QD;         // [16][PD]
-  float *sc = sp + kAttRows * PD;         // [16][Tk]
+  float *sQT = smem;                          // [QD][16]   q transposed
+  float *sP = sQT + QD * kAttRows;            // [16][PD]
+  float *sKT = sP + kAttRows * PD;            // [QD][kAttKStride]
+  float *sc = sKT + QD * kAttKStride;         // [16][Tk]
   const float *base = proj + (long long)off[u] * ldp;
   const int nrow = min(kAttRows, Tk - i0);
-  for (int i = threadIdx.x; i < kAttRows * QD; i += blockDim.x) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kAttRows * QD; i += 256) {
     const int r = i / QD, d = i % QD;
-    sq[i] = r < nrow ? base[(long long)(i0 + r) * ldp + h * QD + d] : 0.f;
+    sQT[d * kAttRows + r] = r < nrow ? base[(long long)(i0 + r) * ldp + h * QD + d] : 0.f;
   }
-  for (int i = threadIdx.x; i < kAttRows * PD; i += blockDim.x) {
+  for (int i = tid; i < kAttRows * PD; i += 256) {
     const int r = i / PD, d = i % PD;
-    sp[i] = r < nrow ? base[(long long)(i0 + r) * ldp + 2 * H * QD + h * PD + d] : 0.f;
+    sP[i] = r < nrow ? base[(long long)(i0 + r) * ldp + 2 * H * QD + h * PD + d] : 0.f;
+  }
+  const int kg = tid & 63, rg = tid >> 6;     // 4 keys kg*4.., 4 rows rg*4..
+  for (int j0 = 0; j0 < Tk; j0 += kAttKeys) {
+    __syncthreads();                          // previous tile consumed (and sQT/sP visible on the first pass)
+    // stage K tile transposed: thread -> (key, 4 consecutive d)
+    for (int i = tid; i < kAttKeys * (QD / 4); i += 256) {
+      const int key = i >> 3, dq = (i & 7) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j0 + key < Tk) v = __ldg(reinterpret_cast<const float4 *>(base + (long long)(j0 + key) * ldp + H * QD + h * QD + dq));
+      sKT[(dq + 0) * kAttKStride + key] = v.x; sKT[(dq + 1) * kAttKStride + key] = v.y;
+      sKT[(dq + 2) * kAttKStride + key] = v.z; sKT[(dq + 3) * kAttKStride + key] = v.w;
+    }
+    __syncthreads();
+    if (j0 + kg * 4 < Tk) {
+      float acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < QD; ++d) {
+        const float4 q4 = *reinterpret_cast<const float4 *>(sQT + d * kAttRows + rg * 4);
+        const float4 k4 = *reinterpret_cast<const float4 *>(sKT + d * kAttKStride + kg * 4);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w}, k[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(q[r], k[c], acc[r][c]);
+      }
+      // relative position: pos row for offset (j - i) is (j - i) + (Lmax - 1); (c - r) spans [-3, 3]
+      const int pbase = (j0 + kg * 4) - (i0 + rg * 4) + (Lmax - 1);
+      float4 pr[7];
+#pragma unroll
+      for (int o = 0; o < 7; ++o) {
+        const int row = min(max(pbase + o - 3, 0), 2 * Lmax - 2);
+        pr[o] = __ldg(reinterpret_cast<const float4 *>(pos + (long long)row * ldpos + h * PD));
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 p4 = *reinterpret_cast<const float4 *>(sP + (rg * 4 + r) * PD);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 w = pr[c - r + 3];
+          float ps = p4.x * w.x;
+          ps = fmaf(p4.y, w.y, ps); ps = fmaf(p4.z, w.z, ps); ps = fmaf(p4.w, w.w, ps);
+          const int j = j0 + kg * 4 + c;
+          if (j < Tk) sc[(rg * 4 + r) * Tk + j] = acc[r][c] + ps;
+        }
+      }
+    }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < Tk; j += blockDim.x) {
-    float kv[QD];
-    const float4 *kr = reinterpret_cast<const float4 *>(base + (long long)j * ldp + H * QD + h * QD);
-#pragma unroll
-    for (int d = 0; d < QD / 4; ++d) {
-      const float4 v = __ldg(kr + d);
-      kv[4 * d] = v.x; kv[4 * d + 1] = v.y; kv[4 * d + 2] = v.z; kv[4 * d + 3] = v.w;
-    }
-#pragma unroll 4
-    for (int r = 0; r < kAttRows; ++r) {
-      if (r >= nrow) break;
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < QD; ++d) s = fmaf(sq[r * QD + d], kv[d], s);
-      // relative position term: pos row for offset (j - i) is (j - i) + (Lmax - 1)
-      const int pr = j - (i0 + r) + (Lmax - 1);
-      const float *pp = pos + (long long)pr * ldpos + h * PD;
-      float ps = 0.f;
-#pragma unroll
-      for (int d = 0; d < PD; ++d) ps = fmaf(sp[r * PD + d], __ldg(pp + d), ps);
-      sc[r * Tk + j] = s + ps;
-    }
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   float *Abase = A + aoff[u] + (long long)h * Tk * Tk;
-  for (int r = warp; r < nrow; r += (blockDim.x >> 5)) {
+  for (int r = warp; r < nrow; r += 8) {
     float *row = sc + r * Tk;
     float mx = -INFINITY;
     for (int j = lane; j < Tk; j += 32) mx = fmaxf(mx, row[j]);
@@ -371,39 +432,39 @@ __global__ void __launch_bounds__(256) attn_weights_kernel(const float *__restri
 }
 
 // ------------------------------------------------------------------ attention application: out = (A_h * V) (* Y)
-// CTA = 64 query rows x CT columns of one utterance; loops over keys in chunks of 32 through shared memory.
-template <int CT, int TR, int TC>
-__global__ void __launch_bounds__(256) attn_apply_kernel(const float *__restrict__ A, const long long *__restrict__ aoff,
-                                                         const int *__restrict__ len, const int *__restrict__ off,
-                                                         const float *__restrict__ X, int ldx, const float *__restrict__ S, int lds,
-                                                         const float *__restrict__ Y, int ldy, int C, int single_head,
-                                                         float *__restrict__ out, int ldo) {
-  constexpr int KC = 32;
-  __shared__ float As[64][KC + 1];
-  __shared__ float Vs[KC][CT];
+// CTA = 32*RPT query rows x 4*CG columns of one utterance; 32*CG threads, warp = column group, lane = row group.
+// Thread tile = RPT rows (lane + 32 r) x 4 columns; keys go through shared memory in chunks of 32
+// (A tile [rows][33]: conflict-free scalar reads; V tile [32][4*CG]: one 128-bit broadcast read per key).
+template <int CG, int RPT>
+__global__ void __launch_bounds__(32 * CG) attn_apply_kernel(const float *__restrict__ A, const long long *__restrict__ aoff,
+                                                             const int *__restrict__ len, const int *__restrict__ off,
+                                                             const float *__restrict__ X, int ldx, const float *__restrict__ S, int lds,
+                                                             const float *__restrict__ Y, int ldy, int C, int single_head,
+                                                             float *__restrict__ out, int ldo) {
+  constexpr int KC = 32, ROWS = 32 * RPT, CT = 4 * CG, NT = 32 * CG;
+  extern __shared__ __align__(16) float smem[];
+  float *As = smem;                    // [ROWS][KC + 1]
+  float *Vs = As + ROWS * (KC + 1);    // [KC][CT]
   const int u = blockIdx.z;
   const int Tk = len[u];
-  const int i0 = blockIdx.x * 64;
+  const int i0 = blockIdx.x * ROWS;
   if (i0 >= Tk) return;
-  const int ctile = blockIdx.y;                 // column tile (== head when !single_head)
+  const int ctile = blockIdx.y;
   const int c0 = ctile * CT;
   const int head = single_head ? 0 : ctile;
   const float *Ah = A + aoff[u] + (long long)head * Tk * Tk;
   const long long rbase = off[u];
-  constexpr int NCG = CT / TC;                  // column groups
-  const int cg = threadIdx.x % NCG, rg = threadIdx.x / NCG;   // rg in [0, 64/TR)
-  float acc[TR][TC];
+  const int cg = threadIdx.x >> 5, rg = threadIdx.x & 31;
+  float acc[RPT][4];
 #pragma unroll
-  for (int a = 0; a < TR; ++a)
-#pragma unroll
-    for (int b = 0; b < TC; ++b) acc[a][b] = 0.f;
+  for (int r = 0; r < RPT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
   for (int j0 = 0; j0 < Tk; j0 += KC) {
-    for (int i = threadIdx.x; i < 64 * KC; i += blockDim.x) {
+    for (int i = threadIdx.x; i < ROWS * KC; i += NT) {
       const int r = i / KC, jj = i % KC;
       const int gi = i0 + r, gj = j0 + jj;
-      As[r][jj] = (gi < Tk && gj < Tk) ? Ah[(long long)gi * Tk + gj] : 0.f;
+      As[r * (KC + 1) + jj] = (gi < Tk && gj < Tk) ? Ah[(long long)gi * Tk + gj] : 0.f;
     }
-    for (int i = threadIdx.x; i < KC * CT; i += blockDim.x) {
+    for (int i = threadIdx.x; i < KC * CT; i += NT) {
       const int jj = i / CT, c = i % CT;
       const int gj = j0 + jj, gc = c0 + c;
       float v = 0.f;
@@ -411,32 +472,30 @@ __global__ void __launch_bounds__(256) attn_apply_kernel(const float *__restrict
         v = X[(rbase + gj) * ldx + gc];
         if (S) v *= tanhf(S[(rbase + gj) * lds + gc]);
       }
-      Vs[jj][c] = v;
+      Vs[jj * CT + c] = v;
     }
     __syncthreads();
 #pragma unroll 8
     for (int jj = 0; jj < KC; ++jj) {
-      float a[TR], v[TC];
+      const float4 v = *reinterpret_cast<const float4 *>(Vs + jj * CT + cg * 4);
 #pragma unroll
-      for (int x = 0; x < TR; ++x) a[x] = As[rg * TR + x][jj];
-#pragma unroll
-      for (int y = 0; y < TC; ++y) v[y] = Vs[jj][cg * TC + y];
-#pragma unroll
-      for (int x = 0; x < TR; ++x)
-#pragma unroll
-        for (int y = 0; y < TC; ++y) acc[x][y] = fmaf(a[x], v[y], acc[x][y]);
+      for (int r = 0; r < RPT; ++r) {
+        const float a = As[(rg + 32 * r) * (KC + 1) + jj];
+        acc[r][0] = fmaf(a, v.x, acc[r][0]); acc[r][1] = fmaf(a, v.y, acc[r][1]);
+        acc[r][2] = fmaf(a, v.z, acc[r][2]); acc[r][3] = fmaf(a, v.w, acc[r][3]);
+      }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int x = 0; x < TR; ++x) {
-    const int gi = i0 + rg * TR + x;
+  for (int r = 0; r < RPT; ++r) {
+    const int gi = i0 + rg + 32 * r;
     if (gi >= Tk) continue;
 #pragma unroll
-    for (int y = 0; y < TC; ++y) {
-      const int gc = c0 + cg * TC + y;
+    for (int c = 0; c < 4; ++c) {
+      const int gc = c0 + cg * 4 + c;
       if (gc >= C) continue;
-      float v = acc[x][y];
+      float v = acc[r][c];
       if (Y) v *= Y[(rbase + gi) * ldy + gc];
       out[(rbase + gi) * ldo + gc] = v;
     }
@@ -515,9 +574,16 @@ void launch_embed_conv2(const float *in, const int *T, const long long *ioff, co
   embed_conv2_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
+void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,
+                          cudaStream_t st) {
+  if (max_T1 <= 0) return;
+  dim3 grid(cdiv((long long)max_T1 * 19 * 72, 256), n);
+  embed_im2col2_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, out);
+  count_launch(); KERNEL_CHECK();
+}
 void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st) {
   if (r.total <= 0) return;
-  dim3 grid(cdiv((long long)r.max_len * 19 * 128, 256), r.n);
+  dim3 grid(cdiv(r.max_len, kDw7Rows), 128 / kDw7Ch, r.n);
   embed_dw7_kernel<<<grid, 256, 0, st>>>(in, r.len, r.off, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
@@ -578,8 +644,8 @@ void launch_attn_weights(const float *proj, int ldp, const float *pos, const Rag
                          int pd, float *A, cudaStream_t st) {
   if (r.total <= 0) return;
   if (qd != 32 || pd != 4) throw CudaError("attn_weights: only query_head_dim=32, pos_head_dim=4 are built");
-  const size_t smem = (size_t)(kAttRows * (qd + pd) + (size_t)kAttRows * r.max_len) * sizeof(float);
-  if (smem > 227 * 1024) throw CudaError("attn_weights: segment too long for one pass (max ~3400 frames at the stack rate)");
+  const size_t smem = (size_t)(kAttRows * (qd + pd) + qd * kAttKStride + (size_t)kAttRows * r.max_len) * sizeof(float);
+  if (smem > 227 * 1024) throw CudaError("attn_weights: segment too long for one pass (max ~2900 frames at the stack rate)");
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_CHECK(cudaFuncSetAttribute(attn_weights_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -593,13 +659,22 @@ void launch_attn_weights(const float *proj, int ldp, const float *pos, const Rag
 void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &r, const float *X, int ldx, const float *S, int lds,
                        const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st) {
   if (r.total <= 0) return;
+  constexpr int RPT = 8, ROWS = 32 * RPT;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<8, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<3, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
   if (single_head) {
-    dim3 grid(cdiv(r.max_len, 64), cdiv(C, 64), r.n);
-    attn_apply_kernel<64, 4, 4><<<grid, 256, 0, st>>>(A, aoff, r.len, r.off, X, ldx, S, lds, Y, ldy, C, 1, out, ldo);
+    const size_t smem = (size_t)(ROWS * 33 + 32 * 32) * sizeof(float);
+    dim3 grid(cdiv(r.max_len, ROWS), cdiv(C, 32), r.n);
+    attn_apply_kernel<8, RPT><<<grid, 256, smem, st>>>(A, aoff, r.len, r.off, X, ldx, S, lds, Y, ldy, C, 1, out, ldo);
   } else {
     if (dv_per_head != 12) throw CudaError("attn_apply: only value_head_dim=12 is built");
-    dim3 grid(cdiv(r.max_len, 64), C / 12, r.n);
-    attn_apply_kernel<12, 1, 3><<<grid, 256, 0, st>>>(A, aoff, r.len, r.off, X, ldx, S, lds, Y, ldy, C, 0, out, ldo);
+    const size_t smem = (size_t)(ROWS * 33 + 32 * 12) * sizeof(float);
+    dim3 grid(cdiv(r.max_len, ROWS), C / 12, r.n);
+    attn_apply_kernel<3, RPT><<<grid, 96, smem, st>>>(A, aoff, r.len, r.off, X, ldx, S, lds, Y, ldy, C, 0, out, ldo);
   }
   count_launch(); KERNEL_CHECK();
 }

@@ -320,11 +320,11 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
     for (int co = 0; co < 32; ++co) for (int ci = 0; ci < 8; ++ci) for (int k = 0; k < 9; ++k)
       t[(k * 8 + ci) * 32 + co] = w1[(co * 8 + ci) * 9 + k];
     w_conv1 = upload(t);
-    const auto &w2 = tensors.at("encoder.embed.conv2.weight").host;   // [128,32,3,3] -> [3][3][32][128]
+    const auto &w2 = tensors.at("encoder.embed.conv2.weight").host;   // [128,32,3,3] -> GEMM weight [128][(kh,kw,ci)]
     W("encoder.embed.conv2.weight", {128, 32, 3, 3});
     t.assign(288 * 128, 0.f);
     for (int co = 0; co < 128; ++co) for (int ci = 0; ci < 32; ++ci) for (int k = 0; k < 9; ++k)
-      t[(k * 32 + ci) * 128 + co] = w2[(co * 32 + ci) * 9 + k];
+      t[(size_t)co * 288 + k * 32 + ci] = w2[(co * 32 + ci) * 9 + k];
     w_conv2 = upload(t);
     const auto &wd = tensors.at("encoder.embed.convnext.dw.weight").host;  // [128,1,7,7] -> [7][7][128]
     W("encoder.embed.convnext.dw.weight", {128, 1, 7, 7});
@@ -647,7 +647,8 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   float *x0 = b_x0.get<float>((size_t)M1 * D0);
   launch_embed_conv0(d_feats, d_T, d_foff, d_c0off, n, maxT, w_conv0, W("encoder.embed.conv0.bias"), c0, st);
   launch_embed_conv1(c0, d_T, d_c0off, d_c1off, n, maxt2, w_conv1, W("encoder.embed.conv1.bias"), c1, st);
-  launch_embed_conv2(c1, d_T, d_c1off, rd[0].off, n, Lr[0], w_conv2, W("encoder.embed.conv2.bias"), c2, st);
+  launch_embed_im2col2(c1, d_T, d_c1off, rd[0].off, n, Lr[0], pw1, st);   // pw1 buffer doubles as the im2col scratch (288 <= 384)
+  gemm(pw1, 288, w_conv2, W("encoder.embed.conv2.bias"), nullptr, 0, c2, 128, M1 * 19, 128, 288, ACT_SWOOSH_R);
   launch_embed_dw7(c2, rd[0], w_dw7, W("encoder.embed.convnext.dw.bias"), dw, st);
   gemm(dw, 128, W("encoder.embed.convnext.pw1.weight"), W("encoder.embed.convnext.pw1.bias"), nullptr, 0, pw1, 384, M1 * 19, 384, 128,
        ACT_SWOOSH_L);

@@ -9,15 +9,16 @@
 // and at the path's shapes (K = 192..512, N = 48..1920) the GEMMs are HBM-bound, so reading the fp32 tensors
 // straight through TMA avoids a conversion pass over every activation while keeping a 10-bit mantissa.
 //
-// CTA = one 128 x BN output tile (BN = 128 or 64). Warp roles (192 threads):
+// Persistent CTAs (one per SM) walk 128 x BN output tiles (BN = 128 or 64). Warp roles:
 //   warp 0      TMA producer (one elected lane): A tile 128x32 fp32 and W tile BNx32 fp32 per stage
-//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 x tcgen05.mma (K=8 each) per stage,
-//               tcgen05.commit releases the stage and finally signals the epilogue
+//   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 (x3) tcgen05.mma (K=8 each) per stage,
+//               tcgen05.commit releases the stage and, after the last K block, hands the accumulator to the epilogue
 //   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / Swoosh / residual, global stores
-// Several CTAs are co-resident per SM (<= 80 KB smem, 128 TMEM columns each) so one tile's epilogue overlaps
-// another tile's main loop.
+//   warps 6..9  (3xTF32 mode) split each landed stage into hi/lo operands
+// Two TMEM accumulators (2 x BN columns) overlap the epilogue of one tile with the main loop of the next.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -29,8 +30,8 @@ namespace {
 constexpr int TBM = 128;       // tile M (UMMA M)
 constexpr int TBK = 32;        // fp32 elements per stage = 128 bytes = one swizzle row
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kStages1 = 5;    // TF32 mode: 5 x (16 + BN/8) KB
+constexpr int kStages3 = 3;    // 3xTF32 mode: 3 x 2 x (16 + BN/8) KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,38 +122,46 @@ struct TcParams {
 // mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32), and each K step issues
 // A_lo*W_hi + A_hi*W_lo + A_hi*W_hi into the same FP32 TMEM accumulator. The dropped lo*lo term and the TF32
 // rounding of lo are ~2^-21 relative, i.e. the product is fp32-grade while still running on the tensor pipe.
-// This is the FP32 (token-exact) mode; the epilogue warps do the split while the main loop runs.
+// This is the FP32 (token-exact) mode.
+//
+// Persistent kernel: grid = min(#tiles, #SMs); each CTA walks tiles (n fastest, so concurrently running CTAs share
+// an A row block in L2). Roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 epilogue,
+// warps 6..9 operand splitter (SPLIT3 only). Two TMEM accumulators (2 x BN columns) let the epilogue of tile i
+// overlap the main loop of tile i+1; the smem stage ring runs continuously across tiles.
 template <int BN, bool SPLIT3>
-__global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                     const __grid_constant__ CUtensorMap map_w, TcParams p) {
+__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
+gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcParams p) {
+  constexpr int NS = SPLIT3 ? kStages3 : kStages1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: 1024-aligned stage buffers first, then barriers
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kABytes = TBM * TBK * 4;   // 16 KB
   constexpr int kWBytes = BN * TBK * 4;    // 16 or 8 KB
   uint8_t *sA = smem;
-  uint8_t *sW = smem + kStages * kABytes;
-  uint8_t *sAlo = sW + kStages * kWBytes;                       // only carved when SPLIT3
-  uint8_t *sWlo = sAlo + (SPLIT3 ? kStages * kABytes : 0);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWlo + (SPLIT3 ? kStages * kWBytes : 0));
-  uint64_t *empty_bar = full_bar + kStages;
-  uint64_t *ready_bar = empty_bar + kStages;                    // split done (SPLIT3)
-  uint64_t *tmem_full_bar = ready_bar + kStages;
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+  uint8_t *sW = smem + NS * kABytes;
+  uint8_t *sAlo = sW + NS * kWBytes;                       // only carved when SPLIT3
+  uint8_t *sWlo = sAlo + (SPLIT3 ? NS * kABytes : 0);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWlo + (SPLIT3 ? NS * kWBytes : 0));
+  uint64_t *empty_bar = full_bar + NS;
+  uint64_t *ready_bar = empty_bar + NS;                    // split done (SPLIT3)
+  uint64_t *tmem_full_bar = ready_bar + NS;                // [2]
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;            // [2]
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * BN;
   const int nk = (p.K + TBK - 1) / TBK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + TBM - 1) / TBM;
+  const int n_tiles = tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)(2 * BN)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -161,123 +170,146 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_tcgen05_kernel(const __gri
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
+    // ===== TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
-        tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes, kb * TBK, m0);
-        tma_load_2d(&map_w, &full_bar[s], sW + s * kWBytes, kb * TBK, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
+          tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes, kb * TBK, m0);
+          tma_load_2d(&map_w, &full_bar[s], sW + s * kWBytes, kb * TBK, n0);
+        }
       }
     }
   } else if (warp == 1) {
+    // ===== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TBM, BN);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(SPLIT3 ? &ready_bar[s] : &full_bar[s], ph);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = make_smem_desc(smem_u32(sA + s * kABytes));
-        const uint64_t dw = make_smem_desc(smem_u32(sW + s * kWBytes));
-        if constexpr (SPLIT3) {
-          const uint64_t dal = make_smem_desc(smem_u32(sAlo + s * kABytes));
-          const uint64_t dwl = make_smem_desc(smem_u32(sWlo + s * kWBytes));
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(SPLIT3 ? &ready_bar[s] : &full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = make_smem_desc(smem_u32(sA + s * kABytes));
+          const uint64_t dw = make_smem_desc(smem_u32(sW + s * kWBytes));
+          if constexpr (SPLIT3) {
+            const uint64_t dal = make_smem_desc(smem_u32(sAlo + s * kABytes));
+            const uint64_t dwl = make_smem_desc(smem_u32(sWlo + s * kWBytes));
 #pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            const uint64_t o = (uint64_t)(k * 2);
-            umma_tf32(tmem_base, dal + o, dw + o, idesc, (kb | k) ? 1u : 0u);   // small terms first
-            umma_tf32(tmem_base, da + o, dwl + o, idesc, 1u);
-            umma_tf32(tmem_base, da + o, dw + o, idesc, 1u);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < TBK / UMMA_K; ++k) {
-            // advance along K inside the 128-byte swizzle row: +32 bytes = +2 in 16-byte units
-            umma_tf32(tmem_base, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          }
-        }
-        umma_commit(&empty_bar[s]);   // frees the stage when these MMAs retire
-      }
-      umma_commit(tmem_full_bar);     // accumulator complete
-    }
-  } else {
-    // epilogue warps 2..5: TMEM lane quarter = warp % 4
-    const int q = warp & 3;
-    if constexpr (SPLIT3) {
-      // operand split while the main loop runs: hi in place, lo into the shadow stage (same swizzled layout)
-      const int t = threadIdx.x - 64;   // 0..127
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        float4 *a4 = reinterpret_cast<float4 *>(sA + s * kABytes), *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
-        float4 *w4 = reinterpret_cast<float4 *>(sW + s * kWBytes), *wl4 = reinterpret_cast<float4 *>(sWlo + s * kWBytes);
-        auto split = [](float4 *hi_p, float4 *lo_p, int i) {
-          const float4 v = hi_p[i];
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          hi_p[i] = h;
-          lo_p[i] = l;
-        };
-#pragma unroll 4
-        for (int i = t; i < kABytes / 16; i += 128) split(a4, al4, i);
-#pragma unroll 4
-        for (int i = t; i < kWBytes / 16; i += 128) split(w4, wl4, i);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
-      }
-    }
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (m < p.M) {
-        float *crow = p.C + (long long)m * p.ldc;
-        const float *rrow = p.R ? p.R + (long long)m * p.ldr : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n + 3 < p.N && ((p.ldc & 3) == 0) && (!rrow || (p.ldr & 3) == 0)) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            for (int k = 0; k < TBK / UMMA_K; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);   // +32 bytes inside the 128-byte swizzle row, in 16-byte units
+              umma_tf32(tmem_d, dal + o, dw + o, idesc, (kb | k) ? 1u : 0u);   // small terms first
+              umma_tf32(tmem_d, da + o, dwl + o, idesc, 1u);
+              umma_tf32(tmem_d, da + o, dw + o, idesc, 1u);
             }
-            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-            if (rrow) {
-              const float4 rr = *reinterpret_cast<const float4 *>(rrow + n);
-              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-            }
-            *reinterpret_cast<float4 *>(crow + n) = v;
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e < p.N) {
-                float v = __uint_as_float(r[j + e]);
-                if (p.bias) v += __ldg(p.bias + n + e);
-                v = apply_act(v, p.act);
-                if (rrow) v += rrow[n + e];
-                crow[n + e] = v;
+            for (int k = 0; k < TBK / UMMA_K; ++k)
+              umma_tf32(tmem_d, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);        // frees the stage when these MMAs retire
+        }
+        umma_commit(&tmem_full_bar[acc]);    // accumulator complete
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
+      const int acc = ti & 1;
+      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        if (m < p.M && n0 + c0 < p.N) {
+          float *crow = p.C + (long long)m * p.ldc;
+          const float *rrow = p.R ? p.R + (long long)m * p.ldr : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = n0 + c0 + j;
+            if (n + 3 < p.N && ((p.ldc & 3) == 0) && (!rrow || (p.ldr & 3) == 0)) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+              if (rrow) {
+                const float4 rr = *reinterpret_cast<const float4 *>(rrow + n);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              *reinterpret_cast<float4 *>(crow + n) = v;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (n + e < p.N) {
+                  float v = __uint_as_float(r[j + e]);
+                  if (p.bias) v += __ldg(p.bias + n + e);
+                  v = apply_act(v, p.act);
+                  if (rrow) v += rrow[n + e];
+                  crow[n + e] = v;
+                }
               }
             }
           }
         }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ===== operand splitter warps 6..9 (SPLIT3): hi in place, lo into the shadow stage (same swizzled layout)
+    if constexpr (SPLIT3) {
+      const int t = threadIdx.x - 192;   // 0..127
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&full_bar[s], ph);
+          float4 *a4 = reinterpret_cast<float4 *>(sA + s * kABytes), *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
+          float4 *w4 = reinterpret_cast<float4 *>(sW + s * kWBytes), *wl4 = reinterpret_cast<float4 *>(sWlo + s * kWBytes);
+          auto split = [](float4 *hi_p, float4 *lo_p, int i) {
+            const float4 v = hi_p[i];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            hi_p[i] = h;
+            lo_p[i] = l;
+          };
+#pragma unroll 4
+          for (int i = t; i < kABytes / 16; i += 128) split(a4, al4, i);
+#pragma unroll 4
+          for (int i = t; i < kWBytes / 16; i += 128) split(w4, wl4, i);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+        }
+      }
+    }
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
   }
 }
 
@@ -301,7 +333,7 @@ void init_once() {
 }
 
 constexpr size_t smem_bytes(int BN, bool split3) {
-  return 1024 + (size_t)kStages * (TBM * TBK * 4 + BN * TBK * 4) * (split3 ? 2 : 1) + (3 * kStages + 1) * 8 + 16;
+  return 1024 + (size_t)(split3 ? kStages3 * 2 : kStages1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16;
 }
 
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
@@ -345,13 +377,20 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map(&mw, g.W, g.N, g.K, g.K, BN);
   TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act};
-  dim3 grid((g.M + TBM - 1) / TBM, (g.N + BN - 1) / BN);
+  const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)std::min<long long>(n_tiles, n_sms);   // persistent: one CTA per SM
   if (split3) {
-    if (BN == 128) gemm_tf32_tcgen05_kernel<128, true><<<grid, kThreads, smem_bytes(128, true), st>>>(ma, mw, p);
-    else gemm_tf32_tcgen05_kernel<64, true><<<grid, kThreads, smem_bytes(64, true), st>>>(ma, mw, p);
+    if (BN == 128) gemm_tf32_tcgen05_kernel<128, true><<<grid, 320, smem_bytes(128, true), st>>>(ma, mw, p);
+    else gemm_tf32_tcgen05_kernel<64, true><<<grid, 320, smem_bytes(64, true), st>>>(ma, mw, p);
   } else {
-    if (BN == 128) gemm_tf32_tcgen05_kernel<128, false><<<grid, kThreads, smem_bytes(128, false), st>>>(ma, mw, p);
-    else gemm_tf32_tcgen05_kernel<64, false><<<grid, kThreads, smem_bytes(64, false), st>>>(ma, mw, p);
+    if (BN == 128) gemm_tf32_tcgen05_kernel<128, false><<<grid, 192, smem_bytes(128, false), st>>>(ma, mw, p);
+    else gemm_tf32_tcgen05_kernel<64, false><<<grid, 192, smem_bytes(64, false), st>>>(ma, mw, p);
   }
   count_launch();
   KERNEL_CHECK();
