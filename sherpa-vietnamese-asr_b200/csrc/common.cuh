@@ -47,6 +47,7 @@ void launch_fbank(const FbankTables &t, const float *samples, const long long *s
 struct GemmArgs {
   const float *A; int lda;
   const float *W;            // [N,K] row-major (ldw = K)
+  const float *Wlo;          // W - trunc_tf32(W), needed by the 3xTF32 tensor-core kernel only (else null)
   const float *bias;         // [N] or null
   const float *R; int ldr;   // residual or null
   float *C; int ldc;
@@ -54,6 +55,7 @@ struct GemmArgs {
   int act;
 };
 void launch_gemm_fp32(const GemmArgs &g, cudaStream_t st);
+void launch_split_lo(const float *w, float *lo, long long n, cudaStream_t st);
 
 // ---------------------------------------------------------------- encoder kernels (encoder.cu)
 struct RaggedDesc {     // per-rate description of the packed batch, all device pointers
@@ -115,6 +117,7 @@ struct SearchModel {
   const float *dec_proj_w; // [jd, dd]
   const float *dec_proj_b;
   const float *join_w;     // [V, jd]
+  const float *join_w_lo;  // low part for the 3xTF32 joiner GEMM (or null)
   const float *join_b;
   int V, dd, jd;
   int blank_id, unk_id;

@@ -105,6 +105,7 @@ struct Engine {
   // embed weights (re-laid out)
   float *w_conv0 = nullptr, *w_conv1 = nullptr, *w_conv2 = nullptr, *w_dw7 = nullptr, *w_out = nullptr;
   std::vector<float *> owned;   // extra device allocations to free
+  std::map<const float *, const float *> w_lo;   // weight -> its pre-split low part (3xTF32 mode)
 
   FbankTables fb{};
   cudaStream_t st = nullptr;
@@ -128,7 +129,7 @@ struct Engine {
   DevBuf b_T, b_c0off, b_c1off, b_len[4], b_off[4], b_aoff;
   DevBuf b_c0, b_c1, b_c2, b_dw, b_pw1, b_cn, b_x0, b_xc, b_sin, b_w1, b_proj, b_hid, b_A, b_pe, b_pp, b_cat, b_enc;
   DevBuf b_stack[6];
-  DevBuf b_tmp;
+  DevBuf b_tmp, b_tmp2;
   // host-side batch description of the last encoder run
   std::vector<int> h_T, h_T1, h_Tp;
   std::vector<std::vector<int>> h_len = std::vector<std::vector<int>>(4), h_off = std::vector<std::vector<int>>(4);
@@ -423,6 +424,13 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   if (precision < 0 || precision > 2) throw std::runtime_error("precision must be 0 (fp32 via 3xTF32 tcgen05), 1 (tf32 tcgen05) or 2 (fp32 CUDA cores)");
   if (precision != 2 && !gemm_tc_available()) throw std::runtime_error("tensor-core GEMM path unavailable (cuTensorMapEncodeTiled not found)");
   search_set_gemm(search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32));
+  if (precision == 0) {
+    float *lo;
+    CUDA_CHECK(cudaMalloc(&lo, (size_t)V * join_dim * sizeof(float)));
+    owned.push_back(lo);
+    launch_split_lo(sm.join_w, lo, (long long)V * join_dim, st);
+    sm.join_w_lo = lo;
+  }
 
   // hotwords file with token ids (modeling_unit token_id); text units are tokenised by the host binding
   const std::string hw = str(c->hotwords_file), mu_ = str(mc.modeling_unit);
@@ -482,6 +490,17 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = Wt; g.bias = bias; g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.act = act;
   if (M <= 0) return;
+  if (precision == 0) {
+    auto it = w_lo.find(Wt);
+    if (it == w_lo.end()) {   // first use of this weight: split once, keep
+      float *lo;
+      CUDA_CHECK(cudaMalloc(&lo, (size_t)N * K * sizeof(float)));
+      owned.push_back(lo);
+      launch_split_lo(Wt, lo, (long long)N * K, st);
+      it = w_lo.emplace(Wt, lo).first;
+    }
+    g.Wlo = it->second;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profiling) {
     if (gemm_ev_used >= gemm_events.size()) {
@@ -1104,6 +1123,11 @@ int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const flo
   GemmArgs g{};
   g.A = dA; g.lda = K; g.W = dW; g.bias = bias ? dB : nullptr; g.R = R ? dR : nullptr; g.ldr = N; g.C = dC; g.ldc = N;
   g.M = M; g.N = N; g.K = K; g.act = act;
+  if (impl == 2) {
+    float *dWlo = e->b_tmp2.get<float>(nW);
+    launch_split_lo(dW, dWlo, (long long)nW, e->st);
+    g.Wlo = dWlo;
+  }
   if (reps < 1) reps = 1;
   auto run = [&]() { if (impl == 1) launch_gemm_tc(g, e->st); else if (impl == 2) launch_gemm_tc3(g, e->st); else launch_gemm_fp32(g, e->st); };
   run();   // warm-up / the checked result

@@ -13,8 +13,10 @@
 //   warp 0      TMA producer (one elected lane): A tile 128x32 fp32 and W tile BNx32 fp32 per stage
 //   warp 1      TMEM allocator + MMA issuer (one elected lane): 4 (x3) tcgen05.mma (K=8 each) per stage,
 //               tcgen05.commit releases the stage and, after the last K block, hands the accumulator to the epilogue
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / Swoosh / residual, global stores
-//   warps 6..9  (3xTF32 mode) split each landed stage into hi/lo operands
+//   warps 2..9  epilogue (lane quarter x column half): tcgen05.ld 32 lanes x 32 columns, transpose through a
+//               per-warp smem tile so every global access is a coalesced 128-byte row, 32 residual loads in
+//               flight per thread, bias / Swoosh / residual
+//   warps 10..13 (3xTF32 mode) split each landed stage into hi/lo operands
 // Two TMEM accumulators (2 x BN columns) overlap the epilogue of one tile with the main loop of the next.
 #include <cuda.h>
 
@@ -104,7 +106,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+// softplus with the SFU exp/log: absolute error ~1e-7 (the 1 + t rounding), i.e. fp32 noise on the O(1) Swoosh
+// output, at a fifth of the instructions of expf/log1pf - the epilogue is issue-bound, not memory-bound.
+__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + __logf(1.0f + __expf(-fabsf(x))); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_SWOOSH_L) return softplus_f(v - 4.0f) - 0.08f * v - 0.035f;
   if (act == ACT_SWOOSH_R) return softplus_f(v - 1.0f) - 0.08f * v - 0.313261687f;
@@ -118,19 +122,21 @@ struct TcParams {
   int M, N, K, act;
 };
 
-// SPLIT3 = error-compensated "3xTF32": every fp32 operand x is split in shared memory into hi = x with the 13 low
-// mantissa bits cleared (exactly representable in TF32) and lo = x - hi (exact in fp32), and each K step issues
+// SPLIT3 = error-compensated "3xTF32": every fp32 operand x is split into hi = x with the 13 low mantissa bits
+// cleared (what the tensor core reads from a raw fp32 anyway) and lo = x - hi (exact in fp32; activations are split
+// in shared memory by dedicated warps, weights are pre-split once at load), and each K step issues
 // A_lo*W_hi + A_hi*W_lo + A_hi*W_hi into the same FP32 TMEM accumulator. The dropped lo*lo term and the TF32
 // rounding of lo are ~2^-21 relative, i.e. the product is fp32-grade while still running on the tensor pipe.
 // This is the FP32 (token-exact) mode.
 //
 // Persistent kernel: grid = min(#tiles, #SMs); each CTA walks tiles (n fastest, so concurrently running CTAs share
-// an A row block in L2). Roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..5 epilogue,
-// warps 6..9 operand splitter (SPLIT3 only). Two TMEM accumulators (2 x BN columns) let the epilogue of tile i
+// an A row block in L2). Roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..9 epilogue,
+// warps 10..13 operand splitter (SPLIT3 only). Two TMEM accumulators (2 x BN columns) let the epilogue of tile i
 // overlap the main loop of tile i+1; the smem stage ring runs continuously across tiles.
 template <int BN, bool SPLIT3>
-__global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1)
-gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, TcParams p) {
+__global__ void __launch_bounds__(SPLIT3 ? 448 : 320, 1)
+gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                         const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   constexpr int NS = SPLIT3 ? kStages3 : kStages1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -146,6 +152,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint64_t *tmem_full_bar = ready_bar + NS;                // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;            // [2]
   uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  float *epi_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 8 warps x 32 x 32 floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nk = (p.K + TBK - 1) / TBK;
@@ -157,7 +164,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -179,9 +186,10 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kABytes + kWBytes);
+          mbar_expect_tx(&full_bar[s], kABytes + kWBytes * (SPLIT3 ? 2 : 1));
           tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes, kb * TBK, m0);
           tma_load_2d(&map_w, &full_bar[s], sW + s * kWBytes, kb * TBK, n0);
+          if constexpr (SPLIT3) tma_load_2d(&map_wlo, &full_bar[s], sWlo + s * kWBytes, kb * TBK, n0);
         }
       }
     }
@@ -222,49 +230,67 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         umma_commit(&tmem_full_bar[acc]);    // accumulator complete
       }
     }
-  } else if (warp < 6) {
-    // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4
+  } else if (warp < 10) {
+    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     int ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
       const int acc = ti & 1;
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int m = m0 + q * 32 + lane;
+      float *stg = epi_stage + (warp - 2) * (32 * 32);   // per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
+      const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                          (!p.R || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
+                          (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        if (m < p.M && n0 + c0 < p.N) {
-          float *crow = p.C + (long long)m * p.ldc;
-          const float *rrow = p.R ? p.R + (long long)m * p.ldr : nullptr;
+        if (n0 + c0 >= p.N) continue;                      // warp-uniform
+        const int mrow0 = m0 + q * 32;
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = n0 + c0 + j;
-            if (n + 3 < p.N && ((p.ldc & 3) == 0) && (!rrow || (p.ldr & 3) == 0)) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-              if (rrow) {
-                const float4 rr = *reinterpret_cast<const float4 *>(rrow + n);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-              }
-              *reinterpret_cast<float4 *>(crow + n) = v;
-            } else {
+        for (int k4 = 0; k4 < 8; ++k4)                      // row = lane; 128-bit stores, conflict-free per quarter warp
+          *reinterpret_cast<float4 *>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(r[4 * k4]), __uint_as_float(r[4 * k4 + 1]), __uint_as_float(r[4 * k4 + 2]), __uint_as_float(r[4 * k4 + 3]));
+        __syncwarp();
+        if (vec_ok) {
+          // thread = (row lane/8 + 4*it, 4 columns (lane%8)*4): a warp instruction covers 4 full 128-byte rows
+          const int c4 = (lane & 7) * 4, rsub = lane >> 3;
+          const int n = n0 + c0 + c4;
+          const bool nv = n < p.N;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias && nv) bv = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+          float4 res[8];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (n + e < p.N) {
-                  float v = __uint_as_float(r[j + e]);
-                  if (p.bias) v += __ldg(p.bias + n + e);
-                  v = apply_act(v, p.act);
-                  if (rrow) v += rrow[n + e];
-                  crow[n + e] = v;
-                }
-              }
+          for (int it = 0; it < 8; ++it) {                   // all residual loads in flight before use
+            const int m = mrow0 + rsub + 4 * it;
+            res[it] = (p.R && nv && m < p.M) ? *reinterpret_cast<const float4 *>(p.R + (long long)m * p.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = rsub + 4 * it, m = mrow0 + rr;
+            if (nv && m < p.M) {
+              float4 v = *reinterpret_cast<const float4 *>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+              v.x = apply_act(v.x + bv.x, p.act) + res[it].x; v.y = apply_act(v.y + bv.y, p.act) + res[it].y;
+              v.z = apply_act(v.z + bv.z, p.act) + res[it].z; v.w = apply_act(v.w + bv.w, p.act) + res[it].w;
+              *reinterpret_cast<float4 *>(p.C + (long long)m * p.ldc + n) = v;
+            }
+          }
+        } else {
+          // generic path: lane = column, one row per iteration
+          const int n = n0 + c0 + lane;
+          const bool nv = n < p.N;
+          const float bs = (p.bias && nv) ? __ldg(p.bias + n) : 0.f;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int m = mrow0 + rr;
+            if (nv && m < p.M) {
+              float v = apply_act(stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)] + bs, p.act);
+              if (p.R) v += p.R[(long long)m * p.ldr + n];
+              p.C[(long long)m * p.ldc + n] = v;
             }
           }
         }
@@ -274,31 +300,29 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
     }
   } else {
-    // ===== operand splitter warps 6..9 (SPLIT3): hi in place, lo into the shadow stage (same swizzled layout)
+    // ===== operand splitter warps 10..13 (SPLIT3): hi in place, lo into the shadow stage (same swizzled layout)
     if constexpr (SPLIT3) {
-      const int t = threadIdx.x - 192;   // 0..127
+      const int t = threadIdx.x - 320;   // 0..127
       int it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(&full_bar[s], ph);
-          float4 *a4 = reinterpret_cast<float4 *>(sA + s * kABytes), *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
-          float4 *w4 = reinterpret_cast<float4 *>(sW + s * kWBytes), *wl4 = reinterpret_cast<float4 *>(sWlo + s * kWBytes);
-          auto split = [](float4 *hi_p, float4 *lo_p, int i) {
-            const float4 v = hi_p[i];
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-            hi_p[i] = h;
-            lo_p[i] = l;
-          };
-#pragma unroll 4
-          for (int i = t; i < kABytes / 16; i += 128) split(a4, al4, i);
-#pragma unroll 4
-          for (int i = t; i < kWBytes / 16; i += 128) split(w4, wl4, i);
+          // The tensor core truncates fp32 operands to TF32 (tools/tf32_rounding_probe.py), so the raw tile IS the
+          // hi operand; only lo = x - trunc(x) has to be produced. W_lo comes pre-split through TMA.
+          const float4 *a4 = reinterpret_cast<const float4 *>(sA + s * kABytes);
+          float4 *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
+#pragma unroll 8
+          for (int i = t; i < kABytes / 16; i += 128) {
+            const float4 v = a4[i];
+            float4 l;
+            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            al4[i] = l;
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
         }
@@ -333,7 +357,7 @@ void init_once() {
 }
 
 constexpr size_t smem_bytes(int BN, bool split3) {
-  return 1024 + (size_t)(split3 ? kStages3 * 2 : kStages1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16;
+  return 1024 + (size_t)(split3 ? kStages3 * 2 : kStages1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
 }
 
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
@@ -373,9 +397,12 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
     attr_done = true;
   }
   const int BN = g.N > 64 ? 128 : 64;
-  CUtensorMap ma, mw;
+  if (split3 && (!g.Wlo || (reinterpret_cast<uintptr_t>(g.Wlo) & 15)))
+    throw CudaError("3xTF32 GEMM needs the pre-split low part of the weights (GemmArgs::Wlo)");
+  CUtensorMap ma, mw, mwl;
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map(&mw, g.W, g.N, g.K, g.K, BN);
+  make_map(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
   TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   static int n_sms = 0;
@@ -386,12 +413,26 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   }
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, n_sms);   // persistent: one CTA per SM
   if (split3) {
-    if (BN == 128) gemm_tf32_tcgen05_kernel<128, true><<<grid, 320, smem_bytes(128, true), st>>>(ma, mw, p);
-    else gemm_tf32_tcgen05_kernel<64, true><<<grid, 320, smem_bytes(64, true), st>>>(ma, mw, p);
+    if (BN == 128) gemm_tf32_tcgen05_kernel<128, true><<<grid, 448, smem_bytes(128, true), st>>>(ma, mw, mwl, p);
+    else gemm_tf32_tcgen05_kernel<64, true><<<grid, 448, smem_bytes(64, true), st>>>(ma, mw, mwl, p);
   } else {
-    if (BN == 128) gemm_tf32_tcgen05_kernel<128, false><<<grid, 192, smem_bytes(128, false), st>>>(ma, mw, p);
-    else gemm_tf32_tcgen05_kernel<64, false><<<grid, 192, smem_bytes(64, false), st>>>(ma, mw, p);
+    if (BN == 128) gemm_tf32_tcgen05_kernel<128, false><<<grid, 320, smem_bytes(128, false), st>>>(ma, mw, mwl, p);
+    else gemm_tf32_tcgen05_kernel<64, false><<<grid, 320, smem_bytes(64, false), st>>>(ma, mw, mwl, p);
   }
+  count_launch();
+  KERNEL_CHECK();
+}
+
+namespace {
+__global__ void split_lo_kernel(const float *__restrict__ w, float *__restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lo[i] = w[i] - __uint_as_float(__float_as_uint(w[i]) & 0xFFFFE000u);
+}
+}  // namespace
+// lo = w - trunc_tf32(w): the pre-split low part the 3xTF32 kernel needs for a weight matrix
+void launch_split_lo(const float *w, float *lo, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  split_lo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w, lo, n);
   count_launch();
   KERNEL_CHECK();
 }

@@ -515,7 +515,7 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     const int cur = t & 1;
     decoder_step_kernel<<<n_active * beam, 256, dec_smem, st>>>(m, d, t, cur);
     GemmArgs ga{};
-    ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
+    ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
     ga.ldc = m.V; ga.M = n_active * beam; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE;
     S->gemm(ga, st);
     if (beam <= 4) select_step_kernel<4><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
