@@ -25,7 +25,8 @@ struct CudaError : std::runtime_error {
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
-enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2 };
+// ACT_TANH_RES: out = tanh(acc + bias + R) (the joiner input tanh(decoder_out + encoder_out)); the others: act(acc + bias) + R
+enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2, ACT_TANH_RES = 3 };
 
 // ---------------------------------------------------------------- fbank (fbank.cu)
 struct FbankTables {
@@ -50,6 +51,7 @@ struct GemmArgs {
   const float *Wlo;          // W - trunc_tf32(W), needed by the 3xTF32 tensor-core kernel only (else null)
   const float *bias;         // [N] or null
   const float *R; int ldr;   // residual or null
+  const int *r_rows;         // optional row map for the residual: row m of C adds row r_rows[m] of R
   float *C; int ldc;
   int M, N, K;
   int act;
@@ -118,9 +120,11 @@ struct SearchModel {
   const float *dec_proj_b;
   const float *join_w;     // [V, jd]
   const float *join_w_lo;  // low part for the 3xTF32 joiner GEMM (or null)
+  const float *dec_proj_w_lo;
   const float *join_b;
   int V, dd, jd;
   int blank_id, unk_id;
+  double ts_max, max_ent;  // Tsallis (alpha = 1/3) and Shannon normalisers for V (core/asr_engine.py:1163-1165)
 };
 
 struct SearchState;   // opaque, search.cu

@@ -395,6 +395,11 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   sm.join_w = W("joiner.output_linear.weight", {V, join_dim});
   sm.join_b = W("joiner.output_linear.bias", {V});
   sm.V = V; sm.dd = dec_dim; sm.jd = join_dim; sm.blank_id = blank_id; sm.unk_id = unk_id;
+  {
+    const double a = 1.0 / 3.0;
+    sm.ts_max = V > 1 ? (1.0 / (a - 1.0)) * (1.0 - pow((double)V, 1.0 - a)) : 1.0;
+    sm.max_ent = V > 1 ? log((double)V) : 1.0;
+  }
 
   // tokens
   const std::string tp = str(mc.tokens);
@@ -430,6 +435,11 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
     owned.push_back(lo);
     launch_split_lo(sm.join_w, lo, (long long)V * join_dim, st);
     sm.join_w_lo = lo;
+    float *lo2;
+    CUDA_CHECK(cudaMalloc(&lo2, (size_t)join_dim * dec_dim * sizeof(float)));
+    owned.push_back(lo2);
+    launch_split_lo(sm.dec_proj_w, lo2, (long long)join_dim * dec_dim, st);
+    sm.dec_proj_w_lo = lo2;
   }
 
   // hotwords file with token ids (modeling_unit token_id); text units are tokenised by the host binding

@@ -118,6 +118,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 struct TcParams {
   const float *bias;
   const float *R; int ldr;
+  const int *r_rows;
   float *C; int ldc;
   int M, N, K, act;
 };
@@ -267,15 +268,25 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 #pragma unroll
           for (int it = 0; it < 8; ++it) {                   // all residual loads in flight before use
             const int m = mrow0 + rsub + 4 * it;
-            res[it] = (p.R && nv && m < p.M) ? *reinterpret_cast<const float4 *>(p.R + (long long)m * p.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.R && nv && m < p.M) {
+              const long long rrow = p.r_rows ? (long long)__ldg(p.r_rows + m) : (long long)m;
+              rv = *reinterpret_cast<const float4 *>(p.R + rrow * p.ldr + n);
+            }
+            res[it] = rv;
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = rsub + 4 * it, m = mrow0 + rr;
             if (nv && m < p.M) {
               float4 v = *reinterpret_cast<const float4 *>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
-              v.x = apply_act(v.x + bv.x, p.act) + res[it].x; v.y = apply_act(v.y + bv.y, p.act) + res[it].y;
-              v.z = apply_act(v.z + bv.z, p.act) + res[it].z; v.w = apply_act(v.w + bv.w, p.act) + res[it].w;
+              if (p.act == ACT_TANH_RES) {
+                v.x = tanhf(v.x + bv.x + res[it].x); v.y = tanhf(v.y + bv.y + res[it].y);
+                v.z = tanhf(v.z + bv.z + res[it].z); v.w = tanhf(v.w + bv.w + res[it].w);
+              } else {
+                v.x = apply_act(v.x + bv.x, p.act) + res[it].x; v.y = apply_act(v.y + bv.y, p.act) + res[it].y;
+                v.z = apply_act(v.z + bv.z, p.act) + res[it].z; v.w = apply_act(v.w + bv.w, p.act) + res[it].w;
+              }
               *reinterpret_cast<float4 *>(p.C + (long long)m * p.ldc + n) = v;
             }
           }
@@ -288,8 +299,10 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           for (int rr = 0; rr < 32; ++rr) {
             const int m = mrow0 + rr;
             if (nv && m < p.M) {
-              float v = apply_act(stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)] + bs, p.act);
-              if (p.R) v += p.R[(long long)m * p.ldr + n];
+              float v = stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)] + bs;
+              const long long rrow = p.r_rows ? (long long)p.r_rows[m] : (long long)m;
+              const float rv = p.R ? p.R[rrow * p.ldr + n] : 0.f;
+              v = (p.act == ACT_TANH_RES) ? tanhf(v + rv) : apply_act(v, p.act) + rv;
               p.C[(long long)m * p.ldc + n] = v;
             }
           }
@@ -361,7 +374,26 @@ constexpr size_t smem_bytes(int BN, bool split3) {
 }
 
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
+void make_map_uncached(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows);
+// Encoding a tensor map costs ~1 us on the host; the per-frame search GEMMs reuse the same few (pointer, shape)
+// pairs 2 x T' times per batch, so keep a small per-thread cache.
 void make_map(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows) {
+  struct Key { const float *p; int rows, K, ld, box; };
+  struct Ent { Key k; CUtensorMap m; };
+  static thread_local Ent cache[16];
+  static thread_local int n_cached = 0, next = 0;
+  for (int i = 0; i < n_cached; ++i) {
+    const Key &k = cache[i].k;
+    if (k.p == ptr && k.rows == rows && k.K == K && k.ld == ld && k.box == box_rows) { *map = cache[i].m; return; }
+  }
+  make_map_uncached(map, ptr, rows, K, ld, box_rows);
+  Ent &e = cache[next];
+  e.k = Key{ptr, rows, K, ld, box_rows};
+  e.m = *map;
+  next = (next + 1) % 16;
+  if (n_cached < 16) ++n_cached;
+}
+void make_map_uncached(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)box_rows};
@@ -403,7 +435,7 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map(&mw, g.W, g.N, g.K, g.K, BN);
   make_map(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act};
+  TcParams p{g.bias, g.R, g.ldr, g.r_rows, g.C, g.ldc, g.M, g.N, g.K, g.act};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   static int n_sms = 0;
   if (n_sms == 0) {

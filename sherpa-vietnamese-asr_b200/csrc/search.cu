@@ -15,6 +15,8 @@
 // Hypotheses live in HBM as back-pointer chains in a per-utterance arena; nothing returns to the host until
 // the last frame. Utterances are processed longest-first so the active set at step t is a prefix.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -56,10 +58,12 @@ struct SearchDev {
   int *hyp_count;              // [2][n]
   int *node_count;             // [n]
   ArenaNode *arena;
-  float *dec;                  // [2][n*beam, jd] ping-pong decoder outputs
+  float *E;                    // [n*beam, dd] relu(conv(embeddings)) of each live hypothesis (decoder GEMM input)
+  int *rowmap;                 // [n*beam] encoder_out row joined with that hypothesis at the next step
   float *X;                    // [n*beam, jd] joiner input tanh(enc+dec)
   float *logits;               // [n*beam, V]
   int n, beam;
+  long long *prof;             // optional per-phase cycle counters of CTA 0 (B200ASR_SEARCH_PROF=1)
 };
 
 // ------------------------------------------------------------------ stateless decoder (App. B.4)
@@ -123,29 +127,6 @@ __global__ void tanh_add_kernel(const float *__restrict__ enc, const float *__re
   if (i < total) X[i] = tanhf(enc[i] + dec[i]);
 }
 
-// step kernel 1: decoder output for every live hypothesis of every active utterance, then X = tanh(enc_t + dec)
-__global__ void __launch_bounds__(256) decoder_step_kernel(SearchModel m, SearchDev d, int t, int cur) {
-  extern __shared__ float s_e[];
-  const int s = blockIdx.x / d.beam, b = blockIdx.x % d.beam;
-  float *xrow = d.X + ((long long)s * d.beam + b) * m.jd;
-  const int count = d.hyp_count[cur * d.n + s];
-  if (t >= d.lens[s] || b >= count) {
-    for (int j = threadIdx.x; j < m.jd; j += blockDim.x) xrow[j] = 0.f;
-    return;
-  }
-  const HypSlot &h = d.hyps[((long long)cur * d.n + s) * kMaxBeam + b];
-  float *dcur = d.dec + ((long long)cur * d.n * d.beam + (long long)s * d.beam + b) * m.jd;
-  if (h.dec_src >= 0) {
-    const float *dprev = d.dec + ((long long)(cur ^ 1) * d.n * d.beam + (long long)s * d.beam + h.dec_src) * m.jd;
-    for (int j = threadIdx.x; j < m.jd; j += blockDim.x) dcur[j] = dprev[j];
-    __syncthreads();
-  } else {
-    decoder_row(m, h.y0, h.y1, s_e, dcur);
-  }
-  const float *erow = d.enc + (d.enc_off[s] + t) * m.jd;
-  for (int j = threadIdx.x; j < m.jd; j += blockDim.x) xrow[j] = tanhf(erow[j] + dcur[j]);
-}
-
 // ------------------------------------------------------------------ selection
 __device__ __forceinline__ unsigned ord_f32(float f) {
   const unsigned u = __float_as_uint(f);
@@ -179,6 +160,15 @@ __device__ bool same_chain(const ArenaNode *arena, int a, int b) {
 
 struct NewNode { int arena_idx; int row; };
 
+#define SEL_PROF(k)                                                               \
+  do {                                                                            \
+    if (d.prof && blockIdx.x == 0 && threadIdx.x == 0) {                          \
+      const long long _now = clock64();                                           \
+      atomicAdd((unsigned long long *)&d.prof[k], (unsigned long long)(_now - _t0)); \
+      _t0 = _now;                                                                 \
+    }                                                                             \
+  } while (0)
+
 template <int KB>
 __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m, SearchDev d, ContextGraphView g, int has_graph,
                                                                   int t, int cur, int greedy, float blank_penalty) {
@@ -193,10 +183,23 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
   __shared__ NewNode s_nodes[kMaxBeam];
   __shared__ int s_n_new, s_n_nodes;
 
+  long long _t0 = clock64();
   const int count = d.hyp_count[cur * d.n + s];
   if (tid < count) s_old[tid] = d.hyps[((long long)cur * d.n + s) * kMaxBeam + tid];
-  float *lg = d.logits + (long long)s * d.beam * V;
+  // stage this utterance's logits rows in shared memory with wide, fully pipelined loads: every later pass
+  // (max, sum-exp, top-k scan, token statistics) would otherwise pay L2 latency per element
+  extern __shared__ __align__(16) float s_dyn[];
+  float *lg = s_dyn;                                  // [count][V]
+  {
+    const float *glg = d.logits + (long long)s * d.beam * V;
+    const int n4 = (count * V) >> 2;                  // V % 4 == 0 (checked on the host)
+    const float4 *g4 = reinterpret_cast<const float4 *>(glg);
+    float4 *l4 = reinterpret_cast<float4 *>(lg);
+#pragma unroll 8
+    for (int i = tid; i < n4; i += kSelThreads) l4[i] = g4[i];
+  }
   __syncthreads();
+  SEL_PROF(0);
 
   // (a) per-row max and log-sum-exp, float32 as the reference (:1096-1098)
   for (int b = warp; b < count; b += kSelThreads / 32) {
@@ -220,22 +223,26 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
   }
   __syncthreads();
 
+  SEL_PROF(1);
   // (b) global top-k over count*V candidates; key = (ordered value, ~flat index) so max = value desc, index asc
   const int k = min(d.beam, count * V);
   unsigned long long loc[KB];   // KB >= beam: per-thread candidates, descending
 #pragma unroll
   for (int i = 0; i < KB; ++i) loc[i] = 0ULL;
-  const int total = count * V;
-  for (int idx = tid; idx < total; idx += kSelThreads) {
-    const int b = idx / V, v = idx - b * V;
-    const float lp = ((lg[idx] - s_mx[b]) - s_lse[b]) + s_prev[b];
-    const unsigned long long key = ((unsigned long long)ord_f32(lp) << 32) | (unsigned)(~(unsigned)idx);
-    if (key > loc[KB - 1]) {
-      // insertion into the descending local list (fully unrolled so it stays in registers)
-      unsigned long long carry = key;
+  for (int b = 0; b < count; ++b) {
+    const float mxb = s_mx[b], lseb = s_lse[b], prevb = s_prev[b];
+    const float *row = lg + b * V;
+    const int base = b * V;
+    for (int v = tid; v < V; v += kSelThreads) {
+      const float lp = ((row[v] - mxb) - lseb) + prevb;
+      const unsigned long long key = ((unsigned long long)ord_f32(lp) << 32) | (unsigned)(~(unsigned)(base + v));
+      if (key > loc[KB - 1]) {
+        // insertion into the descending local list (fully unrolled so it stays in registers)
+        unsigned long long carry = key;
 #pragma unroll
-      for (int i = 0; i < KB; ++i) {
-        if (carry > loc[i]) { const unsigned long long tmp = loc[i]; loc[i] = carry; carry = tmp; }
+        for (int i = 0; i < KB; ++i) {
+          if (carry > loc[i]) { const unsigned long long tmp = loc[i]; loc[i] = carry; carry = tmp; }
+        }
       }
     }
   }
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
     __syncthreads();
   }
 
+  SEL_PROF(2);
   // (c) expansion, hotword arcs, dedup: serial over <= beam winners, exactly in top-k order (:1109-1140)
   ArenaNode *arena = d.arena + d.arena_off[s];
   if (tid == 0) {
@@ -322,6 +330,7 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
   }
   __syncthreads();
 
+  SEL_PROF(3);
   // (d) per emitted token statistics from its logits row (_compute_token_entropy :1159-1181), one warp per token
   for (int e = warp; e < s_n_nodes; e += kSelThreads / 32) {
     const int b = s_nodes[e].row;
@@ -330,8 +339,8 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
     float ent = 0.f, ts = 0.f, t1 = 0.f, t2 = 0.f;
     for (int v = lane; v < V; v += 32) {
       const float p = expf(row[v] - mx) / sum;
-      ent += p * logf(p + 1e-30f);
-      ts += powf(p, 1.0f / 3.0f);
+      ent += p * __logf(p + 1e-30f);
+      ts += exp2f(__log2f(p) * (1.0f / 3.0f));        // p^(1/3); p = 0 -> log2 = -inf -> 0
       if (p > t1) { t2 = t1; t1 = p; } else if (p > t2) { t2 = p; }
     }
 #pragma unroll
@@ -343,9 +352,9 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
     }
     if (lane == 0) {
       const double a = 1.0 / 3.0;
-      const double ts_max = (V > 1) ? (1.0 / (a - 1.0)) * (1.0 - pow((double)V, 1.0 - a)) : 1.0;
+      const double ts_max = m.ts_max;
       const double tsallis = (1.0 / (a - 1.0)) * (1.0 - (double)ts);
-      const double max_ent = V > 1 ? log((double)V) : 1.0;
+      const double max_ent = m.max_ent;
       ArenaNode &nd = arena[s_nodes[e].arena_idx];
       nd.stats[0] = (float)(ts_max > 0 ? tsallis / ts_max : 0.0);
       nd.stats[1] = t1 - (V > 1 ? t2 : 1e-10f);
@@ -354,17 +363,60 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
     }
   }
   if (tid < s_n_new) d.hyps[((long long)(cur ^ 1) * d.n + s) * kMaxBeam + tid] = s_new[tid];
+  SEL_PROF(4);
+
+  // (e) decoder pre-activation for the new hypotheses: E = relu(grouped conv over the two context embeddings).
+  // decoder_proj and the joiner's tanh(enc + dec) then run as ONE tensor-core GEMM over all live hypotheses of
+  // the batch (run_search), so the 1 MB projection is streamed once per step instead of once per utterance.
+  const int n_new = s_n_new;
+  const int next_row = (int)d.enc_off[s] + min(t + 1, d.lens[s] - 1);
+  for (int i = tid; i < n_new * m.dd; i += kSelThreads) {
+    const int q = i / m.dd, o = i - q * m.dd;
+    const HypSlot &hs = s_new[q];
+    const int g4 = (o >> 2) << 2;
+    const float *w = m.conv_w + (long long)o * 8;
+    const float *e0 = m.emb + (long long)hs.y0 * m.dd + g4;
+    const float *e1 = m.emb + (long long)hs.y1 * m.dd + g4;
+    float a2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a2 = fmaf(__ldg(w + k * 2 + 0), __ldg(e0 + k), a2);
+      a2 = fmaf(__ldg(w + k * 2 + 1), __ldg(e1 + k), a2);
+    }
+    d.E[((long long)s * d.beam + q) * m.dd + o] = fmaxf(a2, 0.f);
+  }
+  if (tid < d.beam) d.rowmap[s * d.beam + tid] = next_row;
+  SEL_PROF(7);
 }
 
-__global__ void init_search_kernel(SearchDev d) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= d.n) return;
-  HypSlot h;
-  h.score = 0.0; h.hash = 0x12345ULL; h.node = -1; h.len = 0; h.ctx = 0; h.y0 = 0; h.y1 = 0; h.dec_src = -1;
-  d.hyps[(long long)s * kMaxBeam] = h;     // ys = [-1, 0] -> decoder input [0, 0] (:1051-1052)
-  d.hyp_count[s] = 1;
-  d.hyp_count[d.n + s] = 0;
-  d.node_count[s] = 0;
+__global__ void init_search_kernel(SearchModel m, SearchDev d) {
+  const int s = blockIdx.x;
+  if (threadIdx.x == 0) {
+    HypSlot h;
+    h.score = 0.0; h.hash = 0x12345ULL; h.node = -1; h.len = 0; h.ctx = 0; h.y0 = 0; h.y1 = 0; h.dec_src = -1;
+    d.hyps[(long long)s * kMaxBeam] = h;     // ys = [-1, 0] -> decoder input [0, 0] (:1051-1052)
+    d.hyp_count[s] = 1;
+    d.hyp_count[d.n + s] = 0;
+    d.node_count[s] = 0;
+  }
+  if ((int)threadIdx.x < d.beam) d.rowmap[s * d.beam + threadIdx.x] = (int)d.enc_off[s];   // frame 0 (any valid row if T' = 0)
+  for (int i = threadIdx.x; i < d.beam * m.dd; i += blockDim.x) {
+    const int q = i / m.dd, o = i - q * m.dd;
+    float v = 0.f;
+    if (q == 0) {
+      const int g4 = (o >> 2) << 2;
+      const float *w = m.conv_w + (long long)o * 8;
+      const float *e0 = m.emb + g4;          // token 0 twice
+      float a2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a2 = fmaf(__ldg(w + k * 2 + 0), __ldg(e0 + k), a2);
+        a2 = fmaf(__ldg(w + k * 2 + 1), __ldg(e0 + k), a2);
+      }
+      v = fmaxf(a2, 0.f);
+    }
+    d.E[((long long)s * d.beam + q) * m.dd + o] = v;
+  }
 }
 
 // finalize (:1143-1153): subtract unfinished hotword score, pick first max of log_prob/len(ys), unroll the chain
@@ -419,7 +471,8 @@ struct SearchState {
   int *hyp_count = nullptr; size_t hc_cap = 0;
   int *node_count = nullptr; size_t nc_cap = 0;
   ArenaNode *arena = nullptr; size_t arena_cap = 0;
-  float *dec = nullptr; size_t dec_cap = 0;
+  float *E = nullptr; size_t e_cap = 0;
+  int *rowmap = nullptr; size_t rm_cap = 0;
   float *X = nullptr; size_t x_cap = 0;
   float *logits = nullptr; size_t lg_cap = 0;
   long long *enc_off = nullptr; size_t eo_cap = 0;
@@ -439,7 +492,7 @@ SearchState *search_state_create() { return new SearchState(); }
 void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t)) { s->gemm = fn; }
 void search_state_destroy(SearchState *s) {
   if (!s) return;
-  cudaFree(s->hyps); cudaFree(s->hyp_count); cudaFree(s->node_count); cudaFree(s->arena); cudaFree(s->dec);
+  cudaFree(s->hyps); cudaFree(s->hyp_count); cudaFree(s->node_count); cudaFree(s->arena); cudaFree(s->E); cudaFree(s->rowmap);
   cudaFree(s->X); cudaFree(s->logits); cudaFree(s->enc_off); cudaFree(s->arena_off); cudaFree(s->lens);
   cudaFree(s->orig); cudaFree(s->final_buf); cudaFree(s->o_ntok); cudaFree(s->o_tok); cudaFree(s->o_frm);
   cudaFree(s->o_lp); cudaFree(s->o_st);
@@ -476,7 +529,8 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
   ensure(S->hyp_count, S->hc_cap, 2 * (size_t)n);
   ensure(S->node_count, S->nc_cap, (size_t)n);
   ensure(S->arena, S->arena_cap, (size_t)std::max<long long>(arena_total, 1));
-  ensure(S->dec, S->dec_cap, 2 * rows * m.jd);
+  ensure(S->E, S->e_cap, rows * m.dd);
+  ensure(S->rowmap, S->rm_cap, rows);
   ensure(S->X, S->x_cap, rows * m.jd);
   ensure(S->logits, S->lg_cap, rows * m.V);
   ensure(S->enc_off, S->eo_cap, (size_t)n);
@@ -498,30 +552,54 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
 
   SearchDev d;
   d.enc = enc; d.enc_off = S->enc_off; d.lens = S->lens; d.arena_off = S->arena_off; d.hyps = S->hyps;
-  d.hyp_count = S->hyp_count; d.node_count = S->node_count; d.arena = S->arena; d.dec = S->dec; d.X = S->X;
+  d.hyp_count = S->hyp_count; d.node_count = S->node_count; d.arena = S->arena; d.E = S->E; d.rowmap = S->rowmap; d.X = S->X;
   d.logits = S->logits; d.n = n; d.beam = beam;
+  d.prof = nullptr;
+  static const bool want_prof = getenv("B200ASR_SEARCH_PROF") != nullptr;
+  long long *d_prof = nullptr;
+  if (want_prof) {
+    CUDA_CHECK(cudaMalloc(&d_prof, 8 * sizeof(long long)));
+    CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), st));
+    d.prof = d_prof;
+  }
   ContextGraphView gv{};
   const int has_graph = (g && g->n_nodes > 1 && !greedy) ? 1 : 0;
   if (has_graph)
     gv = ContextGraphView{g->n_nodes, g->edge_start, g->edge_token, g->edge_child, g->fail, g->token, g->is_end, g->output,
                           g->token_score, g->node_score, g->output_score};
 
-  init_search_kernel<<<(n + 127) / 128, 128, 0, st>>>(d);
+  if (m.V & 3) throw CudaError("beam search: vocab_size must be a multiple of 4");
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    if ((size_t)beam * m.V * sizeof(float) > 200 * 1024) throw CudaError("beam * vocab_size too large for the selection kernel");
+  }
+  init_search_kernel<<<n, 128, 0, st>>>(m, d);
   count_launch(); KERNEL_CHECK();
-  const size_t dec_smem = (size_t)m.dd * sizeof(float);
   int n_active = n;
   for (int t = 0; t < max_len; ++t) {
     while (n_active > 0 && lens[n_active - 1] <= t) --n_active;
     const int cur = t & 1;
-    decoder_step_kernel<<<n_active * beam, 256, dec_smem, st>>>(m, d, t, cur);
+    // decoder_proj + joiner input in one GEMM: X = tanh(E * Wp^T + bp + enc[rowmap])
+    GemmArgs gd{};
+    gd.A = S->E; gd.lda = m.dd; gd.W = m.dec_proj_w; gd.Wlo = m.dec_proj_w_lo; gd.bias = m.dec_proj_b; gd.R = enc; gd.ldr = m.jd;
+    gd.r_rows = S->rowmap; gd.C = S->X; gd.ldc = m.jd; gd.M = n_active * beam; gd.N = m.jd; gd.K = m.dd; gd.act = ACT_TANH_RES;
+    S->gemm(gd, st);
+    // joiner output_linear: logits = X * Wj^T + bj
     GemmArgs ga{};
     ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
     ga.ldc = m.V; ga.M = n_active * beam; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE;
     S->gemm(ga, st);
-    if (beam <= 4) select_step_kernel<4><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
-    else if (beam <= 8) select_step_kernel<8><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
-    else select_step_kernel<16><<<n_active, kSelThreads, 0, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
-    count_launch(2);
+    const size_t sel_smem = (size_t)beam * m.V * sizeof(float);
+    if (beam <= 4) select_step_kernel<4><<<n_active, kSelThreads, sel_smem, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    else if (beam <= 8) select_step_kernel<8><<<n_active, kSelThreads, sel_smem, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    else select_step_kernel<16><<<n_active, kSelThreads, sel_smem, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    count_launch();
   }
   KERNEL_CHECK();
   // Utterances that stopped at step T' hold their final state in buffer (T' & 1): select writes to cur^1 = (t+1)&1.
@@ -536,6 +614,15 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     CUDA_CHECK(cudaMemcpyAsync(out->stats, S->o_st, (size_t)n * max_tokens * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (d_prof) {
+    long long h[8];
+    CUDA_CHECK(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(d_prof);
+    const char *names[8] = {"stage logits", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "-", "-", "decoder pre-activation"};
+    fprintf(stderr, "[b200asr search prof] CTA0 cycles over %d steps:", max_len);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f/step", names[i], (double)h[i] / std::max(max_len, 1));
+    fprintf(stderr, "\n");
+  }
 }
 
 void launch_decoder_rows(const SearchModel &m, const long long *y, int rows, float *out, cudaStream_t st) {
