@@ -97,6 +97,22 @@ void launch_attn_weights(const float *proj, int ldp, const float *pos, const Rag
 // out[i, c] = (sum_j A[h(c)][i][j] * V[j,c]) (* Y[i,c]);  V = X (* tanh(S) if S). head = c / dv_per_head (0 if single_head)
 void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &r, const float *X, int ldx, const float *S, int lds,
                        const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st);
+// ---- attention application on the tensor pipe (attn_tc.cu); A rows have pitch Tk4 = (Tk + 3) & ~3
+struct AttnTcLaunch {
+  const void *mapsA, *mapsV, *mapsVlo;   // device arrays of CUtensorMap, one per utterance
+  const int *tile_off;                   // [n_utt + 1]
+  const int *len, *off;
+  int n_utt, n_tiles;
+  int single_head, C, dv;
+  const float *Y; int ldy;
+  float *out; int ldo;
+  int split3;
+};
+void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C, const RaggedDesc &r, const long long *vt_off,
+                        float *VT, float *VTlo, cudaStream_t st);
+void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st);
+void attn_tc_encode_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int rows_mult,
+                         int rows_fixed, int box_rows);
 // conv module middle: h [M, 2D] -> out [M, D] = SwooshR(dwconv_k(x * sigmoid(s)) + b)
 void launch_glu_dwconv(const float *h, const RaggedDesc &r, int D, int k, const float *w, const float *b, float *out, cudaStream_t st);
 

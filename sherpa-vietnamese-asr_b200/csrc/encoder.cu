@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(256) attn_weights_kernel(const float *__restri
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
-  float *Abase = A + aoff[u] + (long long)h * Tk * Tk;
+  const int Tk4 = (Tk + 3) & ~3;                 // row pitch (TMA-legal for the tensor-core consumer)
+  float *Abase = A + aoff[u] + (long long)h * Tk * Tk4;
   for (int r = warp; r < nrow; r += 8) {
     float *row = sc + r * Tk;
     float mx = -INFINITY;
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(256) attn_weights_kernel(const float *__restri
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    float *orow = Abase + (long long)(i0 + r) * Tk;
+    float *orow = Abase + (long long)(i0 + r) * Tk4;
     for (int j = lane; j < Tk; j += 32) orow[j] = row[j] / sum;
   }
 }
@@ -452,7 +453,8 @@ __global__ void __launch_bounds__(32 * CG) attn_apply_kernel(const float *__rest
   const int ctile = blockIdx.y;
   const int c0 = ctile * CT;
   const int head = single_head ? 0 : ctile;
-  const float *Ah = A + aoff[u] + (long long)head * Tk * Tk;
+  const int Tk4 = (Tk + 3) & ~3;
+  const float *Ah = A + aoff[u] + (long long)head * Tk * Tk4;
   const long long rbase = off[u];
   const int cg = threadIdx.x >> 5, rg = threadIdx.x & 31;
   float acc[RPT][4];
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(32 * CG) attn_apply_kernel(const float *__rest
     for (int i = threadIdx.x; i < ROWS * KC; i += NT) {
       const int r = i / KC, jj = i % KC;
       const int gi = i0 + r, gj = j0 + jj;
-      As[r * (KC + 1) + jj] = (gi < Tk && gj < Tk) ? Ah[(long long)gi * Tk + gj] : 0.f;
+      As[r * (KC + 1) + jj] = (gi < Tk && gj < Tk) ? Ah[(long long)gi * Tk4 + gj] : 0.f;
     }
     for (int i = threadIdx.x; i < KC * CT; i += NT) {
       const int jj = i / CT, c = i % CT;

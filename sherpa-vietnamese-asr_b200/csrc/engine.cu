@@ -151,7 +151,20 @@ struct Engine {
   void run_fbank(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n, float **d_feats,
                  std::vector<int> *T);
   void run_encoder(const float *d_feats, const std::vector<int> &T, float **d_enc, std::vector<int> *Tp);
-  void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax);
+  struct AttnPlan {   // tensor-core attention application: per-stack maps / offsets (valid for every layer of the stack)
+    bool use = false;
+    const void *mapsA = nullptr, *mapsV12 = nullptr, *mapsV12lo = nullptr, *mapsVh = nullptr, *mapsVhlo = nullptr;
+    const int *tile_off12 = nullptr, *tile_offh = nullptr;
+    const long long *vt_off12 = nullptr, *vt_offh = nullptr;
+    float *VT12 = nullptr, *VT12lo = nullptr, *VTh = nullptr, *VThlo = nullptr;
+    int n_tiles12 = 0, n_tilesh = 0;
+  };
+  DevBuf b_maps, b_tileoff, b_vtoff, b_vt12, b_vt12lo, b_vth, b_vthlo;
+  void build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const std::vector<long long> &aoff_host);
+  void attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r, const long long *aoff, const float *X, int ldx,
+                  const float *S, int lds, const float *Y, int ldy, int C, bool single_head, float *out, int ldo);
+  void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
+                 const AttnPlan &pl);
   void decode(Stream *const *ss, int n);
   void decode_pcm_device(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n,
                          SearchResultHost *res, std::vector<int> *Tp);
@@ -560,7 +573,74 @@ void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const std::v
 }
 
 // ------------------------------------------------------------------ encoder
-void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax) {
+void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const std::vector<long long> &aoff_host) {
+  *pl = AttnPlan{};
+  if (precision == 2 || n <= 0) return;   // CUDA-core mode keeps the CUDA-core attention kernels
+  const int H = s.H, C12 = H * vd, hid = (3 * s.D) / 4;
+  const std::vector<int> &len = h_len[q];
+  std::vector<long long> vt12(n + 1, 0), vth(n + 1, 0);
+  std::vector<int> t12(n + 1, 0), th(n + 1, 0);
+  for (int u = 0; u < n; ++u) {
+    const int Tk = len[u], Tk4 = (Tk + 3) & ~3, mt = (Tk + 127) / 128;
+    vt12[u + 1] = vt12[u] + (long long)C12 * Tk4;
+    vth[u + 1] = vth[u] + (long long)hid * Tk4;
+    t12[u + 1] = t12[u] + H * mt;
+    th[u + 1] = th[u] + mt * ((hid + 63) / 64);
+  }
+  const bool split3 = precision == 0;
+  pl->VT12 = b_vt12.get<float>((size_t)std::max<long long>(vt12[n], 4));
+  pl->VTh = b_vth.get<float>((size_t)std::max<long long>(vth[n], 4));
+  if (split3) {
+    pl->VT12lo = b_vt12lo.get<float>((size_t)std::max<long long>(vt12[n], 4));
+    pl->VThlo = b_vthlo.get<float>((size_t)std::max<long long>(vth[n], 4));
+  }
+  // tensor maps (128 bytes each): A, V12, V12lo, Vh, Vhlo
+  std::vector<unsigned char> hm((size_t)5 * n * 128 + 64);
+  unsigned char *hp = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hm.data()) + 63) & ~uintptr_t(63));
+  attn_tc_encode_maps(hp + 0 * (size_t)n * 128, n, b_A.ptr<float>(), aoff_host.data(), len.data(), H, 0, 128);
+  attn_tc_encode_maps(hp + 1 * (size_t)n * 128, n, pl->VT12, vt12.data(), len.data(), 0, C12, 16);
+  attn_tc_encode_maps(hp + 2 * (size_t)n * 128, n, split3 ? pl->VT12lo : pl->VT12, vt12.data(), len.data(), 0, C12, 16);
+  attn_tc_encode_maps(hp + 3 * (size_t)n * 128, n, pl->VTh, vth.data(), len.data(), 0, hid, 64);
+  attn_tc_encode_maps(hp + 4 * (size_t)n * 128, n, split3 ? pl->VThlo : pl->VTh, vth.data(), len.data(), 0, hid, 64);
+  unsigned char *dm = b_maps.get<unsigned char>((size_t)5 * n * 128);
+  CUDA_CHECK(cudaMemcpyAsync(dm, hp, (size_t)5 * n * 128, cudaMemcpyHostToDevice, st));
+  int *dt = b_tileoff.get<int>((size_t)2 * (n + 1));
+  CUDA_CHECK(cudaMemcpyAsync(dt, t12.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dt + (n + 1), th.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  long long *dv = b_vtoff.get<long long>((size_t)2 * (n + 1));
+  CUDA_CHECK(cudaMemcpyAsync(dv, vt12.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dv + (n + 1), vth.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));   // host vectors are locals
+  pl->mapsA = dm; pl->mapsV12 = dm + 1 * (size_t)n * 128; pl->mapsV12lo = dm + 2 * (size_t)n * 128;
+  pl->mapsVh = dm + 3 * (size_t)n * 128; pl->mapsVhlo = dm + 4 * (size_t)n * 128;
+  pl->tile_off12 = dt; pl->tile_offh = dt + (n + 1);
+  pl->vt_off12 = dv; pl->vt_offh = dv + (n + 1);
+  pl->n_tiles12 = t12[n]; pl->n_tilesh = th[n];
+  pl->use = true;
+}
+
+void Engine::attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r, const long long *aoff, const float *X, int ldx,
+                        const float *S, int lds, const float *Y, int ldy, int C, bool single_head, float *out, int ldo) {
+  if (!pl.use) {
+    launch_attn_apply(b_A.ptr<float>(), aoff, r, X, ldx, S, lds, Y, ldy, C, vd, single_head ? 1 : 0, out, ldo, st);
+    return;
+  }
+  const bool split3 = precision == 0;
+  AttnTcLaunch a{};
+  a.mapsA = pl.mapsA; a.len = r.len; a.off = r.off; a.n_utt = r.n; a.single_head = single_head ? 1 : 0; a.C = C; a.dv = vd;
+  a.Y = Y; a.ldy = ldy; a.out = out; a.ldo = ldo; a.split3 = split3 ? 1 : 0;
+  if (single_head) {
+    launch_transpose_v(X, ldx, S, lds, C, r, pl.vt_offh, pl.VTh, split3 ? pl.VThlo : nullptr, st);
+    a.mapsV = pl.mapsVh; a.mapsVlo = pl.mapsVhlo; a.tile_off = pl.tile_offh; a.n_tiles = pl.n_tilesh;
+  } else {
+    launch_transpose_v(X, ldx, S, lds, C, r, pl.vt_off12, pl.VT12, split3 ? pl.VT12lo : nullptr, st);
+    a.mapsV = pl.mapsV12; a.mapsVlo = pl.mapsV12lo; a.tile_off = pl.tile_off12; a.n_tiles = pl.n_tiles12;
+  }
+  launch_attn_apply_tc(a, st);
+}
+
+void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
+                       const AttnPlan &pl) {
   const int D = s.D, H = s.H, h = (3 * D) / 4;
   const int pw = H * (2 * qd + pd);
   int maxw = std::max({pw, 3 * h, 2 * D, w.ff_dim[2], H * vd});
@@ -578,12 +658,12 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   gemm(proj, w.ff_dim[0], w.ff_out_w[0], w.ff_out_b[0], src, D, w1, D, M, D, w.ff_dim[0], ACT_NONE);
   // nonlin attention (head 0)
   gemm(w1, D, w.nl_in_w, w.nl_in_b, nullptr, 0, proj, 3 * h, M, 3 * h, D, ACT_NONE);
-  launch_attn_apply(A, aoff, r, proj + h, 3 * h, proj, 3 * h, proj + 2 * h, 3 * h, h, 0, 1, hid, h, st);
+  attn_apply(pl, s, r, aoff, proj + h, 3 * h, proj, 3 * h, proj + 2 * h, 3 * h, h, true, hid, h);
   gemm(hid, h, w.nl_out_w, w.nl_out_b, w1, D, w1, D, M, D, h, ACT_NONE);
   for (int j = 0; j < 2; ++j) {
     // self attention j
     gemm(w1, D, w.sa_in_w[j], w.sa_in_b[j], nullptr, 0, proj, H * vd, M, H * vd, D, ACT_NONE);
-    launch_attn_apply(A, aoff, r, proj, H * vd, nullptr, 0, nullptr, 0, H * vd, vd, 0, hid, H * vd, st);
+    attn_apply(pl, s, r, aoff, proj, H * vd, nullptr, 0, nullptr, 0, H * vd, false, hid, H * vd);
     gemm(hid, H * vd, w.sa_out_w[j], w.sa_out_b[j], w1, D, w1, D, M, D, H * vd, ACT_NONE);
     // conv module j
     gemm(w1, D, w.cv_in_w[j], w.cv_in_b[j], nullptr, 0, proj, 2 * D, M, 2 * D, D, ACT_NONE);
@@ -654,7 +734,7 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   for (size_t i = 0; i < ns; ++i) {
     const int q = rate_idx(stacks[i].ds);
     for (int u = 0; u < n; ++u)
-      aoffs[i][u + 1] = aoffs[i][u] + (long long)stacks[i].H * h_len[q][u] * h_len[q][u];
+      aoffs[i][u + 1] = aoffs[i][u] + (long long)stacks[i].H * h_len[q][u] * ((h_len[q][u] + 3) & ~3);
     maxA = std::max(maxA, aoffs[i][n]);
   }
   long long *d_aoff = b_aoff.get<long long>(ns * (n + 1));
@@ -697,15 +777,17 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
     const long long *aoff = d_aoff + i * (n + 1);
     float *pe = b_pe.get<float>((size_t)(2 * Lr[q] - 1) * pos_dim);
     launch_pos_emb(pe, Lr[q], pos_dim, st);
+    AttnPlan plan;
+    build_attn_plan(&plan, s, q, n, aoffs[i]);
     if (s.ds == 1) {
       launch_convert_channels(x, xC, outb, D, M1, st);
-      for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], outb, rd[0], aoff, M1, Lr[0]);
+      for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], outb, rd[0], aoff, M1, Lr[0], plan);
     } else {
       float *xc = b_xc.get<float>((size_t)M1 * D);
       launch_convert_channels(x, xC, xc, D, M1, st);
       float *sin_ = b_sin.get<float>((size_t)Mr[q] * D);
       launch_downsample(xc, rd[0], rd[q], D, s.ds, s.ds_bias, sin_, st);
-      for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], sin_, rd[q], aoff, Mr[q], Lr[q]);
+      for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], sin_, rd[q], aoff, Mr[q], Lr[q], plan);
       launch_upsample_combine(sin_, rd[q], xc, rd[0], D, s.ds, s.combiner, outb, st);
     }
     x = outb;
