@@ -88,6 +88,73 @@ struct Timings { float fbank = 0, encoder = 0, search = 0, total = 0, h2d = 0, d
 
 struct Stream;
 
+// Page-locked host memory for stream PCM: accept_waveform copies the caller's samples straight into pinned
+// memory, so decode_streams issues true asynchronous H2D copies at PCIe speed. cudaHostAlloc costs ~2 ms per call,
+// far too slow per stream, so blocks (power-of-two size classes) are carved from 64 MB pinned slabs and recycled
+// through per-class free lists; slabs live for the life of the process. Past kMaxPinned the pool hands out
+// pageable blocks (cudaMemcpyAsync stages those itself) instead of pinning unbounded host memory.
+class PinnedPool {
+ public:
+  static PinnedPool &get() { static PinnedPool p; return p; }
+  void *alloc(size_t bytes, size_t *cap) {
+    size_t c = 64 * 1024;
+    while (c < bytes) c <<= 1;
+    *cap = c;
+    std::lock_guard<std::mutex> lk(mu_);
+    auto &fl = free_[c];
+    if (!fl.empty()) { void *p = fl.back(); fl.pop_back(); return p; }
+    if (c > slab_left_) {
+      const size_t slab = std::max(c, kSlab);
+      void *p = nullptr;
+      if (pinned_total_ + slab > kMaxPinned || cudaHostAlloc(&p, slab, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        p = malloc(c);   // pageable block; still recycled through the free list
+        if (!p) throw std::runtime_error("out of host memory for stream audio");
+        return p;
+      }
+      pinned_total_ += slab;
+      slab_cur_ = reinterpret_cast<char *>(p);
+      slab_left_ = slab;
+    }
+    void *p = slab_cur_;
+    slab_cur_ += c;
+    slab_left_ -= c;
+    return p;
+  }
+  void release(void *p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    free_[cap].push_back(p);
+  }
+ private:
+  static constexpr size_t kSlab = 64u << 20, kMaxPinned = 8ull << 30;
+  std::mutex mu_;
+  std::map<size_t, std::vector<void *>> free_;
+  char *slab_cur_ = nullptr;
+  size_t slab_left_ = 0, pinned_total_ = 0;
+};
+
+struct PinnedSamples {
+  float *p = nullptr;
+  size_t n = 0, cap_bytes = 0;
+  ~PinnedSamples() { PinnedPool::get().release(p, cap_bytes); }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  const float *data() const { return p; }
+  void append(const float *src, size_t cnt) {
+    if ((n + cnt) * sizeof(float) > cap_bytes) {
+      size_t ncap = 0;
+      float *np_ = reinterpret_cast<float *>(PinnedPool::get().alloc((n + cnt) * sizeof(float) * (p ? 2 : 1), &ncap));
+      if (n) memcpy(np_, p, n * sizeof(float));
+      PinnedPool::get().release(p, cap_bytes);
+      p = np_;
+      cap_bytes = ncap;
+    }
+    memcpy(p + n, src, cnt * sizeof(float));
+    n += cnt;
+  }
+};
+
 struct Engine {
   // config
   std::map<std::string, std::string> cfg;
@@ -173,7 +240,7 @@ struct Engine {
 
 struct Stream {
   Engine *eng;
-  std::vector<float> samples;
+  PinnedSamples samples;
   // result storage
   B200AsrOfflineRecognizerResult res{};
   std::string text, json;
@@ -1027,7 +1094,7 @@ void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_
   if (!s || !samples || n <= 0) return;
   auto *ms = const_cast<B200AsrOfflineStream *>(s);
   if (sample_rate != 16000) { g_last_error = "accept_waveform: only 16000 Hz is supported (no resampler on the path)"; return; }
-  ms->s.samples.insert(ms->s.samples.end(), samples, samples + n);
+  try { ms->s.samples.append(samples, (size_t)n); } catch (const std::exception &e) { g_last_error = e.what(); return; }
   ms->s.decoded = false;
 }
 

@@ -1,0 +1,21 @@
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+from sherpa_vietnamese_asr_b200.recognizer import OfflineRecognizer
+class A: pass
+args = A(); args.segments=256; args.model="zipformer-68m"
+cfg, paths = bench.model_dir("zipformer-68m", 68)
+rec = OfflineRecognizer.from_transducer(encoder=paths["encoder"], decoder=paths["decoder"], joiner=paths["joiner"], tokens=paths["tokens"], decoding_method="modified_beam_search", max_active_paths=4)
+audios = bench.workload(args, 0)
+for it in range(3):
+    t0=time.perf_counter()
+    ss=[rec.create_stream() for _ in audios]
+    t1=time.perf_counter()
+    for s,a in zip(ss,audios): s.accept_waveform(16000,a)
+    t2=time.perf_counter()
+    rec.decode_streams(ss)
+    t3=time.perf_counter()
+    print("create %.1f ms accept %.1f ms decode %.1f ms"%((t1-t0)*1e3,(t2-t1)*1e3,(t3-t2)*1e3), rec.last_timings())
+    del ss
+    t4=time.perf_counter(); print("del %.1f ms"%((t4-t3)*1e3))
