@@ -239,7 +239,8 @@ def main():
             ss.append(s)
         rec.decode_streams(ss)
         return ss
-    e2e_step()
+    for _ in range(max(1, args.warmup)):   # warm-up also grows the pinned-memory pool to two generations of streams
+        ss = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -21,12 +21,37 @@ struct CudaError : std::runtime_error {
 
 #define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may become resident while the previous
+// kernel in the stream is still running; it must execute pdl_wait() before touching anything that kernel (or an
+// earlier one) produces, and it lets its own successor start launching with pdl_trigger(). Both are no-ops for
+// normal launches.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+#endif
+
 // Global launch counter (host side) so bench.py can report `gpu_launches`.
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
 // ACT_TANH_RES: out = tanh(acc + bias + R) (the joiner input tanh(decoder_out + encoder_out)); the others: act(acc + bias) + R
-enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2, ACT_TANH_RES = 3 };
+// ACT_JOINER (tensor-core kernels only): out = acc + bias (the caller folds a blank penalty into the bias) and, per row and per
+// 32-column part, a partial record {mx = max, S e^(x-mx), S e^(x-mx)(x-mx), S e^((x-mx)/3), top-kb values, top-kb
+// columns}: enough for the log-softmax, the global top-k and the per-token entropy / Tsallis / margin statistics,
+// so the beam-search selection never reads the logits (search.cu); C may be null to skip storing them at all.
+enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2, ACT_TANH_RES = 3, ACT_JOINER = 4 };
+constexpr int kPartCols = 32;                                        // logits columns per partial record
+inline int part_rec_floats(int kb) { return 4 + 2 * kb; }            // floats per record
 
 // ---------------------------------------------------------------- fbank (fbank.cu)
 struct FbankTables {
@@ -55,6 +80,11 @@ struct GemmArgs {
   float *C; int ldc;
   int M, N, K;
   int act;
+  // ACT_JOINER only
+  float *partials;           // [M, ceil(N/32), 4 + 2*part_kb]
+  int part_kb;               // 4, 8 or 16 candidates kept per part
+  unsigned long long *trace; // optional: CTA 0 stores %globaltimer at entry / exit (search step timeline, debug)
+  int pdl;                   // launch with programmatic stream serialization (the kernel prologue overlaps the previous kernel)
 };
 void launch_gemm_fp32(const GemmArgs &g, cudaStream_t st);
 void launch_split_lo(const float *w, float *lo, long long n, cudaStream_t st);
@@ -132,6 +162,8 @@ struct ContextGraphDev {   // flattened Aho-Corasick automaton (BFS order; node 
 struct SearchModel {
   const float *emb;        // [V, dd]
   const float *conv_w;     // [dd, 4, ctx]
+  const float *conv_p0;    // [V, dd] the grouped k=2 convolution applied to each token in context slot 0 ...
+  const float *conv_p1;    // ... and slot 1: relu(conv(emb[y0], emb[y1])) = relu(conv_p0[y0] + conv_p1[y1])
   const float *dec_proj_w; // [jd, dd]
   const float *dec_proj_b;
   const float *join_w;     // [V, jd]
@@ -146,7 +178,8 @@ struct SearchModel {
 struct SearchState;   // opaque, search.cu
 SearchState *search_state_create();
 void search_state_destroy(SearchState *s);
-void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t));   // joiner GEMM implementation
+// joiner GEMM implementation; fused_partials = it implements ACT_JOINER (the tcgen05 kernels do)
+void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t), bool fused_partials);
 // Runs the whole search for a batch. enc [sum T', jd] packed with enc_off; results to device arrays then host.
 struct SearchResultHost {
   int n_utts;

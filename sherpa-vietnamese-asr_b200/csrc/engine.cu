@@ -476,6 +476,25 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   sm.join_b = W("joiner.output_linear.bias", {V});
   sm.V = V; sm.dd = dec_dim; sm.jd = join_dim; sm.blank_id = blank_id; sm.unk_id = unk_id;
   {
+    // per-token halves of the decoder's grouped convolution (groups of 4 channels, kernel 2)
+    const auto &emb = tensors.at("decoder.embedding.weight").host;
+    const auto &cw = tensors.at("decoder.conv.weight").host;   // [dd, 4, 2]
+    std::vector<float> p0((size_t)V * dec_dim), p1((size_t)V * dec_dim);
+    for (int y = 0; y < V; ++y)
+      for (int o = 0; o < dec_dim; ++o) {
+        const int g4 = (o >> 2) << 2;
+        float a0 = 0.f, a1 = 0.f;
+        for (int i = 0; i < 4; ++i) {
+          a0 = fmaf(cw[(size_t)o * 8 + i * 2 + 0], emb[(size_t)y * dec_dim + g4 + i], a0);
+          a1 = fmaf(cw[(size_t)o * 8 + i * 2 + 1], emb[(size_t)y * dec_dim + g4 + i], a1);
+        }
+        p0[(size_t)y * dec_dim + o] = a0;
+        p1[(size_t)y * dec_dim + o] = a1;
+      }
+    sm.conv_p0 = upload(p0);
+    sm.conv_p1 = upload(p1);
+  }
+  {
     const double a = 1.0 / 3.0;
     sm.ts_max = V > 1 ? (1.0 / (a - 1.0)) * (1.0 - pow((double)V, 1.0 - a)) : 1.0;
     sm.max_ent = V > 1 ? log((double)V) : 1.0;
@@ -508,7 +527,7 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   search = search_state_create();
   if (precision < 0 || precision > 2) throw std::runtime_error("precision must be 0 (fp32 via 3xTF32 tcgen05), 1 (tf32 tcgen05) or 2 (fp32 CUDA cores)");
   if (precision != 2 && !gemm_tc_available()) throw std::runtime_error("tensor-core GEMM path unavailable (cuTensorMapEncodeTiled not found)");
-  search_set_gemm(search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32));
+  search_set_gemm(search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32), precision != 2);
   if (precision == 0) {
     float *lo;
     CUDA_CHECK(cudaMalloc(&lo, (size_t)V * join_dim * sizeof(float)));

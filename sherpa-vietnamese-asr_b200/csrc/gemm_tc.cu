@@ -39,12 +39,17 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// smem ring depth: 3xTF32 keeps hi and lo copies of both operands, so 3 stages at BN = 128 and 4 at BN = 64
+__host__ __device__ constexpr int stages_for(int BN, bool split3) { return split3 ? (BN == 64 ? 4 : kStages3) : kStages1; }
+
 struct TcParams {
   const float *bias;
   const float *R; int ldr;
   const int *r_rows;
   float *C; int ldc;
   int M, N, K, act;
+  float *partials;   // joiner epilogue (EPI > 0)
+  unsigned long long *trace;
 };
 
 // SPLIT3 = error-compensated "3xTF32": every fp32 operand x is split into hi = x with the 13 low mantissa bits
@@ -58,11 +63,16 @@ struct TcParams {
 // an A row block in L2). Roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2..9 epilogue,
 // warps 10..13 operand splitter (SPLIT3 only). Two TMEM accumulators (2 x BN columns) let the epilogue of tile i
 // overlap the main loop of tile i+1; the smem stage ring runs continuously across tiles.
-template <int BN, bool SPLIT3>
+//
+// EPI > 0 selects the joiner epilogue (ACT_JOINER): out = acc + bias with the blank penalty applied, and each
+// epilogue thread - it owns 32 consecutive columns of one output row straight out of TMEM - also emits the
+// softmax/top-EPI partial record of those columns, so modified_beam_search's per-frame selection (search.cu) reads
+// 3 KB of records per hypothesis instead of the 8 KB logits row (/root/reference core/asr_engine.py:1096-1106).
+template <int BN, bool SPLIT3, int EPI>
 __global__ void __launch_bounds__(SPLIT3 ? 448 : 320, 1)
 gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                          const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
-  constexpr int NS = SPLIT3 ? kStages3 : kStages1;
+  constexpr int NS = stages_for(BN, SPLIT3);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kABytes = TBM * TBK * 4;   // 16 KB
@@ -80,6 +90,11 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   float *epi_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 8 warps x 32 x 32 floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (EPI > 0 && p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    p.trace[0] = now;
+  }
   const int nk = (p.K + TBK - 1) / TBK;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + TBM - 1) / TBM;
@@ -100,6 +115,16 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();      // (PDL launches) everything above overlapped the previous kernel; its results are visible from here
+  pdl_trigger();   // and the next kernel in the stream may start its own prologue
+  auto mark = [&](int slot) {
+    if (EPI > 0 && p.trace && blockIdx.x == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      p.trace[slot] = now;
+    }
+  };
+  if (threadIdx.x == 0) mark(2);
 
   if (warp == 0) {
     // ===== TMA producer
@@ -132,6 +157,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(SPLIT3 ? &ready_bar[s] : &full_bar[s], ph);
+          if (it == 0) mark(3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = make_smem_desc(smem_u32(sA + s * kABytes));
           const uint64_t dw = make_smem_desc(smem_u32(sW + s * kWBytes));
@@ -164,17 +190,82 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
       const int acc = ti & 1;
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
+      if (ti == 0 && warp == 2 && lane == 0) mark(4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float *stg = epi_stage + (warp - 2) * (32 * 32);   // per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
       const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                           (!p.R || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
-                          (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+                          (!p.bias || EPI > 0 || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
         if (n0 + c0 >= p.N) continue;                      // warp-uniform
         const int mrow0 = m0 + q * 32;
+        if constexpr (EPI > 0) {
+          const int nbase = n0 + c0;
+          float mx = -INFINITY;
+          if (nbase + 32 <= p.N) {                          // warp-uniform; only the last tile of a row is ragged
+            const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + nbase);   // bias is 16-byte aligned (checked on the host)
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 bq = __ldg(b4 + j4);
+              const float x0 = __uint_as_float(r[4 * j4]) + bq.x, x1 = __uint_as_float(r[4 * j4 + 1]) + bq.y;
+              const float x2 = __uint_as_float(r[4 * j4 + 2]) + bq.z, x3 = __uint_as_float(r[4 * j4 + 3]) + bq.w;
+              r[4 * j4] = __float_as_uint(x0); r[4 * j4 + 1] = __float_as_uint(x1);
+              r[4 * j4 + 2] = __float_as_uint(x2); r[4 * j4 + 3] = __float_as_uint(x3);
+              mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nbase + j;
+              const float x = n < p.N ? __uint_as_float(r[j]) + __ldg(p.bias + n) : -INFINITY;
+              r[j] = __float_as_uint(x);
+              mx = fmaxf(mx, x);
+            }
+          }
+          // sum = S e^(x-mx) feeds the log-softmax, su = S e^(x-mx) (x-mx) and st = S e^((x-mx)/3) the per-token entropy /
+          // Tsallis statistics. ex2.approx on (x-mx) log2(e): relative error <= 2^-22 on the terms near the maximum
+          // that carry the sum, far inside the fp32 noise of the logits themselves. Two interleaved accumulator sets
+          // halve the dependent chains (the epilogue is latency-bound, two warps per scheduler).
+          float sum[2] = {0.f, 0.f}, su[2] = {0.f, 0.f}, st[2] = {0.f, 0.f}, tv[EPI];
+          int ti[EPI];
+#pragma unroll
+          for (int i = 0; i < EPI; ++i) { tv[i] = -INFINITY; ti[i] = -1; }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(r[j]);
+            const float dx = x - mx;                        // -inf past N: e = 0, and the product below is skipped
+            const float tl = dx * 1.4426950408889634f;
+            const float e = exp2f(tl);
+            sum[j & 1] += e;
+            if (dx > -INFINITY) su[j & 1] = fmaf(e, dx, su[j & 1]);
+            st[j & 1] += exp2f(tl * (1.0f / 3.0f));
+            if (x > tv[EPI - 1]) {                          // strict: equal values keep the lower column first
+              float cv = x;
+              int ci = nbase + j;
+#pragma unroll
+              for (int i = 0; i < EPI; ++i) {
+                if (cv > tv[i]) { const float fv = tv[i]; const int fi = ti[i]; tv[i] = cv; ti[i] = ci; cv = fv; ci = fi; }
+              }
+            }
+          }
+          const int mrow = mrow0 + lane;
+          if (mrow < p.M) {
+            const int n_parts = (p.N + 31) >> 5;
+            float4 *rec = reinterpret_cast<float4 *>(p.partials + ((long long)mrow * n_parts + (nbase >> 5)) * (4 + 2 * EPI));
+            rec[0] = make_float4(mx, sum[0] + sum[1], su[0] + su[1], st[0] + st[1]);
+#pragma unroll
+            for (int i = 0; i < EPI / 4; ++i) {
+              rec[1 + i] = make_float4(tv[4 * i], tv[4 * i + 1], tv[4 * i + 2], tv[4 * i + 3]);
+              rec[1 + EPI / 4 + i] = make_float4(__int_as_float(ti[4 * i]), __int_as_float(ti[4 * i + 1]), __int_as_float(ti[4 * i + 2]),
+                                                 __int_as_float(ti[4 * i + 3]));
+            }
+          }
+        }
+        if (EPI > 0 && p.C == nullptr) continue;               // records only: the selection never reads the logits
+        const float *bias_late = EPI > 0 ? nullptr : p.bias;   // the joiner epilogue has already added it
         __syncwarp();
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4)                      // row = lane; 128-bit stores, conflict-free per quarter warp
@@ -187,7 +278,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           const int n = n0 + c0 + c4;
           const bool nv = n < p.N;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias && nv) bv = __ldg(reinterpret_cast<const float4 *>(p.bias + n));
+          if (bias_late && nv) bv = __ldg(reinterpret_cast<const float4 *>(bias_late + n));
           float4 res[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {                   // all residual loads in flight before use
@@ -218,7 +309,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           // generic path: lane = column, one row per iteration
           const int n = n0 + c0 + lane;
           const bool nv = n < p.N;
-          const float bs = (p.bias && nv) ? __ldg(p.bias + n) : 0.f;
+          const float bs = (bias_late && nv) ? __ldg(bias_late + n) : 0.f;
 #pragma unroll 4
           for (int rr = 0; rr < 32; ++rr) {
             const int m = mrow0 + rr;
@@ -234,6 +325,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
+      if (ti == 0 && warp == 2 && lane == 0) mark(5);
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
     }
   } else {
@@ -272,6 +364,11 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
   }
+  if (EPI > 0 && p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    p.trace[1] = now;
+  }
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -294,7 +391,7 @@ void init_once() {
 }
 
 constexpr size_t smem_bytes(int BN, bool split3) {
-  return 1024 + (size_t)(split3 ? kStages3 * 2 : kStages1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
+  return 1024 + (size_t)stages_for(BN, split3) * (split3 ? 2 : 1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
 }
 
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
@@ -351,40 +448,62 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   if (!g_ok) throw CudaError("tcgen05 GEMM: cuTensorMapEncodeTiled entry point unavailable");
   // TMA needs 16-byte aligned base and row strides; anything else goes to the CUDA-core kernel
   if ((g.lda & 3) || (g.K & 3) || (reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.W) & 15)) {
+    if (g.act == ACT_JOINER) throw CudaError("joiner GEMM: operands must be 16-byte aligned with K % 4 == 0");
     launch_gemm_fp32(g, st);
     return;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128, false)));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64, false)));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128, true)));
-    CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(64, true)));
-    attr_done = true;
+  const bool joiner = g.act == ACT_JOINER;
+  if (joiner) {
+    if (!g.partials || !g.bias || (g.part_kb != 4 && g.part_kb != 8 && g.part_kb != 16) ||
+        ((reinterpret_cast<uintptr_t>(g.partials) | reinterpret_cast<uintptr_t>(g.bias)) & 15))
+      throw CudaError("joiner GEMM: partials buffer and bias (16-byte aligned) and part_kb in {4,8,16} are required");
   }
-  const int BN = g.N > 64 ? 128 : 64;
-  if (split3 && (!g.Wlo || (reinterpret_cast<uintptr_t>(g.Wlo) & 15)))
-    throw CudaError("3xTF32 GEMM needs the pre-split low part of the weights (GemmArgs::Wlo)");
-  CUtensorMap ma, mw, mwl;
-  make_map_impl(&ma, g.A, g.M, g.K, g.lda, TBM);
-  make_map_impl(&mw, g.W, g.N, g.K, g.K, BN);
-  make_map_impl(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.r_rows, g.C, g.ldc, g.M, g.N, g.K, g.act};
-  const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // The per-frame joiner GEMM is latency-bound (one tile per CTA): halve the tile while the grid still fits one wave
+  int BN = g.N > 64 ? 128 : 64;
+  if (joiner && (long long)((g.M + TBM - 1) / TBM) * ((g.N + 63) / 64) <= n_sms) BN = 64;
+  if (split3 && (!g.Wlo || (reinterpret_cast<uintptr_t>(g.Wlo) & 15)))
+    throw CudaError("3xTF32 GEMM needs the pre-split low part of the weights (GemmArgs::Wlo)");
+  CUtensorMap ma, mw, mwl;
+  make_map_impl(&ma, g.A, g.M, g.K, g.lda, TBM);
+  make_map_impl(&mw, g.W, g.N, g.K, g.K, BN);
+  make_map_impl(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
+  TcParams p{g.bias, g.R, g.ldr, g.r_rows, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace};
+  const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, n_sms);   // persistent: one CTA per SM
-  if (split3) {
-    if (BN == 128) gemm_tf32_tcgen05_kernel<128, true><<<grid, 448, smem_bytes(128, true), st>>>(ma, mw, mwl, p);
-    else gemm_tf32_tcgen05_kernel<64, true><<<grid, 448, smem_bytes(64, true), st>>>(ma, mw, mwl, p);
+  // one launcher per instantiation; the opt-in shared-memory attribute is set on first use
+#define B200_TC_LAUNCH(BN_, S3_, EPI_)                                                                                     \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem_bytes(BN_, S3_)));                                                        \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    launch_pdl(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_>, dim3(grid), dim3((S3_) ? 448 : 320), smem_bytes(BN_, S3_), st,   \
+               g.pdl != 0, ma, mw, mwl, p);                                                                              \
+  } while (0)
+#define B200_TC_JOINER(BN_, S3_)                                                                   \
+  do {                                                                                             \
+    if (g.part_kb == 4) B200_TC_LAUNCH(BN_, S3_, 4);                                               \
+    else if (g.part_kb == 8) B200_TC_LAUNCH(BN_, S3_, 8);                                          \
+    else B200_TC_LAUNCH(BN_, S3_, 16);                                                             \
+  } while (0)
+  if (joiner) {
+    if (split3) { if (BN == 128) B200_TC_JOINER(128, true); else B200_TC_JOINER(64, true); }
+    else { if (BN == 128) B200_TC_JOINER(128, false); else B200_TC_JOINER(64, false); }
+  } else if (split3) {
+    if (BN == 128) B200_TC_LAUNCH(128, true, 0); else B200_TC_LAUNCH(64, true, 0);
   } else {
-    if (BN == 128) gemm_tf32_tcgen05_kernel<128, false><<<grid, 320, smem_bytes(128, false), st>>>(ma, mw, mwl, p);
-    else gemm_tf32_tcgen05_kernel<64, false><<<grid, 320, smem_bytes(64, false), st>>>(ma, mw, mwl, p);
+    if (BN == 128) B200_TC_LAUNCH(128, false, 0); else B200_TC_LAUNCH(64, false, 0);
   }
+#undef B200_TC_JOINER
+#undef B200_TC_LAUNCH
   count_launch();
   KERNEL_CHECK();
 }

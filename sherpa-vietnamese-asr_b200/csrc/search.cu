@@ -8,12 +8,17 @@
 //   * hypotheses with identical token sequences merge with log-add, the first inserted keeps its payload;
 //   * the final pick is the first maximum of log_prob / len(ys) with len counting the 2 context slots.
 //
-// All utterances of a batch advance together: per frame step three launches
-//   decoder_step  (stateless decoder for new contexts / copy for blank extensions, then tanh(enc_t + dec))
-//   joiner GEMM   (gemm.cu / gemm_tc.cu: [active*beam, jd] x [jd, V])
-//   select_step   (one CTA per utterance: log-softmax, top-k, expansion, hotword arcs, dedup, token statistics)
-// Hypotheses live in HBM as back-pointer chains in a per-utterance arena; nothing returns to the host until
-// the last frame. Utterances are processed longest-first so the active set at step t is a prefix.
+// All utterances of a batch advance together; the loop is latency-bound (T' sequential steps), so a step is three
+// lean launches:
+//   decoder_joinin  decoder_proj only for hypotheses whose 2-token context changed (compacted list, fp32 CUDA-core
+//                   tiles), a row copy for blank extensions, and the joiner input X = tanh(enc_t + dec) for every row
+//   joiner GEMM     gemm_tc.cu, [active*beam, jd] x [jd, V] on tcgen05; its epilogue also emits, per row and per
+//                   32-column part, the softmax/top-k partial record (ACT_JOINER)
+//   select          one CTA per utterance merges the records: log-softmax, global top-k, expansion, hotword arcs,
+//                   log-add dedup, per-token statistics (only emitted tokens touch their full logits row)
+// The CUDA-core GEMM mode (precision 2) and shapes the records cannot cover use select_step_kernel on the full
+// logits instead. Hypotheses live in HBM as back-pointer chains in a per-utterance arena; nothing returns to the
+// host until the last frame. Utterances are processed longest-first so the active set at step t is a prefix.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -58,13 +63,28 @@ struct SearchDev {
   int *hyp_count;              // [2][n]
   int *node_count;             // [n]
   ArenaNode *arena;
-  float *E;                    // [n*beam, dd] relu(conv(embeddings)) of each live hypothesis (decoder GEMM input)
-  int *rowmap;                 // [n*beam] encoder_out row joined with that hypothesis at the next step
+  float *E;                    // [n*beam, dd] relu(conv(embeddings)) of hypotheses whose context changed
+  float *dec;                  // [2][n*beam, jd] decoder outputs, ping-pong by frame parity
   float *X;                    // [n*beam, jd] joiner input tanh(enc+dec)
   float *logits;               // [n*beam, V]
+  float *partials;             // [n*beam, ceil(V/32), 4+2*KB] records from the joiner epilogue (or null)
+  int2 *chg_list;              // [2][n*beam] {row, encoder_out row of its next frame} of the hypotheses whose decoder
+                               // output must be recomputed, by frame parity
+  int *chg_count;              // [2]
+  int2 *rowdesc;               // [2][n*beam] per joiner row {parent row to copy dec from | -1 recompute | -2 unused,
+                               //                              encoder_out row of its next frame}, by frame parity
   int n, beam;
   long long *prof;             // optional per-phase cycle counters of CTA 0 (B200ASR_SEARCH_PROF=1)
+  unsigned long long *trace;   // optional [steps][6] %globaltimer at entry/exit of CTA 0 of the three step kernels
 };
+
+__device__ __forceinline__ void trace_mark(unsigned long long *trace, int t, int slot) {
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    trace[t * 16 + slot] = now;
+  }
+}
 
 // ------------------------------------------------------------------ stateless decoder (App. B.4)
 // e[o] = relu(sum_{i<4,k<ctx} w[o,i,k] * emb[y_k][4*(o/4)+i]);  out = Wp e + bp.  One CTA per row.
@@ -169,23 +189,537 @@ struct NewNode { int arena_idx; int row; };
     }                                                                             \
   } while (0)
 
+// ------------------------------------------------------------------ decoder update + joiner input
+// One wave of CTAs (at most one per SM) walks the 32 x 32 output tiles of dec = E[list] * Wp^T + bp over the compacted
+// list of rows whose context changed (the count lives on the device): both operand panels of a tile (32 rows x K
+// of E, 32 rows x K of Wp, K <= 512 per pass) are pulled into shared memory with one burst of cp.async so the
+// kernel pays a single L2 round trip. The rows are gathered and few (tens to hundreds), which is not a tcgen05
+// shape (128-row tiles fed by TMA); the product runs on warp-level mma.sync m16n8k8 TF32 with the same
+// error-compensated 3xTF32 split as the big GEMMs (hi = 13 low mantissa bits cleared, lo = x - hi, small terms
+// first), each of the 8 warps 16 x 8 outputs. The epilogue writes dec and X = tanh(enc_t + dec). While its first panels are in
+// flight every CTA also handles its share of the blank extensions: dec = previous dec of the parent slot.
+constexpr int DJ_TM = 32, DJ_TN = 32, DJ_THREADS = 256, DJ_KC = 512, DJ_LD = DJ_KC + 4;
+constexpr size_t kDjSmem = (size_t)(DJ_TM + DJ_TN) * DJ_LD * sizeof(float);
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;   // 0 -> the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(DJ_THREADS) decoder_joinin_kernel(SearchModel m, SearchDev d, int t, int n_rows) {
+  const int tid = threadIdx.x, warp_ = tid >> 5, lane_ = tid & 31;
+  const int par = t & 1;
+  extern __shared__ __align__(16) float dj_smem[];
+  float *As = dj_smem, *Bs = dj_smem + DJ_TM * DJ_LD;
+  __shared__ int2 s_row[DJ_TM];
+  const int ntn = (m.jd + DJ_TN - 1) / DJ_TN;
+  const int K = m.dd;
+  const int kw0 = min(DJ_KC, K);
+  auto load_w_panel = [&](int n0, int kc0, int kw) {
+    for (int row = 0; row < DJ_TN; ++row) {
+      const int n = n0 + row;
+      for (int c = tid; c < (kw >> 2); c += DJ_THREADS)
+        cp_async16(Bs + row * DJ_LD + c * 4, n < m.jd ? m.dec_proj_w + (long long)n * K + kc0 + c * 4 : m.dec_proj_w, n < m.jd);
+    }
+  };
+  // the weight panel of this CTA's first tile does not depend on the previous kernel: fetch it under its tail
+  load_w_panel(((int)blockIdx.x % ntn) * DJ_TN, 0, kw0);
+  pdl_wait();
+  pdl_trigger();       // the joiner GEMM may become resident now; it waits for this grid before loading X
+  trace_mark(d.trace, t, 0);
+  const size_t plane = (size_t)d.n * d.beam * m.jd;
+  float *dec_new = d.dec + par * plane;
+  const float *dec_old = d.dec + (par ^ 1) * plane;
+  const int2 *list = d.chg_list + (size_t)par * d.n * d.beam;
+  const int2 *rdesc = d.rowdesc + (size_t)par * d.n * d.beam;
+  // count and this CTA's first list entries in one round trip (entries past the count are stale but in range)
+  const int r00 = ((int)blockIdx.x / ntn) * DJ_TM;
+  int2 first_ent = make_int2(-1, 0);
+  if (tid < DJ_TM && r00 + tid < n_rows) first_ent = list[r00 + tid];
+  const int n_chg = d.chg_count[par];
+  const int n_tiles = ((n_chg + DJ_TM - 1) / DJ_TM) * ntn;
+  const int g = lane_ >> 2, tq = lane_ & 3;             // mma fragment coordinates
+  const int rb = (warp_ & 1) * 16, cb = (warp_ >> 1) * 8;
+  bool rows_done = false;
+  // blank extensions: flattened over (row, float4) units, four units in flight per thread. CTAs without a tile take
+  // them all when there are enough of them; otherwise everybody shares them while the first operand panels land.
+  const int free_ctas = (int)gridDim.x - min(n_tiles, (int)gridDim.x);
+  const bool free_only = free_ctas >= 32;
+  auto copy_rows = [&]() {
+    rows_done = true;
+    int part = blockIdx.x, parts = gridDim.x;
+    if (free_only) {
+      if ((int)blockIdx.x < n_tiles) return;
+      part = (int)blockIdx.x - n_tiles; parts = free_ctas;
+    }
+    const int jd4 = m.jd >> 2;
+    const long long total = (long long)n_rows * jd4, stride = (long long)parts * DJ_THREADS;
+    for (long long u0 = (long long)part * DJ_THREADS + tid; u0 < total; u0 += 4 * stride) {
+      int2 ds[4];
+      int rr[4], cc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long u = u0 + i * stride;
+        ds[i] = make_int2(-2, 0);
+        rr[i] = 0; cc[i] = 0;
+        if (u < total) { rr[i] = (int)(u / jd4); cc[i] = (int)(u - (long long)rr[i] * jd4); ds[i] = rdesc[rr[i]]; }
+      }
+      float4 dv[4], ev[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ds[i].x >= 0) {
+          dv[i] = reinterpret_cast<const float4 *>(dec_old + (long long)ds[i].x * m.jd)[cc[i]];
+          ev[i] = __ldg(reinterpret_cast<const float4 *>(d.enc + (long long)ds[i].y * m.jd) + cc[i]);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (ds[i].x >= 0) {
+          reinterpret_cast<float4 *>(dec_new + (long long)rr[i] * m.jd)[cc[i]] = dv[i];
+          reinterpret_cast<float4 *>(d.X + (long long)rr[i] * m.jd)[cc[i]] =
+              make_float4(tanhf(ev[i].x + dv[i].x), tanhf(ev[i].y + dv[i].y), tanhf(ev[i].z + dv[i].z), tanhf(ev[i].w + dv[i].w));
+        }
+    }
+  };
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int r0 = (tile / ntn) * DJ_TM, n0 = (tile % ntn) * DJ_TN;
+    const bool first = tile == (int)blockIdx.x;
+    if (!first) __syncthreads();                          // previous tile's readers are done with s_row / panels
+    if (tid < DJ_TM) {
+      int2 e = first ? first_ent : ((r0 + tid < n_chg) ? list[r0 + tid] : make_int2(-1, 0));
+      if (r0 + tid >= n_chg) e.x = -1;
+      s_row[tid] = e;
+    }
+    __syncthreads();
+    // 3 independent accumulator chains, one per product term (mma.sync latency, not throughput, bounds this)
+    float acc[3][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[a][i] = 0.f;
+    float2 bs = make_float2(0.f, 0.f), ev[2];
+    int rowi[2];
+    for (int kc0 = 0; kc0 < K; kc0 += DJ_KC) {
+      const int kw = min(DJ_KC, K - kc0);
+      const int kw4 = kw >> 2;   // float4 per row in this pass (K % 4 == 0)
+      if (kc0) __syncthreads();
+      for (int row = 0; row < DJ_TM; ++row) {
+        const int r = s_row[row].x;
+        for (int c = tid; c < kw4; c += DJ_THREADS)
+          cp_async16(As + row * DJ_LD + c * 4, r >= 0 ? d.E + (long long)r * K + kc0 + c * 4 : d.E, r >= 0);
+      }
+      if (!(first && kc0 == 0)) load_w_panel(n0, kc0, kw);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (first) trace_mark(d.trace, t, 10);
+      if (kc0 == 0) {
+        // epilogue operands, requested before the product so they are in registers when it ends
+        const int n = n0 + cb + 2 * tq;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int2 e = s_row[rb + g + 8 * h];
+          rowi[h] = e.x;
+          ev[h] = (e.x >= 0 && n < m.jd) ? __ldg(reinterpret_cast<const float2 *>(d.enc + (long long)e.y * m.jd + n)) : make_float2(0.f, 0.f);
+        }
+        if (n < m.jd) bs = __ldg(reinterpret_cast<const float2 *>(m.dec_proj_b + n));
+      }
+      if (!rows_done) copy_rows();
+      if (first) trace_mark(d.trace, t, 11);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (first) trace_mark(d.trace, t, 12);
+      // fragment reads are bank-conflict free: row stride 516 words -> bank = 4 * row + k (mod 32)
+      const float *ap0 = As + (rb + g) * DJ_LD + tq, *ap1 = ap0 + 8 * DJ_LD;
+      const float *bp0 = Bs + (cb + g) * DJ_LD + tq;
+#pragma unroll 4
+      for (int k0 = 0; k0 + 8 <= kw; k0 += 8) {
+        const float av[4] = {ap0[k0], ap1[k0], ap0[k0 + 4], ap1[k0 + 4]};
+        const float bv[2] = {bp0[k0], bp0[k0 + 4]};
+        unsigned ahi[4], alo[4], bhi[2], blo[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ahi[i] = __float_as_uint(av[i]) & 0xFFFFE000u;
+          alo[i] = __float_as_uint(av[i] - __uint_as_float(ahi[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          bhi[i] = __float_as_uint(bv[i]) & 0xFFFFE000u;
+          blo[i] = __float_as_uint(bv[i] - __uint_as_float(bhi[i]));
+        }
+        mma_tf32_16x8x8(acc[0], alo, bhi);
+        mma_tf32_16x8x8(acc[1], ahi, blo);
+        mma_tf32_16x8x8(acc[2], ahi, bhi);
+      }
+    }
+    if (first) trace_mark(d.trace, t, 13);
+    // accumulator fragment: c0,c1 -> row g, columns 2 tq, 2 tq + 1; c2,c3 -> row g + 8
+    const int n = n0 + cb + 2 * tq;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = rowi[h];
+      if (r < 0 || n >= m.jd) continue;          // jd % 4 == 0, n even -> n + 1 < jd
+      const float2 dv = make_float2((acc[0][2 * h] + acc[1][2 * h]) + acc[2][2 * h] + bs.x,
+                                    (acc[0][2 * h + 1] + acc[1][2 * h + 1]) + acc[2][2 * h + 1] + bs.y);
+      *reinterpret_cast<float2 *>(dec_new + (long long)r * m.jd + n) = dv;
+      *reinterpret_cast<float2 *>(d.X + (long long)r * m.jd + n) = make_float2(tanhf(ev[h].x + dv.x), tanhf(ev[h].y + dv.y));
+    }
+    if (first) trace_mark(d.trace, t, 14);
+  }
+  if (!rows_done) copy_rows();
+  asm volatile("cp.async.wait_all;" ::: "memory");   // a CTA without tiles still has its speculative weight panel in flight
+  trace_mark(d.trace, t, 1);
+}
+
+// ------------------------------------------------------------------ selection: shared tail
+// Expansion of the k winners (serial, exactly in top-k order :1109-1140), hotword arcs, log-add dedup, the per-token
+// statistics of emitted tokens (_compute_token_entropy :1159-1181) from their logits rows (`rows`, shared or global
+// memory; null = already in sh.rstats), write-back of the new beam, and for hypotheses whose context changed the decoder pre-activation
+// E = relu(grouped conv over the two context embeddings) plus their entry in the next step's recompute list.
+struct SelShared {
+  HypSlot old_[kMaxBeam], new_[kMaxBeam];
+  float mx[kMaxBeam], lse[kMaxBeam], sum[kMaxBeam], prev[kMaxBeam];
+  unsigned long long win[kMaxBeam];
+  NewNode nodes[kMaxBeam];
+  int chg_pos[kMaxBeam];
+  float rstats[kMaxBeam][4];   // per-row token statistics when they come from the partial records
+  int n_new, n_nodes;
+  int node_count0;             // arena fill of this utterance, fetched at kernel start (off the serial section)
+};
+
+__device__ void finish_step(const SearchModel &m, const SearchDev &d, const ContextGraphView &g, int has_graph, int s, int t, int cur,
+                            int greedy, int k, SelShared &sh, const float *rows, long long row_stride, long long &_t0) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = m.V;
+  ArenaNode *arena = d.arena + d.arena_off[s];
+  const bool more = t + 1 < d.lens[s];      // another frame follows: the new beam needs joiner inputs
+  if (tid == 0) {
+    int n_new = 0, n_nodes = 0;
+    int node_count = sh.node_count0;
+    for (int r = 0; r < k; ++r) {
+      const unsigned long long key = sh.win[r];
+      if (key == 0ULL) break;
+      const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
+      const float lp32 = unord_f32((unsigned)(key >> 32));
+      const int hi = idx / V, tok = idx - hi * V;
+      const HypSlot &p = sh.old_[hi];
+      HypSlot c;
+      c.score = (double)lp32;
+      bool is_blank = (tok == m.blank_id);
+      if (is_blank) {
+        c.hash = p.hash; c.node = p.node; c.len = p.len; c.ctx = p.ctx; c.y0 = p.y0; c.y1 = p.y1; c.dec_src = hi;
+      } else {
+        c.hash = mix_hash(p.hash, tok);
+        c.len = p.len + 1; c.ctx = p.ctx; c.y0 = p.y1; c.y1 = tok; c.dec_src = -1; c.node = -1;
+        if (has_graph && !greedy && tok != m.unk_id) {
+          int nxt;
+          c.score += cg_forward_one_step(g, p.ctx, tok, &nxt);
+          c.ctx = nxt;
+        }
+      }
+      if (greedy) c.score = 0.0;
+      // dedup against already inserted hypotheses (same token sequence)
+      int dup = -1;
+      for (int q = 0; q < n_new && dup < 0; ++q) {
+        if (sh.new_[q].len != c.len || sh.new_[q].hash != c.hash) continue;
+        if (is_blank) {
+          if (same_chain(arena, sh.new_[q].node, p.node)) dup = q;
+        } else {
+          const int qn = sh.new_[q].node;
+          if (qn >= 0 && arena[qn].token == tok && same_chain(arena, arena[qn].parent, p.node)) dup = q;
+        }
+      }
+      if (dup >= 0) {
+        sh.new_[dup].score = log_add_d(sh.new_[dup].score, c.score);
+        continue;
+      }
+      if (!is_blank) {
+        const int ai = node_count++;
+        ArenaNode nd;
+        nd.parent = p.node; nd.token = tok; nd.frame = t;
+        nd.tok_lp = (float)((double)lp32 - (greedy ? 0.0 : p.score));   // (:1121)
+        if (rows) { nd.stats[0] = nd.stats[1] = nd.stats[2] = nd.stats[3] = 0.f; }
+        else { nd.stats[0] = sh.rstats[hi][0]; nd.stats[1] = sh.rstats[hi][1]; nd.stats[2] = sh.rstats[hi][2]; nd.stats[3] = sh.rstats[hi][3]; }
+        arena[ai] = nd;
+        c.node = ai;
+        sh.nodes[n_nodes].arena_idx = ai;
+        sh.nodes[n_nodes].row = hi;
+        ++n_nodes;
+      }
+      sh.new_[n_new++] = c;
+    }
+    sh.n_new = n_new;
+    sh.n_nodes = n_nodes;
+    d.node_count[s] = node_count;
+    d.hyp_count[(cur ^ 1) * d.n + s] = n_new;
+    // rows of the new beam whose decoder output has to be recomputed before the next joiner step, and the per-row
+    // descriptors of the blank extensions (parent row to copy from); both carry the encoder_out row of frame t + 1
+    int n_chg = 0;
+    for (int q = 0; q < n_new; ++q) {
+      sh.chg_pos[q] = -1;
+      if (more && sh.new_[q].dec_src < 0) sh.chg_pos[q] = n_chg++;
+    }
+    const int enc_next = (int)d.enc_off[s] + t + 1;
+    int2 *rdesc = d.rowdesc + (size_t)((t + 1) & 1) * d.n * d.beam + (size_t)s * d.beam;
+    for (int q = 0; q < d.beam; ++q) {
+      int src = -2;
+      if (more && q < n_new) src = sh.new_[q].dec_src < 0 ? -1 : s * d.beam + sh.new_[q].dec_src;
+      rdesc[q] = make_int2(src, enc_next);
+    }
+    if (n_chg > 0) {
+      const int base = atomicAdd(&d.chg_count[(t + 1) & 1], n_chg);
+      int2 *list = d.chg_list + (size_t)((t + 1) & 1) * d.n * d.beam;
+      for (int q = 0; q < n_new; ++q)
+        if (sh.chg_pos[q] >= 0) list[base + sh.chg_pos[q]] = make_int2(s * d.beam + q, enc_next);
+    }
+  }
+  __syncthreads();
+  SEL_PROF(3);
+
+  // per emitted token statistics from its logits row, one warp per token (full-logits selection only; the
+  // partial-record selection has them per row already)
+  for (int e = warp; rows && e < sh.n_nodes; e += kSelThreads / 32) {
+    const int b = sh.nodes[e].row;
+    const float *row = rows + (long long)b * row_stride;
+    const float mx = sh.mx[b], sum = sh.sum[b];
+    float ent = 0.f, ts = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int v = lane; v < V; v += 32) {
+      const float p = expf(row[v] - mx) / sum;
+      ent += p * __logf(p + 1e-30f);
+      ts += exp2f(__log2f(p) * (1.0f / 3.0f));        // p^(1/3); p = 0 -> log2 = -inf -> 0
+      if (p > t1) { t2 = t1; t1 = p; } else if (p > t2) { t2 = p; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ent += __shfl_xor_sync(0xffffffffu, ent, o);
+      ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      const float o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+      if (o1 > t1) { t2 = fmaxf(t1, o2); t1 = o1; } else { t2 = fmaxf(t2, o1); }
+    }
+    if (lane == 0) {
+      const double a = 1.0 / 3.0;
+      const double ts_max = m.ts_max;
+      const double tsallis = (1.0 / (a - 1.0)) * (1.0 - (double)ts);
+      const double max_ent = m.max_ent;
+      ArenaNode &nd = arena[sh.nodes[e].arena_idx];
+      nd.stats[0] = (float)(ts_max > 0 ? tsallis / ts_max : 0.0);
+      nd.stats[1] = t1 - (V > 1 ? t2 : 1e-10f);
+      nd.stats[2] = (float)((-(double)ent) / max_ent);
+      nd.stats[3] = t1;
+    }
+  }
+  const int n_new = sh.n_new;
+  if (tid < n_new) d.hyps[((long long)(cur ^ 1) * d.n + s) * kMaxBeam + tid] = sh.new_[tid];
+  SEL_PROF(4);
+
+  // decoder pre-activation for the hypotheses with a new context: E = relu(P0[y0] + P1[y1]), the grouped k=2
+  // convolution split into its two per-token halves (tables built once at load)
+  if (more) {
+    const int dd4 = m.dd >> 2;
+    for (int i = tid; i < n_new * dd4; i += kSelThreads) {
+      const int q = i / dd4, c = i - q * dd4;
+      if (sh.chg_pos[q] < 0) continue;
+      const HypSlot &hs = sh.new_[q];
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(m.conv_p0 + (long long)hs.y0 * m.dd) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(m.conv_p1 + (long long)hs.y1 * m.dd) + c);
+      reinterpret_cast<float4 *>(d.E + ((long long)s * d.beam + q) * m.dd)[c] =
+          make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+    }
+  }
+  SEL_PROF(7);
+}
+
+// block-wide top-k over per-thread descending candidate lists loc[KB] (0 = empty): per warp KB shuffle rounds, then
+// warp 0 merges the 8 x KB survivors. Two barriers in total. Results in sh.win[0..k).
+template <int KB>
+__device__ void block_topk(unsigned long long (&loc)[KB], int k, SelShared &sh, unsigned long long *s_wk /* [8*KB] */) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int head = 0;
+#pragma unroll 1
+  for (int round = 0; round < KB; ++round) {
+    if (round >= k) {                       // block-uniform: only the top k of each warp can matter
+      if (lane == 0) s_wk[warp * KB + round] = 0ULL;
+      continue;
+    }
+    unsigned long long best = 0ULL;
+#pragma unroll
+    for (int i = 0; i < KB; ++i) if (i == head) best = loc[i];
+    unsigned long long wb = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
+      wb = other > wb ? other : wb;
+    }
+    if (best == wb && wb != 0ULL) ++head;
+    if (lane == 0) s_wk[warp * KB + round] = wb;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int NC = (kSelThreads / 32) * KB;   // 32, 64 or 128 survivors
+    constexpr int PER = (NC + 31) / 32;
+    unsigned long long c[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) c[j] = (lane + 32 * j < NC) ? s_wk[lane + 32 * j] : 0ULL;
+    for (int round = 0; round < k; ++round) {
+      unsigned long long best = 0ULL;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) best = c[j] > best ? c[j] : best;
+      unsigned long long wb = best;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
+        wb = other > wb ? other : wb;
+      }
+      if (wb != 0ULL) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) if (c[j] == wb) c[j] = 0ULL;   // keys are unique (they carry the flat index)
+      }
+      if (lane == 0) sh.win[round] = wb;
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ selection from the joiner's partial records
+template <int KB>
+__global__ void __launch_bounds__(kSelThreads) select_partials_kernel(SearchModel m, SearchDev d, ContextGraphView g, int has_graph,
+                                                                      int t, int cur, int greedy) {
+  const int s = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();       // next step's decoder_joinin may become resident; it waits for this grid before reading anything
+  trace_mark(d.trace, t, 8);
+  if (s == 0 && threadIdx.x == 0) d.chg_count[t & 1] = 0;   // consumed by this step's decoder_joinin; refilled at t + 1
+  if (t >= d.lens[s]) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = m.V;
+  constexpr int REC = 4 + 2 * KB;
+  constexpr int RPT = KB <= 4 ? 1 : (KB <= 8 ? 2 : 4);     // records per thread (host checks beam * parts <= 256 * RPT)
+  __shared__ SelShared sh;
+  __shared__ unsigned long long s_wk[(kSelThreads / 32) * KB];
+  extern __shared__ __align__(16) float s_dyn[];           // [6][count][parts]: part max, sums (3), two best values
+  long long _t0 = clock64();
+  const int count = d.hyp_count[cur * d.n + s];
+  const int P = (V + kPartCols - 1) / kPartCols;
+  if (tid < count) sh.old_[tid] = d.hyps[((long long)cur * d.n + s) * kMaxBeam + tid];
+  if (tid == kSelThreads - 1) sh.node_count0 = d.node_count[s];
+  const int nrec = count * P;
+  float *pm = s_dyn, *ps = pm + nrec, *pu = ps + nrec, *pt = pu + nrec, *pv0 = pt + nrec, *pv1 = pv0 + nrec;
+  const float4 *recs = reinterpret_cast<const float4 *>(d.partials + (long long)s * d.beam * P * REC);
+  float4 rv[RPT][KB / 4], ri[RPT][KB / 4];
+#pragma unroll
+  for (int it = 0; it < RPT; ++it) {
+    const int i = tid + it * kSelThreads;
+    if (i < nrec) {
+      const float4 *rc = recs + (long long)i * (REC / 4);
+      const float4 h = rc[0];
+#pragma unroll
+      for (int j = 0; j < KB / 4; ++j) { rv[it][j] = rc[1 + j]; ri[it][j] = rc[1 + KB / 4 + j]; }
+      pm[i] = h.x; ps[i] = h.y; pu[i] = h.z; pt[i] = h.w;
+      pv0[i] = rv[it][0].x; pv1[i] = rv[it][0].y;
+    }
+  }
+  __syncthreads();
+  SEL_PROF(0);
+  // (a) per row, from its parts: max and log-sum-exp in float32 as the reference (:1096-1098), and the token
+  // statistics of _compute_token_entropy (:1159-1181) with p = e^(x-M)/S:
+  //   sum p log p = (1/S) sum_parts e^(m-M) (U + (m-M) S_part) - log S,   sum p^(1/3) = S^(-1/3) sum_parts e^((m-M)/3) T
+  for (int b = warp; b < count; b += kSelThreads / 32) {
+    float mx = -INFINITY;
+    for (int q = lane; q < P; q += 32) mx = fmaxf(mx, pm[b * P + q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f, su = 0.f, st = 0.f, t1 = -INFINITY, t2 = -INFINITY;
+    for (int q = lane; q < P; q += 32) {
+      const int i = b * P + q;
+      const float dm = pm[i] - mx, e = expf(dm);
+      sum = fmaf(ps[i], e, sum);
+      su = fmaf(e, fmaf(dm, ps[i], pu[i]), su);
+      st = fmaf(__expf(dm * (1.0f / 3.0f)), pt[i], st);
+      const float a0 = pv0[i], a1 = pv1[i];            // a0 >= a1
+      if (a0 > t1) { t2 = fmaxf(t1, a1); t1 = a0; } else { t2 = fmaxf(t2, a0); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      su += __shfl_xor_sync(0xffffffffu, su, o);
+      st += __shfl_xor_sync(0xffffffffu, st, o);
+      const float o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+      if (o1 > t1) { t2 = fmaxf(t1, o2); t1 = o1; } else { t2 = fmaxf(t2, o1); }
+    }
+    if (lane == 0) {
+      const float lse = logf(sum);
+      sh.mx[b] = mx;
+      sh.sum[b] = sum;
+      sh.lse[b] = lse;
+      sh.prev[b] = greedy ? 0.f : (float)sh.old_[b].score;   // score rounded to f32 before the add (:1099-1100)
+      const double a = 1.0 / 3.0;
+      const double tsallis = (1.0 / (a - 1.0)) * (1.0 - (double)(st * __expf(-lse * (1.0f / 3.0f))));
+      const float p1 = expf(t1 - mx) / sum, p2 = V > 1 ? expf(t2 - mx) / sum : 1e-10f;
+      sh.rstats[b][0] = (float)(m.ts_max > 0 ? tsallis / m.ts_max : 0.0);
+      sh.rstats[b][1] = p1 - p2;
+      sh.rstats[b][2] = (float)(-((double)(su / sum) - (double)lse) / m.max_ent);
+      sh.rstats[b][3] = p1;
+    }
+  }
+  __syncthreads();
+  SEL_PROF(1);
+  // (b) global top-k; key = (ordered value, ~flat index) so max = value desc, index asc
+  const int k = min(d.beam, count * V);
+  unsigned long long loc[KB];
+#pragma unroll
+  for (int i = 0; i < KB; ++i) loc[i] = 0ULL;
+#pragma unroll
+  for (int it = 0; it < RPT; ++it) {
+    const int i = tid + it * kSelThreads;
+    if (i < nrec) {
+      const int b = i / P;
+      const float mxb = sh.mx[b], lseb = sh.lse[b], prevb = sh.prev[b];
+#pragma unroll
+      for (int j = 0; j < KB; ++j) {
+        const float4 v4 = rv[it][j >> 2], i4 = ri[it][j >> 2];
+        const float v = (j & 3) == 0 ? v4.x : (j & 3) == 1 ? v4.y : (j & 3) == 2 ? v4.z : v4.w;
+        const int col = __float_as_int((j & 3) == 0 ? i4.x : (j & 3) == 1 ? i4.y : (j & 3) == 2 ? i4.z : i4.w);
+        if (col < 0) continue;
+        const float lp = ((v - mxb) - lseb) + prevb;
+        const unsigned long long key = ((unsigned long long)ord_f32(lp) << 32) | (unsigned)(~(unsigned)(b * V + col));
+        if (key > loc[KB - 1]) {
+          unsigned long long carry = key;
+#pragma unroll
+          for (int q = 0; q < KB; ++q) {
+            if (carry > loc[q]) { const unsigned long long tmp = loc[q]; loc[q] = carry; carry = tmp; }
+          }
+        }
+      }
+    }
+  }
+  block_topk<KB>(loc, k, sh, s_wk);
+  SEL_PROF(2);
+  finish_step(m, d, g, has_graph, s, t, cur, greedy, k, sh, nullptr, 0, _t0);
+  trace_mark(d.trace, t, 9);
+}
+
+// ------------------------------------------------------------------ selection from the full logits (CUDA-core GEMM
+// mode, and vocabulary/beam combinations the partial records do not cover)
 template <int KB>
 __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m, SearchDev d, ContextGraphView g, int has_graph,
                                                                   int t, int cur, int greedy, float blank_penalty) {
   const int s = blockIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  if (s == 0 && threadIdx.x == 0) d.chg_count[t & 1] = 0;
   if (t >= d.lens[s]) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = m.V;
-  __shared__ HypSlot s_old[kMaxBeam], s_new[kMaxBeam];
-  __shared__ float s_mx[kMaxBeam], s_lse[kMaxBeam], s_sum[kMaxBeam], s_prev[kMaxBeam];
-  __shared__ unsigned long long s_warpbest[kSelThreads / 32];
-  __shared__ unsigned long long s_win[kMaxBeam];
-  __shared__ NewNode s_nodes[kMaxBeam];
-  __shared__ int s_n_new, s_n_nodes;
+  __shared__ SelShared sh;
+  __shared__ unsigned long long s_wk[(kSelThreads / 32) * KB];
 
   long long _t0 = clock64();
   const int count = d.hyp_count[cur * d.n + s];
-  if (tid < count) s_old[tid] = d.hyps[((long long)cur * d.n + s) * kMaxBeam + tid];
+  if (tid < count) sh.old_[tid] = d.hyps[((long long)cur * d.n + s) * kMaxBeam + tid];
+  if (tid == kSelThreads - 1) sh.node_count0 = d.node_count[s];
   // stage this utterance's logits rows in shared memory with wide, fully pipelined loads: every later pass
   // (max, sum-exp, top-k scan, token statistics) would otherwise pay L2 latency per element
   extern __shared__ __align__(16) float s_dyn[];
@@ -215,10 +749,10 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) {
-      s_mx[b] = mx;
-      s_sum[b] = sum;
-      s_lse[b] = logf(sum);
-      s_prev[b] = greedy ? 0.f : (float)s_old[b].score;   // score rounded to f32 before the add (:1099-1100)
+      sh.mx[b] = mx;
+      sh.sum[b] = sum;
+      sh.lse[b] = logf(sum);
+      sh.prev[b] = greedy ? 0.f : (float)sh.old_[b].score;   // score rounded to f32 before the add (:1099-1100)
     }
   }
   __syncthreads();
@@ -230,7 +764,7 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
 #pragma unroll
   for (int i = 0; i < KB; ++i) loc[i] = 0ULL;
   for (int b = 0; b < count; ++b) {
-    const float mxb = s_mx[b], lseb = s_lse[b], prevb = s_prev[b];
+    const float mxb = sh.mx[b], lseb = sh.lse[b], prevb = sh.prev[b];
     const float *row = lg + b * V;
     const int base = b * V;
     for (int v = tid; v < V; v += kSelThreads) {
@@ -246,147 +780,14 @@ __global__ void __launch_bounds__(kSelThreads) select_step_kernel(SearchModel m,
       }
     }
   }
-  int head = 0;
-  for (int round = 0; round < k; ++round) {
-    unsigned long long best = 0ULL;
-#pragma unroll
-    for (int i = 0; i < KB; ++i) if (i == head) best = loc[i];
-    unsigned long long wb = best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
-      wb = other > wb ? other : wb;
-    }
-    if (lane == 0) s_warpbest[warp] = wb;
-    __syncthreads();
-    unsigned long long win = 0ULL;
-#pragma unroll
-    for (int w = 0; w < kSelThreads / 32; ++w) win = s_warpbest[w] > win ? s_warpbest[w] : win;
-    if (best == win && win != 0ULL) ++head;
-    if (tid == 0) s_win[round] = win;
-    __syncthreads();
-  }
-
+  block_topk<KB>(loc, k, sh, s_wk);
   SEL_PROF(2);
-  // (c) expansion, hotword arcs, dedup: serial over <= beam winners, exactly in top-k order (:1109-1140)
-  ArenaNode *arena = d.arena + d.arena_off[s];
-  if (tid == 0) {
-    int n_new = 0, n_nodes = 0;
-    int node_count = d.node_count[s];
-    for (int r = 0; r < k; ++r) {
-      const unsigned long long key = s_win[r];
-      const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
-      const float lp32 = unord_f32((unsigned)(key >> 32));
-      const int hi = idx / V, tok = idx - hi * V;
-      const HypSlot &p = s_old[hi];
-      HypSlot c;
-      c.score = (double)lp32;
-      bool is_blank = (tok == m.blank_id);
-      if (is_blank) {
-        c.hash = p.hash; c.node = p.node; c.len = p.len; c.ctx = p.ctx; c.y0 = p.y0; c.y1 = p.y1; c.dec_src = hi;
-      } else {
-        c.hash = mix_hash(p.hash, tok);
-        c.len = p.len + 1; c.ctx = p.ctx; c.y0 = p.y1; c.y1 = tok; c.dec_src = -1; c.node = -1;
-        if (has_graph && !greedy && tok != m.unk_id) {
-          int nxt;
-          c.score += cg_forward_one_step(g, p.ctx, tok, &nxt);
-          c.ctx = nxt;
-        }
-      }
-      if (greedy) c.score = 0.0;
-      // dedup against already inserted hypotheses (same token sequence)
-      int dup = -1;
-      for (int q = 0; q < n_new && dup < 0; ++q) {
-        if (s_new[q].len != c.len || s_new[q].hash != c.hash) continue;
-        if (is_blank) {
-          if (same_chain(arena, s_new[q].node, p.node)) dup = q;
-        } else {
-          const int qn = s_new[q].node;
-          if (qn >= 0 && arena[qn].token == tok && same_chain(arena, arena[qn].parent, p.node)) dup = q;
-        }
-      }
-      if (dup >= 0) {
-        s_new[dup].score = log_add_d(s_new[dup].score, c.score);
-        continue;
-      }
-      if (!is_blank) {
-        const int ai = node_count++;
-        ArenaNode nd;
-        nd.parent = p.node; nd.token = tok; nd.frame = t;
-        nd.tok_lp = (float)((double)lp32 - (greedy ? 0.0 : p.score));   // (:1121)
-        nd.stats[0] = nd.stats[1] = nd.stats[2] = nd.stats[3] = 0.f;
-        arena[ai] = nd;
-        c.node = ai;
-        s_nodes[n_nodes].arena_idx = ai;
-        s_nodes[n_nodes].row = hi;
-        ++n_nodes;
-      }
-      s_new[n_new++] = c;
-    }
-    s_n_new = n_new;
-    s_n_nodes = n_nodes;
-    d.node_count[s] = node_count;
-    d.hyp_count[(cur ^ 1) * d.n + s] = n_new;
-  }
-  __syncthreads();
+  finish_step(m, d, g, has_graph, s, t, cur, greedy, k, sh, lg, V, _t0);
+}
 
-  SEL_PROF(3);
-  // (d) per emitted token statistics from its logits row (_compute_token_entropy :1159-1181), one warp per token
-  for (int e = warp; e < s_n_nodes; e += kSelThreads / 32) {
-    const int b = s_nodes[e].row;
-    const float *row = lg + (long long)b * V;
-    const float mx = s_mx[b], sum = s_sum[b];
-    float ent = 0.f, ts = 0.f, t1 = 0.f, t2 = 0.f;
-    for (int v = lane; v < V; v += 32) {
-      const float p = expf(row[v] - mx) / sum;
-      ent += p * __logf(p + 1e-30f);
-      ts += exp2f(__log2f(p) * (1.0f / 3.0f));        // p^(1/3); p = 0 -> log2 = -inf -> 0
-      if (p > t1) { t2 = t1; t1 = p; } else if (p > t2) { t2 = p; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ent += __shfl_xor_sync(0xffffffffu, ent, o);
-      ts += __shfl_xor_sync(0xffffffffu, ts, o);
-      const float o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
-      if (o1 > t1) { t2 = fmaxf(t1, o2); t1 = o1; } else { t2 = fmaxf(t2, o1); }
-    }
-    if (lane == 0) {
-      const double a = 1.0 / 3.0;
-      const double ts_max = m.ts_max;
-      const double tsallis = (1.0 / (a - 1.0)) * (1.0 - (double)ts);
-      const double max_ent = m.max_ent;
-      ArenaNode &nd = arena[s_nodes[e].arena_idx];
-      nd.stats[0] = (float)(ts_max > 0 ? tsallis / ts_max : 0.0);
-      nd.stats[1] = t1 - (V > 1 ? t2 : 1e-10f);
-      nd.stats[2] = (float)((-(double)ent) / max_ent);
-      nd.stats[3] = t1;
-    }
-  }
-  if (tid < s_n_new) d.hyps[((long long)(cur ^ 1) * d.n + s) * kMaxBeam + tid] = s_new[tid];
-  SEL_PROF(4);
-
-  // (e) decoder pre-activation for the new hypotheses: E = relu(grouped conv over the two context embeddings).
-  // decoder_proj and the joiner's tanh(enc + dec) then run as ONE tensor-core GEMM over all live hypotheses of
-  // the batch (run_search), so the 1 MB projection is streamed once per step instead of once per utterance.
-  const int n_new = s_n_new;
-  const int next_row = (int)d.enc_off[s] + min(t + 1, d.lens[s] - 1);
-  for (int i = tid; i < n_new * m.dd; i += kSelThreads) {
-    const int q = i / m.dd, o = i - q * m.dd;
-    const HypSlot &hs = s_new[q];
-    const int g4 = (o >> 2) << 2;
-    const float *w = m.conv_w + (long long)o * 8;
-    const float *e0 = m.emb + (long long)hs.y0 * m.dd + g4;
-    const float *e1 = m.emb + (long long)hs.y1 * m.dd + g4;
-    float a2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      a2 = fmaf(__ldg(w + k * 2 + 0), __ldg(e0 + k), a2);
-      a2 = fmaf(__ldg(w + k * 2 + 1), __ldg(e1 + k), a2);
-    }
-    d.E[((long long)s * d.beam + q) * m.dd + o] = fmaxf(a2, 0.f);
-  }
-  if (tid < d.beam) d.rowmap[s * d.beam + tid] = next_row;
-  SEL_PROF(7);
+__global__ void bias_penalty_kernel(const float *__restrict__ b, int V, int blank_id, float penalty, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < V) out[i] = b[i] - (i == blank_id ? penalty : 0.f);
 }
 
 __global__ void init_search_kernel(SearchModel m, SearchDev d) {
@@ -398,25 +799,15 @@ __global__ void init_search_kernel(SearchModel m, SearchDev d) {
     d.hyp_count[s] = 1;
     d.hyp_count[d.n + s] = 0;
     d.node_count[s] = 0;
+    d.chg_list[s] = make_int2(s * d.beam, (int)d.enc_off[s]);   // frame 0: every utterance's first row needs its decoder output
+    if (s == 0) { d.chg_count[0] = d.n; d.chg_count[1] = 0; }
   }
-  if ((int)threadIdx.x < d.beam) d.rowmap[s * d.beam + threadIdx.x] = (int)d.enc_off[s];   // frame 0 (any valid row if T' = 0)
-  for (int i = threadIdx.x; i < d.beam * m.dd; i += blockDim.x) {
-    const int q = i / m.dd, o = i - q * m.dd;
-    float v = 0.f;
-    if (q == 0) {
-      const int g4 = (o >> 2) << 2;
-      const float *w = m.conv_w + (long long)o * 8;
-      const float *e0 = m.emb + g4;          // token 0 twice
-      float a2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a2 = fmaf(__ldg(w + k * 2 + 0), __ldg(e0 + k), a2);
-        a2 = fmaf(__ldg(w + k * 2 + 1), __ldg(e0 + k), a2);
-      }
-      v = fmaxf(a2, 0.f);
-    }
-    d.E[((long long)s * d.beam + q) * m.dd + o] = v;
+  if ((int)threadIdx.x < d.beam) {
+    d.rowdesc[(size_t)s * d.beam + threadIdx.x] = make_int2(threadIdx.x == 0 ? -1 : -2, (int)d.enc_off[s]);
+    d.rowdesc[(size_t)(d.n + s) * d.beam + threadIdx.x] = make_int2(-2, 0);
   }
+  for (int o = threadIdx.x; o < m.dd; o += blockDim.x)   // context [0, 0]
+    d.E[((long long)s * d.beam) * m.dd + o] = fmaxf(__ldg(m.conv_p0 + o) + __ldg(m.conv_p1 + o), 0.f);
 }
 
 // finalize (:1143-1153): subtract unfinished hotword score, pick first max of log_prob/len(ys), unroll the chain
@@ -472,9 +863,14 @@ struct SearchState {
   int *node_count = nullptr; size_t nc_cap = 0;
   ArenaNode *arena = nullptr; size_t arena_cap = 0;
   float *E = nullptr; size_t e_cap = 0;
-  int *rowmap = nullptr; size_t rm_cap = 0;
+  float *dec = nullptr; size_t dec_cap = 0;
   float *X = nullptr; size_t x_cap = 0;
   float *logits = nullptr; size_t lg_cap = 0;
+  float *partials = nullptr; size_t pt_cap = 0;
+  float *bias_pen = nullptr; size_t bp_cap = 0;
+  int2 *chg_list = nullptr; size_t cl_cap = 0;
+  int2 *rowdesc = nullptr; size_t rd_cap = 0;
+  int *chg_count = nullptr; size_t cc_cap = 0;
   long long *enc_off = nullptr; size_t eo_cap = 0;
   long long *arena_off = nullptr; size_t ao_cap = 0;
   int *lens = nullptr; size_t ln_cap = 0;
@@ -486,14 +882,19 @@ struct SearchState {
   float *o_lp = nullptr; size_t ol_cap = 0;
   float *o_st = nullptr; size_t os_cap = 0;
   void (*gemm)(const GemmArgs &, cudaStream_t) = launch_gemm_fp32;
+  bool fused_partials = false;
 };
 
 SearchState *search_state_create() { return new SearchState(); }
-void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t)) { s->gemm = fn; }
+void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t), bool fused_partials) {
+  s->gemm = fn;
+  s->fused_partials = fused_partials;
+}
 void search_state_destroy(SearchState *s) {
   if (!s) return;
-  cudaFree(s->hyps); cudaFree(s->hyp_count); cudaFree(s->node_count); cudaFree(s->arena); cudaFree(s->E); cudaFree(s->rowmap);
-  cudaFree(s->X); cudaFree(s->logits); cudaFree(s->enc_off); cudaFree(s->arena_off); cudaFree(s->lens);
+  cudaFree(s->hyps); cudaFree(s->hyp_count); cudaFree(s->node_count); cudaFree(s->arena); cudaFree(s->E); cudaFree(s->dec);
+  cudaFree(s->X); cudaFree(s->logits); cudaFree(s->partials); cudaFree(s->bias_pen); cudaFree(s->chg_list); cudaFree(s->rowdesc); cudaFree(s->chg_count);
+  cudaFree(s->enc_off); cudaFree(s->arena_off); cudaFree(s->lens);
   cudaFree(s->orig); cudaFree(s->final_buf); cudaFree(s->o_ntok); cudaFree(s->o_tok); cudaFree(s->o_frm);
   cudaFree(s->o_lp); cudaFree(s->o_st);
   delete s;
@@ -524,15 +925,25 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     max_len = std::max(max_len, lens[s]);
     final_buf[s] = lens[s] & 1;   // after T' steps the live state sits in buffer (T' mod 2)
   }
+  // selection from the joiner's partial records when the GEMM emits them and one CTA pass covers beam x parts
+  const int KB = beam <= 4 ? 4 : (beam <= 8 ? 8 : 16);
+  const int RPT = KB <= 4 ? 1 : (KB <= 8 ? 2 : 4);
+  const int P = (m.V + kPartCols - 1) / kPartCols;
+  const bool fused = S->fused_partials && (long long)beam * P <= (long long)kSelThreads * RPT && (m.jd & 3) == 0 && (m.dd & 3) == 0;
+  const int REC = part_rec_floats(KB);
   const size_t rows = (size_t)n * beam;
   ensure(S->hyps, S->hyps_cap, 2 * (size_t)n * kMaxBeam);
   ensure(S->hyp_count, S->hc_cap, 2 * (size_t)n);
   ensure(S->node_count, S->nc_cap, (size_t)n);
   ensure(S->arena, S->arena_cap, (size_t)std::max<long long>(arena_total, 1));
   ensure(S->E, S->e_cap, rows * m.dd);
-  ensure(S->rowmap, S->rm_cap, rows);
+  ensure(S->dec, S->dec_cap, 2 * rows * m.jd);
   ensure(S->X, S->x_cap, rows * m.jd);
-  ensure(S->logits, S->lg_cap, rows * m.V);
+  if (!fused) ensure(S->logits, S->lg_cap, rows * m.V);
+  if (fused) ensure(S->partials, S->pt_cap, rows * P * REC);
+  ensure(S->chg_list, S->cl_cap, 2 * rows);
+  ensure(S->rowdesc, S->rd_cap, 2 * rows);
+  ensure(S->chg_count, S->cc_cap, (size_t)2);
   ensure(S->enc_off, S->eo_cap, (size_t)n);
   ensure(S->arena_off, S->ao_cap, (size_t)n);
   ensure(S->lens, S->ln_cap, (size_t)n);
@@ -552,8 +963,9 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
 
   SearchDev d;
   d.enc = enc; d.enc_off = S->enc_off; d.lens = S->lens; d.arena_off = S->arena_off; d.hyps = S->hyps;
-  d.hyp_count = S->hyp_count; d.node_count = S->node_count; d.arena = S->arena; d.E = S->E; d.rowmap = S->rowmap; d.X = S->X;
-  d.logits = S->logits; d.n = n; d.beam = beam;
+  d.hyp_count = S->hyp_count; d.node_count = S->node_count; d.arena = S->arena; d.E = S->E; d.dec = S->dec; d.X = S->X;
+  d.logits = S->logits; d.partials = fused ? S->partials : nullptr; d.chg_list = S->chg_list; d.chg_count = S->chg_count; d.rowdesc = S->rowdesc;
+  d.n = n; d.beam = beam;
   d.prof = nullptr;
   static const bool want_prof = getenv("B200ASR_SEARCH_PROF") != nullptr;
   long long *d_prof = nullptr;
@@ -562,6 +974,13 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     CUDA_CHECK(cudaMemsetAsync(d_prof, 0, 8 * sizeof(long long), st));
     d.prof = d_prof;
   }
+  d.trace = nullptr;
+  unsigned long long *d_trace = nullptr;
+  if (want_prof && fused) {
+    CUDA_CHECK(cudaMalloc(&d_trace, (size_t)std::max(max_len, 1) * 16 * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(d_trace, 0, (size_t)std::max(max_len, 1) * 16 * sizeof(unsigned long long), st));
+    d.trace = d_trace;
+  }
   ContextGraphView gv{};
   const int has_graph = (g && g->n_nodes > 1 && !greedy) ? 1 : 0;
   if (has_graph)
@@ -569,7 +988,7 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
                           g->token_score, g->node_score, g->output_score};
 
   if (m.V & 3) throw CudaError("beam search: vocab_size must be a multiple of 4");
-  {
+  if (!fused) {
     static bool attr_set = false;
     if (!attr_set) {
       CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -579,26 +998,63 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     }
     if ((size_t)beam * m.V * sizeof(float) > 200 * 1024) throw CudaError("beam * vocab_size too large for the selection kernel");
   }
+  {
+    static bool dj_attr = false;
+    if (!dj_attr) {
+      CUDA_CHECK(cudaFuncSetAttribute(decoder_joinin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDjSmem));
+      dj_attr = true;
+    }
+  }
+  if (!m.conv_p0 || !m.conv_p1) throw CudaError("beam search: decoder convolution tables are missing");
   init_search_kernel<<<n, 128, 0, st>>>(m, d);
   count_launch(); KERNEL_CHECK();
+  // the joiner epilogue takes the blank penalty folded into its bias
+  const float *join_bias = m.join_b;
+  if (fused && blank_penalty != 0.f) {
+    ensure(S->bias_pen, S->bp_cap, (size_t)m.V);
+    bias_penalty_kernel<<<(m.V + 255) / 256, 256, 0, st>>>(m.join_b, m.V, m.blank_id, blank_penalty, S->bias_pen);
+    count_launch(); KERNEL_CHECK();
+    join_bias = S->bias_pen;
+  }
   int n_active = n;
+  // programmatic dependent launch: each step kernel becomes resident (and runs its prologue) while its predecessor
+  // drains; B200ASR_NO_PDL=1 falls back to plain stream order (debugging)
+  static const bool use_pdl = getenv("B200ASR_NO_PDL") == nullptr;
+  const int ntn = (m.jd + DJ_TN - 1) / DJ_TN;
+  int n_sms = 148;
+  {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   for (int t = 0; t < max_len; ++t) {
     while (n_active > 0 && lens[n_active - 1] <= t) --n_active;
     const int cur = t & 1;
-    // decoder_proj + joiner input in one GEMM: X = tanh(E * Wp^T + bp + enc[rowmap])
-    GemmArgs gd{};
-    gd.A = S->E; gd.lda = m.dd; gd.W = m.dec_proj_w; gd.Wlo = m.dec_proj_w_lo; gd.bias = m.dec_proj_b; gd.R = enc; gd.ldr = m.jd;
-    gd.r_rows = S->rowmap; gd.C = S->X; gd.ldc = m.jd; gd.M = n_active * beam; gd.N = m.jd; gd.K = m.dd; gd.act = ACT_TANH_RES;
-    S->gemm(gd, st);
-    // joiner output_linear: logits = X * Wj^T + bj
+    const int act_rows = n_active * beam;
+    // decoder outputs for the changed contexts + joiner input X = tanh(enc_t + dec) for every live row
+    const int dj_grid = std::min(n_sms, std::max(((act_rows + DJ_TM - 1) / DJ_TM) * ntn, 1));
+    launch_pdl(decoder_joinin_kernel, dim3(dj_grid), dim3(DJ_THREADS), kDjSmem, st, use_pdl, m, d, t, act_rows);
+    count_launch();
+    // joiner output_linear: logits = X * Wj^T + bj (+ partial records)
     GemmArgs ga{};
     ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
-    ga.ldc = m.V; ga.M = n_active * beam; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE;
+    ga.ldc = m.V; ga.M = act_rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE; ga.pdl = use_pdl ? 1 : 0;
+    if (fused) {   // records only: nothing downstream reads the logits
+      ga.act = ACT_JOINER; ga.C = nullptr; ga.partials = S->partials; ga.part_kb = KB; ga.bias = join_bias;
+      ga.trace = d_trace ? d_trace + (size_t)t * 16 + 2 : nullptr;
+    }
     S->gemm(ga, st);
-    const size_t sel_smem = (size_t)beam * m.V * sizeof(float);
-    if (beam <= 4) select_step_kernel<4><<<n_active, kSelThreads, sel_smem, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
-    else if (beam <= 8) select_step_kernel<8><<<n_active, kSelThreads, sel_smem, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
-    else select_step_kernel<16><<<n_active, kSelThreads, sel_smem, st>>>(m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    if (fused) {
+      const size_t smem = (size_t)6 * beam * P * sizeof(float);
+      if (KB == 4) launch_pdl(select_partials_kernel<4>, dim3(n_active), dim3(kSelThreads), smem, st, use_pdl, m, d, gv, has_graph, t, cur, greedy);
+      else if (KB == 8) launch_pdl(select_partials_kernel<8>, dim3(n_active), dim3(kSelThreads), smem, st, use_pdl, m, d, gv, has_graph, t, cur, greedy);
+      else launch_pdl(select_partials_kernel<16>, dim3(n_active), dim3(kSelThreads), smem, st, use_pdl, m, d, gv, has_graph, t, cur, greedy);
+    } else {
+      const size_t sel_smem = (size_t)beam * m.V * sizeof(float);
+      if (KB == 4) launch_pdl(select_step_kernel<4>, dim3(n_active), dim3(kSelThreads), sel_smem, st, use_pdl, m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+      else if (KB == 8) launch_pdl(select_step_kernel<8>, dim3(n_active), dim3(kSelThreads), sel_smem, st, use_pdl, m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+      else launch_pdl(select_step_kernel<16>, dim3(n_active), dim3(kSelThreads), sel_smem, st, use_pdl, m, d, gv, has_graph, t, cur, greedy, blank_penalty);
+    }
     count_launch();
   }
   KERNEL_CHECK();
@@ -618,10 +1074,36 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     long long h[8];
     CUDA_CHECK(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
     cudaFree(d_prof);
-    const char *names[8] = {"stage logits", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "-", "-", "decoder pre-activation"};
+    const char *names[8] = {"load", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "-", "-", "decoder pre-activation"};
     fprintf(stderr, "[b200asr search prof] CTA0 cycles over %d steps:", max_len);
     for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f/step", names[i], (double)h[i] / std::max(max_len, 1));
     fprintf(stderr, "\n");
+  }
+  if (d_trace) {
+    std::vector<unsigned long long> h((size_t)max_len * 16);
+    CUDA_CHECK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
+    // average timeline of a step (CTA 0 of each kernel), microseconds relative to decoder_joinin's entry
+    const char *names[16] = {"dj.in", "dj.out", "gemm.in", "gemm.out", "gemm.prologue", "gemm.first_operands", "gemm.acc_done",
+                             "gemm.epilogue_done", "sel.in", "sel.out", "dj.issued", "dj.rows", "dj.landed", "dj.mma", "dj.tile0", ""};
+    double acc[16] = {0};
+    double step = 0;
+    int cnt = 0;
+    for (int t = 1; t + 1 < max_len; ++t) {
+      const unsigned long long *r = &h[(size_t)t * 16], *nx = &h[(size_t)(t + 1) * 16];
+      bool ok = nx[0] != 0;
+      for (int i = 0; i < 15; ++i) ok = ok && r[i] != 0;
+      if (!ok) continue;
+      for (int i = 0; i < 15; ++i) acc[i] += (double)((long long)(r[i] - r[0]));
+      step += (double)(nx[0] - r[0]);
+      ++cnt;
+    }
+    if (cnt) {
+      fprintf(stderr, "[b200asr search trace] %d steps, mean us from step start:", cnt);
+      const int order[15] = {0, 10, 11, 12, 13, 14, 1, 2, 4, 5, 6, 7, 3, 8, 9};
+      for (int i : order) fprintf(stderr, " %s=%.2f", names[i], acc[i] / cnt / 1e3);
+      fprintf(stderr, " next_step=%.2f\n", step / cnt / 1e3);
+    }
   }
 }
 

@@ -156,7 +156,8 @@ def _oracle_enc(orec, cfg, audios):
     return out
 
 
-@pytest.mark.parametrize("method,beam", [("greedy_search", 1), ("modified_beam_search", 4), ("modified_beam_search", 8)])
+@pytest.mark.parametrize("method,beam", [("greedy_search", 1), ("modified_beam_search", 4), ("modified_beam_search", 8),
+                                         ("modified_beam_search", 16)])
 def test_search_from_oracle_encoder_out(m30, method, beam):
     """Search alone: same encoder_out (the oracle's) on both sides, so token ids must be identical."""
     from sherpa_vietnamese_asr_b200 import synth
@@ -166,6 +167,40 @@ def test_search_from_oracle_encoder_out(m30, method, beam):
     encs = _oracle_enc(orec, ocfg, audios)
     n_tok = _search_case(rec, orec, encs, beam, method)
     assert n_tok > 10
+
+
+def _window_cases(orec, ocfg, n_cases):
+    """Many ragged encoder_out sequences cut from a few oracle encoder runs (each window is a valid input)."""
+    from sherpa_vietnamese_asr_b200 import synth
+    audios = [synth.speech_like(16000 * 7, 700 + i) for i in range(3)]
+    base = _oracle_enc(orec, ocfg, audios)
+    rng = np.random.default_rng(77)
+    out = []
+    for i in range(n_cases):
+        e = base[i % len(base)]
+        a = int(rng.integers(0, e.shape[0] - 12))
+        b = int(rng.integers(a + 1, min(e.shape[0], a + 60) + 1))
+        out.append(np.ascontiguousarray(e[a:b]))
+    return out
+
+
+def test_search_batch_spanning_several_row_tiles(m30):
+    """70 utterances x beam 4 = 280 joiner rows (three 128-row tiles) with ragged lengths: the active prefix shrinks
+    through tile boundaries while the per-row partial records, the recompute list and the row copies stay aligned."""
+    cfg, paths, rec = m30
+    orec, ocfg, _ = oracle_recognizer(paths, beam=4)
+    encs = _window_cases(orec, ocfg, 70)
+    assert _search_case(rec, orec, encs, 4, "modified_beam_search") > 50
+
+
+def test_search_cuda_core_mode_uses_full_logits_selection(model_dirs):
+    """precision='fp32_simt': CUDA-core joiner GEMM + selection from the full logits rows (no partial records)."""
+    cfg, paths, d = model_dirs("zipformer-30m", 30)
+    rec = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4, precision="fp32_simt")
+    orec, ocfg, _ = oracle_recognizer(paths, beam=4)
+    encs = _window_cases(orec, ocfg, 9)
+    assert _search_case(rec, orec, encs, 4, "modified_beam_search") > 5
+    assert _search_case(rec, orec, encs, 1, "greedy_search") > 5
 
 
 def test_search_with_hotwords(m30):
