@@ -42,6 +42,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // smem ring depth: 3xTF32 keeps hi and lo copies of both operands, so 3 stages at BN = 128 and 4 at BN = 64
 __host__ __device__ constexpr int stages_for(int BN, bool split3) { return split3 ? (BN == 64 ? 4 : kStages3) : kStages1; }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct TcParams {
   const float *bias;
   const float *R; int ldr;
@@ -238,10 +244,10 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const float x = __uint_as_float(r[j]);
             const float dx = x - mx;                        // -inf past N: e = 0, and the product below is skipped
             const float tl = dx * 1.4426950408889634f;
-            const float e = exp2f(tl);
+            const float e = ex2_approx(tl);
             sum[j & 1] += e;
-            if (dx > -INFINITY) su[j & 1] = fmaf(e, dx, su[j & 1]);
-            st[j & 1] += exp2f(tl * (1.0f / 3.0f));
+            su[j & 1] = fmaf(e, fmaxf(dx, -3.0e38f), su[j & 1]);   // dx = -inf past N: 0 * finite
+            st[j & 1] += ex2_approx(tl * (1.0f / 3.0f));
             if (x > tv[EPI - 1]) {                          // strict: equal values keep the lower column first
               float cv = x;
               int ci = nbase + j;

@@ -190,15 +190,16 @@ struct NewNode { int arena_idx; int row; };
   } while (0)
 
 // ------------------------------------------------------------------ decoder update + joiner input
-// One wave of CTAs (at most one per SM) walks the 32 x 32 output tiles of dec = E[list] * Wp^T + bp over the compacted
-// list of rows whose context changed (the count lives on the device): both operand panels of a tile (32 rows x K
+// One wave of CTAs (at most two per SM) walks the 16 x 32 output tiles of dec = E[list] * Wp^T + bp over the compacted
+// list of rows whose context changed (the count lives on the device): both operand panels of a tile (16 rows x K
 // of E, 32 rows x K of Wp, K <= 512 per pass) are pulled into shared memory with one burst of cp.async so the
 // kernel pays a single L2 round trip. The rows are gathered and few (tens to hundreds), which is not a tcgen05
 // shape (128-row tiles fed by TMA); the product runs on warp-level mma.sync m16n8k8 TF32 with the same
 // error-compensated 3xTF32 split as the big GEMMs (hi = 13 low mantissa bits cleared, lo = x - hi, small terms
-// first), each of the 8 warps 16 x 8 outputs. The epilogue writes dec and X = tanh(enc_t + dec). While its first panels are in
+// first); a tile is 16 rows x 32 columns, one 16 x 8 mma tile per warp (the legacy tensor path is the bound here,
+// so many small tiles spread over all SMs beat fewer large ones). The epilogue writes dec and X = tanh(enc_t + dec). While its first panels are in
 // flight every CTA also handles its share of the blank extensions: dec = previous dec of the parent slot.
-constexpr int DJ_TM = 32, DJ_TN = 32, DJ_THREADS = 256, DJ_KC = 512, DJ_LD = DJ_KC + 4;
+constexpr int DJ_TM = 16, DJ_TN = 32, DJ_THREADS = 128, DJ_KC = 512, DJ_LD = DJ_KC + 4;
 constexpr size_t kDjSmem = (size_t)(DJ_TM + DJ_TN) * DJ_LD * sizeof(float);
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(DJ_THREADS) decoder_joinin_kernel(SearchModel 
   const int n_chg = d.chg_count[par];
   const int n_tiles = ((n_chg + DJ_TM - 1) / DJ_TM) * ntn;
   const int g = lane_ >> 2, tq = lane_ & 3;             // mma fragment coordinates
-  const int rb = (warp_ & 1) * 16, cb = (warp_ >> 1) * 8;
+  const int rb = 0, cb = warp_ * 8;
   bool rows_done = false;
   // blank extensions: flattened over (row, float4) units, four units in flight per thread. CTAs without a tile take
   // them all when there are enough of them; otherwise everybody shares them while the first operand panels land.
@@ -1032,7 +1033,7 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     const int cur = t & 1;
     const int act_rows = n_active * beam;
     // decoder outputs for the changed contexts + joiner input X = tanh(enc_t + dec) for every live row
-    const int dj_grid = std::min(n_sms, std::max(((act_rows + DJ_TM - 1) / DJ_TM) * ntn, 1));
+    const int dj_grid = std::min(2 * n_sms, std::max(((act_rows + DJ_TM - 1) / DJ_TM) * ntn, 1));
     launch_pdl(decoder_joinin_kernel, dim3(dj_grid), dim3(DJ_THREADS), kDjSmem, st, use_pdl, m, d, t, act_rows);
     count_launch();
     // joiner output_linear: logits = X * Wj^T + bj (+ partial records)
