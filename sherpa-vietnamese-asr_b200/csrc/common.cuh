@@ -124,6 +124,11 @@ void launch_pos_emb(float *pe, int max_len, int pos_dim, cudaStream_t st);  // [
 // attention weights: proj [M, H*(2*qd+pd)], pos [2*max_len-1, H*pd] -> A packed per utterance: H*len*len at aoff[n]
 void launch_attn_weights(const float *proj, int ldp, const float *pos, const RaggedDesc &r, const long long *aoff, int H, int qd,
                          int pd, float *A, cudaStream_t st);
+// the same on the tensor pipe (attn_weights_tc.cu; query_head_dim 32, pos_head_dim 4): tile_off = cumulative
+// H * ceil(len / 128) per utterance, A row pitch (len + 3) & ~3
+bool attn_weights_tc_supported(int qd, int pd);
+void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float *pos, const RaggedDesc &r, const long long *aoff,
+                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st);
 // out[i, c] = (sum_j A[h(c)][i][j] * V[j,c]) (* Y[i,c]);  V = X (* tanh(S) if S). head = c / dv_per_head (0 if single_head)
 void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &r, const float *X, int ldx, const float *S, int lds,
                        const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st);

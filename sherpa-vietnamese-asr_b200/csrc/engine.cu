@@ -738,7 +738,10 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   // attention weights (computed once per layer from the layer input)
   gemm(src, D, w.attn_in_w, w.attn_in_b, nullptr, 0, proj, pw, M, pw, D, ACT_NONE);
   gemm(b_pe.ptr<float>(), pos_dim, w.pos_w, nullptr, nullptr, 0, pp, H * pd, 2 * Lmax - 1, H * pd, pos_dim, ACT_NONE);
-  launch_attn_weights(proj, pw, pp, r, aoff, H, qd, pd, A, st);
+  if (pl.use && attn_weights_tc_supported(qd, pd) && !getenv("B200ASR_ATTN_SIMT"))
+    launch_attn_weights_tc(proj, pw, M, pp, r, aoff, pl.tile_off12, pl.n_tiles12, H, A, precision == 0, st);
+  else
+    launch_attn_weights(proj, pw, pp, r, aoff, H, qd, pd, A, st);
   // feed_forward1
   gemm(src, D, w.ff_in_w[0], w.ff_in_b[0], nullptr, 0, proj, w.ff_dim[0], M, w.ff_dim[0], D, ACT_SWOOSH_L);
   gemm(proj, w.ff_dim[0], w.ff_out_w[0], w.ff_out_b[0], src, D, w1, D, M, D, w.ff_dim[0], ACT_NONE);

@@ -434,7 +434,23 @@ void make_map_uncached_impl(CUtensorMap *map, const float *ptr, int rows, int K,
 }  // namespace
 
 namespace tc {
-void make_map(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows) { make_map_impl(map, ptr, rows, K, ld, box_rows); }
+void make_map(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows) {
+  init_once();
+  if (!g_ok) throw CudaError("cuTensorMapEncodeTiled entry point unavailable");
+  make_map_impl(map, ptr, rows, K, ld, box_rows);
+}
+void make_map_plain(CUtensorMap *map, const float *ptr, int rows, int cols, int ld, int box_cols, int box_rows) {
+  init_once();
+  if (!g_ok) throw CudaError("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (plain) failed (" + std::to_string((int)r) + ")");
+}
 void make_map_uncached(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows) {
   init_once();
   if (!g_ok) throw CudaError("cuTensorMapEncodeTiled entry point unavailable");

@@ -91,6 +91,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
 void make_map(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows);            // cached
 void make_map_uncached(CUtensorMap *map, const float *ptr, int rows, int K, int ld, int box_rows);
+// same tensor without swizzle and with a free box (box_cols * 4 bytes must be a multiple of 16)
+void make_map_plain(CUtensorMap *map, const float *ptr, int rows, int cols, int ld, int box_cols, int box_rows);
 bool tc_init();   // resolves cuTensorMapEncodeTiled; false if unavailable
 
 }  // namespace tc
