@@ -113,13 +113,14 @@ void launch_biasnorm_bypass(const float *x, const float *orig, int M, int D, con
                             const float *bypass, float *out, cudaStream_t st);
 void launch_bypass(const float *x, const float *orig, long long M, int D, const float *scale, float *out, cudaStream_t st);
 void launch_convert_channels(const float *in, int Cin, float *out, int Cout, long long M, cudaStream_t st);
-void launch_downsample(const float *in, const RaggedDesc &rin, const RaggedDesc &rout, int C, int ds, const float *bias,
-                       float *out, cudaStream_t st);
-void launch_upsample_combine(const float *y, const RaggedDesc &rlow, const float *orig, const RaggedDesc &rfull, int C, int ds,
-                             const float *scale, float *out, cudaStream_t st);
+// row maps between the full frame rate (r1) and a stack's rate (rq): up[rows at r1], down[rows at rq] (encoder.cu)
+void launch_build_row_maps(const RaggedDesc &r1, const RaggedDesc &rq, int ds, int *up, int2 *down, cudaStream_t st);
+void launch_downsample(const float *in, const int2 *down, int rows_out, int C, int ds, const float *bias, float *out, cudaStream_t st);
+void launch_upsample_combine(const float *y, const int *up, const float *orig, int rows_full, int C, const float *scale, float *out,
+                             cudaStream_t st);
 struct ConcatPiece { const float *src; int ld; int c0; int c1; };
-void launch_concat_downsample2(const ConcatPiece *pieces, int n_pieces, const RaggedDesc &rin, const RaggedDesc &rout, int C,
-                               const float *bias, float *out, cudaStream_t st);
+void launch_concat_downsample2(const ConcatPiece *pieces, int n_pieces, const int2 *down, int rows_out, int C, const float *bias,
+                               float *out, cudaStream_t st);
 void launch_pos_emb(float *pe, int max_len, int pos_dim, cudaStream_t st);  // [2*max_len-1, pos_dim]
 // attention weights: proj [M, H*(2*qd+pd)], pos [2*max_len-1, H*pd] -> A packed per utterance: H*len*len at aoff[n]
 void launch_attn_weights(const float *proj, int ldp, const float *pos, const RaggedDesc &r, const long long *aoff, int H, int qd,
@@ -148,8 +149,10 @@ void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C,
 void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st);
 void attn_tc_encode_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int rows_mult,
                          int rows_fixed, int box_rows);
-// conv module middle: h [M, 2D] -> out [M, D] = SwooshR(dwconv_k(x * sigmoid(s)) + b)
-void launch_glu_dwconv(const float *h, const RaggedDesc &r, int D, int k, const float *w, const float *b, float *out, cudaStream_t st);
+// conv module middle: h [M, 2D] -> out [M, D] = SwooshR(dwconv_k(x * sigmoid(s)) + b); tile_off = cumulative
+// ceil(len / 128) per utterance
+void launch_glu_dwconv(const float *h, const RaggedDesc &r, const int *tile_off, int n_tiles, int D, int k, const float *w,
+                       const float *b, float *out, cudaStream_t st);
 
 // ---------------------------------------------------------------- search kernels (search.cu)
 struct ContextGraphDev {   // flattened Aho-Corasick automaton (BFS order; node 0 = root)

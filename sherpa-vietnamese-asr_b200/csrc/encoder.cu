@@ -228,57 +228,68 @@ __global__ void biasnorm_kernel(const float *__restrict__ x, const float *__rest
   }
 }
 
-__global__ void bypass_kernel(const float *__restrict__ x, const float *__restrict__ orig, long long total, int D,
-                              const float *__restrict__ scale, float *__restrict__ out) {
+// The elementwise kernels below run flat over the packed rows (no per-utterance grid dimension: a ragged batch would
+// launch mostly empty CTAs) with 128-bit accesses; every channel count on the path is a multiple of 4.
+__global__ void bypass_kernel(const float4 *__restrict__ x, const float4 *__restrict__ orig, long long total4, int D4,
+                              const float4 *__restrict__ scale, float4 *__restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const float o0 = orig[i];
-  out[i] = o0 + (x[i] - o0) * __ldg(scale + (int)(i % D));
+  if (i >= total4) return;
+  const float4 o0 = orig[i], v = x[i], sc = __ldg(scale + (int)(i % D4));
+  out[i] = make_float4(o0.x + (v.x - o0.x) * sc.x, o0.y + (v.y - o0.y) * sc.y, o0.z + (v.z - o0.z) * sc.z, o0.w + (v.w - o0.w) * sc.w);
 }
 
-__global__ void convert_channels_kernel(const float *__restrict__ in, int Cin, float *__restrict__ out, int Cout, long long M) {
+__global__ void convert_channels_kernel(const float4 *__restrict__ in, int Cin4, float4 *__restrict__ out, int Cout4, long long M) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= M * Cout) return;
-  const long long m = i / Cout;
-  const int c = (int)(i % Cout);
-  out[i] = c < Cin ? in[m * Cin + c] : 0.f;
+  if (i >= M * Cout4) return;
+  const long long m = i / Cout4;
+  const int c = (int)(i - m * Cout4);
+  out[i] = c < Cin4 ? in[m * Cin4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------ SimpleDownsample / SimpleUpsample (App. B.3)
-__global__ void downsample_kernel(const float *__restrict__ in, const int *__restrict__ len_in, const int *__restrict__ off_in,
-                                  const int *__restrict__ len_out, const int *__restrict__ off_out, int C, int ds,
-                                  const float *__restrict__ bias, float *__restrict__ out) {
-  const int u = blockIdx.y;
-  const int Lo = len_out[u], Li = len_in[u];
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)Lo * C) return;
-  const int t = (int)(idx / C), c = (int)(idx % C);
-  // softmax over the ds bias entries
-  float mx = -INFINITY;
-  for (int k = 0; k < ds; ++k) mx = fmaxf(mx, __ldg(bias + k));
-  float den = 0.f;
-  for (int k = 0; k < ds; ++k) den += expf(__ldg(bias + k) - mx);
-  const float *x = in + (long long)off_in[u] * C;
-  float acc = 0.f;
-  for (int k = 0; k < ds; ++k) {
-    const int ti = min(t * ds + k, Li - 1);   // right-pad by repeating the utterance's own last frame
-    acc += x[(long long)ti * C + c] * (expf(__ldg(bias + k) - mx) / den);
-  }
-  out[((long long)off_out[u] + t) * C + c] = acc;
+// Row maps between the full frame rate and a stack's rate, built once per batch: up[R] = low-rate row of full-rate
+// row R; down[Rq] = {first full-rate row feeding low-rate row Rq, last row of that utterance} (the right padding
+// repeats the utterance's own last frame).
+__global__ void build_row_maps_kernel(const int *__restrict__ len1, const int *__restrict__ off1, const int *__restrict__ lenq,
+                                      const int *__restrict__ offq, int ds, int *__restrict__ up, int2 *__restrict__ down) {
+  const int u = blockIdx.x;
+  const int L1 = len1[u], o1 = off1[u], Lq = lenq[u], oq = offq[u];
+  for (int t = threadIdx.x; t < L1; t += blockDim.x) up[o1 + t] = oq + t / ds;
+  for (int t = threadIdx.x; t < Lq; t += blockDim.x) down[oq + t] = make_int2(o1 + t * ds, o1 + L1 - 1);
 }
 
-__global__ void upsample_combine_kernel(const float *__restrict__ y, const int *__restrict__ off_low, const float *__restrict__ orig,
-                                        const int *__restrict__ len_full, const int *__restrict__ off_full, int C, int ds,
-                                        const float *__restrict__ scale, float *__restrict__ out) {
-  const int u = blockIdx.y;
-  const int L = len_full[u];
+template <int DS>
+__global__ void downsample_kernel(const float4 *__restrict__ in, const int2 *__restrict__ down, long long total4, int C4,
+                                  const float *__restrict__ bias, float4 *__restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)L * C) return;
-  const int t = (int)(idx / C), c = (int)(idx % C);
-  const long long o = ((long long)off_full[u] + t) * C + c;
-  const float o0 = orig[o];
-  const float v = y[((long long)off_low[u] + t / ds) * C + c];
-  out[o] = o0 + (v - o0) * __ldg(scale + c);
+  if (idx >= total4) return;
+  const int r = (int)(idx / C4), c = (int)(idx - (long long)r * C4);
+  // softmax over the ds bias entries
+  float wk[DS], mx = -INFINITY, den = 0.f;
+#pragma unroll
+  for (int k = 0; k < DS; ++k) mx = fmaxf(mx, __ldg(bias + k));
+#pragma unroll
+  for (int k = 0; k < DS; ++k) { wk[k] = expf(__ldg(bias + k) - mx); den += wk[k]; }
+  const int2 fl = __ldg(down + r);
+  float4 v[DS];
+#pragma unroll
+  for (int k = 0; k < DS; ++k) v[k] = in[(long long)min(fl.x + k, fl.y) * C4 + c];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < DS; ++k) {
+    const float w = wk[k] / den;
+    acc.x += v[k].x * w; acc.y += v[k].y * w; acc.z += v[k].z * w; acc.w += v[k].w * w;
+  }
+  out[idx] = acc;
+}
+
+__global__ void upsample_combine_kernel(const float4 *__restrict__ y, const int *__restrict__ up, const float4 *__restrict__ orig,
+                                        long long total4, int C4, const float4 *__restrict__ scale, float4 *__restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total4) return;
+  const int r = (int)(idx / C4), c = (int)(idx - (long long)r * C4);
+  const float4 o0 = orig[idx], v = y[(long long)__ldg(up + r) * C4 + c], sc = __ldg(scale + c);
+  out[idx] = make_float4(o0.x + (v.x - o0.x) * sc.x, o0.y + (v.y - o0.y) * sc.y, o0.z + (v.z - o0.z) * sc.z, o0.w + (v.w - o0.w) * sc.w);
 }
 
 struct ConcatArgs {
@@ -286,14 +297,11 @@ struct ConcatArgs {
   int ld[4], c0[4], c1[4];
   int n;
 };
-__global__ void concat_downsample2_kernel(ConcatArgs a, const int *__restrict__ len_in, const int *__restrict__ off_in,
-                                          const int *__restrict__ len_out, const int *__restrict__ off_out, int C,
-                                          const float *__restrict__ bias, float *__restrict__ out) {
-  const int u = blockIdx.y;
-  const int Lo = len_out[u], Li = len_in[u];
+__global__ void concat_downsample2_kernel(ConcatArgs a, const int2 *__restrict__ down, long long total4, int C4,
+                                          const float *__restrict__ bias, float4 *__restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)Lo * C) return;
-  const int t = (int)(idx / C), c = (int)(idx % C);
+  if (idx >= total4) return;
+  const int r = (int)(idx / C4), c = (int)(idx - (long long)r * C4) * 4;
   const float b0 = __ldg(bias), b1 = __ldg(bias + 1);
   const float mx = fmaxf(b0, b1);
   const float e0 = expf(b0 - mx), e1 = expf(b1 - mx);
@@ -301,13 +309,15 @@ __global__ void concat_downsample2_kernel(ConcatArgs a, const int *__restrict__ 
   const float *src = nullptr;
   int ld = 0;
   for (int p = 0; p < a.n; ++p)
-    if (c >= a.c0[p] && c < a.c1[p]) { src = a.src[p]; ld = a.ld[p]; }
-  const long long r0 = (long long)off_in[u] + min(2 * t, Li - 1);
-  const long long r1 = (long long)off_in[u] + min(2 * t + 1, Li - 1);
-  float acc = 0.f;
-  acc += src[r0 * ld + c] * (e0 / den);
-  acc += src[r1 * ld + c] * (e1 / den);
-  out[((long long)off_out[u] + t) * C + c] = acc;
+    if (c >= a.c0[p] && c < a.c1[p]) { src = a.src[p]; ld = a.ld[p]; }   // piece boundaries are multiples of 4
+  const int2 fl = __ldg(down + r);
+  const float4 v0 = *reinterpret_cast<const float4 *>(src + (long long)fl.x * ld + c);
+  const float4 v1 = *reinterpret_cast<const float4 *>(src + (long long)min(fl.x + 1, fl.y) * ld + c);
+  const float w0 = e0 / den, w1 = e1 / den;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  acc.x += v0.x * w0; acc.y += v0.y * w0; acc.z += v0.z * w0; acc.w += v0.w * w0;
+  acc.x += v1.x * w1; acc.y += v1.y * w1; acc.z += v1.z * w1; acc.w += v1.w * w1;
+  out[idx] = acc;
 }
 
 // ------------------------------------------------------------------ CompactRelPositionalEncoding
@@ -505,48 +515,63 @@ __global__ void __launch_bounds__(32 * CG) attn_apply_kernel(const float *__rest
 }
 
 // ------------------------------------------------------------------ conv module: GLU -> depthwise conv -> SwooshR
-// CTA = 32 frames x 64 channels of one utterance; GLU values (with k-1 halo, zero outside the utterance) in smem.
-constexpr int kDwT = 32, kDwC = 64, kDwMaxK = 31;
+// CTA = one 128-frame tile of one utterance (tile list over the ragged batch, no empty CTAs) x 64 channels. The GLU
+// values x * sigmoid(gate) of the tile plus its (k-1)-frame halo (zero outside the utterance) are staged once in
+// shared memory with 128-bit loads; each thread then owns one channel and 32 consecutive frames and slides a register
+// window over them, so a staged value is read from shared memory once per 8 outputs instead of once per tap.
+constexpr int kDwT = 128, kDwC = 64, kDwMaxK = 31;
 __global__ void __launch_bounds__(256) glu_dwconv_kernel(const float *__restrict__ h, const int *__restrict__ len,
-                                                         const int *__restrict__ off, int D, int k, const float *__restrict__ w,
-                                                         const float *__restrict__ b, float *__restrict__ out) {
-  __shared__ float g[(kDwT + kDwMaxK - 1)][kDwC];
-  const int u = blockIdx.z;
+                                                         const int *__restrict__ off, const int *__restrict__ tile_off, int n_utt,
+                                                         int D, int k, const float *__restrict__ w, const float *__restrict__ b,
+                                                         float *__restrict__ out) {
+  __shared__ __align__(16) float g[(kDwT + kDwMaxK - 1)][kDwC];
+  int lo = 0, hi = n_utt - 1;
+  const int tile = blockIdx.x;
+  while (lo < hi) {   // last u with tile_off[u] <= tile
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(tile_off + mid) <= tile) lo = mid; else hi = mid - 1;
+  }
+  const int u = lo;
   const int L = len[u];
-  const int t0 = blockIdx.x * kDwT;
-  if (t0 >= L) return;
+  const int t0 = (tile - __ldg(tile_off + u)) * kDwT;
   const int c0 = blockIdx.y * kDwC;
   const int pad = k / 2;
   const long long rbase = off[u];
-  const int rows = kDwT + k - 1;
-  for (int i = threadIdx.x; i < rows * kDwC; i += blockDim.x) {
-    const int r = i / kDwC, c = i % kDwC;
-    const int t = t0 - pad + r, gc = c0 + c;
-    float v = 0.f;
-    if (t >= 0 && t < L && gc < D) {
+  const int rows = min(kDwT, L - t0) + k - 1;
+  for (int i = threadIdx.x; i < rows * (kDwC / 4); i += blockDim.x) {
+    const int r = i / (kDwC / 4), c4 = (i % (kDwC / 4)) * 4;
+    const int t = t0 - pad + r, gc = c0 + c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < L && gc < D) {     // D % 4 == 0
       const float *row = h + (rbase + t) * (2LL * D);
-      v = row[gc] * sigmoid_f(row[D + gc]);
+      const float4 x = *reinterpret_cast<const float4 *>(row + gc), s4 = *reinterpret_cast<const float4 *>(row + D + gc);
+      v = make_float4(x.x * sigmoid_f(s4.x), x.y * sigmoid_f(s4.y), x.z * sigmoid_f(s4.z), x.w * sigmoid_f(s4.w));
     }
-    g[r][c] = v;
+    *reinterpret_cast<float4 *>(&g[r][c4]) = v;
   }
   __syncthreads();
-  const int c = threadIdx.x % kDwC, tq = threadIdx.x / kDwC;  // 4 groups x 8 frames
+  const int c = threadIdx.x % kDwC, tq = threadIdx.x / kDwC;  // 4 groups x 32 frames
   const int gc = c0 + c;
   if (gc >= D) return;
   float wr[kDwMaxK];
 #pragma unroll
   for (int j = 0; j < kDwMaxK; ++j) wr[j] = j < k ? __ldg(w + j * D + gc) : 0.f;
   const float bias = __ldg(b + gc);
+  const int tend = min(kDwT, L - t0);
+#pragma unroll 1
+  for (int f0 = tq * 32; f0 < tq * 32 + 32 && f0 < tend; f0 += 8) {
+    // register window: outputs f0..f0+7 read staged rows f0..f0+7+k-1 (rows past the staged range belong to frames
+    // that are not written)
+    float win[8 + kDwMaxK - 1];
 #pragma unroll
-  for (int f = 0; f < 8; ++f) {
-    const int tl = tq * 8 + f;
-    const int t = t0 + tl;
-    if (t >= L) break;
-    float acc = bias;
+    for (int j = 0; j < 8 + kDwMaxK - 1; ++j) win[j] = (j < 8 + k - 1 && f0 + j < rows) ? g[f0 + j][c] : 0.f;
 #pragma unroll
-    for (int j = 0; j < kDwMaxK; ++j)
-      if (j < k) acc = fmaf(wr[j], g[tl + j][c], acc);
-    out[(rbase + t) * D + gc] = swoosh_r(acc);
+    for (int f = 0; f < 8; ++f) {
+      float acc = bias;
+#pragma unroll
+      for (int j = 0; j < kDwMaxK; ++j) acc = fmaf(wr[j], win[f + j], acc);   // wr[j] = 0 for j >= k
+      if (f0 + f < tend) out[(rbase + t0 + f0 + f) * D + gc] = swoosh_r(acc);
+    }
   }
 }
 
@@ -602,38 +627,58 @@ void launch_biasnorm_bypass(const float *x, const float *orig, int M, int D, con
 }
 void launch_bypass(const float *x, const float *orig, long long M, int D, const float *scale, float *out, cudaStream_t st) {
   if (M <= 0) return;
-  bypass_kernel<<<cdiv(M * D, 256), 256, 0, st>>>(x, orig, M * D, D, scale, out);
+  if (D & 3) throw CudaError("bypass: channel count must be a multiple of 4");
+  const long long total4 = M * (D / 4);
+  bypass_kernel<<<cdiv(total4, 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(orig), total4,
+                                                   D / 4, reinterpret_cast<const float4 *>(scale), reinterpret_cast<float4 *>(out));
   count_launch(); KERNEL_CHECK();
 }
 void launch_convert_channels(const float *in, int Cin, float *out, int Cout, long long M, cudaStream_t st) {
   if (M <= 0) return;
-  convert_channels_kernel<<<cdiv(M * Cout, 256), 256, 0, st>>>(in, Cin, out, Cout, M);
+  if ((Cin | Cout) & 3) throw CudaError("convert_channels: channel counts must be multiples of 4");
+  convert_channels_kernel<<<cdiv(M * (Cout / 4), 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(in), Cin / 4,
+                                                                    reinterpret_cast<float4 *>(out), Cout / 4, M);
   count_launch(); KERNEL_CHECK();
 }
-void launch_downsample(const float *in, const RaggedDesc &rin, const RaggedDesc &rout, int C, int ds, const float *bias,
-                       float *out, cudaStream_t st) {
-  if (rout.total <= 0) return;
-  dim3 grid(cdiv((long long)rout.max_len * C, 256), rout.n);
-  downsample_kernel<<<grid, 256, 0, st>>>(in, rin.len, rin.off, rout.len, rout.off, C, ds, bias, out);
+void launch_build_row_maps(const RaggedDesc &r1, const RaggedDesc &rq, int ds, int *up, int2 *down, cudaStream_t st) {
+  if (r1.n <= 0) return;
+  build_row_maps_kernel<<<r1.n, 256, 0, st>>>(r1.len, r1.off, rq.len, rq.off, ds, up, down);
   count_launch(); KERNEL_CHECK();
 }
-void launch_upsample_combine(const float *y, const RaggedDesc &rlow, const float *orig, const RaggedDesc &rfull, int C, int ds,
-                             const float *scale, float *out, cudaStream_t st) {
-  if (rfull.total <= 0) return;
-  dim3 grid(cdiv((long long)rfull.max_len * C, 256), rfull.n);
-  upsample_combine_kernel<<<grid, 256, 0, st>>>(y, rlow.off, orig, rfull.len, rfull.off, C, ds, scale, out);
+void launch_downsample(const float *in, const int2 *down, int rows_out, int C, int ds, const float *bias, float *out, cudaStream_t st) {
+  if (rows_out <= 0) return;
+  if (C & 3) throw CudaError("downsample: channel count must be a multiple of 4");
+  const long long total4 = (long long)rows_out * (C / 4);
+  const float4 *i4 = reinterpret_cast<const float4 *>(in);
+  float4 *o4 = reinterpret_cast<float4 *>(out);
+  if (ds == 2) downsample_kernel<2><<<cdiv(total4, 256), 256, 0, st>>>(i4, down, total4, C / 4, bias, o4);
+  else if (ds == 4) downsample_kernel<4><<<cdiv(total4, 256), 256, 0, st>>>(i4, down, total4, C / 4, bias, o4);
+  else if (ds == 8) downsample_kernel<8><<<cdiv(total4, 256), 256, 0, st>>>(i4, down, total4, C / 4, bias, o4);
+  else throw CudaError("downsample: factor must be 2, 4 or 8");
   count_launch(); KERNEL_CHECK();
 }
-void launch_concat_downsample2(const ConcatPiece *pieces, int n_pieces, const RaggedDesc &rin, const RaggedDesc &rout, int C,
-                               const float *bias, float *out, cudaStream_t st) {
-  if (rout.total <= 0) return;
+void launch_upsample_combine(const float *y, const int *up, const float *orig, int rows_full, int C, const float *scale, float *out,
+                             cudaStream_t st) {
+  if (rows_full <= 0) return;
+  if (C & 3) throw CudaError("upsample: channel count must be a multiple of 4");
+  const long long total4 = (long long)rows_full * (C / 4);
+  upsample_combine_kernel<<<cdiv(total4, 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(y), up, reinterpret_cast<const float4 *>(orig),
+                                                             total4, C / 4, reinterpret_cast<const float4 *>(scale),
+                                                             reinterpret_cast<float4 *>(out));
+  count_launch(); KERNEL_CHECK();
+}
+void launch_concat_downsample2(const ConcatPiece *pieces, int n_pieces, const int2 *down, int rows_out, int C, const float *bias,
+                               float *out, cudaStream_t st) {
+  if (rows_out <= 0) return;
   ConcatArgs a{};
   a.n = n_pieces;
   for (int i = 0; i < n_pieces && i < 4; ++i) {
     a.src[i] = pieces[i].src; a.ld[i] = pieces[i].ld; a.c0[i] = pieces[i].c0; a.c1[i] = pieces[i].c1;
+    if ((pieces[i].ld | pieces[i].c0 | pieces[i].c1) & 3) throw CudaError("concat: piece boundaries must be multiples of 4");
   }
-  dim3 grid(cdiv((long long)rout.max_len * C, 256), rout.n);
-  concat_downsample2_kernel<<<grid, 256, 0, st>>>(a, rin.len, rin.off, rout.len, rout.off, C, bias, out);
+  if (C & 3) throw CudaError("concat: channel count must be a multiple of 4");
+  const long long total4 = (long long)rows_out * (C / 4);
+  concat_downsample2_kernel<<<cdiv(total4, 256), 256, 0, st>>>(a, down, total4, C / 4, bias, reinterpret_cast<float4 *>(out));
   count_launch(); KERNEL_CHECK();
 }
 void launch_pos_emb(float *pe, int max_len, int pos_dim, cudaStream_t st) {
@@ -681,11 +726,13 @@ void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &
   count_launch(); KERNEL_CHECK();
 }
 
-void launch_glu_dwconv(const float *h, const RaggedDesc &r, int D, int k, const float *w, const float *b, float *out, cudaStream_t st) {
-  if (r.total <= 0) return;
+void launch_glu_dwconv(const float *h, const RaggedDesc &r, const int *tile_off, int n_tiles, int D, int k, const float *w,
+                       const float *b, float *out, cudaStream_t st) {
+  if (r.total <= 0 || n_tiles <= 0) return;
   if (k > kDwMaxK) throw CudaError("glu_dwconv: kernel size > 31 not built");
-  dim3 grid(cdiv(r.max_len, kDwT), cdiv(D, kDwC), r.n);
-  glu_dwconv_kernel<<<grid, 256, 0, st>>>(h, r.len, r.off, D, k, w, b, out);
+  if (D & 3) throw CudaError("glu_dwconv: channel count must be a multiple of 4");
+  dim3 grid(n_tiles, cdiv(D, kDwC));
+  glu_dwconv_kernel<<<grid, 256, 0, st>>>(h, r.len, r.off, tile_off, r.n, D, k, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
 

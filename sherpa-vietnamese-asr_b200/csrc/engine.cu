@@ -9,12 +9,16 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <fstream>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200asr.h"
@@ -134,6 +138,73 @@ class PinnedPool {
   size_t slab_left_ = 0, pinned_total_ = 0;
 };
 
+// accept_waveform is a host memcpy of the caller's samples into pinned memory; one core moves ~8 GB/s, so a 256-stream
+// batch (180 MB) spends >20 ms there. Large copies are split over a few helper threads that keep spinning for a short
+// while after a job (an accept loop issues the next one within microseconds) and otherwise sleep on a condition variable.
+class ParallelCopy {
+ public:
+  static ParallelCopy &get() { static ParallelCopy p; return p; }
+  void copy(void *dst, const void *src, size_t bytes) {
+    if (n_workers_ == 0 || bytes < kMinBytes) { memcpy(dst, src, bytes); return; }
+    std::lock_guard<std::mutex> serial(call_mu_);       // one job at a time
+    const int parts = n_workers_ + 1;
+    const size_t chunk = ((bytes / parts) + 4095) & ~size_t(4095);
+    dst_ = static_cast<char *>(dst); src_ = static_cast<const char *>(src); bytes_ = bytes; chunk_ = chunk;
+    pending_.store(n_workers_, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      epoch_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    run_part(0);
+    while (pending_.load(std::memory_order_acquire) != 0) { /* spin: the parts are equal */ }
+  }
+  ~ParallelCopy() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; epoch_.fetch_add(1, std::memory_order_release); }
+    cv_.notify_all();
+    for (auto &t : threads_) t.join();
+  }
+ private:
+  static constexpr size_t kMinBytes = 256 * 1024;
+  ParallelCopy() {
+    int n = 3;
+    if (const char *e = getenv("B200ASR_COPY_THREADS")) n = atoi(e) - 1;
+    const int hw = (int)std::thread::hardware_concurrency();
+    n_workers_ = std::max(0, std::min(n, hw > 1 ? hw - 1 : 0));
+    for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this, i] { worker(i + 1); });
+  }
+  void run_part(int part) {
+    const size_t b = (size_t)part * chunk_;
+    if (b < bytes_) memcpy(dst_ + b, src_ + b, std::min(chunk_, bytes_ - b));
+  }
+  void worker(int part) {
+    unsigned long long seen = 0;
+    for (;;) {
+      // spin briefly for the next job, then block
+      const auto t0 = std::chrono::steady_clock::now();
+      while (epoch_.load(std::memory_order_acquire) == seen) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) {
+          std::unique_lock<std::mutex> lk(mu_);
+          cv_.wait(lk, [&] { return epoch_.load(std::memory_order_acquire) != seen; });
+          break;
+        }
+      }
+      seen = epoch_.load(std::memory_order_acquire);
+      if (stop_) return;
+      run_part(part);
+      pending_.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  std::vector<std::thread> threads_;
+  int n_workers_ = 0;
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_;
+  std::atomic<unsigned long long> epoch_{0};
+  std::atomic<int> pending_{0};
+  bool stop_ = false;
+  char *dst_ = nullptr; const char *src_ = nullptr; size_t bytes_ = 0, chunk_ = 0;
+};
+
 struct PinnedSamples {
   float *p = nullptr;
   size_t n = 0, cap_bytes = 0;
@@ -150,7 +221,7 @@ struct PinnedSamples {
       p = np_;
       cap_bytes = ncap;
     }
-    memcpy(p + n, src, cnt * sizeof(float));
+    ParallelCopy::get().copy(p + n, src, cnt * sizeof(float));
     n += cnt;
   }
 };
@@ -225,7 +296,10 @@ struct Engine {
     const long long *vt_off12 = nullptr, *vt_offh = nullptr;
     float *VT12 = nullptr, *VT12lo = nullptr, *VTh = nullptr, *VThlo = nullptr;
     int n_tiles12 = 0, n_tilesh = 0;
+    const int *dw_tile_off = nullptr;   // cumulative ceil(len / 128) per utterance at the stack's rate (conv module tiles)
+    int dw_tiles = 0;
   };
+  DevBuf b_up[4], b_down[4], b_dwt;
   DevBuf b_maps, b_tileoff, b_vtoff, b_vt12, b_vt12lo, b_vth, b_vthlo;
   void build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const std::vector<long long> &aoff_host);
   void attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r, const long long *aoff, const float *X, int ldx,
@@ -756,7 +830,7 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
     gemm(hid, H * vd, w.sa_out_w[j], w.sa_out_b[j], w1, D, w1, D, M, D, H * vd, ACT_NONE);
     // conv module j
     gemm(w1, D, w.cv_in_w[j], w.cv_in_b[j], nullptr, 0, proj, 2 * D, M, 2 * D, D, ACT_NONE);
-    launch_glu_dwconv(proj, r, D, s.k, w.cv_dw_w[j], w.cv_dw_b[j], hid, st);
+    launch_glu_dwconv(proj, r, pl.dw_tile_off, pl.dw_tiles, D, s.k, w.cv_dw_w[j], w.cv_dw_b[j], hid, st);
     gemm(hid, D, w.cv_out_w[j], w.cv_out_b[j], w1, D, w1, D, M, D, D, ACT_NONE);
     // feed forward 2 / 3
     const int f = w.ff_dim[j + 1];
@@ -815,6 +889,19 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
     CUDA_CHECK(cudaMemcpyAsync(dof, h_off[q].data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
     rd[q] = RaggedDesc{dl, dof, n, Mr[q], Lr[q]};
   }
+  // row maps between the full rate and each stack rate; 128-frame tile lists per rate (conv module)
+  int *d_up[4] = {nullptr, nullptr, nullptr, nullptr};
+  int2 *d_down[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int q = 1; q < 4; ++q) {
+    d_up[q] = b_up[q].get<int>((size_t)std::max(Mr[0], 1));
+    d_down[q] = b_down[q].get<int2>((size_t)std::max(Mr[q], 1));
+    launch_build_row_maps(rd[0], rd[q], rates[q], d_up[q], d_down[q], st);
+  }
+  std::vector<int> dwt((size_t)4 * (n + 1), 0);
+  for (int q = 0; q < 4; ++q)
+    for (int u = 0; u < n; ++u) dwt[(size_t)q * (n + 1) + u + 1] = dwt[(size_t)q * (n + 1) + u] + (h_len[q][u] + 127) / 128;
+  int *d_dwt = b_dwt.get<int>(dwt.size());
+  CUDA_CHECK(cudaMemcpyAsync(d_dwt, dwt.data(), dwt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   // attention-weight offsets per stack and the max A size
   const size_t ns = stacks.size();
   std::vector<std::vector<long long>> aoffs(ns, std::vector<long long>(n + 1, 0));
@@ -868,6 +955,8 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
     launch_pos_emb(pe, Lr[q], pos_dim, st);
     AttnPlan plan;
     build_attn_plan(&plan, s, q, n, aoffs[i]);
+    plan.dw_tile_off = d_dwt + (size_t)q * (n + 1);
+    plan.dw_tiles = dwt[(size_t)q * (n + 1) + n];
     if (s.ds == 1) {
       launch_convert_channels(x, xC, outb, D, M1, st);
       for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], outb, rd[0], aoff, M1, Lr[0], plan);
@@ -875,9 +964,9 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
       float *xc = b_xc.get<float>((size_t)M1 * D);
       launch_convert_channels(x, xC, xc, D, M1, st);
       float *sin_ = b_sin.get<float>((size_t)Mr[q] * D);
-      launch_downsample(xc, rd[0], rd[q], D, s.ds, s.ds_bias, sin_, st);
+      launch_downsample(xc, d_down[q], Mr[q], D, s.ds, s.ds_bias, sin_, st);
       for (int l = 0; l < s.L; ++l) run_layer(s, s.layers[l], sin_, rd[q], aoff, Mr[q], Lr[q], plan);
-      launch_upsample_combine(sin_, rd[q], xc, rd[0], D, s.ds, s.combiner, outb, st);
+      launch_upsample_combine(sin_, d_up[q], xc, M1, D, s.combiner, outb, st);
     }
     x = outb;
     xC = D;
@@ -894,7 +983,7 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   }
   if (pieces.size() > 4) throw std::runtime_error("more than 4 output pieces not built");
   float *cat = b_cat.get<float>((size_t)Mr[1] * out_dim);
-  launch_concat_downsample2(pieces.data(), (int)pieces.size(), rd[0], rd[1], out_dim, W("encoder.downsample_output.bias"), cat, st);
+  launch_concat_downsample2(pieces.data(), (int)pieces.size(), d_down[1], Mr[1], out_dim, W("encoder.downsample_output.bias"), cat, st);
   gemm(cat, out_dim, W("encoder.encoder_proj.weight"), W("encoder.encoder_proj.bias"), nullptr, 0, enc, join_dim, Mr[1], join_dim,
        out_dim, ACT_NONE);
   CUDA_CHECK(cudaStreamSynchronize(st));   // host descriptor vectors are locals
