@@ -19,6 +19,7 @@
 //   warps 10..13 (3xTF32 mode) split each landed stage into hi/lo operands
 // Two TMEM accumulators (2 x BN columns) overlap the epilogue of one tile with the main loop of the next.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <mutex>
@@ -74,19 +75,30 @@ struct TcParams {
 // epilogue thread - it owns 32 consecutive columns of one output row straight out of TMEM - also emits the
 // softmax/top-EPI partial record of those columns, so modified_beam_search's per-frame selection (search.cu) reads
 // 3 KB of records per hypothesis instead of the 8 KB logits row (/root/reference core/asr_engine.py:1096-1106).
-template <int BN, bool SPLIT3, int EPI>
+//
+// ATMEM (3xTF32 only): the activation operand goes through tensor memory. In SS mode the kernel is bound by shared
+// memory bandwidth, not by the tensor pipe: per 32-wide K block the three MMAs read A and W tiles 12 times (96 KB),
+// TMA writes 48 KB and the splitter moves 32 KB, against 98 KB the SM can move in the 768 cycles the MMAs need
+// (ncu: tensor pipe 56 % active). With ATMEM the splitter warps read the landed A tile once, and store hi and lo
+// rows to TMEM (tcgen05.st, lane = row); the MMAs take A from there, so shared memory only carries the TMA writes,
+// the W reads and one A read (112 KB), and the freed A_lo buffers pay for a fourth stage.
+template <int BN, bool SPLIT3, int EPI, bool ATMEM>
 __global__ void __launch_bounds__(SPLIT3 ? 448 : 320, 1)
 gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                          const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
-  constexpr int NS = stages_for(BN, SPLIT3);
+  static_assert(!ATMEM || SPLIT3, "A-in-TMEM is the 3xTF32 path");
+  constexpr int NS = ATMEM ? 4 : stages_for(BN, SPLIT3);
+  constexpr uint32_t kAccCols = 2 * BN;                       // two accumulators
+  constexpr uint32_t kTmemACol = 256;                         // ATMEM: A stages at columns 256 + 64 s (hi) / + 32 (lo)
+  constexpr uint32_t kTmemCols = ATMEM ? 512u : kAccCols;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kABytes = TBM * TBK * 4;   // 16 KB
   constexpr int kWBytes = BN * TBK * 4;    // 16 or 8 KB
   uint8_t *sA = smem;
   uint8_t *sW = smem + NS * kABytes;
-  uint8_t *sAlo = sW + NS * kWBytes;                       // only carved when SPLIT3
-  uint8_t *sWlo = sAlo + (SPLIT3 ? NS * kABytes : 0);
+  uint8_t *sAlo = sW + NS * kWBytes;                       // only carved when SPLIT3 without ATMEM
+  uint8_t *sWlo = sAlo + ((SPLIT3 && !ATMEM) ? NS * kABytes : 0);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWlo + (SPLIT3 ? NS * kWBytes : 0));
   uint64_t *empty_bar = full_bar + NS;
   uint64_t *ready_bar = empty_bar + NS;                    // split done (SPLIT3)
@@ -114,7 +126,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)(2 * BN)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -167,7 +179,17 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = make_smem_desc(smem_u32(sA + s * kABytes));
           const uint64_t dw = make_smem_desc(smem_u32(sW + s * kWBytes));
-          if constexpr (SPLIT3) {
+          if constexpr (ATMEM) {
+            const uint64_t dwl = make_smem_desc(smem_u32(sWlo + s * kWBytes));
+            const uint32_t ta_hi = tmem_base + kTmemACol + (uint32_t)(s * 64), ta_lo = ta_hi + 32;
+#pragma unroll
+            for (int k = 0; k < TBK / UMMA_K; ++k) {
+              const uint64_t o = (uint64_t)(k * 2);
+              umma_tf32_ta(tmem_d, ta_lo + k * UMMA_K, dw + o, idesc, (kb | k) ? 1u : 0u);   // small terms first
+              umma_tf32_ta(tmem_d, ta_hi + k * UMMA_K, dwl + o, idesc, 1u);
+              umma_tf32_ta(tmem_d, ta_hi + k * UMMA_K, dw + o, idesc, 1u);
+            }
+          } else if constexpr (SPLIT3) {
             const uint64_t dal = make_smem_desc(smem_u32(sAlo + s * kABytes));
             const uint64_t dwl = make_smem_desc(smem_u32(sWlo + s * kWBytes));
 #pragma unroll
@@ -346,6 +368,26 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           mbar_wait(&full_bar[s], ph);
           // The tensor core truncates fp32 operands to TF32 (tools/tf32_rounding_probe.py), so the raw tile IS the
           // hi operand; only lo = x - trunc(x) has to be produced. W_lo comes pre-split through TMA.
+          if constexpr (ATMEM) {
+            // thread = one row of the tile: its 128 bytes sit in 16-byte chunks XOR-swizzled by (row & 7), so lanes
+            // reading the same logical chunk hit different banks. hi = the raw value (the MMA truncates), lo = x - trunc.
+            const int row = (warp & 3) * 32 + lane;
+            const float4 *rowp = reinterpret_cast<const float4 *>(sA + s * kABytes + row * 128);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = rowp[c ^ (row & 7)];
+              hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+              hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lo[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xFFFFE000u));
+            const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemACol + (uint32_t)(s * 64);
+            tmem_st_32x32(ta, hi);
+            tmem_st_32x32(ta + 32, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          } else {
           const float4 *a4 = reinterpret_cast<const float4 *>(sA + s * kABytes);
           float4 *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
 #pragma unroll 8
@@ -359,6 +401,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             al4[i] = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+          }
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
         }
       }
@@ -368,7 +411,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
   if (EPI > 0 && p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long now;
@@ -396,7 +439,8 @@ void init_once() {
   });
 }
 
-constexpr size_t smem_bytes(int BN, bool split3) {
+constexpr size_t smem_bytes(int BN, bool split3, bool atmem = false) {
+  if (atmem) return 1024 + (size_t)4 * (TBM * TBK * 4 + 2 * BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
   return 1024 + (size_t)stages_for(BN, split3) * (split3 ? 2 : 1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
 }
 
@@ -499,16 +543,23 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, n_sms);   // persistent: one CTA per SM
   // one launcher per instantiation; the opt-in shared-memory attribute is set on first use
-#define B200_TC_LAUNCH(BN_, S3_, EPI_)                                                                                     \
+#define B200_TC_LAUNCH_(BN_, S3_, EPI_, ATM_)                                                                              \
   do {                                                                                                                    \
     static bool attr = false;                                                                                             \
     if (!attr) {                                                                                                          \
-      CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)smem_bytes(BN_, S3_)));                                                        \
+      CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_, ATM_>,                                     \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(BN_, S3_, ATM_)));     \
       attr = true;                                                                                                        \
     }                                                                                                                     \
-    launch_pdl(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_>, dim3(grid), dim3((S3_) ? 448 : 320), smem_bytes(BN_, S3_), st,   \
-               g.pdl != 0, ma, mw, mwl, p);                                                                              \
+    launch_pdl(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_, ATM_>, dim3(grid), dim3((S3_) ? 448 : 320),                       \
+               smem_bytes(BN_, S3_, ATM_), st, g.pdl != 0, ma, mw, mwl, p);                                               \
+  } while (0)
+  // 3xTF32 takes the A-in-TMEM kernel unless B200ASR_GEMM_SS is set (the shared-memory-operand variant, kept for A/B runs)
+  static const bool use_atmem = getenv("B200ASR_GEMM_SS") == nullptr;
+#define B200_TC_LAUNCH(BN_, S3_, EPI_)                                                                                     \
+  do {                                                                                                                    \
+    if ((S3_) && use_atmem) B200_TC_LAUNCH_(BN_, S3_, EPI_, (S3_));                                                       \
+    else B200_TC_LAUNCH_(BN_, S3_, EPI_, false);                                                                          \
   } while (0)
 #define B200_TC_JOINER(BN_, S3_)                                                                   \
   do {                                                                                             \
@@ -526,6 +577,7 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   }
 #undef B200_TC_JOINER
 #undef B200_TC_LAUNCH
+#undef B200_TC_LAUNCH_
   count_launch();
   KERNEL_CHECK();
 }
