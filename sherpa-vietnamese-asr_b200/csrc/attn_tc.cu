@@ -22,7 +22,8 @@ using namespace tc;
 
 namespace {
 
-constexpr int kNS = 4;   // smem stages
+// smem stages: the 12-wide value tiles are tiny, so the kernel is bound by how many bytes of A it keeps in flight
+constexpr int stages_of(int BN) { return BN <= 16 ? 4 : 4; }
 
 struct AttnTcParams {
   const CUtensorMap *mapsA, *mapsV, *mapsVlo;
@@ -77,6 +78,7 @@ template <int BN, bool SPLIT3>
 __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kernel(AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kNS = stages_of(BN);
   constexpr int kABytes = TBM * TBK * 4;               // 16 KB
   constexpr int kVBytes = BN * TBK * 4;                // 2 / 8 KB
   constexpr int kVStride = (kVBytes + 1023) & ~1023;   // keep every stage buffer 1024-byte aligned
@@ -214,17 +216,16 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
           const int s = it % kNS;
           const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&full_bar[s], ph);
-          const float4 *a4 = reinterpret_cast<const float4 *>(sA + s * kABytes);
-          float4 *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
+          const uint32_t a4 = smem_u32(sA + s * kABytes), al4 = smem_u32(sAlo + s * kABytes);
 #pragma unroll 8
           for (int i = tix; i < kABytes / 16; i += 128) {
-            const float4 v = a4[i];
+            const float4 v = lds128(a4 + i * 16);
             float4 l;
             l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
             l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
             l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            al4[i] = l;
+            sts128(al4 + i * 16, l);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const float *__restric
 }
 
 constexpr size_t attn_smem(int BN, bool split3) {
-  return 1024 + (size_t)kNS * (TBM * TBK * 4 + ((BN * TBK * 4 + 1023) & ~1023)) * (split3 ? 2 : 1) + (3 * kNS + 4) * 8 + 64;
+  return 1024 + (size_t)stages_of(BN) * (TBM * TBK * 4 + ((BN * TBK * 4 + 1023) & ~1023)) * (split3 ? 2 : 1) + (3 * stages_of(BN) + 4) * 8 + 64;
 }
 
 }  // namespace

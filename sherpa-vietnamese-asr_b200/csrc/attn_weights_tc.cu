@@ -188,10 +188,10 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
           const int nvalid = min(32, t.Tk - j0);             // warp-uniform; <= 0: this column group is past the keys
           if (nvalid > 0) {
             // positional term: window index of (i, j) is (j - kt*128) - il + 127; scores replace the raw accumulators in r[]
-            const float4 *win = reinterpret_cast<const float4 *>(sW + s * kWinBytes) + (cg * 32 - il + 127);
+            const uint32_t win = smem_u32(sW + s * kWinBytes) + (uint32_t)(cg * 32 - il + 127) * 16u;
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
-              const float4 w = win[jj];
+              const float4 w = lds128(win + jj * 16);   // explicit ld.shared: a generic load here stalls on the long scoreboard
               float ps = pi.x * w.x;
               ps = fmaf(pi.y, w.y, ps); ps = fmaf(pi.z, w.z, ps); ps = fmaf(pi.w, w.w, ps);
               r[jj] = __float_as_uint(jj < nvalid ? __uint_as_float(r[jj]) + ps : -INFINITY);
@@ -261,17 +261,16 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
     if constexpr (SPLIT3) {
       const int tix = threadIdx.x - (kEpiWarps + 2) * 32;   // 0..127
       auto split = [&](const uint8_t *src, uint8_t *dst) {
-        const float4 *a4 = reinterpret_cast<const float4 *>(src);
-        float4 *l4 = reinterpret_cast<float4 *>(dst);
+        const uint32_t a4 = smem_u32(src), l4 = smem_u32(dst);
 #pragma unroll 8
         for (int i = tix; i < kTileBytes / 16; i += 128) {
-          const float4 v = a4[i];
+          const float4 v = lds128(a4 + i * 16);
           float4 lo;
           lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
           lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
           lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
           lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          l4[i] = lo;
+          sts128(l4 + i * 16, lo);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       };

@@ -100,8 +100,9 @@ struct RaggedDesc {     // per-rate description of the packed batch, all device 
 
 void launch_embed_conv0(const float *feats, const int *T, const long long *foff, const long long *ooff, int n, int max_T,
                         const float *w, const float *b, float *out, cudaStream_t st);
-void launch_embed_conv1(const float *in, const int *T, const long long *ioff, const long long *ooff, int n, int max_t2,
-                        const float *w, const float *b, float *out, cudaStream_t st);
+// ioff / ooff: [n+1] packed row offsets of the conv0 / conv1 outputs; total_rows = ooff[n]
+void launch_embed_conv1(const float *in, const long long *ioff, const long long *ooff, int n, long long total_rows, const float *w,
+                        const float *b, float *out, cudaStream_t st);
 void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,
                         const float *w, const float *b, float *out, cudaStream_t st);
 void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,

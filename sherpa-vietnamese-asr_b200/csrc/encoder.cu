@@ -10,6 +10,8 @@
 // execution computes.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace b200asr {
@@ -49,45 +51,55 @@ __global__ void embed_conv0_kernel(const float *__restrict__ feats, const int *_
 }
 
 // conv1: [(T-2),80,8] -> [t2,39,32], k3 stride 2, SwooshR.   w: [3][3][8][32]
-__global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restrict__ in, const int *__restrict__ T,
-                                                          const long long *__restrict__ ioff, const long long *__restrict__ ooff,
+// Persistent CTAs (the 9 KB of weights are staged in shared memory once per CTA) walk the packed output pixels of
+// the whole ragged batch; thread -> (pixel, group of 8 output channels); the utterance of a pixel is found by a
+// binary search over the packed row offsets.
+__global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restrict__ in, const long long *__restrict__ ioff,
+                                                          const long long *__restrict__ ooff, int n_utt,
                                                           const float *__restrict__ w, const float *__restrict__ b,
                                                           float *__restrict__ out) {
-  __shared__ float sw[72 * 32];
+  __shared__ __align__(16) float sw[72 * 32];
   __shared__ float sb[32];
   for (int i = threadIdx.x; i < 72 * 32; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
-  const int u = blockIdx.y;
-  const int Tu = T[u];
-  const int t2 = Tu >= 5 ? (Tu - 5) / 2 + 1 : 0;
-  // thread -> (pixel, group of 8 output channels)
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pix = idx >> 2, cg = (idx & 3) * 8;
-  if (pix >= t2 * 39) return;
-  const int t = pix / 39, f = pix % 39;
-  const float *x = in + ioff[u] * 80 * 8;
-  float acc[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = sb[cg + c];
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const float *px = x + ((long long)(2 * t + kh) * 80 + (2 * f + kw)) * 8;
-      const float4 v0 = __ldg(reinterpret_cast<const float4 *>(px));
-      const float4 v1 = __ldg(reinterpret_cast<const float4 *>(px + 4));
-      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-      for (int ci = 0; ci < 8; ++ci) {
-        const float *wr = sw + ((kh * 3 + kw) * 8 + ci) * 32 + cg;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v[ci], wr[c], acc[c]);
-      }
+  const long long total = ooff[n_utt] * 39 * 4;     // (pixel, channel group) items
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx >> 2;
+    const int cg = (int)(idx & 3) * 8;
+    const long long row = pix / 39;                 // packed output row (utterance, t)
+    const int f = (int)(pix - row * 39);
+    int lo = 0, hi = n_utt - 1;
+    while (lo < hi) {   // last u with ooff[u] <= row
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(ooff + mid) <= row) lo = mid; else hi = mid - 1;
     }
-  float *o = out + ((ooff[u] + t) * 39 + f) * 32 + cg;
+    const int t = (int)(row - __ldg(ooff + lo));
+    const float *x = in + __ldg(ioff + lo) * 80 * 8;
+    float acc[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) o[c] = swoosh_r(acc[c]);
+    for (int c = 0; c < 8; ++c) acc[c] = sb[cg + c];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float *px = x + ((long long)(2 * t + kh) * 80 + (2 * f + kw)) * 8;
+        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(px));
+        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(px + 4));
+        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const float4 w0 = *reinterpret_cast<const float4 *>(sw + ((kh * 3 + kw) * 8 + ci) * 32 + cg);
+          const float4 w1 = *reinterpret_cast<const float4 *>(sw + ((kh * 3 + kw) * 8 + ci) * 32 + cg + 4);
+          acc[0] = fmaf(v[ci], w0.x, acc[0]); acc[1] = fmaf(v[ci], w0.y, acc[1]); acc[2] = fmaf(v[ci], w0.z, acc[2]);
+          acc[3] = fmaf(v[ci], w0.w, acc[3]); acc[4] = fmaf(v[ci], w1.x, acc[4]); acc[5] = fmaf(v[ci], w1.y, acc[5]);
+          acc[6] = fmaf(v[ci], w1.z, acc[6]); acc[7] = fmaf(v[ci], w1.w, acc[7]);
+        }
+      }
+    float4 *o = reinterpret_cast<float4 *>(out + pix * 32 + cg);
+    o[0] = make_float4(swoosh_r(acc[0]), swoosh_r(acc[1]), swoosh_r(acc[2]), swoosh_r(acc[3]));
+    o[1] = make_float4(swoosh_r(acc[4]), swoosh_r(acc[5]), swoosh_r(acc[6]), swoosh_r(acc[7]));
+  }
 }
 
 // conv2: [t2,39,32] -> [T1,19,128], k3 stride (1,2), SwooshR.  w: [3][3][32][128]
@@ -587,11 +599,18 @@ void launch_embed_conv0(const float *feats, const int *T, const long long *foff,
   embed_conv0_kernel<<<grid, 256, 0, st>>>(feats, T, foff, ooff, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
-void launch_embed_conv1(const float *in, const int *T, const long long *ioff, const long long *ooff, int n, int max_t2,
-                        const float *w, const float *b, float *out, cudaStream_t st) {
-  if (max_t2 <= 0) return;
-  dim3 grid(cdiv((long long)max_t2 * 39 * 4, 256), n);
-  embed_conv1_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, w, b, out);
+void launch_embed_conv1(const float *in, const long long *ioff, const long long *ooff, int n, long long total_rows, const float *w,
+                        const float *b, float *out, cudaStream_t st) {
+  if (total_rows <= 0) return;
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long items = total_rows * 39 * 4;
+  const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)n_sms * 8);
+  embed_conv1_kernel<<<grid, 256, 0, st>>>(in, ioff, ooff, n, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
 void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,

@@ -220,7 +220,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
       if (ti == 0 && warp == 2 && lane == 0) mark(4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float *stg = epi_stage + (warp - 2) * (32 * 32);   // per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
+      const uint32_t stg = smem_u32(epi_stage + (warp - 2) * (32 * 32));   // per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
       const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                           (!p.R || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
                           (!p.bias || EPI > 0 || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
@@ -297,8 +297,8 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         __syncwarp();
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4)                      // row = lane; 128-bit stores, conflict-free per quarter warp
-          *reinterpret_cast<float4 *>(stg + lane * 32 + ((k4 ^ (lane & 7)) << 2)) =
-              make_float4(__uint_as_float(r[4 * k4]), __uint_as_float(r[4 * k4 + 1]), __uint_as_float(r[4 * k4 + 2]), __uint_as_float(r[4 * k4 + 3]));
+          sts128(stg + (uint32_t)(lane * 32 + ((k4 ^ (lane & 7)) << 2)) * 4u,
+                 make_float4(__uint_as_float(r[4 * k4]), __uint_as_float(r[4 * k4 + 1]), __uint_as_float(r[4 * k4 + 2]), __uint_as_float(r[4 * k4 + 3])));
         __syncwarp();
         if (vec_ok) {
           // thread = (row lane/8 + 4*it, 4 columns (lane%8)*4): a warp instruction covers 4 full 128-byte rows
@@ -322,7 +322,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           for (int it = 0; it < 8; ++it) {
             const int rr = rsub + 4 * it, m = mrow0 + rr;
             if (nv && m < p.M) {
-              float4 v = *reinterpret_cast<const float4 *>(stg + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+              float4 v = lds128(stg + (uint32_t)(rr * 32 + (((lane & 7) ^ (rr & 7)) << 2)) * 4u);
               if (p.act == ACT_TANH_RES) {
                 v.x = tanhf(v.x + bv.x + res[it].x); v.y = tanhf(v.y + bv.y + res[it].y);
                 v.z = tanhf(v.z + bv.z + res[it].z); v.w = tanhf(v.w + bv.w + res[it].w);
@@ -342,7 +342,8 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           for (int rr = 0; rr < 32; ++rr) {
             const int m = mrow0 + rr;
             if (nv && m < p.M) {
-              float v = stg[rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)] + bs;
+              const float4 v4 = lds128(stg + (uint32_t)(rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2)) * 4u);
+              float v = ((lane & 3) == 0 ? v4.x : (lane & 3) == 1 ? v4.y : (lane & 3) == 2 ? v4.z : v4.w) + bs;
               const long long rrow = p.r_rows ? (long long)p.r_rows[m] : (long long)m;
               const float rv = p.R ? p.R[rrow * p.ldr + n] : 0.f;
               v = (p.act == ACT_TANH_RES) ? tanhf(v + rv) : apply_act(v, p.act) + rv;
@@ -372,11 +373,11 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             // thread = one row of the tile: its 128 bytes sit in 16-byte chunks XOR-swizzled by (row & 7), so lanes
             // reading the same logical chunk hit different banks. hi = the raw value (the MMA truncates), lo = x - trunc.
             const int row = (warp & 3) * 32 + lane;
-            const float4 *rowp = reinterpret_cast<const float4 *>(sA + s * kABytes + row * 128);
+            const uint32_t rowp = smem_u32(sA + s * kABytes + row * 128);
             uint32_t hi[32], lo[32];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float4 v = rowp[c ^ (row & 7)];
+              const float4 v = lds128(rowp + ((c ^ (row & 7)) << 4));
               hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
               hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
             }
@@ -388,17 +389,16 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           } else {
-          const float4 *a4 = reinterpret_cast<const float4 *>(sA + s * kABytes);
-          float4 *al4 = reinterpret_cast<float4 *>(sAlo + s * kABytes);
+          const uint32_t a4 = smem_u32(sA + s * kABytes), al4 = smem_u32(sAlo + s * kABytes);
 #pragma unroll 8
           for (int i = t; i < kABytes / 16; i += 128) {
-            const float4 v = a4[i];
+            const float4 v = lds128(a4 + i * 16);
             float4 l;
             l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
             l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
             l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
             l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            al4[i] = l;
+            sts128(al4 + i * 16, l);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
           }

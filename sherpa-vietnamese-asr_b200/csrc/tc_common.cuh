@@ -16,6 +16,18 @@ constexpr int kStages3 = 3;    // 3xTF32 mode: 3 x 2 x (16 + BN/8) KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Explicit shared-space 128-bit accesses. Pointers into the 1024-byte-aligned dynamic shared buffer are computed through
+// uintptr_t, which makes them generic for the compiler: it then emits LD.E / ST.E that go through the global-memory
+// path of L1TEX (long scoreboard) instead of LDS / STS.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4 &v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
