@@ -281,6 +281,18 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     ach = (gs["flops"] / (gs["ms"] * 1e-3)) / 1e12 if gs["ms"] > 0 else None
     enc_fl = sum(encoder_flops(cfg, (len(a) + 80) // 160) for a in audios)
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (two mid-encoder launches)
+    traffic, traffic_note = None, "no ncu capture committed"
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))
+        traffic = float(np.mean([c["dram_read_bytes"] + c["dram_write_bytes"] for c in cap]))
+        traffic_note = ("mean dram__bytes_read+write per launch over the %d captured launches in profiles/r1_gemm_traffic.json "
+                        "(algorithmic bytes of the same launches: %.0f)" % (len(cap), np.mean([c["algorithmic_bytes"] for c in cap])))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    fb_bytes = pcm_bytes + sum(((len(a) + 80) // 160) * 320 for a in audios)
+    n_steps = max(((((len(a) + 80) // 160) - 7) // 2 + 1) // 2 for a in audios)
     line = {
         "metric": "RTFx (audio-s/s) Zipformer-68M batch ASR", "value": total_audio / (ms_dev * 1e-3), "unit": "audio-s/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -291,13 +303,21 @@ def main():
                    "l2": f"inputs larger than L2 ({pcm_bytes / 1e6:.0f} MB PCM, multi-GB activations per step)",
                    "precision": args.precision, "wall_ms_per_step": wall_step,
                    "stage_ms": {k: v / args.steps for k, v in stage.items()},
-                   "encoder_algorithmic_tflop_per_step": enc_fl / 1e12},
+                   "encoder_algorithmic_tflop_per_step": enc_fl / 1e12,
+                   "stage_rooflines": {
+                       "fbank": {"bound": "hbm", "achieved_gbs": fb_bytes / 1e9 / (stage["fbank_ms"] / args.steps * 1e-3),
+                                 "peak_gbs": hbm, "frac": fb_bytes / 1e9 / (stage["fbank_ms"] / args.steps * 1e-3) / hbm},
+                       "encoder": {"bound": "tensor", "achieved_tflops": enc_fl / 1e12 / (stage["encoder_ms"] / args.steps * 1e-3),
+                                   "peak_tflops": peak_tf, "frac": enc_fl / 1e12 / (stage["encoder_ms"] / args.steps * 1e-3) / peak_tf},
+                       "beam_search": {"bound": "latency", "frame_steps": n_steps,
+                                       "us_per_frame_step": 1e3 * stage["search_ms"] / args.steps / max(n_steps, 1)}}},
         "clocks": clocks,
         "e2e": {"value": total_audio / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": pcm_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm (all Linear layers of the encoder)", "achieved": ach, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": None, "peak_source": peak_src,
+                     "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None, "traffic": traffic, "traffic_note": traffic_note,
+                     "peak_source": peak_src, "note": "FP32 mode issues 3 TF32 MMAs per K step (error-compensated split); achieved counts 2MNK once",
                      "gemm_ms_per_step": gs["ms"], "gemm_launches_per_step": gs["launches"],
                      "gemm_share_of_step": gs["ms"] / tm_prof["total_ms"] if tm_prof["total_ms"] else None},
     }

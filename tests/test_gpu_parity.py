@@ -222,6 +222,49 @@ def test_search_with_hotwords(m30):
     rec.set_hotwords_token_ids([], [])
 
 
+def test_search_with_500_hotwords(m30):
+    """BASELINE config C3: a 500-entry ContextGraph (planted phrases so boosts fire), beam 4, ragged batch."""
+    from oracle import search_ref as sr
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = m30
+    orec, ocfg, _ = oracle_recognizer(paths, beam=4)
+    encs = _window_cases(orec, ocfg, 12)
+    planted = []
+    for e in encs[:6]:
+        orec["dec_cache"].clear()
+        planted.append(sr.modified_beam_search(orec, None, 4, enc_out=e)[0])
+    seqs, scores = synth.random_hotwords(500, ocfg.vocab_size, 500, planted=[p for p in planted if len(p) >= 2])
+    assert len(seqs) == 500
+    assert _search_case(rec, orec, encs, 4, "modified_beam_search", graph_args=(seqs, scores)) > 10
+    rec.set_hotwords_token_ids([], [])
+
+
+def test_rover_two_models_matches_oracle(model_dirs):
+    """BASELINE config C4: two models over the same chunks, word lists combined with ROVER; the product path
+    (GPU decode -> words_from_result -> rover_merge_words) against the oracle's decode_chunk + rover_merge_words."""
+    from oracle import fbank_ref, search_ref as sr
+    from sherpa_vietnamese_asr_b200 import asr_engine, synth
+    chunks = [synth.speech_like(n, 1200 + i) for i, n in enumerate([16000 * 4, 16000 * 6 + 99, 16000 * 3])]
+    recs, orecs = [], []
+    for name, seed in (("zipformer-30m", 30), ("zipformer-tiny", 3)):
+        cfg, paths, d = model_dirs(name, seed)
+        recs.append(asr_engine.create_recognizer(d, max_active_paths=4))
+        orecs.append(oracle_recognizer(paths, beam=4)[0])
+    got = asr_engine.rover_decode_chunks(recs[0], recs[1], chunks, time_offsets=[0.0, 10.0, 20.0])
+    for c, off, (merged, disagree) in zip(chunks, [0.0, 10.0, 20.0], got):
+        feats = fbank_ref.fbank(c, np.float64)
+        want_words = []
+        for o in orecs:
+            o["dec_cache"].clear()
+            want_words.append(sr.decode_chunk(o, c, off, precomputed_features=feats))
+        want, want_dis = sr.rover_merge_words(want_words[0], want_words[1])
+        assert [w["text"] for w in merged] == [w["text"] for w in want]
+        assert disagree == want_dis
+        for a, b in zip(merged, want):
+            assert abs(a["start"] - b["start"]) <= 1e-6 and abs(a["end"] - b["end"]) <= 1e-6
+            assert abs(a["prob"] - b["prob"]) <= 2e-3
+
+
 def test_context_graph_matches_oracle(m30):
     from sherpa_vietnamese_asr_b200 import synth
     cfg, paths, rec = m30
