@@ -277,6 +277,15 @@ struct Engine {
   std::map<int, Staged> staged;
   int next_handle = 0;
 
+  // Host staging data of the asynchronous descriptor uploads of one pass: kept alive until the next pass starts, so
+  // no upload needs a stream synchronisation (each one used to stall the GPU while the host prepared the next plan).
+  std::vector<std::shared_ptr<void>> host_keep;
+  template <typename T>
+  const T *keep(std::vector<T> &&v) {
+    auto p = std::make_shared<std::vector<T>>(std::move(v));
+    host_keep.push_back(p);
+    return p->data();
+  }
   ~Engine();
   void load(const B200AsrOfflineRecognizerConfig *c);
   void load_container(const std::string &path, const std::string &prefix);
@@ -725,10 +734,10 @@ void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const std::v
     maxT = std::max(maxT, (*T)[u]);
   }
   long long *d_foff = b_foff.get<long long>(n + 1);
-  CUDA_CHECK(cudaMemcpyAsync(d_foff, foff.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-  float *feats = b_feats.get<float>((size_t)std::max<long long>(foff[n], 1) * 80);
+  const long long total_frames = foff[n];
+  CUDA_CHECK(cudaMemcpyAsync(d_foff, keep(std::move(foff)), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  float *feats = b_feats.get<float>((size_t)std::max<long long>(total_frames, 1) * 80);
   launch_fbank(fb, d_pcm, d_soff, d_foff, n, maxT, feats, st);
-  CUDA_CHECK(cudaStreamSynchronize(st));   // foff is a local; keep it alive until the copy is done
   *d_feats = feats;
 }
 
@@ -755,8 +764,8 @@ void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const 
     pl->VThlo = b_vthlo.get<float>((size_t)std::max<long long>(vth[n], 4));
   }
   // tensor maps (128 bytes each): A, V12, V12lo, Vh, Vhlo
-  std::vector<unsigned char> hm((size_t)5 * n * 128 + 64);
-  unsigned char *hp = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hm.data()) + 63) & ~uintptr_t(63));
+  unsigned char *hm = const_cast<unsigned char *>(keep(std::vector<unsigned char>((size_t)5 * n * 128 + 64)));
+  unsigned char *hp = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hm) + 63) & ~uintptr_t(63));
   attn_tc_encode_maps(hp + 0 * (size_t)n * 128, n, b_A.ptr<float>(), aoff_host.data(), len.data(), H, 0, 128);
   attn_tc_encode_maps(hp + 1 * (size_t)n * 128, n, pl->VT12, vt12.data(), len.data(), 0, C12, 16);
   attn_tc_encode_maps(hp + 2 * (size_t)n * 128, n, split3 ? pl->VT12lo : pl->VT12, vt12.data(), len.data(), 0, C12, 16);
@@ -764,18 +773,18 @@ void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const 
   attn_tc_encode_maps(hp + 4 * (size_t)n * 128, n, split3 ? pl->VThlo : pl->VTh, vth.data(), len.data(), 0, hid, 64);
   unsigned char *dm = b_maps.get<unsigned char>((size_t)5 * n * 128);
   CUDA_CHECK(cudaMemcpyAsync(dm, hp, (size_t)5 * n * 128, cudaMemcpyHostToDevice, st));
+  const int nt12 = t12[n], nth = th[n];
   int *dt = b_tileoff.get<int>((size_t)2 * (n + 1));
-  CUDA_CHECK(cudaMemcpyAsync(dt, t12.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaMemcpyAsync(dt + (n + 1), th.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dt, keep(std::move(t12)), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dt + (n + 1), keep(std::move(th)), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   long long *dv = b_vtoff.get<long long>((size_t)2 * (n + 1));
-  CUDA_CHECK(cudaMemcpyAsync(dv, vt12.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaMemcpyAsync(dv + (n + 1), vth.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-  CUDA_CHECK(cudaStreamSynchronize(st));   // host vectors are locals
+  CUDA_CHECK(cudaMemcpyAsync(dv, keep(std::move(vt12)), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(dv + (n + 1), keep(std::move(vth)), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   pl->mapsA = dm; pl->mapsV12 = dm + 1 * (size_t)n * 128; pl->mapsV12lo = dm + 2 * (size_t)n * 128;
   pl->mapsVh = dm + 3 * (size_t)n * 128; pl->mapsVhlo = dm + 4 * (size_t)n * 128;
   pl->tile_off12 = dt; pl->tile_offh = dt + (n + 1);
   pl->vt_off12 = dv; pl->vt_offh = dv + (n + 1);
-  pl->n_tiles12 = t12[n]; pl->n_tilesh = th[n];
+  pl->n_tiles12 = nt12; pl->n_tilesh = nth;
   pl->use = true;
 }
 
@@ -919,7 +928,11 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   b_A.get<float>((size_t)maxA);
   float *enc = b_enc.get<float>((size_t)std::max(Mr[1], 1) * join_dim);
   *d_enc = enc;
-  if (M1 <= 0) { CUDA_CHECK(cudaStreamSynchronize(st)); return; }
+  if (M1 <= 0) {
+    keep(std::move(foff)); keep(std::move(c0off)); keep(std::move(c1off)); keep(std::move(Tclamped)); keep(std::move(dwt));
+    for (auto &v : aoffs) keep(std::move(v));
+    return;
+  }
 
   // ---- Conv2dSubsampling
   const int D0 = enc_dim[0];
@@ -986,7 +999,9 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   launch_concat_downsample2(pieces.data(), (int)pieces.size(), d_down[1], Mr[1], out_dim, W("encoder.downsample_output.bias"), cat, st);
   gemm(cat, out_dim, W("encoder.encoder_proj.weight"), W("encoder.encoder_proj.bias"), nullptr, 0, enc, join_dim, Mr[1], join_dim,
        out_dim, ACT_NONE);
-  CUDA_CHECK(cudaStreamSynchronize(st));   // host descriptor vectors are locals
+  // the descriptor vectors uploaded asynchronously above stay alive until the next pass (no synchronisation here)
+  keep(std::move(foff)); keep(std::move(c0off)); keep(std::move(c1off)); keep(std::move(Tclamped)); keep(std::move(dwt));
+  for (auto &v : aoffs) keep(std::move(v));
 }
 
 // ------------------------------------------------------------------ full pipeline on device-resident PCM
@@ -994,6 +1009,7 @@ void Engine::decode_pcm_device(const float *d_pcm, const long long *d_soff, cons
                                SearchResultHost *res, std::vector<int> *Tp) {
   gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
+  host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
   CUDA_CHECK(cudaEventRecord(ev[0], st));
   float *d_feats = nullptr, *d_enc = nullptr;
   std::vector<int> T;
@@ -1054,8 +1070,6 @@ void Engine::decode(Stream *const *ss, int n) {
                                    cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(ev[5], st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
     // results
     std::vector<int> Tp;
     SearchResultHost res{};
@@ -1070,6 +1084,7 @@ void Engine::decode(Stream *const *ss, int n) {
     std::vector<float> lp((size_t)nb * cap), stt((size_t)nb * cap * 4);
     res.n_tokens = ntok.data(); res.tokens = toks.data(); res.frames = frm.data(); res.tok_lp = lp.data(); res.stats = stt.data();
     decode_pcm_device(d_pcm, d_soff, soff, nb, &res, &Tp);
+    cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
     for (int i = 0; i < nb; ++i) {
       Stream *s = ss[begin + i];
       const int cnt = std::min(ntok[i], res.max_tokens);
@@ -1260,6 +1275,7 @@ int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const float *sample
   CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->st));
   float *d_feats = nullptr;
   std::vector<int> T;
+  e->host_keep.clear();
   e->run_fbank(d_pcm, d_soff, soff, n, &d_feats, &T);
   CUDA_CHECK(cudaMemcpyAsync(out, d_feats, (size_t)total_frames * 80 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
@@ -1293,6 +1309,7 @@ int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, co
   float *d_enc = nullptr;
   std::vector<int> Tp;
   e->gemm_flops = 0; e->gemm_launches = 0; e->gemm_ev_used = 0;
+  e->host_keep.clear();
   e->run_encoder(d_feats, T, &d_enc, &Tp);
   CUDA_CHECK(cudaMemcpyAsync(out, d_enc, (size_t)totp * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
