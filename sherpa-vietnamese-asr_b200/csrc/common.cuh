@@ -64,9 +64,10 @@ struct FbankTables {
 };
 void fbank_tables_create(FbankTables *t);
 void fbank_tables_destroy(FbankTables *t);
-// samples: packed PCM, sample_off[n+1], frame_off[n+1]; out [total_frames, 80]
-void launch_fbank(const FbankTables &t, const float *samples, const long long *sample_off, const long long *frame_off,
-                  int n_utts, int max_frames, float *out, cudaStream_t st);
+// samples + sample_off[u] = first sample of utterance u; its length is sample_len[u], or sample_off[u+1] - sample_off[u] when
+// sample_len is null (packed PCM); frame_off[n+1]; out [total_frames, 80]
+void launch_fbank(const FbankTables &t, const float *samples, const long long *sample_off, const long long *sample_len,
+                  const long long *frame_off, int n_utts, int max_frames, float *out, cudaStream_t st);
 
 // ---------------------------------------------------------------- GEMM (gemm.cu / gemm_tc.cu)
 // C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ R[M,N] if R). Row strides lda / ldc / ldr in elements.

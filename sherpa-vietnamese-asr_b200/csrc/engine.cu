@@ -167,9 +167,9 @@ class ParallelCopy {
  private:
   static constexpr size_t kMinBytes = 256 * 1024;
   ParallelCopy() {
-    int n = 3;
-    if (const char *e = getenv("B200ASR_COPY_THREADS")) n = atoi(e) - 1;
     const int hw = (int)std::thread::hardware_concurrency();
+    int n = std::min(7, hw / 2 - 1);                       // helpers besides the calling thread
+    if (const char *e = getenv("B200ASR_COPY_THREADS")) n = atoi(e) - 1;
     n_workers_ = std::max(0, std::min(n, hw > 1 ? hw - 1 : 0));
     for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this, i] { worker(i + 1); });
   }
@@ -205,10 +205,104 @@ class ParallelCopy {
   char *dst_ = nullptr; const char *src_ = nullptr; size_t bytes_ = 0, chunk_ = 0;
 };
 
+// Device blocks for the accept-time PCM upload, one pool and one copy stream per device: accept_waveform enqueues the
+// host->device copy of the samples it has just taken, so by the time decode_streams is called the PCM of the batch is
+// (mostly) resident and the pass starts with fbank instead of a 180 MB transfer. Blocks are power-of-two size classes
+// carved from 256 MB slabs and recycled; one copy stream per device keeps reuse of a recycled block stream-ordered.
+class DevicePcmPool {
+ public:
+  static DevicePcmPool &get(int device) {
+    static std::mutex m;
+    static std::map<int, std::unique_ptr<DevicePcmPool>> pools;
+    std::lock_guard<std::mutex> lk(m);
+    auto &p = pools[device];
+    if (!p) p.reset(new DevicePcmPool(device));
+    return *p;
+  }
+  cudaStream_t stream() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!st_ && cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); st_ = nullptr; }
+    return st_;
+  }
+  float *alloc(size_t bytes, size_t *cap) {
+    size_t c = 64 * 1024;
+    while (c < bytes) c <<= 1;
+    *cap = c;
+    std::lock_guard<std::mutex> lk(mu_);
+    auto &fl = free_[c];
+    if (!fl.empty()) { float *p = fl.back(); fl.pop_back(); return p; }
+    if (c > slab_left_) {
+      const size_t slab = std::max(c, kSlab);
+      void *p = nullptr;
+      if (total_ + slab > kMax || cudaMalloc(&p, slab) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      total_ += slab;
+      slab_cur_ = reinterpret_cast<char *>(p);
+      slab_left_ = slab;
+    }
+    float *p = reinterpret_cast<float *>(slab_cur_);
+    slab_cur_ += c;
+    slab_left_ -= c;
+    return p;
+  }
+  void release(float *p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    free_[cap].push_back(p);
+  }
+ private:
+  explicit DevicePcmPool(int) {}
+  static constexpr size_t kSlab = 256u << 20, kMax = 16ull << 30;
+  std::mutex mu_;
+  std::map<size_t, std::vector<float *>> free_;
+  char *slab_cur_ = nullptr;
+  size_t slab_left_ = 0, total_ = 0;
+  cudaStream_t st_ = nullptr;
+};
+
 struct PinnedSamples {
   float *p = nullptr;
   size_t n = 0, cap_bytes = 0;
-  ~PinnedSamples() { PinnedPool::get().release(p, cap_bytes); }
+  // device copy maintained by accept_waveform (null when the pool is exhausted or uploads are disabled)
+  float *d = nullptr;
+  size_t dcap_bytes = 0, n_up = 0;
+  int device = -1;
+  bool in_flight = false;   // uploads queued since the last pass that waited for them (decode clears it)
+  // a pinned block must not go back to the pool (and be overwritten by another stream) while a DMA still reads it
+  void settle() {
+    if (in_flight && device >= 0) {
+      if (cudaSetDevice(device) == cudaSuccess) cudaStreamSynchronize(DevicePcmPool::get(device).stream());
+      cudaGetLastError();
+      in_flight = false;
+    }
+  }
+  ~PinnedSamples() {
+    settle();
+    PinnedPool::get().release(p, cap_bytes);
+    if (d) DevicePcmPool::get(device).release(d, dcap_bytes);
+  }
+  bool on_device() const { return d != nullptr && n_up == n; }
+  // enqueue the upload of the samples not yet on the device (copy stream of `dev`)
+  void upload(int dev) {
+    static const bool enabled = getenv("B200ASR_NO_EAGER_UPLOAD") == nullptr;
+    if (!enabled || n == 0) return;
+    DevicePcmPool &pool = DevicePcmPool::get(dev);
+    cudaStream_t cst = pool.stream();
+    if (!cst) return;
+    if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (n * sizeof(float) > dcap_bytes) {
+      size_t ncap = 0;
+      float *nd = pool.alloc(std::max(cap_bytes, n * sizeof(float)), &ncap);
+      if (d) pool.release(d, dcap_bytes);
+      d = nd; dcap_bytes = nd ? ncap : 0; n_up = 0; device = dev;
+      if (!nd) return;
+    }
+    if (cudaMemcpyAsync(d + n_up, p + n_up, (n - n_up) * sizeof(float), cudaMemcpyHostToDevice, cst) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    n_up = n;
+    in_flight = true;
+  }
   size_t size() const { return n; }
   bool empty() const { return n == 0; }
   const float *data() const { return p; }
@@ -217,6 +311,7 @@ struct PinnedSamples {
       size_t ncap = 0;
       float *np_ = reinterpret_cast<float *>(PinnedPool::get().alloc((n + cnt) * sizeof(float) * (p ? 2 : 1), &ncap));
       if (n) memcpy(np_, p, n * sizeof(float));
+      settle();
       PinnedPool::get().release(p, cap_bytes);
       p = np_;
       cap_bytes = ncap;
@@ -248,6 +343,7 @@ struct Engine {
   FbankTables fb{};
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8]{};
+  cudaEvent_t ev_copy = nullptr;   // marks the accept-time uploads a pass has to wait for
   SearchState *search = nullptr;
   SearchModel sm{};
   ContextGraphHost cg_host;
@@ -295,8 +391,9 @@ struct Engine {
             int K, int act);
   void set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n);
   // pipeline pieces (device pointers)
-  void run_fbank(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n, float **d_feats,
-                 std::vector<int> *T);
+  // h_len[u] = samples of utterance u; d_slen null = packed PCM (lengths from consecutive offsets)
+  void run_fbank(const float *d_pcm, const long long *d_soff, const long long *d_slen, const std::vector<long long> &h_len, int n,
+                 float **d_feats, std::vector<int> *T);
   void run_encoder(const float *d_feats, const std::vector<int> &T, float **d_enc, std::vector<int> *Tp);
   struct AttnPlan {   // tensor-core attention application: per-stack maps / offsets (valid for every layer of the stack)
     bool use = false;
@@ -316,8 +413,8 @@ struct Engine {
   void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
                  const AttnPlan &pl);
   void decode(Stream *const *ss, int n);
-  void decode_pcm_device(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n,
-                         SearchResultHost *res, std::vector<int> *Tp);
+  void decode_pcm_device(const float *d_pcm, const long long *d_soff, const long long *d_slen, const std::vector<long long> &h_len,
+                         int n, SearchResultHost *res, std::vector<int> *Tp);
   void collect_gemm_times();
 };
 
@@ -332,6 +429,7 @@ struct Stream {
   std::vector<int32_t> token_ids, frames;
   std::vector<float> timestamps, lps, tsallis, margin, entropy, top1;
   bool decoded = false;
+  bool json_built = false;
 };
 
 Engine::~Engine() {
@@ -340,6 +438,7 @@ Engine::~Engine() {
   if (fb.window) fbank_tables_destroy(&fb);
   if (search) search_state_destroy(search);
   for (auto &e : ev) if (e) cudaEventDestroy(e);
+  if (ev_copy) cudaEventDestroy(ev_copy);
   for (auto &p : gemm_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &kv : staged) { cudaFree(kv.second.pcm); cudaFree(kv.second.soff); }
   int *ptrs[] = {cg_dev.edge_start, cg_dev.edge_token, cg_dev.edge_child, cg_dev.fail, cg_dev.token, cg_dev.is_end, cg_dev.output};
@@ -448,6 +547,7 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   if (prop.major != 10) throw std::runtime_error("libb200asr is built for sm_100a only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
   CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
 
   load_container(str(mc.transducer.encoder), "encoder.");
   load_container(str(mc.transducer.decoder), "decoder.");
@@ -722,13 +822,13 @@ void Engine::collect_gemm_times() {
 }
 
 // ------------------------------------------------------------------ fbank
-void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n, float **d_feats,
-                       std::vector<int> *T) {
+void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const long long *d_slen, const std::vector<long long> &h_len,
+                       int n, float **d_feats, std::vector<int> *T) {
   std::vector<long long> foff(n + 1, 0);
   T->assign(n, 0);
   int maxT = 0;
   for (int u = 0; u < n; ++u) {
-    const long long ns = h_soff[u + 1] - h_soff[u];
+    const long long ns = h_len[u];
     (*T)[u] = (int)((ns + 80) / 160);
     foff[u + 1] = foff[u] + (*T)[u];
     maxT = std::max(maxT, (*T)[u]);
@@ -737,7 +837,7 @@ void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const std::v
   const long long total_frames = foff[n];
   CUDA_CHECK(cudaMemcpyAsync(d_foff, keep(std::move(foff)), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   float *feats = b_feats.get<float>((size_t)std::max<long long>(total_frames, 1) * 80);
-  launch_fbank(fb, d_pcm, d_soff, d_foff, n, maxT, feats, st);
+  launch_fbank(fb, d_pcm, d_soff, d_slen, d_foff, n, maxT, feats, st);
   *d_feats = feats;
 }
 
@@ -1005,15 +1105,15 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
 }
 
 // ------------------------------------------------------------------ full pipeline on device-resident PCM
-void Engine::decode_pcm_device(const float *d_pcm, const long long *d_soff, const std::vector<long long> &h_soff, int n,
-                               SearchResultHost *res, std::vector<int> *Tp) {
+void Engine::decode_pcm_device(const float *d_pcm, const long long *d_soff, const long long *d_slen,
+                               const std::vector<long long> &h_len, int n, SearchResultHost *res, std::vector<int> *Tp) {
   gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
   CUDA_CHECK(cudaEventRecord(ev[0], st));
   float *d_feats = nullptr, *d_enc = nullptr;
   std::vector<int> T;
-  run_fbank(d_pcm, d_soff, h_soff, n, &d_feats, &T);
+  run_fbank(d_pcm, d_soff, d_slen, h_len, n, &d_feats, &T);
   CUDA_CHECK(cudaEventRecord(ev[1], st));
   run_encoder(d_feats, T, &d_enc, Tp);
   CUDA_CHECK(cudaEventRecord(ev[2], st));
@@ -1044,6 +1144,24 @@ static std::string json_escape(const std::string &s) {
   return o;
 }
 
+
+// sherpa-onnx style result JSON, built lazily: a batch decode should not pay for strings nobody reads
+static void build_json(Stream *s) {
+  if (s->json_built) return;
+  const int cnt = s->res.count;
+  std::string js = "{\"lang\": \"\", \"emotion\": \"\", \"event\": \"\", \"text\": \"" + json_escape(s->text) + "\", \"timestamps\": [";
+  char buf[64];
+  for (int j = 0; j < cnt; ++j) { snprintf(buf, sizeof buf, "%s%.3f", j ? ", " : "", s->timestamps[j]); js += buf; }
+  js += "], \"tokens\": [";
+  for (int j = 0; j < cnt; ++j) js += std::string(j ? ", " : "") + "\"" + json_escape(s->tok_str[j]) + "\"";
+  js += "], \"ys_log_probs\": [";
+  for (int j = 0; j < cnt; ++j) { snprintf(buf, sizeof buf, "%s%.6f", j ? ", " : "", s->lps[j]); js += buf; }
+  js += "], \"words\": []}";
+  s->json = js;
+  s->res.json = s->json.c_str();
+  s->json_built = true;
+}
+
 void Engine::decode(Stream *const *ss, int n) {
   if (n <= 0) return;
   std::lock_guard<std::mutex> lk(mu);
@@ -1059,15 +1177,41 @@ void Engine::decode(Stream *const *ss, int n) {
       ++end;
     }
     const int nb = end - begin;
-    std::vector<long long> soff(nb + 1, 0);
-    for (int i = 0; i < nb; ++i) soff[i + 1] = soff[i] + (long long)ss[begin + i]->samples.size();
-    float *d_pcm = b_pcm.get<float>((size_t)std::max<long long>(soff[nb], 1));
-    long long *d_soff = b_soff.get<long long>(nb + 1);
+    const auto hp0 = std::chrono::steady_clock::now();
+    std::vector<long long> soff(nb + 1, 0), slen(nb, 0);
+    for (int i = 0; i < nb; ++i) {
+      slen[i] = (long long)ss[begin + i]->samples.size();
+      soff[i + 1] = soff[i] + slen[i];
+    }
+    // Streams whose PCM accept_waveform has already sent to this device are read where they sit (offsets relative to
+    // the staging buffer's base, lengths explicit); only if some stream has no device copy is the whole batch packed
+    // into the staging buffer the old way.
+    bool resident = true;
+    for (int i = 0; i < nb; ++i) {
+      Stream *s = ss[begin + i];
+      if (!s->samples.empty() && !(s->samples.on_device() && s->samples.device == device)) { resident = false; break; }
+    }
+    float *d_pcm = b_pcm.get<float>((size_t)std::max<long long>(resident ? 1 : soff[nb], 1));
+    long long *d_soff = b_soff.get<long long>(2 * (size_t)nb + 1);
+    long long *d_slen = nullptr;
     CUDA_CHECK(cudaEventRecord(ev[4], st));
-    for (int i = 0; i < nb; ++i)
-      if (!ss[begin + i]->samples.empty())
-        CUDA_CHECK(cudaMemcpyAsync(d_pcm + soff[i], ss[begin + i]->samples.data(), ss[begin + i]->samples.size() * sizeof(float),
-                                   cudaMemcpyHostToDevice, st));
+    if (resident) {
+      for (int i = 0; i < nb; ++i) {
+        const float *dp = ss[begin + i]->samples.empty() ? d_pcm : ss[begin + i]->samples.d;
+        soff[i] = (long long)((reinterpret_cast<intptr_t>(dp) - reinterpret_cast<intptr_t>(d_pcm)) / (intptr_t)sizeof(float));
+      }
+      d_slen = d_soff + nb + 1;
+      CUDA_CHECK(cudaMemcpyAsync(d_slen, slen.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, st));
+      // the pass must see the uploads accept_waveform queued on the device's copy stream
+      CUDA_CHECK(cudaEventRecord(ev_copy, DevicePcmPool::get(device).stream()));
+      CUDA_CHECK(cudaStreamWaitEvent(st, ev_copy, 0));
+      for (int i = 0; i < nb; ++i) ss[begin + i]->samples.in_flight = false;   // this pass ends synchronised, after them
+    } else {
+      for (int i = 0; i < nb; ++i)
+        if (!ss[begin + i]->samples.empty())
+          CUDA_CHECK(cudaMemcpyAsync(d_pcm + soff[i], ss[begin + i]->samples.data(), ss[begin + i]->samples.size() * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+    }
     CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(ev[5], st));
     // results
@@ -1075,7 +1219,7 @@ void Engine::decode(Stream *const *ss, int n) {
     SearchResultHost res{};
     int cap = 1;
     for (int i = 0; i < nb; ++i) {
-      const long long ns = soff[i + 1] - soff[i];
+      const long long ns = slen[i];
       const int T = (int)((ns + 80) / 160);
       const int T1 = T >= 9 ? (T - 7) / 2 : 0;
       cap = std::max(cap, (T1 + 1) / 2);
@@ -1083,7 +1227,9 @@ void Engine::decode(Stream *const *ss, int n) {
     std::vector<int> ntok(nb), toks((size_t)nb * cap), frm((size_t)nb * cap);
     std::vector<float> lp((size_t)nb * cap), stt((size_t)nb * cap * 4);
     res.n_tokens = ntok.data(); res.tokens = toks.data(); res.frames = frm.data(); res.tok_lp = lp.data(); res.stats = stt.data();
-    decode_pcm_device(d_pcm, d_soff, soff, nb, &res, &Tp);
+    const auto hp1 = std::chrono::steady_clock::now();
+    decode_pcm_device(d_pcm, d_soff, d_slen, slen, nb, &res, &Tp);
+    const auto hp2 = std::chrono::steady_clock::now();
     cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
     for (int i = 0; i < nb; ++i) {
       Stream *s = ss[begin + i];
@@ -1113,21 +1259,23 @@ void Engine::decode(Stream *const *ss, int n) {
       }
       size_t a = txt.find_first_not_of(' '), b = txt.find_last_not_of(' ');
       s->text = (a == std::string::npos) ? "" : txt.substr(a, b - a + 1);
-      std::string js = "{\"lang\": \"\", \"emotion\": \"\", \"event\": \"\", \"text\": \"" + json_escape(s->text) + "\", \"timestamps\": [";
-      char buf[64];
-      for (int j = 0; j < cnt; ++j) { snprintf(buf, sizeof buf, "%s%.3f", j ? ", " : "", s->timestamps[j]); js += buf; }
-      js += "], \"tokens\": [";
-      for (int j = 0; j < cnt; ++j) js += std::string(j ? ", " : "") + "\"" + json_escape(s->tok_str[j]) + "\"";
-      js += "], \"ys_log_probs\": [";
-      for (int j = 0; j < cnt; ++j) { snprintf(buf, sizeof buf, "%s%.6f", j ? ", " : "", s->lps[j]); js += buf; }
-      js += "], \"words\": []}";
-      s->json = js;
-      s->res.text = s->text.c_str(); s->res.json = s->json.c_str(); s->res.tokens = s->tok_ptr.data();
+      s->json.clear();
+      s->json_built = false;   // built on first request of the result (B200AsrGetOfflineStreamResult / ...AsJson)
+      s->res.text = s->text.c_str(); s->res.json = nullptr; s->res.tokens = s->tok_ptr.data();
       s->res.token_ids = s->token_ids.data(); s->res.timestamps = s->timestamps.data(); s->res.frames = s->frames.data();
       s->res.ys_log_probs = s->lps.data(); s->res.tsallis = s->tsallis.data(); s->res.margin = s->margin.data();
       s->res.entropy = s->entropy.data(); s->res.top1 = s->top1.data(); s->res.count = cnt; s->res.num_frames = Tp[i];
       s->res.duration = dur;
       s->decoded = true;
+    }
+    {
+      const auto hp3 = std::chrono::steady_clock::now();
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      tm.d2h = (float)ms(hp2, hp3);   // host-side result unpacking
+      static const bool host_prof = getenv("B200ASR_HOST_PROF") != nullptr;
+      if (host_prof)
+        fprintf(stderr, "[b200asr host prof] %d streams: stage+enqueue H2D %.2f ms | device pass (wall) %.2f ms | unpack results %.2f ms\n",
+                nb, ms(hp0, hp1), ms(hp1, hp2), ms(hp2, hp3));
     }
     begin = end;
   }
@@ -1221,6 +1369,7 @@ void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_
   auto *ms = const_cast<B200AsrOfflineStream *>(s);
   if (sample_rate != 16000) { g_last_error = "accept_waveform: only 16000 Hz is supported (no resampler on the path)"; return; }
   try { ms->s.samples.append(samples, (size_t)n); } catch (const std::exception &e) { g_last_error = e.what(); return; }
+  ms->s.samples.upload(ms->s.eng->device);
   ms->s.decoded = false;
 }
 
@@ -1242,11 +1391,13 @@ int32_t B200AsrDecodeOfflineStream(const B200AsrOfflineRecognizer *r, const B200
 
 const B200AsrOfflineRecognizerResult *B200AsrGetOfflineStreamResult(const B200AsrOfflineStream *s) {
   if (!s || !s->s.decoded) { g_last_error = "stream has not been decoded"; return nullptr; }
+  build_json(const_cast<Stream *>(&s->s));
   return &s->s.res;
 }
 void B200AsrDestroyOfflineRecognizerResult(const B200AsrOfflineRecognizerResult *) {}
 const char *B200AsrGetOfflineStreamResultAsJson(const B200AsrOfflineStream *s) {
   if (!s || !s->s.decoded) { g_last_error = "stream has not been decoded"; return nullptr; }
+  build_json(const_cast<Stream *>(&s->s));
   return strdup(s->s.json.c_str());
 }
 void B200AsrDestroyOfflineStreamResultJson(const char *s) { free(const_cast<char *>(s)); }
@@ -1276,7 +1427,9 @@ int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const float *sample
   float *d_feats = nullptr;
   std::vector<int> T;
   e->host_keep.clear();
-  e->run_fbank(d_pcm, d_soff, soff, n, &d_feats, &T);
+  std::vector<long long> slen(n);
+  for (int i = 0; i < n; ++i) slen[i] = soff[i + 1] - soff[i];
+  e->run_fbank(d_pcm, d_soff, nullptr, slen, n, &d_feats, &T);
   CUDA_CHECK(cudaMemcpyAsync(out, d_feats, (size_t)total_frames * 80 * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
   return (int32_t)total_frames;
@@ -1476,7 +1629,9 @@ int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle,
   std::vector<int> Tp, ntok(sgd.n);
   SearchResultHost res{};
   res.n_tokens = ntok.data();   // token arrays stay on the device; only counts come back
-  e->decode_pcm_device(sgd.pcm, sgd.soff, sgd.h_soff, sgd.n, &res, &Tp);
+  std::vector<long long> slen(sgd.n);
+  for (int i = 0; i < sgd.n; ++i) slen[i] = sgd.h_soff[i + 1] - sgd.h_soff[i];
+  e->decode_pcm_device(sgd.pcm, sgd.soff, nullptr, slen, sgd.n, &res, &Tp);
   if (n_tokens) memcpy(n_tokens, ntok.data(), sgd.n * sizeof(int));
   return 0;
   API_CATCH(-1)

@@ -26,13 +26,14 @@ constexpr float kFltEps = 1.1920929e-07f;
 __device__ __forceinline__ int bitrev8(int v) { return (int)(__brev((unsigned)v) >> 24); }
 
 __global__ void __launch_bounds__(kWarps * 32) fbank_kernel(const float *__restrict__ samples, const long long *__restrict__ sample_off,
+                                                            const long long *__restrict__ sample_len,
                                                             const long long *__restrict__ frame_off, const float *__restrict__ window,
                                                             const float *__restrict__ twiddle, const int *__restrict__ mel_start,
                                                             const int *__restrict__ mel_count, const int *__restrict__ mel_off,
                                                             const float *__restrict__ mel_w, float *__restrict__ out) {
   const int u = blockIdx.y;
   const long long s_begin = sample_off[u];
-  const long long n = sample_off[u + 1] - s_begin;
+  const long long n = sample_len ? sample_len[u] : sample_off[u + 1] - s_begin;   // explicit lengths: utterances need not be packed
   const long long f_begin = frame_off[u];
   const int T = (int)(frame_off[u + 1] - f_begin);
   const int f0 = blockIdx.x * kFramesPerCta;
@@ -193,12 +194,12 @@ void fbank_tables_destroy(FbankTables *t) {
   *t = FbankTables{};
 }
 
-void launch_fbank(const FbankTables &t, const float *samples, const long long *sample_off, const long long *frame_off, int n_utts,
-                  int max_frames, float *out, cudaStream_t st) {
+void launch_fbank(const FbankTables &t, const float *samples, const long long *sample_off, const long long *sample_len,
+                  const long long *frame_off, int n_utts, int max_frames, float *out, cudaStream_t st) {
   if (n_utts <= 0 || max_frames <= 0) return;
   // grid.x covers the longest utterance; CTAs past a shorter utterance's end exit immediately.
   dim3 grid((max_frames + kFramesPerCta - 1) / kFramesPerCta, n_utts);
-  fbank_kernel<<<grid, kWarps * 32, 0, st>>>(samples, sample_off, frame_off, t.window, t.twiddle, t.mel_start, t.mel_count,
+  fbank_kernel<<<grid, kWarps * 32, 0, st>>>(samples, sample_off, sample_len, frame_off, t.window, t.twiddle, t.mel_start, t.mel_count,
                                              t.mel_off, t.mel_w, out);
   count_launch();
   KERNEL_CHECK();
