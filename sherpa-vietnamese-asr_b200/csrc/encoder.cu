@@ -201,13 +201,27 @@ __global__ void __launch_bounds__(256) embed_dw7_kernel(const float *__restrict_
   for (int k = 0; k < 49; ++k) wr[k] = __ldg(w + k * 128 + c0 + c);
   const float bias = __ldg(b + c0 + c);
   float *o = out + ((long long)off[u] + t0 + tr) * 19 * 128 + c0 + c;
-  for (int f = 0; f < 19; ++f) {
-    float acc = bias;
+  // per kernel row a register window slides over the frequency axis (two halves of 10 + 9 outputs keep it small), so a
+  // patch value is read from shared memory once per kernel row instead of once per tap
 #pragma unroll
-    for (int dt = 0; dt < 7; ++dt)
+  for (int half = 0; half < 2; ++half) {
+    const int fb = half * 10;
+    float acc[10];
 #pragma unroll
-      for (int df = 0; df < 7; ++df) acc = fmaf(wr[dt * 7 + df], patch[((tr + dt) * 25 + f + df) * kDw7Ch + c], acc);
-    o[f * 128] = acc;
+    for (int f = 0; f < 10; ++f) acc[f] = bias;
+#pragma unroll
+    for (int dt = 0; dt < 7; ++dt) {
+      float row[16];
+#pragma unroll
+      for (int ff = 0; ff < 16; ++ff) row[ff] = (fb + ff < 25) ? patch[((tr + dt) * 25 + fb + ff) * kDw7Ch + c] : 0.f;
+#pragma unroll
+      for (int f = 0; f < 10; ++f)
+#pragma unroll
+        for (int df = 0; df < 7; ++df) acc[f] = fmaf(wr[dt * 7 + df], row[f + df], acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < 10; ++f)
+      if (fb + f < 19) o[(fb + f) * 128] = acc[f];
   }
 }
 
@@ -532,7 +546,10 @@ __global__ void __launch_bounds__(32 * CG) attn_apply_kernel(const float *__rest
 // shared memory with 128-bit loads; each thread then owns one channel and 32 consecutive frames and slides a register
 // window over them, so a staged value is read from shared memory once per 8 outputs instead of once per tap.
 constexpr int kDwT = 128, kDwC = 64, kDwMaxK = 31;
-__global__ void __launch_bounds__(256) glu_dwconv_kernel(const float *__restrict__ h, const int *__restrict__ len,
+// KMAX = 15 or 31: the register window and tap array are sized for the stack's kernel, so the k = 15 stacks run at
+// twice the occupancy of the k = 31 ones
+template <int KMAX>
+__global__ void __launch_bounds__(256, KMAX <= 15 ? 4 : 3) glu_dwconv_kernel(const float *__restrict__ h, const int *__restrict__ len,
                                                          const int *__restrict__ off, const int *__restrict__ tile_off, int n_utt,
                                                          int D, int k, const float *__restrict__ w, const float *__restrict__ b,
                                                          float *__restrict__ out) {
@@ -565,23 +582,23 @@ __global__ void __launch_bounds__(256) glu_dwconv_kernel(const float *__restrict
   const int c = threadIdx.x % kDwC, tq = threadIdx.x / kDwC;  // 4 groups x 32 frames
   const int gc = c0 + c;
   if (gc >= D) return;
-  float wr[kDwMaxK];
+  float wr[KMAX];
 #pragma unroll
-  for (int j = 0; j < kDwMaxK; ++j) wr[j] = j < k ? __ldg(w + j * D + gc) : 0.f;
+  for (int j = 0; j < KMAX; ++j) wr[j] = j < k ? __ldg(w + j * D + gc) : 0.f;
   const float bias = __ldg(b + gc);
   const int tend = min(kDwT, L - t0);
 #pragma unroll 1
   for (int f0 = tq * 32; f0 < tq * 32 + 32 && f0 < tend; f0 += 8) {
     // register window: outputs f0..f0+7 read staged rows f0..f0+7+k-1 (rows past the staged range belong to frames
     // that are not written)
-    float win[8 + kDwMaxK - 1];
+    float win[8 + KMAX - 1];
 #pragma unroll
-    for (int j = 0; j < 8 + kDwMaxK - 1; ++j) win[j] = (j < 8 + k - 1 && f0 + j < rows) ? g[f0 + j][c] : 0.f;
+    for (int j = 0; j < 8 + KMAX - 1; ++j) win[j] = (j < 8 + k - 1 && f0 + j < rows) ? g[f0 + j][c] : 0.f;
 #pragma unroll
     for (int f = 0; f < 8; ++f) {
       float acc = bias;
 #pragma unroll
-      for (int j = 0; j < kDwMaxK; ++j) acc = fmaf(wr[j], win[f + j], acc);   // wr[j] = 0 for j >= k
+      for (int j = 0; j < KMAX; ++j) acc = fmaf(wr[j], win[f + j], acc);   // wr[j] = 0 for j >= k
       if (f0 + f < tend) out[(rbase + t0 + f0 + f) * D + gc] = swoosh_r(acc);
     }
   }
@@ -751,7 +768,8 @@ void launch_glu_dwconv(const float *h, const RaggedDesc &r, const int *tile_off,
   if (k > kDwMaxK) throw CudaError("glu_dwconv: kernel size > 31 not built");
   if (D & 3) throw CudaError("glu_dwconv: channel count must be a multiple of 4");
   dim3 grid(n_tiles, cdiv(D, kDwC));
-  glu_dwconv_kernel<<<grid, 256, 0, st>>>(h, r.len, r.off, tile_off, r.n, D, k, w, b, out);
+  if (k <= 15) glu_dwconv_kernel<15><<<grid, 256, 0, st>>>(h, r.len, r.off, tile_off, r.n, D, k, w, b, out);
+  else glu_dwconv_kernel<31><<<grid, 256, 0, st>>>(h, r.len, r.off, tile_off, r.n, D, k, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
 
