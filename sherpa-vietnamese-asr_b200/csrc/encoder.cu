@@ -52,8 +52,8 @@ __global__ void embed_conv0_kernel(const float *__restrict__ feats, const int *_
 
 // conv1: [(T-2),80,8] -> [t2,39,32], k3 stride 2, SwooshR.   w: [3][3][8][32]
 // Persistent CTAs (the 9 KB of weights are staged in shared memory once per CTA) walk the packed output pixels of
-// the whole ragged batch; thread -> (pixel, group of 8 output channels); the utterance of a pixel is found by a
-// binary search over the packed row offsets.
+// the whole ragged batch; thread -> one output pixel (all 32 channels); the utterance of a pixel is found by a binary
+// search over the packed row offsets.
 __global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restrict__ in, const long long *__restrict__ ioff,
                                                           const long long *__restrict__ ooff, int n_utt,
                                                           const float *__restrict__ w, const float *__restrict__ b,
@@ -63,10 +63,8 @@ __global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restric
   for (int i = threadIdx.x; i < 72 * 32; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
-  const long long total = ooff[n_utt] * 39 * 4;     // (pixel, channel group) items
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long pix = idx >> 2;
-    const int cg = (int)(idx & 3) * 8;
+  const long long total = ooff[n_utt] * 39;         // output pixels
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
     const long long row = pix / 39;                 // packed output row (utterance, t)
     const int f = (int)(pix - row * 39);
     int lo = 0, hi = n_utt - 1;
@@ -76,9 +74,10 @@ __global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restric
     }
     const int t = (int)(row - __ldg(ooff + lo));
     const float *x = in + __ldg(ioff + lo) * 80 * 8;
-    float acc[8];
+    // one thread = one output pixel, all 32 output channels: each of the 72 input values is loaded once and feeds 32 FMAs
+    float acc[32];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = sb[cg + c];
+    for (int c = 0; c < 32; ++c) acc[c] = sb[c];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -89,16 +88,19 @@ __global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restric
         const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
-          const float4 w0 = *reinterpret_cast<const float4 *>(sw + ((kh * 3 + kw) * 8 + ci) * 32 + cg);
-          const float4 w1 = *reinterpret_cast<const float4 *>(sw + ((kh * 3 + kw) * 8 + ci) * 32 + cg + 4);
-          acc[0] = fmaf(v[ci], w0.x, acc[0]); acc[1] = fmaf(v[ci], w0.y, acc[1]); acc[2] = fmaf(v[ci], w0.z, acc[2]);
-          acc[3] = fmaf(v[ci], w0.w, acc[3]); acc[4] = fmaf(v[ci], w1.x, acc[4]); acc[5] = fmaf(v[ci], w1.y, acc[5]);
-          acc[6] = fmaf(v[ci], w1.z, acc[6]); acc[7] = fmaf(v[ci], w1.w, acc[7]);
+          const float4 *wr = reinterpret_cast<const float4 *>(sw + ((kh * 3 + kw) * 8 + ci) * 32);   // same address in the whole warp
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 w4 = wr[c4];
+            acc[4 * c4] = fmaf(v[ci], w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(v[ci], w4.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(v[ci], w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(v[ci], w4.w, acc[4 * c4 + 3]);
+          }
         }
       }
-    float4 *o = reinterpret_cast<float4 *>(out + pix * 32 + cg);
-    o[0] = make_float4(swoosh_r(acc[0]), swoosh_r(acc[1]), swoosh_r(acc[2]), swoosh_r(acc[3]));
-    o[1] = make_float4(swoosh_r(acc[4]), swoosh_r(acc[5]), swoosh_r(acc[6]), swoosh_r(acc[7]));
+    float4 *o = reinterpret_cast<float4 *>(out + pix * 32);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4)
+      o[c4] = make_float4(swoosh_r(acc[4 * c4]), swoosh_r(acc[4 * c4 + 1]), swoosh_r(acc[4 * c4 + 2]), swoosh_r(acc[4 * c4 + 3]));
   }
 }
 
@@ -625,7 +627,7 @@ void launch_embed_conv1(const float *in, const long long *ioff, const long long 
     CUDA_CHECK(cudaGetDevice(&dev));
     CUDA_CHECK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const long long items = total_rows * 39 * 4;
+  const long long items = total_rows * 39;
   const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)n_sms * 8);
   embed_conv1_kernel<<<grid, 256, 0, st>>>(in, ioff, ooff, n, w, b, out);
   count_launch(); KERNEL_CHECK();

@@ -656,12 +656,13 @@ __global__ void __launch_bounds__(kSelThreads) select_partials_kernel(SearchMode
       sh.sum[b] = sum;
       sh.lse[b] = lse;
       sh.prev[b] = greedy ? 0.f : (float)sh.old_[b].score;   // score rounded to f32 before the add (:1099-1100)
-      const double a = 1.0 / 3.0;
-      const double tsallis = (1.0 / (a - 1.0)) * (1.0 - (double)(st * __expf(-lse * (1.0f / 3.0f))));
+      // fp32 is ample for statistics compared at 1e-4 (FP64 is a slow path on this part and sits on the step's critical path)
+      const float ts_max = (float)m.ts_max, max_ent = (float)m.max_ent;
+      const float tsallis = -1.5f * (1.0f - st * __expf(-lse * (1.0f / 3.0f)));   // 1 / (alpha - 1), alpha = 1/3
       const float p1 = expf(t1 - mx) / sum, p2 = V > 1 ? expf(t2 - mx) / sum : 1e-10f;
-      sh.rstats[b][0] = (float)(m.ts_max > 0 ? tsallis / m.ts_max : 0.0);
+      sh.rstats[b][0] = ts_max > 0.f ? tsallis / ts_max : 0.f;
       sh.rstats[b][1] = p1 - p2;
-      sh.rstats[b][2] = (float)(-((double)(su / sum) - (double)lse) / m.max_ent);
+      sh.rstats[b][2] = -(su / sum - lse) / max_ent;
       sh.rstats[b][3] = p1;
     }
   }

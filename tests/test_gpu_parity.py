@@ -315,6 +315,28 @@ def test_end_to_end_streams_match_oracle(m30):
     assert exact == len(audios)
 
 
+def test_c1_greedy_10s_clip_end_to_end(model_dirs):
+    """BASELINE config C1: Zipformer-30M, greedy_search, one synthetic 10 s 16 kHz clip (seed 1234) through
+    create_stream / accept_waveform / decode_stream, against the oracle's fbank -> encoder -> greedy search."""
+    from oracle import fbank_ref, search_ref as sr
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, d = model_dirs("zipformer-30m", 30)
+    rec = _gpu_rec(paths, decoding_method="greedy_search")
+    orec, ocfg, _ = oracle_recognizer(paths, beam=1)
+    a = synth.speech_like(160000, 1234)
+    s = rec.create_stream()
+    s.accept_waveform(16000, a)
+    rec.decode_stream(s)
+    feats = fbank_ref.fbank(a, np.float64)
+    assert feats.shape == (1000, 80)
+    toks, frames, lps, T, _ = sr.greedy_search(orec, feats)
+    assert T == 248 and s.result.num_frames == 248
+    assert s.result.token_ids == toks and len(toks) > 5
+    assert s.result.frames == frames
+    np.testing.assert_allclose(s.result.ys_log_probs, lps, atol=5e-3)
+    assert abs(s.result.timestamps[0] - frames[0] / 248 * 10.0) < 1e-4
+
+
 # ----------------------------------------------------------------------------- GEMM kernels
 GEMM_SHAPES = [(1000, 272, 192), (517, 48, 192), (4096, 640, 192), (130, 2000, 512), (777, 192, 2432), (64, 16, 48),
                (2500, 384, 128), (3000, 512, 512), (129, 130, 36)]
