@@ -44,12 +44,12 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
 
-// ACT_TANH_RES: out = tanh(acc + bias + R) (the joiner input tanh(decoder_out + encoder_out)); the others: act(acc + bias) + R
+// out = act(acc + bias) + R
 // ACT_JOINER (tensor-core kernels only): out = acc + bias (the caller folds a blank penalty into the bias) and, per row and per
 // 32-column part, a partial record {mx = max, S e^(x-mx), S e^(x-mx)(x-mx), S e^((x-mx)/3), top-kb values, top-kb
 // columns}: enough for the log-softmax, the global top-k and the per-token entropy / Tsallis / margin statistics,
 // so the beam-search selection never reads the logits (search.cu); C may be null to skip storing them at all.
-enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2, ACT_TANH_RES = 3, ACT_JOINER = 4 };
+enum Act : int { ACT_NONE = 0, ACT_SWOOSH_L = 1, ACT_SWOOSH_R = 2, ACT_JOINER = 4 };
 constexpr int kPartCols = 32;                                        // logits columns per partial record
 inline int part_rec_floats(int kb) { return 4 + 2 * kb; }            // floats per record
 
@@ -77,7 +77,6 @@ struct GemmArgs {
   const float *Wlo;          // W - trunc_tf32(W), needed by the 3xTF32 tensor-core kernel only (else null)
   const float *bias;         // [N] or null
   const float *R; int ldr;   // residual or null
-  const int *r_rows;         // optional row map for the residual: row m of C adds row r_rows[m] of R
   float *C; int ldc;
   int M, N, K;
   int act;
@@ -104,8 +103,6 @@ void launch_embed_conv0(const float *feats, const int *T, const long long *foff,
 // ioff / ooff: [n+1] packed row offsets of the conv0 / conv1 outputs; total_rows = ooff[n]
 void launch_embed_conv1(const float *in, const long long *ioff, const long long *ooff, int n, long long total_rows, const float *w,
                         const float *b, float *out, cudaStream_t st);
-void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,
-                        const float *w, const float *b, float *out, cudaStream_t st);
 void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,
                           cudaStream_t st);
 void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st);
@@ -178,7 +175,6 @@ struct SearchModel {
   const float *dec_proj_b;
   const float *join_w;     // [V, jd]
   const float *join_w_lo;  // low part for the 3xTF32 joiner GEMM (or null)
-  const float *dec_proj_w_lo;
   const float *join_b;
   int V, dd, jd;
   int blank_id, unk_id;

@@ -104,61 +104,7 @@ __global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restric
   }
 }
 
-// conv2: [t2,39,32] -> [T1,19,128], k3 stride (1,2), SwooshR.  w: [3][3][32][128]
-// CTA = 4 output time rows of one utterance; the 6x39x32 input patch sits in shared memory; thread = one
-// output channel x half of the 19 frequency positions.
-constexpr int kC2Rows = 4;
-__global__ void __launch_bounds__(256) embed_conv2_kernel(const float *__restrict__ in, const int *__restrict__ T,
-                                                          const long long *__restrict__ ioff, const int *__restrict__ ooff,
-                                                          const float *__restrict__ w, const float *__restrict__ b,
-                                                          float *__restrict__ out) {
-  __shared__ __align__(16) float patch[(kC2Rows + 2) * 39 * 32];
-  const int u = blockIdx.y;
-  const int Tu = T[u];
-  const int T1 = (Tu - 7) / 2;
-  const int t0 = blockIdx.x * kC2Rows;
-  if (Tu < 9 || t0 >= T1) return;
-  const int t2 = (Tu - 5) / 2 + 1;
-  const float *x = in + ioff[u] * 39 * 32;
-  const int rows = min(kC2Rows + 2, t2 - t0);
-  for (int i = threadIdx.x; i < (kC2Rows + 2) * 39 * 32 / 4; i += blockDim.x) {
-    const int r = i / (39 * 32 / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < rows) v = __ldg(reinterpret_cast<const float4 *>(x + (long long)t0 * 39 * 32) + i);
-    reinterpret_cast<float4 *>(patch)[i] = v;
-  }
-  __syncthreads();
-  const int co = threadIdx.x & 127, fh = threadIdx.x >> 7;  // fh 0: f 0..9, fh 1: f 10..18
-  const int fbeg = fh * 10, fcnt = fh ? 9 : 10;
-  float acc[kC2Rows][10];
-#pragma unroll
-  for (int r = 0; r < kC2Rows; ++r)
-#pragma unroll
-    for (int j = 0; j < 10; ++j) acc[r][j] = 0.f;
-  for (int kh = 0; kh < 3; ++kh)
-    for (int kw = 0; kw < 3; ++kw)
-      for (int ci = 0; ci < 32; ++ci) {
-        const float wv = __ldg(w + ((kh * 3 + kw) * 32 + ci) * 128 + co);
-#pragma unroll
-        for (int r = 0; r < kC2Rows; ++r) {
-          const float *pr = patch + ((r + kh) * 39 + kw) * 32 + ci;
-#pragma unroll
-          for (int j = 0; j < 10; ++j)
-            if (j < fcnt) acc[r][j] = fmaf(wv, pr[(2 * (fbeg + j)) * 32], acc[r][j]);
-        }
-      }
-  const float bias = __ldg(b + co);
-#pragma unroll
-  for (int r = 0; r < kC2Rows; ++r) {
-    const int t = t0 + r;
-    if (t >= T1) break;
-#pragma unroll
-    for (int j = 0; j < 10; ++j)
-      if (j < fcnt) out[((long long)(ooff[u] + t) * 19 + fbeg + j) * 128 + co] = swoosh_r(acc[r][j] + bias);
-  }
-}
-
-// conv2 as a GEMM: im2col rows [pixel (t,f)][(kh,kw,ci)] = 9 contiguous 128-byte chunks of the channels-last
+// conv2 ([t2,39,32] -> [T1,19,128], k3 stride (1,2), SwooshR) as a GEMM: im2col rows [pixel (t,f)][(kh,kw,ci)] = 9 contiguous 128-byte chunks of the channels-last
 // conv1 output, so both the gather reads and the row writes are fully coalesced; the 288 -> 128 contraction then
 // runs on the tensor pipe (gemm_tc.cu) with bias + SwooshR in its epilogue.
 __global__ void embed_im2col2_kernel(const float *__restrict__ in, const int *__restrict__ T, const long long *__restrict__ ioff,
@@ -630,13 +576,6 @@ void launch_embed_conv1(const float *in, const long long *ioff, const long long 
   const long long items = total_rows * 39;
   const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)n_sms * 8);
   embed_conv1_kernel<<<grid, 256, 0, st>>>(in, ioff, ooff, n, w, b, out);
-  count_launch(); KERNEL_CHECK();
-}
-void launch_embed_conv2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1,
-                        const float *w, const float *b, float *out, cudaStream_t st) {
-  if (max_T1 <= 0) return;
-  dim3 grid(cdiv(max_T1, kC2Rows), n);
-  embed_conv2_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
 void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,

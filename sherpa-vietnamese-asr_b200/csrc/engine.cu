@@ -717,11 +717,6 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
     owned.push_back(lo);
     launch_split_lo(sm.join_w, lo, (long long)V * join_dim, st);
     sm.join_w_lo = lo;
-    float *lo2;
-    CUDA_CHECK(cudaMalloc(&lo2, (size_t)join_dim * dec_dim * sizeof(float)));
-    owned.push_back(lo2);
-    launch_split_lo(sm.dec_proj_w, lo2, (long long)join_dim * dec_dim, st);
-    sm.dec_proj_w_lo = lo2;
   }
 
   // hotwords file with token ids (modeling_unit token_id); text units are tokenised by the host binding

@@ -126,13 +126,8 @@ __global__ void __launch_bounds__(NT) gemm_fp32_kernel(GemmArgs g) {
         if (n >= g.N) continue;
         float val = acc[i][v * 4 + j];
         if (g.bias) val += __ldg(g.bias + n);
-        const long long rrow = g.r_rows ? (long long)g.r_rows[m] : (long long)m;
-        if (g.act == ACT_TANH_RES) {
-          val = tanhf(val + (g.R ? g.R[rrow * g.ldr + n] : 0.f));
-        } else {
-          val = apply_act(val, g.act);
-          if (g.R) val += g.R[rrow * g.ldr + n];
-        }
+        val = apply_act(val, g.act);
+        if (g.R) val += g.R[(long long)m * g.ldr + n];
         g.C[(long long)m * g.ldc + n] = val;
       }
     }

@@ -52,7 +52,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct TcParams {
   const float *bias;
   const float *R; int ldr;
-  const int *r_rows;
   float *C; int ldc;
   int M, N, K, act;
   float *partials;   // joiner epilogue (EPI > 0)
@@ -312,10 +311,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
           for (int it = 0; it < 8; ++it) {                   // all residual loads in flight before use
             const int m = mrow0 + rsub + 4 * it;
             float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.R && nv && m < p.M) {
-              const long long rrow = p.r_rows ? (long long)__ldg(p.r_rows + m) : (long long)m;
-              rv = *reinterpret_cast<const float4 *>(p.R + rrow * p.ldr + n);
-            }
+            if (p.R && nv && m < p.M) rv = *reinterpret_cast<const float4 *>(p.R + (long long)m * p.ldr + n);
             res[it] = rv;
           }
 #pragma unroll
@@ -323,13 +319,8 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const int rr = rsub + 4 * it, m = mrow0 + rr;
             if (nv && m < p.M) {
               float4 v = lds128(stg + (uint32_t)(rr * 32 + (((lane & 7) ^ (rr & 7)) << 2)) * 4u);
-              if (p.act == ACT_TANH_RES) {
-                v.x = tanhf(v.x + bv.x + res[it].x); v.y = tanhf(v.y + bv.y + res[it].y);
-                v.z = tanhf(v.z + bv.z + res[it].z); v.w = tanhf(v.w + bv.w + res[it].w);
-              } else {
-                v.x = apply_act(v.x + bv.x, p.act) + res[it].x; v.y = apply_act(v.y + bv.y, p.act) + res[it].y;
-                v.z = apply_act(v.z + bv.z, p.act) + res[it].z; v.w = apply_act(v.w + bv.w, p.act) + res[it].w;
-              }
+              v.x = apply_act(v.x + bv.x, p.act) + res[it].x; v.y = apply_act(v.y + bv.y, p.act) + res[it].y;
+              v.z = apply_act(v.z + bv.z, p.act) + res[it].z; v.w = apply_act(v.w + bv.w, p.act) + res[it].w;
               *reinterpret_cast<float4 *>(p.C + (long long)m * p.ldc + n) = v;
             }
           }
@@ -344,9 +335,8 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             if (nv && m < p.M) {
               const float4 v4 = lds128(stg + (uint32_t)(rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2)) * 4u);
               float v = ((lane & 3) == 0 ? v4.x : (lane & 3) == 1 ? v4.y : (lane & 3) == 2 ? v4.z : v4.w) + bs;
-              const long long rrow = p.r_rows ? (long long)p.r_rows[m] : (long long)m;
-              const float rv = p.R ? p.R[rrow * p.ldr + n] : 0.f;
-              v = (p.act == ACT_TANH_RES) ? tanhf(v + rv) : apply_act(v, p.act) + rv;
+              const float rv = p.R ? p.R[(long long)m * p.ldr + n] : 0.f;
+              v = apply_act(v, p.act) + rv;
               p.C[(long long)m * p.ldc + n] = v;
             }
           }
@@ -539,7 +529,7 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   make_map_impl(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_impl(&mw, g.W, g.N, g.K, g.K, BN);
   make_map_impl(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.r_rows, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace};
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, n_sms);   // persistent: one CTA per SM
   // one launcher per instantiation; the opt-in shared-memory attribute is set on first use
