@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(SPLIT3 ? 448 : 320, 1)
 gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                          const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
   static_assert(!ATMEM || SPLIT3, "A-in-TMEM is the 3xTF32 path");
+  // EPI <= 0 also carries the activation as a compile-time constant (0 none, -1 SwooshL, -2 SwooshR): the epilogue of
+  // the K = 192..256 layers is as long as their main loop, and a run-time switch per element showed up in it
+  constexpr int kAct = EPI == -1 ? (int)ACT_SWOOSH_L : (EPI == -2 ? (int)ACT_SWOOSH_R : (int)ACT_NONE);
   constexpr int NS = ATMEM ? 4 : stages_for(BN, SPLIT3);
   constexpr uint32_t kAccCols = 2 * BN;                       // two accumulators
   constexpr uint32_t kTmemACol = 256;                         // ATMEM: A stages at columns 256 + 64 s (hi) / + 32 (lo)
@@ -319,8 +322,8 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const int rr = rsub + 4 * it, m = mrow0 + rr;
             if (nv && m < p.M) {
               float4 v = lds128(stg + (uint32_t)(rr * 32 + (((lane & 7) ^ (rr & 7)) << 2)) * 4u);
-              v.x = apply_act(v.x + bv.x, p.act) + res[it].x; v.y = apply_act(v.y + bv.y, p.act) + res[it].y;
-              v.z = apply_act(v.z + bv.z, p.act) + res[it].z; v.w = apply_act(v.w + bv.w, p.act) + res[it].w;
+              v.x = apply_act(v.x + bv.x, kAct) + res[it].x; v.y = apply_act(v.y + bv.y, kAct) + res[it].y;
+              v.z = apply_act(v.z + bv.z, kAct) + res[it].z; v.w = apply_act(v.w + bv.w, kAct) + res[it].w;
               *reinterpret_cast<float4 *>(p.C + (long long)m * p.ldc + n) = v;
             }
           }
@@ -336,7 +339,7 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
               const float4 v4 = lds128(stg + (uint32_t)(rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2)) * 4u);
               float v = ((lane & 3) == 0 ? v4.x : (lane & 3) == 1 ? v4.y : (lane & 3) == 2 ? v4.z : v4.w) + bs;
               const float rv = p.R ? p.R[(long long)m * p.ldr + n] : 0.f;
-              v = apply_act(v, p.act) + rv;
+              v = apply_act(v, kAct) + rv;
               p.C[(long long)m * p.ldc + n] = v;
             }
           }
@@ -560,10 +563,17 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   if (joiner) {
     if (split3) { if (BN == 128) B200_TC_JOINER(128, true); else B200_TC_JOINER(64, true); }
     else { if (BN == 128) B200_TC_JOINER(128, false); else B200_TC_JOINER(64, false); }
-  } else if (split3) {
-    if (BN == 128) B200_TC_LAUNCH(128, true, 0); else B200_TC_LAUNCH(64, true, 0);
   } else {
-    if (BN == 128) B200_TC_LAUNCH(128, false, 0); else B200_TC_LAUNCH(64, false, 0);
+#define B200_TC_ACT(BN_, S3_)                                                                      \
+  do {                                                                                             \
+    if (g.act == ACT_SWOOSH_L) B200_TC_LAUNCH(BN_, S3_, -1);                                       \
+    else if (g.act == ACT_SWOOSH_R) B200_TC_LAUNCH(BN_, S3_, -2);                                  \
+    else B200_TC_LAUNCH(BN_, S3_, 0);                                                              \
+  } while (0)
+    if (g.act != ACT_NONE && g.act != ACT_SWOOSH_L && g.act != ACT_SWOOSH_R) throw CudaError("tcgen05 GEMM: unknown activation");
+    if (split3) { if (BN == 128) B200_TC_ACT(128, true); else B200_TC_ACT(64, true); }
+    else { if (BN == 128) B200_TC_ACT(128, false); else B200_TC_ACT(64, false); }
+#undef B200_TC_ACT
   }
 #undef B200_TC_JOINER
 #undef B200_TC_LAUNCH
