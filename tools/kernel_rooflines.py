@@ -79,9 +79,11 @@ def main():
             continue
         gbs = by / 1e9 / (t * 1e-6)
         print(f"| `{key}` | {c} | {t / 1e3:.2f} | HBM | {by / 1e9:.2f} GB | {gbs:.0f} GB/s | {gbs / hbm:.3f} |")
-    c, t = fam("gemm_tf32_tcgen05_kernel<128, 1, 0")
-    c2, t2_ = fam("gemm_tf32_tcgen05_kernel<64, 1, 0")
-    c, t = c + c2, t + t2_
+    c = t = 0
+    for pre in ("gemm_tf32_tcgen05_kernel<128, 1, 0", "gemm_tf32_tcgen05_kernel<64, 1, 0", "gemm_tf32_tcgen05_kernel<128, 1, -",
+                "gemm_tf32_tcgen05_kernel<64, 1, -"):   # EPI 0 / -1 / -2 = encoder Linears (none / SwooshL / SwooshR)
+        cc, tt = fam(pre)
+        c, t = c + cc, t + tt
     if c:
         a = fl_gemm / 1e12 / (t * 1e-6)
         print(f"| `gemm_tf32_tcgen05_kernel` (encoder Linears, 3xTF32) | {c} | {t / 1e3:.2f} | tensor | {fl_gemm / 1e12:.2f} TFLOP (x3 MMAs issued) | "

@@ -15,7 +15,8 @@ def load(path):
         v = float(x["Metric Value"].replace(",", ""))
         u = x["Metric Unit"]
         v = v / 1e3 if u == "ns" else v * 1e3 if u == "ms" else v
-        name = re.sub(r"\(.*", "", x["Kernel Name"]).replace("unnamed>::", "").replace("void ", "")
+        name = re.sub(r"\((int|bool|unsigned int)\)", "", x["Kernel Name"])      # template-argument casts, e.g. <128, 1, (int)-1, 1>
+        name = re.sub(r"\(.*", "", name).replace("unnamed>::", "").replace("void ", "")
         rows.append((int(x["ID"]), name, x["Grid Size"], x["Block Size"], v))
     return rows
 
