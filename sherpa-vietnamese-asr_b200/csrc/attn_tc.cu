@@ -295,14 +295,10 @@ void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C,
 void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st) {
   if (a.n_tiles <= 0) return;
   if (!tc_init()) throw CudaError("tcgen05 attention: cuTensorMapEncodeTiled entry point unavailable");
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_tcgen05_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(16, false)));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_tcgen05_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(16, true)));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_tcgen05_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(64, false)));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_tcgen05_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(64, true)));
-    attr_done = true;
-  }
+  set_max_dynamic_smem(attn_apply_tcgen05_kernel<16, false>, attn_smem(16, false));
+  set_max_dynamic_smem(attn_apply_tcgen05_kernel<16, true>, attn_smem(16, true));
+  set_max_dynamic_smem(attn_apply_tcgen05_kernel<64, false>, attn_smem(64, false));
+  set_max_dynamic_smem(attn_apply_tcgen05_kernel<64, true>, attn_smem(64, true));
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev = 0;

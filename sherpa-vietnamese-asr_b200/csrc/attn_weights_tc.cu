@@ -307,12 +307,8 @@ void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float
                             const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st) {
   if (n_tiles <= 0 || r.total <= 0) return;
   if (!tc_init()) throw CudaError("tcgen05 attention weights: cuTensorMapEncodeTiled entry point unavailable");
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_CHECK(cudaFuncSetAttribute(attn_weights_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAwSmem));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_weights_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAwSmem));
-    attr_done = true;
-  }
+  set_max_dynamic_smem(attn_weights_tcgen05_kernel<true>, kAwSmem);
+  set_max_dynamic_smem(attn_weights_tcgen05_kernel<false>, kAwSmem);
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev = 0;

@@ -40,6 +40,12 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 }
 #endif
 
+// Opt-in dynamic shared memory: the attribute belongs to the (function, device) pair, so remember what has been set per
+// device - a process may hold recognizers on several GPUs.
+void set_max_dynamic_smem_impl(const void *func, int bytes);
+template <typename F>
+inline void set_max_dynamic_smem(F *func, size_t bytes) { set_max_dynamic_smem_impl(reinterpret_cast<const void *>(func), (int)bytes); }
+
 // Global launch counter (host side) so bench.py can report `gpu_launches`.
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }

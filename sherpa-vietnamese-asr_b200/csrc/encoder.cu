@@ -670,11 +670,7 @@ void launch_attn_weights(const float *proj, int ldp, const float *pos, const Rag
   if (qd != 32 || pd != 4) throw CudaError("attn_weights: only query_head_dim=32, pos_head_dim=4 are built");
   const size_t smem = (size_t)(kAttRows * (qd + pd) + qd * kAttKStride + (size_t)kAttRows * r.max_len) * sizeof(float);
   if (smem > 227 * 1024) throw CudaError("attn_weights: segment too long for one pass (max ~2900 frames at the stack rate)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(attn_weights_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  set_max_dynamic_smem(attn_weights_kernel<32, 4>, 227 * 1024);
   dim3 grid(cdiv(r.max_len, kAttRows), H, r.n);
   attn_weights_kernel<32, 4><<<grid, 256, smem, st>>>(proj, ldp, pos, H * pd, r.len, r.off, aoff, H, r.max_len, A);
   count_launch(); KERNEL_CHECK();
@@ -684,12 +680,8 @@ void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &
                        const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st) {
   if (r.total <= 0) return;
   constexpr int RPT = 8, ROWS = 32 * RPT;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<8, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    CUDA_CHECK(cudaFuncSetAttribute(attn_apply_kernel<3, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
+  set_max_dynamic_smem(attn_apply_kernel<8, RPT>, 64 * 1024);
+  set_max_dynamic_smem(attn_apply_kernel<3, RPT>, 64 * 1024);
   if (single_head) {
     const size_t smem = (size_t)(ROWS * 33 + 32 * 32) * sizeof(float);
     dim3 grid(cdiv(r.max_len, ROWS), cdiv(C, 32), r.n);

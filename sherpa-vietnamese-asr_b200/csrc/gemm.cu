@@ -6,11 +6,26 @@
 //
 // Tiling: 128 x BN x 16 per CTA, 256 threads, 8 x (BN/16) outputs per thread, register-staged double buffering,
 // operands transposed into shared memory so the inner product reads are conflict-free 128-bit loads.
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.cuh"
 
 namespace b200asr {
 
 long long g_launches = 0;
+
+void set_max_dynamic_smem_impl(const void *func, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void *, int>> done;   // (function, device)
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({func, dev})) return;
+  CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.insert({func, dev});
+}
 
 namespace {
 

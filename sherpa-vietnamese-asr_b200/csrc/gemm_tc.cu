@@ -538,12 +538,7 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   // one launcher per instantiation; the opt-in shared-memory attribute is set on first use
 #define B200_TC_LAUNCH_(BN_, S3_, EPI_, ATM_)                                                                              \
   do {                                                                                                                    \
-    static bool attr = false;                                                                                             \
-    if (!attr) {                                                                                                          \
-      CUDA_CHECK(cudaFuncSetAttribute(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_, ATM_>,                                     \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(BN_, S3_, ATM_)));     \
-      attr = true;                                                                                                        \
-    }                                                                                                                     \
+    set_max_dynamic_smem(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_, ATM_>, smem_bytes(BN_, S3_, ATM_));                     \
     launch_pdl(gemm_tf32_tcgen05_kernel<BN_, S3_, EPI_, ATM_>, dim3(grid), dim3((S3_) ? 448 : 320),                       \
                smem_bytes(BN_, S3_, ATM_), st, g.pdl != 0, ma, mw, mwl, p);                                               \
   } while (0)

@@ -991,22 +991,12 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
 
   if (m.V & 3) throw CudaError("beam search: vocab_size must be a multiple of 4");
   if (!fused) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    set_max_dynamic_smem(select_step_kernel<4>, 200 * 1024);
+    set_max_dynamic_smem(select_step_kernel<8>, 200 * 1024);
+    set_max_dynamic_smem(select_step_kernel<16>, 200 * 1024);
     if ((size_t)beam * m.V * sizeof(float) > 200 * 1024) throw CudaError("beam * vocab_size too large for the selection kernel");
   }
-  {
-    static bool dj_attr = false;
-    if (!dj_attr) {
-      CUDA_CHECK(cudaFuncSetAttribute(decoder_joinin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDjSmem));
-      dj_attr = true;
-    }
-  }
+  set_max_dynamic_smem(decoder_joinin_kernel, kDjSmem);
   if (!m.conv_p0 || !m.conv_p1) throw CudaError("beam search: decoder convolution tables are missing");
   init_search_kernel<<<n, 128, 0, st>>>(m, d);
   count_launch(); KERNEL_CHECK();
