@@ -321,7 +321,7 @@ def main():
                      "gemm_ms_per_step": gs["ms"], "gemm_launches_per_step": gs["launches"],
                      "gemm_share_of_step": gs["ms"] / tm_prof["total_ms"] if tm_prof["total_ms"] else None},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the bounded CPU sample is an N=1 figure (rank 0's host cores)
         cores = min(physical_cores(), 32)
         sample = audios[: args.cpu_sample]
         dt, _ = cpu_reference_pass(cfg, paths, sample, args.beam, cores)
