@@ -776,6 +776,10 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
                   int N, int K, int act) {
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = Wt; g.bias = bias; g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.act = act;
+  // programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch) runs on SMs
+  // the previous kernel has already left; it waits for that kernel's completion before its first global access
+  static const bool enc_pdl = getenv("B200ASR_NO_PDL") == nullptr;
+  g.pdl = (enc_pdl && !profiling) ? 1 : 0;
   if (M <= 0) return;
   if (precision == 0) {
     auto it = w_lo.find(Wt);
