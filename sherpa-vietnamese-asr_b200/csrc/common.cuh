@@ -104,14 +104,18 @@ struct RaggedDesc {     // per-rate description of the packed batch, all device 
   int max_len;
 };
 
-void launch_embed_conv0(const float *feats, const int *T, const long long *foff, const long long *ooff, int n, int max_T,
-                        const float *w, const float *b, float *out, cudaStream_t st);
+// foff / ooff: [n+1] packed row offsets of the features / conv0 outputs; total_rows = ooff[n]
+void launch_embed_conv0(const float *feats, const long long *foff, const long long *ooff, int n, long long total_rows, const float *w,
+                        const float *b, float *out, cudaStream_t st);
 // ioff / ooff: [n+1] packed row offsets of the conv0 / conv1 outputs; total_rows = ooff[n]
 void launch_embed_conv1(const float *in, const long long *ioff, const long long *ooff, int n, long long total_rows, const float *w,
                         const float *b, float *out, cudaStream_t st);
-void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,
+// ioff: [n+1] packed row offsets of the conv1 outputs, ooff: [n+1] of the conv2 outputs; total_rows = ooff[n]
+void launch_embed_im2col2(const float *in, const long long *ioff, const int *ooff, int n, long long total_rows, float *out,
                           cudaStream_t st);
-void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st);
+// tile_off = cumulative ceil(len / 128) per utterance
+void launch_embed_dw7(const float *in, const RaggedDesc &r, const int *tile_off, int n_tiles, const float *w, const float *b,
+                      float *out, cudaStream_t st);
 void launch_biasnorm(const float *x, int M, int D, const float *bias, const float *log_scale, float *out, cudaStream_t st);
 // out = orig + (biasnorm(x) - orig) * bypass
 void launch_biasnorm_bypass(const float *x, const float *orig, int M, int D, const float *bias, const float *log_scale,

@@ -23,16 +23,29 @@ __device__ __forceinline__ float swoosh_r(float v) { return softplus_f(v - 1.0f)
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ------------------------------------------------------------------ Conv2dSubsampling (App. B.2)
+// last u with off[u] <= row (off ascending, off[n] = total)
+template <typename T>
+__device__ __forceinline__ int find_utt(const T *__restrict__ off, int n, long long row) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)__ldg(off + mid) <= row) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 // conv0: [T,80] -> [(T-2),80,8] channels-last, k3, pad (0,1), SwooshR.   w: [3][3][8] (kh,kw,co)
-__global__ void embed_conv0_kernel(const float *__restrict__ feats, const int *__restrict__ T, const long long *__restrict__ foff,
-                                   const long long *__restrict__ ooff, const float *__restrict__ w, const float *__restrict__ b,
-                                   float *__restrict__ out) {
-  const int u = blockIdx.y;
-  const int To = T[u] - 2;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (To <= 0 || idx >= To * 80) return;
-  const int t = idx / 80, f = idx % 80;
-  const float *x = feats + foff[u] * 80;
+// flat over the packed output pixels (row, f) of the whole ragged batch; thread = one pixel, 8 channels
+__global__ void embed_conv0_kernel(const float *__restrict__ feats, const long long *__restrict__ foff,
+                                   const long long *__restrict__ ooff, int n_utt, const float *__restrict__ w,
+                                   const float *__restrict__ b, float *__restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ooff[n_utt] * 80) return;
+  const long long row = idx / 80;
+  const int f = (int)(idx - row * 80);
+  const int u = find_utt(ooff, n_utt, row);
+  const int t = (int)(row - __ldg(ooff + u));
+  const float *x = feats + __ldg(foff + u) * 80;
   float acc[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) acc[c] = __ldg(b + c);
@@ -45,9 +58,9 @@ __global__ void embed_conv0_kernel(const float *__restrict__ feats, const int *_
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, __ldg(w + (kh * 3 + kw) * 8 + c), acc[c]);
     }
-  float *o = out + ((ooff[u] + t) * 80 + f) * 8;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) o[c] = swoosh_r(acc[c]);
+  float4 *o = reinterpret_cast<float4 *>(out + idx * 8);
+  o[0] = make_float4(swoosh_r(acc[0]), swoosh_r(acc[1]), swoosh_r(acc[2]), swoosh_r(acc[3]));
+  o[1] = make_float4(swoosh_r(acc[4]), swoosh_r(acc[5]), swoosh_r(acc[6]), swoosh_r(acc[7]));
 }
 
 // conv1: [(T-2),80,8] -> [t2,39,32], k3 stride 2, SwooshR.   w: [3][3][8][32]
@@ -107,20 +120,27 @@ __global__ void __launch_bounds__(256) embed_conv1_kernel(const float *__restric
 // conv2 ([t2,39,32] -> [T1,19,128], k3 stride (1,2), SwooshR) as a GEMM: im2col rows [pixel (t,f)][(kh,kw,ci)] = 9 contiguous 128-byte chunks of the channels-last
 // conv1 output, so both the gather reads and the row writes are fully coalesced; the 288 -> 128 contraction then
 // runs on the tensor pipe (gemm_tc.cu) with bias + SwooshR in its epilogue.
-__global__ void embed_im2col2_kernel(const float *__restrict__ in, const int *__restrict__ T, const long long *__restrict__ ioff,
-                                     const int *__restrict__ ooff, float *__restrict__ out) {
-  const int u = blockIdx.y;
-  const int Tu = T[u];
-  const int T1 = Tu >= 9 ? (Tu - 7) / 2 : 0;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of one chunk
-  if (idx >= (long long)T1 * 19 * 72) return;
+// Flat over the packed output pixels; thread = (pixel, one float4 of the 32-channel chunk) walks the 9 taps.
+__global__ void embed_im2col2_kernel(const float *__restrict__ in, const long long *__restrict__ ioff, const int *__restrict__ ooff,
+                                     int n_utt, float *__restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_pix = (long long)ooff[n_utt] * 19;
+  if (idx >= n_pix * 8) return;
   const int q = (int)(idx & 7);            // float4 within the 32-channel chunk
-  const int tap = (int)((idx >> 3) % 9);   // kh*3+kw
-  const long long pix = (idx >> 3) / 9;
-  const int f = (int)(pix % 19), t = (int)(pix / 19);
-  const int kh = tap / 3, kw = tap % 3;
-  const float4 v = __ldg(reinterpret_cast<const float4 *>(in + ((ioff[u] + t + kh) * 39 + (2 * f + kw)) * 32) + q);
-  reinterpret_cast<float4 *>(out + ((long long)ooff[u] * 19 + pix) * 288 + tap * 32)[q] = v;
+  const long long pix = idx >> 3;          // packed output pixel
+  const long long row = pix / 19;
+  const int f = (int)(pix - row * 19);
+  const int u = find_utt(ooff, n_utt, row);
+  const int t = (int)(row - __ldg(ooff + u));
+  const float *src = in + ((__ldg(ioff + u) + t) * 39 + 2 * f) * 32;
+  float4 v[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) v[kh * 3 + kw] = __ldg(reinterpret_cast<const float4 *>(src + ((long long)kh * 39 + kw) * 32) + q);
+  float4 *dst = reinterpret_cast<float4 *>(out + pix * 288) + q;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) dst[tap * 8] = v[tap];
 }
 
 // ConvNeXt depthwise 7x7 over (time, freq) of [T1,19,128], zero padded at each utterance's own edges. w: [7][7][128]
@@ -128,18 +148,23 @@ __global__ void embed_im2col2_kernel(const float *__restrict__ in, const int *__
 // thread = (channel, time row) keeps its 49 taps in registers and slides over frequency.
 constexpr int kDw7Rows = 8, kDw7Ch = 32;
 __global__ void __launch_bounds__(256) embed_dw7_kernel(const float *__restrict__ in, const int *__restrict__ len,
-                                                        const int *__restrict__ off, const float *__restrict__ w,
-                                                        const float *__restrict__ b, float *__restrict__ out) {
-  __shared__ float patch[(kDw7Rows + 6) * 25 * kDw7Ch];
-  const int u = blockIdx.z;
+                                                        const int *__restrict__ off, const int *__restrict__ tile_off, int n_utt,
+                                                        const float *__restrict__ w, const float *__restrict__ b,
+                                                        float *__restrict__ out) {
+  __shared__ __align__(16) float patch[(kDw7Rows + 6) * 25 * kDw7Ch];
+  // blockIdx.x = (128-frame tile of the ragged batch) * 16 + 8-row sub-tile
+  const int tile = blockIdx.x >> 4;
+  const int u = find_utt(tile_off, n_utt, tile);
   const int T1 = len[u];
-  const int t0 = blockIdx.x * kDw7Rows;
+  const int t0 = (tile - __ldg(tile_off + u)) * 128 + (blockIdx.x & 15) * kDw7Rows;
   if (t0 >= T1) return;
   const int c0 = blockIdx.y * kDw7Ch;
   const float *x = in + (long long)off[u] * 19 * 128;
-  for (int i = threadIdx.x; i < (kDw7Rows + 6) * 25 * kDw7Ch; i += 256) {
-    const int c = i % kDw7Ch, ff = (i / kDw7Ch) % 25 - 3, tt = t0 + i / (kDw7Ch * 25) - 3;
-    patch[i] = (tt >= 0 && tt < T1 && ff >= 0 && ff < 19) ? __ldg(x + ((long long)tt * 19 + ff) * 128 + c0 + c) : 0.f;
+  for (int i = threadIdx.x; i < (kDw7Rows + 6) * 25 * (kDw7Ch / 4); i += 256) {
+    const int c4 = (i % (kDw7Ch / 4)) * 4, ff = (i / (kDw7Ch / 4)) % 25 - 3, tt = t0 + i / ((kDw7Ch / 4) * 25) - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt >= 0 && tt < T1 && ff >= 0 && ff < 19) v = __ldg(reinterpret_cast<const float4 *>(x + ((long long)tt * 19 + ff) * 128 + c0 + c4));
+    reinterpret_cast<float4 *>(patch)[i] = v;
   }
   __syncthreads();
   const int c = threadIdx.x % kDw7Ch, tr = threadIdx.x / kDw7Ch;
@@ -557,11 +582,10 @@ inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) /
 }  // namespace
 
 // ====================================================================== launchers
-void launch_embed_conv0(const float *feats, const int *T, const long long *foff, const long long *ooff, int n, int max_T,
-                        const float *w, const float *b, float *out, cudaStream_t st) {
-  if (max_T <= 2) return;
-  dim3 grid(cdiv((long long)(max_T - 2) * 80, 256), n);
-  embed_conv0_kernel<<<grid, 256, 0, st>>>(feats, T, foff, ooff, w, b, out);
+void launch_embed_conv0(const float *feats, const long long *foff, const long long *ooff, int n, long long total_rows, const float *w,
+                        const float *b, float *out, cudaStream_t st) {
+  if (total_rows <= 0) return;
+  embed_conv0_kernel<<<cdiv(total_rows * 80, 256), 256, 0, st>>>(feats, foff, ooff, n, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
 void launch_embed_conv1(const float *in, const long long *ioff, const long long *ooff, int n, long long total_rows, const float *w,
@@ -578,17 +602,17 @@ void launch_embed_conv1(const float *in, const long long *ioff, const long long 
   embed_conv1_kernel<<<grid, 256, 0, st>>>(in, ioff, ooff, n, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
-void launch_embed_im2col2(const float *in, const int *T, const long long *ioff, const int *ooff, int n, int max_T1, float *out,
+void launch_embed_im2col2(const float *in, const long long *ioff, const int *ooff, int n, long long total_rows, float *out,
                           cudaStream_t st) {
-  if (max_T1 <= 0) return;
-  dim3 grid(cdiv((long long)max_T1 * 19 * 72, 256), n);
-  embed_im2col2_kernel<<<grid, 256, 0, st>>>(in, T, ioff, ooff, out);
+  if (total_rows <= 0) return;
+  embed_im2col2_kernel<<<cdiv(total_rows * 19 * 8, 256), 256, 0, st>>>(in, ioff, ooff, n, out);
   count_launch(); KERNEL_CHECK();
 }
-void launch_embed_dw7(const float *in, const RaggedDesc &r, const float *w, const float *b, float *out, cudaStream_t st) {
-  if (r.total <= 0) return;
-  dim3 grid(cdiv(r.max_len, kDw7Rows), 128 / kDw7Ch, r.n);
-  embed_dw7_kernel<<<grid, 256, 0, st>>>(in, r.len, r.off, w, b, out);
+void launch_embed_dw7(const float *in, const RaggedDesc &r, const int *tile_off, int n_tiles, const float *w, const float *b,
+                      float *out, cudaStream_t st) {
+  if (r.total <= 0 || n_tiles <= 0) return;
+  dim3 grid(n_tiles * 16, 128 / kDw7Ch);
+  embed_dw7_kernel<<<grid, 256, 0, st>>>(in, r.len, r.off, tile_off, r.n, w, b, out);
   count_launch(); KERNEL_CHECK();
 }
 void launch_biasnorm(const float *x, int M, int D, const float *bias, const float *log_scale, float *out, cudaStream_t st) {

@@ -1042,11 +1042,11 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   float *pw1 = b_pw1.get<float>((size_t)M1 * 19 * 384);
   float *cn = b_cn.get<float>((size_t)M1 * 2432);
   float *x0 = b_x0.get<float>((size_t)M1 * D0);
-  launch_embed_conv0(d_feats, d_T, d_foff, d_c0off, n, maxT, w_conv0, W("encoder.embed.conv0.bias"), c0, st);
+  launch_embed_conv0(d_feats, d_foff, d_c0off, n, c0off[n], w_conv0, W("encoder.embed.conv0.bias"), c0, st);
   launch_embed_conv1(c0, d_c0off, d_c1off, n, c1off[n], w_conv1, W("encoder.embed.conv1.bias"), c1, st);
-  launch_embed_im2col2(c1, d_T, d_c1off, rd[0].off, n, Lr[0], pw1, st);   // pw1 buffer doubles as the im2col scratch (288 <= 384)
+  launch_embed_im2col2(c1, d_c1off, rd[0].off, n, M1, pw1, st);   // pw1 buffer doubles as the im2col scratch (288 <= 384)
   gemm(pw1, 288, w_conv2, W("encoder.embed.conv2.bias"), nullptr, 0, c2, 128, M1 * 19, 128, 288, ACT_SWOOSH_R);
-  launch_embed_dw7(c2, rd[0], w_dw7, W("encoder.embed.convnext.dw.bias"), dw, st);
+  launch_embed_dw7(c2, rd[0], d_dwt, dwt[n], w_dw7, W("encoder.embed.convnext.dw.bias"), dw, st);
   gemm(dw, 128, W("encoder.embed.convnext.pw1.weight"), W("encoder.embed.convnext.pw1.bias"), nullptr, 0, pw1, 384, M1 * 19, 384, 128,
        ACT_SWOOSH_L);
   gemm(pw1, 384, W("encoder.embed.convnext.pw2.weight"), W("encoder.embed.convnext.pw2.bias"), c2, 128, cn, 128, M1 * 19, 128, 384,
