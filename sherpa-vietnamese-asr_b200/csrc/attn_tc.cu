@@ -244,12 +244,20 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
 // VT[u][c][j] = X[off[u]+j][c] (* tanh(S[...])) with row pitch Tk4; VTlo = VT - trunc_tf32(VT). 32x32 smem transpose.
 __global__ void __launch_bounds__(256) transpose_v_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ S, int lds,
                                                           int C, const int *__restrict__ len, const int *__restrict__ off,
+                                                          const int *__restrict__ tile_off, int n_utt,
                                                           const long long *__restrict__ vt_off, float *__restrict__ VT,
                                                           float *__restrict__ VTlo) {
   __shared__ float tile[32][33];
-  const int u = blockIdx.z;
+  // blockIdx.x = (128-frame tile of the ragged batch) * 4 + 32-frame sub-tile: no CTA lands past a short utterance's end
+  const int t128 = blockIdx.x >> 2;
+  int lo = 0, hi = n_utt - 1;
+  while (lo < hi) {   // last u with tile_off[u] <= t128
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(tile_off + mid) <= t128) lo = mid; else hi = mid - 1;
+  }
+  const int u = lo;
   const int Tk = len[u];
-  const int j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int j0 = (t128 - __ldg(tile_off + u)) * 128 + (blockIdx.x & 3) * 32, c0 = blockIdx.y * 32;
   if (j0 >= Tk) return;
   const int Tk4 = (Tk + 3) & ~3;
   const long long rbase = off[u];
@@ -283,11 +291,11 @@ constexpr size_t attn_smem(int BN, bool split3) {
 
 }  // namespace
 
-void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C, const RaggedDesc &r, const long long *vt_off,
-                        float *VT, float *VTlo, cudaStream_t st) {
-  if (r.total <= 0) return;
-  dim3 grid((r.max_len + 31) / 32, (C + 31) / 32, r.n);
-  transpose_v_kernel<<<grid, 256, 0, st>>>(X, ldx, S, lds, C, r.len, r.off, vt_off, VT, VTlo);
+void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C, const RaggedDesc &r, const int *tile_off, int n_tiles,
+                        const long long *vt_off, float *VT, float *VTlo, cudaStream_t st) {
+  if (r.total <= 0 || n_tiles <= 0) return;
+  dim3 grid(n_tiles * 4, (C + 31) / 32);
+  transpose_v_kernel<<<grid, 256, 0, st>>>(X, ldx, S, lds, C, r.len, r.off, tile_off, r.n, vt_off, VT, VTlo);
   count_launch();
   KERNEL_CHECK();
 }

@@ -153,8 +153,9 @@ struct AttnTcLaunch {
   float *out; int ldo;
   int split3;
 };
-void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C, const RaggedDesc &r, const long long *vt_off,
-                        float *VT, float *VTlo, cudaStream_t st);
+// tile_off = cumulative ceil(len / 128) per utterance
+void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C, const RaggedDesc &r, const int *tile_off, int n_tiles,
+                        const long long *vt_off, float *VT, float *VTlo, cudaStream_t st);
 void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st);
 void attn_tc_encode_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int rows_mult,
                          int rows_fixed, int box_rows);

@@ -898,10 +898,10 @@ void Engine::attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r
   a.mapsA = pl.mapsA; a.len = r.len; a.off = r.off; a.n_utt = r.n; a.single_head = single_head ? 1 : 0; a.C = C; a.dv = vd;
   a.Y = Y; a.ldy = ldy; a.out = out; a.ldo = ldo; a.split3 = split3 ? 1 : 0;
   if (single_head) {
-    launch_transpose_v(X, ldx, S, lds, C, r, pl.vt_offh, pl.VTh, split3 ? pl.VThlo : nullptr, st);
+    launch_transpose_v(X, ldx, S, lds, C, r, pl.dw_tile_off, pl.dw_tiles, pl.vt_offh, pl.VTh, split3 ? pl.VThlo : nullptr, st);
     a.mapsV = pl.mapsVh; a.mapsVlo = pl.mapsVhlo; a.tile_off = pl.tile_offh; a.n_tiles = pl.n_tilesh;
   } else {
-    launch_transpose_v(X, ldx, S, lds, C, r, pl.vt_off12, pl.VT12, split3 ? pl.VT12lo : nullptr, st);
+    launch_transpose_v(X, ldx, S, lds, C, r, pl.dw_tile_off, pl.dw_tiles, pl.vt_off12, pl.VT12, split3 ? pl.VT12lo : nullptr, st);
     a.mapsV = pl.mapsV12; a.mapsVlo = pl.mapsV12lo; a.tile_off = pl.tile_off12; a.n_tiles = pl.n_tiles12;
   }
   launch_attn_apply_tc(a, st);
