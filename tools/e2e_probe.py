@@ -1,3 +1,5 @@
+"""End-to-end probe on a B200: create_stream / accept_waveform / decode_streams over the C2 batch, with the host phases of
+decode (B200ASR_HOST_PROF) and the stage timings of the pass. Usage: python tools/e2e_probe.py"""
 import sys, os, time
 os.environ.setdefault("B200ASR_HOST_PROF", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,3 +1,5 @@
+"""Separates the accept-time PCM upload from the decode pass: accept, device-wide sync, decode, with two generations of
+streams alive as in bench.py. Usage: python tools/upload_probe.py"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("B200ASR_HOST_PROF", "1")
