@@ -4,6 +4,7 @@
 // (/root/reference core/asr_engine.py:1209-1253, chunk loop :2326-2397); the encoder schedule follows
 // SURVEY.md Appendix B (icefall Zipformer2 inference graph).
 #include <math.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -167,10 +168,16 @@ class ParallelCopy {
  private:
   static constexpr size_t kMinBytes = 256 * 1024;
   ParallelCopy() {
-    const int hw = (int)std::thread::hardware_concurrency();
-    int n = std::min(7, hw / 2 - 1);                       // helpers besides the calling thread
+    // cores this process may use (affinity / cgroup aware), shared with the other ranks of a torchrun job on the box
+    int hw = (int)std::thread::hardware_concurrency();
+    cpu_set_t cs;
+    if (sched_getaffinity(0, sizeof cs, &cs) == 0 && CPU_COUNT(&cs) > 0) hw = std::min(hw > 0 ? hw : CPU_COUNT(&cs), CPU_COUNT(&cs));
+    int ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    const int share = std::max(1, hw / ranks);
+    int n = std::min(7, share / 2 - 1);                    // helpers besides the calling thread
     if (const char *e = getenv("B200ASR_COPY_THREADS")) n = atoi(e) - 1;
-    n_workers_ = std::max(0, std::min(n, hw > 1 ? hw - 1 : 0));
+    n_workers_ = std::max(0, std::min(n, share > 1 ? share - 1 : 0));
     for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this, i] { worker(i + 1); });
   }
   void run_part(int part) {
