@@ -9,6 +9,7 @@ This script runs the oracle encoder on synthetic audio with the bench model's ra
 operands, and compares the schemes against a float64 product. No GPU needed.
 
     python tools/fp16_split_study.py [zipformer-30m|zipformer-68m] [seconds]
+    python tools/fp16_split_study.py --tokens [model]      # decoded token ids under each scheme vs fp32
 """
 import os
 import sys
@@ -108,5 +109,55 @@ def main():
         print(f"  worst max-error / output scale, {k:10s}: {v:.3e}")
 
 
+
+
+def token_study(name="zipformer-30m", secs=(5.0, 3.0, 7.0), beam=4):
+    """End to end on the CPU oracle: every Linear (encoder, decoder_proj, joiner) computed with an emulated operand scheme,
+    modified_beam_search on top, token ids compared with the plain fp32 run."""
+    from oracle import search_ref as sr
+    cfg = weights.CONFIGS[name]()
+    d = tempfile.mkdtemp()
+    paths = weights.write_model_dir(d, cfg, 68 if "68" in name else 30)
+    tensors = {}
+    for part in ("encoder", "decoder", "joiner"):
+        tensors.update(weights.load_container(paths[part])[1])
+    audios = [synth.speech_like(int(16000 * s), 40 + i) for i, s in enumerate(secs)]
+    feats = [fbank_ref.fbank(a, np.float64) for a in audios]
+    orig = F.linear
+
+    def tf32_1(a, w):
+        return (tf32_trunc(a).astype(np.float64) @ tf32_trunc(w).astype(np.float64).T).astype(np.float32)
+
+    schemes = {"fp32": None, "tf32 x1": tf32_1, "3xtf32": gemm_3xtf32, "f16+bf16lo": gemm_f16_bf16lo,
+               "2xfp16": lambda a, w: gemm_2xfp16(a, w)[0]}
+    results = {}
+    for sname, fn in schemes.items():
+        def lin(x, w, b=None, fn=fn):
+            if fn is None or x.dim() != 2:
+                return orig(x, w, b)
+            y = torch.from_numpy(fn(np.ascontiguousarray(x.detach().numpy(), dtype=np.float32),
+                                    np.ascontiguousarray(w.detach().numpy(), dtype=np.float32)))
+            return y + b if b is not None else y
+        F.linear = lin
+        try:
+            rec = zr.make_recognizer(tensors, cfg, max_active_paths=beam)
+            toks = []
+            with torch.no_grad():
+                for f in feats:
+                    rec["dec_cache"].clear()
+                    toks.append(sr.modified_beam_search(rec, f, beam)[0])
+        finally:
+            F.linear = orig
+        results[sname] = toks
+    base = results["fp32"]
+    print(f"token study, {name}, beam {beam}, {sum(len(t) for t in base)} tokens in the fp32 decode of {len(base)} utterances")
+    for sname, toks in results.items():
+        diff = sum(1 for a, b in zip(toks, base) if a != b)
+        print(f"  {sname:10s}: {diff} of {len(base)} utterances differ from fp32")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--tokens":
+        token_study(*(sys.argv[2:3] or ["zipformer-30m"]))
+    else:
+        main()
