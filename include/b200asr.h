@@ -102,7 +102,8 @@ B200ASR_API int32_t B200AsrSetHotwordsTokenIds(const B200AsrOfflineRecognizer *r
 B200ASR_API const B200AsrOfflineStream *B200AsrCreateOfflineStream(const B200AsrOfflineRecognizer *r);
 B200ASR_API void B200AsrDestroyOfflineStream(const B200AsrOfflineStream *s);
 /* SherpaOnnxAcceptWaveformOffline (sherpa-onnx-asr.js:1798-1806; streaming_asr.py:285,312,355): copies the
- * samples ([-1,1] floats) and appends on repeated calls. */
+ * samples ([-1,1] floats) and appends on repeated calls. The copy lands in pinned host memory and its upload to the
+ * recognizer's GPU is queued at once, so a later decode call finds the PCM resident. */
 B200ASR_API void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n);
 /* SherpaOnnxDecodeOfflineStream (sherpa-onnx-asr.js:1869-1871; streaming_asr.py:358,408) */
 B200ASR_API int32_t B200AsrDecodeOfflineStream(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *s);
