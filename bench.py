@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument("--model", default="zipformer-68m")
     ap.add_argument("--beam", type=int, default=4)
     ap.add_argument("--precision", default=os.environ.get("B200ASR_PRECISION", "fp32"), choices=["fp32", "bf16"])
-    ap.add_argument("--cpu-sample", type=int, default=6, help="segments in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=24, help="segments in the bounded CPU sample (~7 s of CPU work per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
