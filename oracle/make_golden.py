@@ -11,6 +11,10 @@ What is pinned, and by what:
   entropy.json               `_compute_token_entropy` (:1159-1181) on seeded logits rows.
   words.json                 `decode_chunk` (:1209-1326) word lists (with precomputed_features + fake encoder).
   rover.json                 `rover_merge_words` (:1446-1577) on seeded word lists.
+  chunking.json              `find_overlap_alignment` / `merge_chunks_with_overlap` (:70-237), `find_silent_regions` /
+                             `find_best_split_point` (:521-573), the inline chunk plan (:2141-2161, executed from the
+                             reference file), `chunk_long_segment` / `concat_vad_speech` / `map_concat_time_to_original`
+                             (:583-676) on the seeded inputs of oracle/chunk_cases.py.
   fbank_5000.npz             torchaudio.compliance.kaldi.fbank (independent Kaldi restatement) on a seeded clip;
                              kaldi-native-fbank itself is not installable offline.
 """
@@ -197,6 +201,47 @@ def fbank_case():
     np.savez_compressed(os.path.join(GOLD, "fbank_5000.npz"), audio=a, feats=ta.numpy().astype(np.float64))
 
 
+def reference_plan(ae, total, silent_regions):
+    """The chunk plan is inline in the reference's transcription method (core/asr_engine.py:2141-2161); run those very
+    lines, read from the file where it lies, on our inputs."""
+    import textwrap
+    with open(os.path.join(REF, "core", "asr_engine.py"), encoding="utf-8") as f:
+        lines = f.read().split("\n")
+    a = next(i for i, l in enumerate(lines) if l.strip() == "segment_samples = 16000 * 30")
+    b = next(i for i in range(a, len(lines)) if lines[i].strip().startswith('print(f"[Chunk]'))
+    ns = {"concat_total": total, "concat_silent_regions": silent_regions, "find_best_split_point": ae.find_best_split_point,
+          "OVERLAP_SAMPLES": ae.OVERLAP_SAMPLES}
+    exec(textwrap.dedent("\n".join(lines[a:b])), ns)
+    return [list(map(int, c)) for c in ns["chunk_plan"]]
+
+
+def chunking_cases(ae):
+    from oracle import chunk_cases as cc
+    out = {}
+    with redirect_stdout(io.StringIO()):
+        out["alignment"] = [list(ae.find_overlap_alignment(t, h)) for t, h in cc.alignment_cases()]
+        merges = []
+        for chunks in cc.merge_cases():
+            words, text = ae.merge_chunks_with_overlap(copy.deepcopy(chunks))
+            merges.append({"text": text, "starts": [w["start"] for w in words]})
+        out["merge"] = merges
+        out["silence"] = [[list(map(int, r)) for r in ae.find_silent_regions(cc.silence_audio(seed, sec))]
+                          for seed, sec in cc.silence_cases()]
+        out["plan"] = [reference_plan(ae, total, regions) for total, regions in cc.plan_cases()]
+        out["split"] = [int(ae.find_best_split_point(total // 2, total, regions)) for total, regions in cc.plan_cases()]
+        out["segment"] = [[list(map(int, c)) for c in ae.chunk_long_segment(s, e)] for s, e in cc.segment_cases()]
+        maps = []
+        for segs, total, times in cc.offset_map_cases():
+            audio = np.zeros(total, np.float32)
+            concat, omap = ae.concat_vad_speech(audio, segs)
+            maps.append({"len": int(len(concat)), "map": [list(map(int, m)) for m in omap],
+                         "times": [ae.map_concat_time_to_original(t, omap) for t in times]})
+        out["offset_map"] = maps
+    with open(os.path.join(GOLD, "chunking.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ae, hc = load_reference()
@@ -208,6 +253,8 @@ def main():
     print("word cases:", [len(x["words"]) for x in w])
     rover_cases(ae)
     fbank_case()
+    c = chunking_cases(ae)
+    print("chunking cases:", {k: len(v) for k, v in c.items()})
     print("golden written to", GOLD)
 
 

@@ -6,6 +6,10 @@ What `TranscriberPipeline` calls in the reference and what stands for it here:
   compute_fbank_ort(audio)                    :698-721                      -> compute_fbank_ort (CUDA fbank)
   decode_chunk(recognizer, chunk, t0, feats)  :1209-1326                    -> decode_chunk / decode_chunks (batched)
   rover_merge_words(words_a, words_b)         :1446-1577                    -> rover_merge_words
+  find_silent_regions / find_best_split_point / chunk plan / concat_vad_speech / map_concat_time_to_original /
+  merge_chunks_with_overlap                   :44-237, :521-676, :2141-2161 -> chunking.py (re-exported here), and
+                                                                               chunking.transcribe_long = plan -> one
+                                                                               ragged GPU batch -> stitch
   enc_sess / dec_sess / joi_sess `.run`       :1047,1055,1085,1092          -> session adapters on the raw CUDA stages
 
 The token -> word merge, ROVER and time mapping are host glue in the reference too; the per-token entropy
@@ -22,6 +26,9 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
+from .chunking import (chunk_long_segment, concat_vad_speech, find_best_split_point, find_overlap_alignment,  # noqa: F401
+                       find_silent_regions, map_concat_time_to_original, merge_chunks_with_overlap, plan_chunks,
+                       transcribe_long, words_match)
 from .recognizer import OfflineRecognizer
 
 ROVER_MODEL_IDS = ["zipformer-30m-rnnt-6000h", "sherpa-onnx-zipformer-vi-2025-04-20"]

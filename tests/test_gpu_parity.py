@@ -400,3 +400,32 @@ def test_tensor_core_mode_end_to_end(model_dirs):
         tot += len(toks)
     print("tensor-core mode token edit distance:", dist, "/", tot)
     assert dist <= max(2, 0.05 * tot)
+
+
+def test_transcribe_long_matches_oracle_chunks(model_dirs):
+    """a long recording through the chunk planner -> ONE ragged GPU batch -> overlap stitcher.
+    Per-chunk word lists equal the oracle's decode of the same chunks; the stitched result is the stitcher applied to them."""
+    import copy
+    from oracle import fbank_ref, search_ref as sr
+    from sherpa_vietnamese_asr_b200 import asr_engine, chunking, synth
+    cfg, paths, d = model_dirs("zipformer-tiny", 3)
+    rec = asr_engine.create_recognizer(d, max_active_paths=4)
+    orec = oracle_recognizer(paths, beam=4)[0]
+    audio = synth.speech_like(16000 * 41 + 321, 4100)
+    for a, b in [(9.6, 10.3), (19.0, 19.5), (31.2, 32.0)]:           # silences for the planner to snap to
+        audio[int(a * 16000):int(b * 16000)] *= 0.01
+    vad = [(8000, 16000 * 25), (16000 * 26, len(audio) - 4000)]
+    res = chunking.transcribe_long(rec, audio, vad, segment_samples=16000 * 10)
+    speech, omap = chunking.concat_vad_speech(audio, vad)
+    assert len(res["chunk_plan"]) >= 4 and res["chunk_plan"][-1][1] == len(speech)
+    tm = chunking.ConcatTimeMap(omap)
+    for (s, e, o), got in zip(res["chunk_plan"], res["chunk_results"]):
+        orec["dec_cache"].clear()
+        chunk = speech[s:e]
+        want = sr.decode_chunk(orec, chunk, s / 16000.0, precomputed_features=fbank_ref.fbank(chunk, np.float64))
+        assert [w["text"] for w in got["words"]] == [w["text"] for w in want]
+        for a, b in zip(got["words"], want):
+            assert abs(a["start"] - tm(b["start"])) <= 1e-4 and abs(a["local_start"] - b["local_start"]) <= 1e-6
+            assert abs(a["prob"] - b["prob"]) <= 2e-3
+    words, text = chunking.merge_chunks_with_overlap(copy.deepcopy(res["chunk_results"]))
+    assert text == res["text"] and len(words) == len(res["words"]) > 0
