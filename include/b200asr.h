@@ -131,6 +131,11 @@ B200ASR_API int32_t B200AsrFbank(const B200AsrOfflineRecognizer *r, const float 
  * frame_offsets[n_utts+1] written. */
 B200ASR_API int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const float *samples, const int64_t *sample_offsets,
                                       int32_t n_utts, float *out, int64_t *frame_offsets);
+/* Energy scan of find_silent_regions (core/asr_engine.py:521-553): quiet[f] = 1 when the RMS of the 10 ms frame
+ * samples[160 f .. 160 f + 160) is below `threshold`, computed in NumPy's float32 arithmetic (same flags as the reference,
+ * bit for bit). Needs no recognizer. `quiet` may be NULL to query the frame count n / 160. Returns the frame count or <0. */
+B200ASR_API int32_t B200AsrSilentFrames(const float *samples, int64_t n, int32_t sample_rate, float threshold, uint8_t *quiet,
+                                        int32_t device_id);
 /* enc_sess.run (core/asr_engine.py:1045-1049): packed features [sum T, 80] with x_lens[n] ->
  * packed encoder_out [sum T', 512], out_lens[n]. `out` may be NULL to query lengths only. */
 B200ASR_API int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, const int32_t *x_lens,

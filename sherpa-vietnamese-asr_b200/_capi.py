@@ -66,6 +66,7 @@ SYMBOLS = {
     "B200AsrEncoderOutDim": (C.c_int32, [_P]),
     "B200AsrFbank": (C.c_int32, [_P, _F, C.c_int32, _F]),
     "B200AsrFbankBatch": (C.c_int32, [_P, _F, _I64, C.c_int32, _F, _I64]),
+    "B200AsrSilentFrames": (C.c_int32, [_F, C.c_int64, C.c_int32, C.c_float, C.POINTER(C.c_uint8), C.c_int32]),
     "B200AsrEncoder": (C.c_int32, [_P, _F, _I32, C.c_int32, _F, _I32]),
     "B200AsrEncoderTap": (C.c_int32, [_P, C.c_char_p, _F, _I32]),
     "B200AsrDecoder": (C.c_int32, [_P, _I64, C.c_int32, _F]),

@@ -38,23 +38,43 @@ MIN_SEGMENT_SAMPLES = 20 * 16000       # :2147 (a split closer than 20 s to the 
                                        # two thirds of the segment when a caller asks for another segment length
 
 
+def _quiet_runs(quiet: np.ndarray, frame: int, n_samples: int, min_silence_duration: float) -> List[Tuple[int, int]]:
+    """Run-length encoding of the per-frame quiet flags: runs of at least min_silence_duration, in samples."""
+    edges = np.flatnonzero(np.diff(np.concatenate(([0], quiet.astype(np.int8), [0]))))
+    starts, ends = edges[0::2], edges[1::2]
+    min_frames = int(min_silence_duration / 0.01)
+    return [(s * frame, min(e * frame, n_samples)) for s, e in zip(starts.tolist(), ends.tolist()) if e - s >= min_frames]
+
+
+def find_silent_regions_gpu(audio: np.ndarray, sample_rate: int = 16000, threshold: float = 0.01,
+                            min_silence_duration: float = 0.3, device_id: int = 0) -> List[Tuple[int, int]]:
+    """`find_silent_regions` with the energy scan on the GPU (csrc/energy.cu through B200AsrSilentFrames); the kernel
+    reproduces NumPy's float32 arithmetic, so the regions are the reference's regions. float32 PCM at 16 kHz only."""
+    from . import _capi
+    if sample_rate != 16000:
+        raise ValueError("the GPU energy scan handles 16 kHz audio only")
+    x = np.ascontiguousarray(audio, dtype=np.float32)
+    n = len(x) // 160
+    if n == 0:
+        return []
+    quiet = np.empty(n, dtype=np.uint8)
+    rc = _capi.lib().B200AsrSilentFrames(_capi.fptr(x), len(x), sample_rate, float(np.float32(threshold)),
+                                         quiet.ctypes.data_as(_capi.C.POINTER(_capi.C.c_uint8)), device_id)
+    if rc != n:
+        raise RuntimeError("B200AsrSilentFrames failed: " + _capi.last_error())
+    return _quiet_runs(quiet, 160, len(x), min_silence_duration)
+
+
 def find_silent_regions(audio: np.ndarray, sample_rate: int = 16000, threshold: float = 0.01,
                         min_silence_duration: float = 0.3) -> List[Tuple[int, int]]:
+    """Host NumPy version (any sample rate / dtype); the reference's own loop restated as array operations."""
     frame = int(sample_rate * 0.01)
     n = len(audio) // frame
     if n == 0:
         return []
     x = np.asarray(audio[: n * frame]).reshape(n, frame)
     quiet = np.sqrt(np.mean(x ** 2, axis=1)) < threshold
-    # run-length encode the quiet mask
-    edges = np.flatnonzero(np.diff(np.concatenate(([0], quiet.astype(np.int8), [0]))))
-    starts, ends = edges[0::2], edges[1::2]
-    min_frames = int(min_silence_duration / 0.01)
-    out = []
-    for s, e in zip(starts.tolist(), ends.tolist()):
-        if e - s >= min_frames:
-            out.append((s * frame, min(e * frame, len(audio))))
-    return out
+    return _quiet_runs(quiet, frame, len(audio), min_silence_duration)
 
 
 def find_best_split_point(target: int, total: int, silent_regions: Sequence[Tuple[int, int]], search_window: int = 2 * 16000) -> int:
@@ -225,7 +245,13 @@ def transcribe_long(recognizer, audio: np.ndarray, vad_segments: Sequence[Tuple[
     Returns {"words", "text", "chunk_plan", "chunk_results"}."""
     audio = np.ascontiguousarray(audio, dtype=np.float32)
     speech, offset_map = concat_vad_speech(audio, list(vad_segments))
-    plan = plan_chunks(len(speech), find_silent_regions(speech), segment_samples, overlap_samples)
+    # real engine -> the energy scan runs on the GPU as well (same flags as NumPy, csrc/energy.cu); an injected decoder
+    # (tests on CPU) keeps the host scan
+    if decode_chunks is not None:
+        regions = find_silent_regions(speech)
+    else:
+        regions = find_silent_regions_gpu(speech, device_id=int(recognizer.engine._cfg.device_id))
+    plan = plan_chunks(len(speech), regions, segment_samples, overlap_samples)
     chunks = [speech[s:e] for s, e, _ in plan]
     offsets = [s / 16000.0 for s, _, _ in plan]
     if decode_chunks is None:

@@ -1310,6 +1310,10 @@ static Engine *E(const B200AsrOfflineRecognizer *r) {
   return const_cast<Engine *>(&r->eng);
 }
 
+namespace b200asr {
+void set_last_error(const std::string &msg) { g_last_error = msg; }   // for entry points living in other translation units
+}
+
 extern "C" {
 
 const char *B200AsrGetLastError(void) { return g_last_error.c_str(); }

@@ -429,3 +429,33 @@ def test_transcribe_long_matches_oracle_chunks(model_dirs):
             assert abs(a["prob"] - b["prob"]) <= 2e-3
     words, text = chunking.merge_chunks_with_overlap(copy.deepcopy(res["chunk_results"]))
     assert text == res["text"] and len(words) == len(res["words"]) > 0
+
+
+def test_energy_scan_flags_equal_numpy():
+    """csrc/energy.cu through B200AsrSilentFrames: per-frame quiet flags equal NumPy's float32 flags, including frames whose
+    RMS sits on the threshold; regions equal the host find_silent_regions (core/asr_engine.py:521-553)."""
+    import ctypes as C
+    from oracle import chunk_cases as cc
+    from sherpa_vietnamese_asr_b200 import _capi, chunking
+    rng = np.random.default_rng(12)
+    # RMS log-uniform around the 0.01 threshold, many frames within a few ulp-scale steps of it
+    n_frames = 200_003
+    scale = np.exp(rng.uniform(np.log(0.003), np.log(0.03), n_frames)).astype(np.float32)
+    scale[::7] = np.float32(0.01) * (1 + rng.uniform(-3e-7, 3e-7, len(scale[::7]))).astype(np.float32)
+    x = (rng.normal(0, 1, (n_frames, 160)).astype(np.float32))
+    x /= np.sqrt(np.mean(x.astype(np.float64) ** 2, axis=1, keepdims=True)).astype(np.float32)
+    x = np.ascontiguousarray((x * scale[:, None]).reshape(-1))
+    x = np.concatenate([x, rng.normal(0, 0.1, 77).astype(np.float32)])        # a partial last frame is ignored
+    want = np.sqrt(np.mean(x[:n_frames * 160].reshape(n_frames, 160) ** 2, axis=1)) < 0.01
+    assert 0.2 < want.mean() < 0.8
+    quiet = np.full(n_frames, 9, dtype=np.uint8)
+    lib = _capi.lib()
+    assert lib.B200AsrSilentFrames(_capi.fptr(x), len(x), 16000, 0.01, None, 0) == n_frames
+    rc = lib.B200AsrSilentFrames(_capi.fptr(x), len(x), 16000, float(np.float32(0.01)), quiet.ctypes.data_as(C.POINTER(C.c_uint8)), 0)
+    assert rc == n_frames, _capi.last_error()
+    assert np.array_equal(quiet.astype(bool), want)
+    assert lib.B200AsrSilentFrames(_capi.fptr(x), len(x), 8000, 0.01, quiet.ctypes.data_as(C.POINTER(C.c_uint8)), 0) < 0
+    for seed, sec in [(1, 0.005), (3, 7.3), (5, 125.7), (6, 400.0)]:
+        audio = cc.silence_audio(seed, sec)
+        assert chunking.find_silent_regions_gpu(audio) == chunking.find_silent_regions(audio)
+        assert chunking.find_silent_regions_gpu(audio, 16000, 0.02, 0.1) == chunking.find_silent_regions(audio, 16000, 0.02, 0.1)

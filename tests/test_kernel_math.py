@@ -126,3 +126,38 @@ def test_fbank_fft_decomposition_matches_numpy():
             k = k1 + 8 * c + 64 * (((b & 1) << 1) | (b >> 1))
             addr.append((k + 8 * (k >> 6)) % 32)
         assert len(set(addr)) == 32
+
+
+# ----------------------------------------------------------------------------- energy scan (csrc/energy.cu)
+def _energy_kernel_order(frames):
+    """The kernel's arithmetic, lane for lane, in NumPy float32: two halves of 80 squares, 8 interleaved accumulators
+    per half added in index order, xor-tree fold (1, 2, 4), half 0 + half 1, / 160, sqrt."""
+    sq = (frames * frames).astype(np.float32)
+    halves = []
+    for h in range(2):
+        a = sq[:, h * 80:(h + 1) * 80].reshape(-1, 10, 8)
+        r = a[:, 0, :].copy()
+        for i in range(1, 10):
+            r = (r + a[:, i, :]).astype(np.float32)
+        for step in (1, 2, 4):                       # lane j receives r[j] + r[j ^ step]
+            r = (r + r[:, np.arange(8) ^ step]).astype(np.float32)
+        halves.append(r[:, 0])
+    tot = (halves[0] + halves[1]).astype(np.float32)
+    return np.sqrt((tot / np.float32(160)).astype(np.float32)).astype(np.float32)
+
+
+def test_energy_scan_order_reproduces_numpy_float32_bits():
+    """The flags decide where chunks are cut, so the kernel restates NumPy's pairwise float32 summation exactly; this
+    pins that statement against NumPy itself (the reference computes np.sqrt(np.mean(frame ** 2)) per frame,
+    core/asr_engine.py:537-541)."""
+    rng = np.random.default_rng(0)
+    for scale in (1e-20, 1e-3, 0.01, 0.3, 1.0):
+        x = rng.normal(0, scale, (50000, 160)).astype(np.float32)
+        got = _energy_kernel_order(x)
+        want = np.sqrt(np.mean(x ** 2, axis=1))
+        assert want.dtype == np.float32
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        per_frame = np.array([np.sqrt(np.mean(f ** 2)) for f in x[:500]])
+        assert np.array_equal(per_frame.view(np.uint32), got[:500].view(np.uint32))
+        # and the comparison the reference makes (weak Python float against float32)
+        assert np.array_equal(got < np.float32(0.01), want < 0.01)
