@@ -67,7 +67,7 @@ def find_silent_regions_gpu(audio: np.ndarray, sample_rate: int = 16000, thresho
 
 def find_silent_regions(audio: np.ndarray, sample_rate: int = 16000, threshold: float = 0.01,
                         min_silence_duration: float = 0.3) -> List[Tuple[int, int]]:
-    """Host NumPy version (any sample rate / dtype); the reference's own loop restated as array operations."""
+    """Host NumPy version (any sample rate / dtype)."""
     frame = int(sample_rate * 0.01)
     n = len(audio) // frame
     if n == 0:

@@ -1,6 +1,6 @@
 // Energy scan for the chunk planner: per 10 ms frame, is the RMS under a threshold?
-// Replaces the per-frame NumPy loop of /root/reference core/asr_engine.py:521-553 (`find_silent_regions`):
-//     rms = np.sqrt(np.mean(frame ** 2));  is_silent = rms < threshold        (float32 throughout)
+// Replaces the host NumPy pass of /root/reference core/asr_engine.py:521-553 (`find_silent_regions`, :532-536):
+//     energies = np.sqrt(np.mean(frames ** 2, axis=1));  is_silent = energies < threshold        (float32 throughout)
 // The comparison decides where a 30 s chunk is cut, so the flags have to be the reference's flags, not "close": the kernel
 // reproduces NumPy's float32 arithmetic exactly - squares rounded to fp32, NumPy's pairwise summation of the 160 squares
 // (two halves of 80; in each half 8 interleaved accumulators a[j], a[8+j], ... added in index order, then combined as

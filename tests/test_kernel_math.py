@@ -148,8 +148,8 @@ def _energy_kernel_order(frames):
 
 def test_energy_scan_order_reproduces_numpy_float32_bits():
     """The flags decide where chunks are cut, so the kernel restates NumPy's pairwise float32 summation exactly; this
-    pins that statement against NumPy itself (the reference computes np.sqrt(np.mean(frame ** 2)) per frame,
-    core/asr_engine.py:537-541)."""
+    pins that statement against NumPy itself (the reference computes np.sqrt(np.mean(frames ** 2, axis=1)),
+    core/asr_engine.py:532-536)."""
     rng = np.random.default_rng(0)
     for scale in (1e-20, 1e-3, 0.01, 0.3, 1.0):
         x = rng.normal(0, scale, (50000, 160)).astype(np.float32)
