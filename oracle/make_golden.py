@@ -15,6 +15,10 @@ What is pinned, and by what:
                              `find_best_split_point` (:521-573), the inline chunk plan (:2141-2161, executed from the
                              reference file), `chunk_long_segment` / `concat_vad_speech` / `map_concat_time_to_original`
                              (:583-676) on the seeded inputs of oracle/chunk_cases.py.
+  postprocess.json           `suspect_detect` (with the VAD-probability cache of core/vad_utils.py set to seeded values),
+                             `remove_filler_words`, `count_energy_peaks`, `_compute_gap_features`,
+                             `compute_disagree_indices` (:1587-1865) and core/asr_json.py `serialize_segments` /
+                             `deserialize_segments` on the seeded inputs of oracle/post_cases.py.
   fbank_5000.npz             torchaudio.compliance.kaldi.fbank (independent Kaldi restatement) on a seeded clip;
                              kaldi-native-fbank itself is not installable offline.
 """
@@ -242,6 +246,39 @@ def chunking_cases(ae):
     return out
 
 
+def _suspect_summary(words):
+    return [[w.get("_suspect_level"), w.get("gap_after_ms"), w.get("gap_before_ms")] for w in words]
+
+
+def postprocess_cases(ae):
+    import core.asr_json as aj
+    import core.vad_utils as vu
+    from oracle import post_cases as pc
+    out = {}
+    with redirect_stdout(io.StringIO()):
+        sus = []
+        for words, audio, disagree, vad in pc.suspect_cases():
+            vu._last_vad_probs = vad          # the cache suspect_detect reads (core/vad_utils.py:51-55)
+            got = ae.suspect_detect(copy.deepcopy(words), audio, disagree_indices=disagree)
+            kept = ae.remove_filler_words(got)
+            sus.append({"flags": _suspect_summary(got), "kept": [w["start"] for w in kept]})
+        vu._last_vad_probs = None
+        out["suspect"] = sus
+        out["gap"] = [{"peaks": ae.count_energy_peaks(seg), "features": list(ae._compute_gap_features(seg))} for seg in pc.gap_segments()]
+        out["disagree"] = [sorted(ae.compute_disagree_indices(m, o)) for m, o in pc.disagree_cases()]
+        ser = []
+        for c in pc.segment_cases():
+            data = aj.serialize_segments(copy.deepcopy(c["segments"]), c["speaker_name_mapping"], c["speaker_colors"], c["model_name"],
+                                         c["model_type"], c["duration_sec"], c["timing"], c["overlap_segments"])
+            data.pop("created_at")
+            back = aj.deserialize_segments(json.loads(json.dumps(data)))
+            ser.append({"json": data, "back": list(back)})
+        out["serialize"] = ser
+    with open(os.path.join(GOLD, "postprocess.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ae, hc = load_reference()
@@ -255,6 +292,8 @@ def main():
     fbank_case()
     c = chunking_cases(ae)
     print("chunking cases:", {k: len(v) for k, v in c.items()})
+    c = postprocess_cases(ae)
+    print("postprocess cases:", {k: len(v) for k, v in c.items()})
     print("golden written to", GOLD)
 
 

@@ -10,6 +10,8 @@ What `TranscriberPipeline` calls in the reference and what stands for it here:
   merge_chunks_with_overlap                   :44-237, :521-676, :2141-2161 -> chunking.py (re-exported here), and
                                                                                chunking.transcribe_long = plan -> one
                                                                                ragged GPU batch -> stitch
+  suspect_detect / remove_filler_words / compute_disagree_indices / count_energy_peaks   :1587-1865 -> postprocess.py
+  core/asr_json.py serialize_segments / deserialize_segments                  -> postprocess.py
   enc_sess / dec_sess / joi_sess `.run`       :1047,1055,1085,1092          -> session adapters on the raw CUDA stages
 
 The token -> word merge, ROVER and time mapping are host glue in the reference too; the per-token entropy
@@ -29,6 +31,8 @@ import numpy as np
 from .chunking import (chunk_long_segment, concat_vad_speech, find_best_split_point, find_overlap_alignment,  # noqa: F401
                        find_silent_regions, map_concat_time_to_original, merge_chunks_with_overlap, plan_chunks,
                        transcribe_long, words_match)
+from .postprocess import (compute_disagree_indices, count_energy_peaks, finish_transcript, remove_filler_words,  # noqa: F401
+                          suspect_detect)
 from .recognizer import OfflineRecognizer
 
 ROVER_MODEL_IDS = ["zipformer-30m-rnnt-6000h", "sherpa-onnx-zipformer-vi-2025-04-20"]
