@@ -19,6 +19,8 @@ What is pinned, and by what:
                              `remove_filler_words`, `count_energy_peaks`, `_compute_gap_features`,
                              `compute_disagree_indices` (:1587-1865) and core/asr_json.py `serialize_segments` /
                              `deserialize_segments` on the seeded inputs of oracle/post_cases.py.
+  staging.json               core/audio_preprocessing.py `per_segment_rms_normalize` / `preprocess_audio` digests on the
+                             seeded cases of tests/test_staging.py.
   fbank_5000.npz             torchaudio.compliance.kaldi.fbank (independent Kaldi restatement) on a seeded clip;
                              kaldi-native-fbank itself is not installable offline.
 """
@@ -279,6 +281,22 @@ def postprocess_cases(ae):
     return out
 
 
+def staging_cases_golden():
+    """core/audio_preprocessing.py per_segment_rms_normalize / preprocess_audio on the seeded cases of
+    tests/test_staging.py; full-length outputs are summarised as (length, sum, sum |x|, max |x|) in float64."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_staging import _digest, staging_cases
+    with redirect_stdout(io.StringIO()):
+        import core.audio_preprocessing as ap
+    out = []
+    for audio, segs in staging_cases():
+        out.append({"rms": _digest(ap.per_segment_rms_normalize(audio.copy(), segs)), "pre": _digest(ap.preprocess_audio(audio, segs)),
+                    "limit": _digest(ap.preprocess_audio(audio, segs, enable_rms_normalize=False))})
+    with open(os.path.join(GOLD, "staging.json"), "w", encoding="utf-8") as f:
+        json.dump(out, f)
+    return out
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ae, hc = load_reference()
@@ -294,6 +312,7 @@ def main():
     print("chunking cases:", {k: len(v) for k, v in c.items()})
     c = postprocess_cases(ae)
     print("postprocess cases:", {k: len(v) for k, v in c.items()})
+    print("staging cases:", len(staging_cases_golden()))
     print("golden written to", GOLD)
 
 
