@@ -1,0 +1,50 @@
+"""CPU check of the one-call transcription phase (pipeline.transcribe_recording): it is exactly the composition of the
+parity-tested steps, in the reference's order (core/asr_engine.py:2076-2161, :2326-2496, :2556-2580)."""
+import copy
+
+import numpy as np
+
+from oracle import chunk_cases as cc
+from sherpa_vietnamese_asr_b200 import chunking, pipeline, postprocess, staging, vad
+
+
+def _fake_decode(rec, chunks, offsets):
+    out = []
+    for c, off in zip(chunks, offsets):
+        n = len(c) // 8000
+        out.append([{"text": ["ờ", "xin", "chào", "bạn"][(int(round(off * 2)) + i) % 4], "start": off + 0.5 * i, "end": off + 0.5 * i + 0.3,
+                     "local_start": 0.5 * i, "local_end": 0.5 * i + 0.3, "prob": 0.8, "tsallis_max": 0.01 * (i % 9), "margin_min": 0.5}
+                    for i in range(n)])
+    return out
+
+
+def _prob(rows):
+    return (1.0 - np.exp(-12.0 * np.sqrt(np.mean(rows.astype(np.float64) ** 2, axis=1)))).astype(np.float32)
+
+
+def test_transcribe_recording_is_the_composition_of_its_steps():
+    audio = (cc.silence_audio(21, 95.0) * np.float32(1.7)).astype(np.float32)
+    audio[16000 * 40:16000 * 52] = 0                                   # a pause longer than the 5 s merge
+    res = pipeline.transcribe_recording(None, audio, vad_prob_fn=_prob, rms_normalize=True, decode_chunks=_fake_decode)
+
+    segs, probs = vad.get_vad_segments(audio, _prob)
+    staged = staging.preprocess_audio(audio, segs, enable_rms_normalize=True)
+    merged = vad.merge_close_segments(segs, vad.MAX_VAD_GAP, True)
+    long = chunking.transcribe_long(None, staged, merged, decode_chunks=_fake_decode)
+    words, text = postprocess.finish_transcript(copy.deepcopy(long["words"]), staged, False, probs)
+    assert res["vad_segments"] == merged and len(merged) >= 2
+    assert res["chunk_plan"] == long["chunk_plan"] and len(res["chunk_plan"]) >= 3
+    assert res["words"] == words and res["text"] == text
+    assert np.max(np.abs(staged)) <= 0.95 + 1e-6 and np.max(np.abs(audio)) > 0.95
+    assert all(w["text"] != "ờ" for w in res["words"]) and any(w.get("_suspect_level") for w in res["words"])
+    assert res["text"][0].isupper()
+
+
+def test_transcribe_recording_without_vad_uses_the_whole_recording():
+    audio = cc.silence_audio(22, 33.0)
+    res = pipeline.transcribe_recording(None, audio, decode_chunks=_fake_decode)
+    assert res["vad_segments"] is None
+    assert res["chunk_plan"] == chunking.plan_chunks(len(audio), chunking.find_silent_regions(audio))
+    given = pipeline.transcribe_recording(None, audio, vad_segments=[(0, 16000 * 10), (16000 * 12, len(audio))], skip_preprocessing=True,
+                                          decode_chunks=_fake_decode)
+    assert given["vad_segments"] == [(0, len(audio))]                  # 2 s gap: merged by the 5 s rule
