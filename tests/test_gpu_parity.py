@@ -459,3 +459,72 @@ def test_energy_scan_flags_equal_numpy():
         audio = cc.silence_audio(seed, sec)
         assert chunking.find_silent_regions_gpu(audio) == chunking.find_silent_regions(audio)
         assert chunking.find_silent_regions_gpu(audio, 16000, 0.02, 0.1) == chunking.find_silent_regions(audio, 16000, 0.02, 0.1)
+
+
+def _stream_case(rec, orec, audios, beam=4):
+    from oracle import fbank_ref, search_ref as sr
+    streams = []
+    for a in audios:
+        s = rec.create_stream()
+        if len(a):
+            s.accept_waveform(16000, a)
+        streams.append(s)
+    rec.decode_streams(streams)
+    n_tok = 0
+    for a, s in zip(audios, streams):
+        feats = fbank_ref.fbank(a, np.float64) if len(a) else np.zeros((0, 80))
+        if feats.shape[0] < 9:
+            assert s.result.token_ids == [] and s.result.text == ""
+            continue
+        orec["dec_cache"].clear()
+        toks, frames, lps, T, _ = sr.modified_beam_search(orec, feats, beam)
+        assert s.result.num_frames == T
+        assert s.result.token_ids == toks and s.result.frames == frames
+        np.testing.assert_allclose(s.result.ys_log_probs, lps, atol=5e-3)
+        n_tok += len(toks)
+    return n_tok
+
+
+def test_long_and_degenerate_utterances(tiny, m30):
+    """Maximum sizes and empties: 35 s (the longest chunk the planner makes) and 61 s utterances, no samples at all, less
+    than one frame, one sample - in one ragged batch; and a 35 s chunk through the 30M model."""
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = tiny
+    orec = oracle_recognizer(paths, beam=4)[0]
+    sizes = [16000 * 35, 16000 * 61 + 77, 0, 79, 1, 16000 * 2]
+    audios = [synth.speech_like(n, 7000 + i) if n else np.zeros(0, np.float32) for i, n in enumerate(sizes)]
+    assert _stream_case(rec, orec, audios) > 50
+    cfg, paths, rec = m30
+    orec = oracle_recognizer(paths, beam=4)[0]
+    assert _stream_case(rec, orec, [synth.speech_like(16000 * 35 + 123, 7100)]) > 5
+
+
+def test_batch_of_300_short_streams(tiny):
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = tiny
+    orec = oracle_recognizer(paths, beam=4)[0]
+    rng = np.random.default_rng(5)
+    audios = [synth.speech_like(int(n), 7200 + i) for i, n in enumerate(rng.integers(1600, 24000, 300))]
+    assert _stream_case(rec, orec, audios) > 300
+
+
+def test_regrown_stream_is_decoded_again(tiny):
+    """decode_stream is re-callable on a stream that received more audio (streaming_asr.py:408) and idempotent on an
+    unchanged one."""
+    from oracle import fbank_ref, search_ref as sr
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, rec = tiny
+    orec = oracle_recognizer(paths, beam=4)[0]
+    a = synth.speech_like(16000 * 5, 7300)
+    s = rec.create_stream()
+    s.accept_waveform(16000, a[:32000])
+    rec.decode_stream(s)
+    first = list(s.result.token_ids)
+    s.accept_waveform(16000, a[32000:])
+    rec.decode_stream(s)
+    second = list(s.result.token_ids)
+    rec.decode_stream(s)
+    for part, got in ((a[:32000], first), (a, second), (a, list(s.result.token_ids))):
+        orec["dec_cache"].clear()
+        assert got == sr.modified_beam_search(orec, fbank_ref.fbank(part, np.float64), 4)[0]
+    assert len(second) > len(first) > 0
