@@ -528,3 +528,46 @@ def test_regrown_stream_is_decoded_again(tiny):
         orec["dec_cache"].clear()
         assert got == sr.modified_beam_search(orec, fbank_ref.fbank(part, np.float64), 4)[0]
     assert len(second) > len(first) > 0
+
+
+def test_threads_share_recognizers(tiny, m30):
+    """Threading contract (SURVEY section 8b): recognizers shared by several Python threads, each with its own streams;
+    results equal the single-threaded decode (which the tests above pin to the oracle)."""
+    import threading
+    from sherpa_vietnamese_asr_b200 import synth
+    recs = [tiny[2], m30[2]]
+    rng = np.random.default_rng(1)
+    n_threads, n_iter, n_utt = 4, 4, 5
+
+    def decode(rec, audios, split):
+        ss = []
+        for a in audios:
+            s = rec.create_stream()
+            if split:
+                s.accept_waveform(16000, a[: len(a) // 3])
+                s.accept_waveform(16000, a[len(a) // 3:])
+            else:
+                s.accept_waveform(16000, a)
+            ss.append(s)
+        rec.decode_streams(ss)
+        return [(list(s.result.token_ids), list(s.result.frames)) for s in ss]
+
+    audio = {(t, i): [synth.speech_like(int(rng.integers(8000, 90000)), 8000 + 100 * t + 10 * i + u) for u in range(n_utt)]
+             for t in range(n_threads) for i in range(n_iter)}
+    want = {k: decode(recs[k[0] % 2], v, False) for k, v in audio.items()}
+    got, errors = {}, []
+
+    def worker(t):
+        try:
+            for i in range(n_iter):
+                got[(t, i)] = decode(recs[t % 2], audio[(t, i)], bool(i % 2))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not errors and got == want
+    assert sum(len(tk) for v in want.values() for tk, _ in v) > 100
