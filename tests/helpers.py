@@ -1,7 +1,7 @@
 """Shared helpers for the parity tests (oracle side is CPU only)."""
 import numpy as np
 
-from oracle import fbank_ref, search_ref, zipformer_ref
+from oracle import search_ref, zipformer_ref
 from sherpa_vietnamese_asr_b200 import weights
 
 

@@ -8,7 +8,6 @@ import os
 import sys
 from contextlib import redirect_stdout
 
-import numpy as np
 import pytest
 
 from oracle import post_cases as pc

@@ -4,7 +4,6 @@ import os
 import socket
 
 import numpy as np
-import pytest
 
 from sherpa_vietnamese_asr_b200 import sharding
 
