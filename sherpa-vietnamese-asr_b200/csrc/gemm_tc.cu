@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "gemm_tc_epilogue.cuh"
 
 namespace b200asr {
 
@@ -33,30 +34,8 @@ using namespace tc;
 
 namespace {
 
-__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + __logf(1.0f + __expf(-fabsf(x))); }
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_SWOOSH_L) return softplus_f(v - 4.0f) - 0.08f * v - 0.035f;
-  if (act == ACT_SWOOSH_R) return softplus_f(v - 1.0f) - 0.08f * v - 0.313261687f;
-  return v;
-}
-
 // smem ring depth: 3xTF32 keeps hi and lo copies of both operands, so 3 stages at BN = 128 and 4 at BN = 64
 __host__ __device__ constexpr int stages_for(int BN, bool split3) { return split3 ? (BN == 64 ? 4 : kStages3) : kStages1; }
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-struct TcParams {
-  const float *bias;
-  const float *R; int ldr;
-  float *C; int ldc;
-  int M, N, K, act;
-  float *partials;   // joiner epilogue (EPI > 0)
-  unsigned long long *trace;
-};
 
 // SPLIT3 = error-compensated "3xTF32": every fp32 operand x is split into hi = x with the 13 low mantissa bits
 // cleared (what the tensor core reads from a raw fp32 anyway) and lo = x - hi (exact in fp32; activations are split
@@ -88,7 +67,6 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   static_assert(!ATMEM || SPLIT3, "A-in-TMEM is the 3xTF32 path");
   // EPI <= 0 also carries the activation as a compile-time constant (0 none, -1 SwooshL, -2 SwooshR): the epilogue of
   // the K = 192..256 layers is as long as their main loop, and a run-time switch per element showed up in it
-  constexpr int kAct = EPI == -1 ? (int)ACT_SWOOSH_L : (EPI == -2 ? (int)ACT_SWOOSH_R : (int)ACT_NONE);
   constexpr int NS = ATMEM ? 4 : stages_for(BN, SPLIT3);
   constexpr uint32_t kAccCols = 2 * BN;                       // two accumulators
   constexpr uint32_t kTmemACol = 256;                         // ATMEM: A stages at columns 256 + 64 s (hi) / + 32 (lo)
@@ -212,144 +190,8 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
       }
     }
   } else if (warp < 10) {
-    // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
-    const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;
-    int ti = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
-      const int acc = ti & 1;
-      mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
-      if (ti == 0 && warp == 2 && lane == 0) mark(4);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t stg = smem_u32(epi_stage + (warp - 2) * (32 * 32));   // per-warp 32x32 transpose tile, 16-byte chunks XOR-swizzled by row
-      const bool vec_ok = ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                          (!p.R || (((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0))) &&
-                          (!p.bias || EPI > 0 || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
-#pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        if (n0 + c0 >= p.N) continue;                      // warp-uniform
-        const int mrow0 = m0 + q * 32;
-        if constexpr (EPI > 0) {
-          const int nbase = n0 + c0;
-          float mx = -INFINITY;
-          if (nbase + 32 <= p.N) {                          // warp-uniform; only the last tile of a row is ragged
-            const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + nbase);   // bias is 16-byte aligned (checked on the host)
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 bq = __ldg(b4 + j4);
-              const float x0 = __uint_as_float(r[4 * j4]) + bq.x, x1 = __uint_as_float(r[4 * j4 + 1]) + bq.y;
-              const float x2 = __uint_as_float(r[4 * j4 + 2]) + bq.z, x3 = __uint_as_float(r[4 * j4 + 3]) + bq.w;
-              r[4 * j4] = __float_as_uint(x0); r[4 * j4 + 1] = __float_as_uint(x1);
-              r[4 * j4 + 2] = __float_as_uint(x2); r[4 * j4 + 3] = __float_as_uint(x3);
-              mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = nbase + j;
-              const float x = n < p.N ? __uint_as_float(r[j]) + __ldg(p.bias + n) : -INFINITY;
-              r[j] = __float_as_uint(x);
-              mx = fmaxf(mx, x);
-            }
-          }
-          // sum = S e^(x-mx) feeds the log-softmax, su = S e^(x-mx) (x-mx) and st = S e^((x-mx)/3) the per-token entropy /
-          // Tsallis statistics. ex2.approx on (x-mx) log2(e): relative error <= 2^-22 on the terms near the maximum
-          // that carry the sum, far inside the fp32 noise of the logits themselves. Two interleaved accumulator sets
-          // halve the dependent chains (the epilogue is latency-bound, two warps per scheduler).
-          float sum[2] = {0.f, 0.f}, su[2] = {0.f, 0.f}, st[2] = {0.f, 0.f}, tv[EPI];
-          int ti[EPI];
-#pragma unroll
-          for (int i = 0; i < EPI; ++i) { tv[i] = -INFINITY; ti[i] = -1; }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(r[j]);
-            const float dx = x - mx;                        // -inf past N: e = 0, and the product below is skipped
-            const float tl = dx * 1.4426950408889634f;
-            const float e = ex2_approx(tl);
-            sum[j & 1] += e;
-            su[j & 1] = fmaf(e, fmaxf(dx, -3.0e38f), su[j & 1]);   // dx = -inf past N: 0 * finite
-            st[j & 1] += ex2_approx(tl * (1.0f / 3.0f));
-            if (x > tv[EPI - 1]) {                          // strict: equal values keep the lower column first
-              float cv = x;
-              int ci = nbase + j;
-#pragma unroll
-              for (int i = 0; i < EPI; ++i) {
-                if (cv > tv[i]) { const float fv = tv[i]; const int fi = ti[i]; tv[i] = cv; ti[i] = ci; cv = fv; ci = fi; }
-              }
-            }
-          }
-          const int mrow = mrow0 + lane;
-          if (mrow < p.M) {
-            const int n_parts = (p.N + 31) >> 5;
-            float4 *rec = reinterpret_cast<float4 *>(p.partials + ((long long)mrow * n_parts + (nbase >> 5)) * (4 + 2 * EPI));
-            rec[0] = make_float4(mx, sum[0] + sum[1], su[0] + su[1], st[0] + st[1]);
-#pragma unroll
-            for (int i = 0; i < EPI / 4; ++i) {
-              rec[1 + i] = make_float4(tv[4 * i], tv[4 * i + 1], tv[4 * i + 2], tv[4 * i + 3]);
-              rec[1 + EPI / 4 + i] = make_float4(__int_as_float(ti[4 * i]), __int_as_float(ti[4 * i + 1]), __int_as_float(ti[4 * i + 2]),
-                                                 __int_as_float(ti[4 * i + 3]));
-            }
-          }
-        }
-        if (EPI > 0 && p.C == nullptr) continue;               // records only: the selection never reads the logits
-        const float *bias_late = EPI > 0 ? nullptr : p.bias;   // the joiner epilogue has already added it
-        __syncwarp();
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4)                      // row = lane; 128-bit stores, conflict-free per quarter warp
-          sts128(stg + (uint32_t)(lane * 32 + ((k4 ^ (lane & 7)) << 2)) * 4u,
-                 make_float4(__uint_as_float(r[4 * k4]), __uint_as_float(r[4 * k4 + 1]), __uint_as_float(r[4 * k4 + 2]), __uint_as_float(r[4 * k4 + 3])));
-        __syncwarp();
-        if (vec_ok) {
-          // thread = (row lane/8 + 4*it, 4 columns (lane%8)*4): a warp instruction covers 4 full 128-byte rows
-          const int c4 = (lane & 7) * 4, rsub = lane >> 3;
-          const int n = n0 + c0 + c4;
-          const bool nv = n < p.N;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias_late && nv) bv = __ldg(reinterpret_cast<const float4 *>(bias_late + n));
-          float4 res[8];
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {                   // all residual loads in flight before use
-            const int m = mrow0 + rsub + 4 * it;
-            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.R && nv && m < p.M) rv = *reinterpret_cast<const float4 *>(p.R + (long long)m * p.ldr + n);
-            res[it] = rv;
-          }
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = rsub + 4 * it, m = mrow0 + rr;
-            if (nv && m < p.M) {
-              float4 v = lds128(stg + (uint32_t)(rr * 32 + (((lane & 7) ^ (rr & 7)) << 2)) * 4u);
-              v.x = apply_act(v.x + bv.x, kAct) + res[it].x; v.y = apply_act(v.y + bv.y, kAct) + res[it].y;
-              v.z = apply_act(v.z + bv.z, kAct) + res[it].z; v.w = apply_act(v.w + bv.w, kAct) + res[it].w;
-              *reinterpret_cast<float4 *>(p.C + (long long)m * p.ldc + n) = v;
-            }
-          }
-        } else {
-          // generic path: lane = column, one row per iteration
-          const int n = n0 + c0 + lane;
-          const bool nv = n < p.N;
-          const float bs = (bias_late && nv) ? __ldg(bias_late + n) : 0.f;
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int m = mrow0 + rr;
-            if (nv && m < p.M) {
-              const float4 v4 = lds128(stg + (uint32_t)(rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2)) * 4u);
-              float v = ((lane & 3) == 0 ? v4.x : (lane & 3) == 1 ? v4.y : (lane & 3) == 2 ? v4.z : v4.w) + bs;
-              const float rv = p.R ? p.R[(long long)m * p.ldr + n] : 0.f;
-              v = apply_act(v, kAct) + rv;
-              p.C[(long long)m * p.ldc + n] = v;
-            }
-          }
-        }
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (ti == 0 && warp == 2 && lane == 0) mark(5);
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
-    }
+    // ===== epilogue warps 2..9 (gemm_tc_epilogue.cuh)
+    tc_epilogue_warps<BN, EPI>(p, tmem_base, tmem_full_bar, tmem_empty_bar, epi_stage, n_tiles, tiles_n, warp, lane);
   } else {
     // ===== operand splitter warps 10..13 (SPLIT3): hi in place, lo into the shadow stage (same swizzled layout)
     if constexpr (SPLIT3) {
@@ -494,6 +336,19 @@ void make_map_uncached(CUtensorMap *map, const float *ptr, int rows, int K, int 
   make_map_uncached_impl(map, ptr, rows, K, ld, box_rows);
 }
 bool tc_init() { init_once(); return g_ok; }
+// 16-bit row-major [rows, K] (fp16 or bf16), box = 64 x box_rows = 128-byte rows, 128-byte swizzle, OOB -> 0 (gemm_tc_f16.cu)
+void make_map_16(CUtensorMap *map, const void *ptr, bool bf16, int rows, int K, int ld, int box_rows) {
+  init_once();
+  if (!g_ok) throw CudaError("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(ptr),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (16-bit) failed (" + std::to_string((int)r) + ")");
+}
 }  // namespace tc
 
 bool gemm_tc_available() {
@@ -592,7 +447,14 @@ void launch_split_lo(const float *w, float *lo, long long n, cudaStream_t st) {
 }
 
 void launch_gemm_tc(const GemmArgs &g, cudaStream_t st) { launch_tc_impl(g, st, false); }
+bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st);   // gemm_tc_f16.cu (experimental)
 // FP32-grade product on the tensor pipe (error-compensated 3xTF32)
-void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st) { launch_tc_impl(g, st, true); }
+void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st) {
+  // B200ASR_GEMM_F16SPLIT=1: the fp16-hi / bf16-lo operand split (experimental, see gemm_tc_f16.cu); shapes it does not take
+  // fall through to 3xTF32
+  static const bool f16split = getenv("B200ASR_GEMM_F16SPLIT") != nullptr;
+  if (f16split && launch_gemm_f16split(g, st)) return;
+  launch_tc_impl(g, st, true);
+}
 
 }  // namespace b200asr
