@@ -179,7 +179,9 @@ def words_match(w1: str, w2: str, threshold: float = FUZZY_MATCH_THRESHOLD) -> b
         return False
     if len(w1) > 2 and len(w2) > 2 and (w1 in w2 or w2 in w1):
         return True
-    return SequenceMatcher(None, w1, w2).ratio() >= threshold
+    m = SequenceMatcher(None, w1, w2)
+    # difflib's two upper bounds on ratio() first: most word pairs of an overlap window are unrelated
+    return m.real_quick_ratio() >= threshold and m.quick_ratio() >= threshold and m.ratio() >= threshold
 
 
 def _mean_prob(words: Sequence[dict]) -> float:
