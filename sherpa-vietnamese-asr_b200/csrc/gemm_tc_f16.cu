@@ -5,9 +5,12 @@
 // replays every Linear of the oracle encoder and shows that the split  x = hi + lo,  hi = fp16(x), lo = bf16(x - hi)  with
 //     A*W ~ A_lo*W_hi + A_hi*W_lo + A_hi*W_hi        (FP32 accumulation in TMEM, mixed a/b formats per MMA)
 // has the same error as 3xTF32 (9e-7 vs 7e-7 relative, native fp32 1.2e-6) and keeps the decoded token ids exact, while
-// kind::f16 runs at twice the TF32 rate and the weight tiles are half the bytes. lo is bf16, not fp16, so values under the
-// fp16 range lose nothing (hi flushes towards 0, lo carries them with fp32's exponent); hi is clamped to +-65504 so values
-// over the range degrade to bf16 precision instead of producing infinities.
+// kind::f16 runs at twice the TF32 rate and the weight tiles are half the bytes. Range: inside fp16's normal range
+// (6.1e-5 .. 65504) the two terms carry x to 2^-20; lo is bf16 (fp32's exponent), so under that range the pair degrades
+// smoothly - |x - (hi + lo)| <= max(2^-20 |x|, 6e-11), i.e. down to bf16 precision for |x| < 6e-8 - which is harmless next
+// to O(1) terms of the same dot product but would show if a whole operand were tiny (a power-of-two pre-scale of W would
+// remove that; not done); hi is clamped to +-65504, so values over the range also degrade to bf16 precision instead of
+// producing infinities. tests/test_kernel_math.py::test_f16_split_product_is_fp32_grade pins these statements on the CPU.
 //
 // Same structure as the A-in-TMEM 3xTF32 kernel: persistent CTAs over 128 x BN tiles; warp 0 TMA producer, warp 1 MMA
 // issuer, warps 2..9 epilogue (gemm_tc_epilogue.cuh), warps 10..13 read the landed fp32 A tile once, convert it and store

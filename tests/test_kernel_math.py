@@ -161,3 +161,38 @@ def test_energy_scan_order_reproduces_numpy_float32_bits():
         assert np.array_equal(per_frame.view(np.uint32), got[:500].view(np.uint32))
         # and the comparison the reference makes (weak Python float against float32)
         assert np.array_equal(got < np.float32(0.01), want < 0.01)
+
+
+# ----------------------------------------------------------------------------- fp16-hi / bf16-lo operand split (csrc/gemm_tc_f16.cu)
+def _bf16_rn(x):
+    u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def _split16(x):
+    """The converter's arithmetic (split_pair / split_w16_kernel): hi = fp16(clamp(x, +-65504)), lo = bf16(x - hi)."""
+    hi = np.clip(x, -65504.0, 65504.0).astype(np.float16).astype(np.float32)
+    return hi, _bf16_rn((x - hi).astype(np.float32))
+
+
+def test_f16_split_product_is_fp32_grade():
+    """A*W ~ A_lo*W_hi + A_hi*W_lo + A_hi*W_hi with fp32 accumulation: relative error of the split itself (products in
+    float64 here, so only the operand rounding shows) stays at the 3xTF32 level at the network's operand scales; a whole
+    operand far under the fp16 normal range (6.1e-5) or over 65504 degrades smoothly towards bf16 precision - never to
+    zeros or infinities."""
+    rng = np.random.default_rng(0)
+    for scale_a, scale_w, tol in ((1.0, 0.05, 2e-6), (0.01, 1e-3, 2e-6), (6.9, 1.0, 2e-6), (1e-6, 1e-3, 1e-4), (3e5, 1.0, 2e-2)):
+        a = (rng.normal(0, scale_a, (64, 256))).astype(np.float32)
+        w = (rng.normal(0, scale_w, (48, 256))).astype(np.float32)
+        ah, al = _split16(a)
+        wh, wl = _split16(w)
+        f = np.float64
+        got = al.astype(f) @ wh.astype(f).T + ah.astype(f) @ wl.astype(f).T + ah.astype(f) @ wh.astype(f).T
+        want = a.astype(f) @ w.astype(f).T
+        assert np.isfinite(got).all()
+        err = np.abs(got - want).max() / np.abs(want).max()
+        assert err < tol, (scale_a, err)
+    # one operand: |x - (hi + lo)| <= max(2^-19 |x|, 2^-33) over 12 decades, overflow side excluded
+    x = (rng.normal(0, 1, 200000) * 10.0 ** rng.uniform(-9, 3, 200000)).astype(np.float32)
+    hi, lo = _split16(x)
+    assert np.all(np.abs(x - (hi + lo)) <= np.maximum(2.0 ** -19 * np.abs(x), 2.0 ** -33))
