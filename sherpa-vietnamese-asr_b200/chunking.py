@@ -252,7 +252,7 @@ def transcribe_long(recognizer, audio: np.ndarray, vad_segments: Sequence[Tuple[
     if decode_chunks is not None:
         regions = find_silent_regions(speech)
     else:
-        regions = find_silent_regions_gpu(speech, device_id=int(recognizer.engine._cfg.device_id))
+        regions = find_silent_regions_gpu(speech, device_id=int(recognizer.engine.device_id))
     plan = plan_chunks(len(speech), regions, segment_samples, overlap_samples)
     chunks = [speech[s:e] for s, e, _ in plan]
     offsets = [s / 16000.0 for s, _, _ in plan]

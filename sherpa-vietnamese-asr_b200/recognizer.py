@@ -175,6 +175,7 @@ class OfflineRecognizer:
             raise RuntimeError("B200AsrCreateOfflineRecognizer failed: " + _capi.last_error())
         self.vocab_size = _capi.lib().B200AsrVocabSize(self._h)
         self.joiner_dim = _capi.lib().B200AsrEncoderOutDim(self._h)
+        self.device_id = device_id
         self.decoding_method = decoding_method
         self.max_active_paths = max_active_paths
         self.hotwords_score = hotwords_score
