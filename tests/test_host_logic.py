@@ -126,3 +126,27 @@ def test_synthetic_workloads_are_seeded_and_shaped():
 def test_create_recognizer_discovery_errors(tmp_path):
     with pytest.raises(FileNotFoundError):
         asr_engine.create_recognizer(str(tmp_path))
+
+
+def test_result_marshalling_from_the_c_struct():
+    """OfflineStream.result copies the library-owned result arrays into Python lists: same values and Python types as
+    element-wise ctypes reads (float32 values widened to Python floats, int32 to ints), empty results included."""
+    import ctypes as C
+    from sherpa_vietnamese_asr_b200.recognizer import result_from_struct
+    n = 7
+    rng = np.random.default_rng(0)
+    ids = (C.c_int32 * n)(*[int(x) for x in rng.integers(0, 2000, n)])
+    frames = (C.c_int32 * n)(*range(3, 3 + n))
+    f = lambda: (C.c_float * n)(*[float(x) for x in rng.normal(0, 1, n).astype(np.float32)])
+    ts, lps, tsl, mg, en, t1 = f(), f(), f(), f(), f(), f()
+    toks = (C.c_char_p * n)(*[("▁t%d" % i).encode("utf-8") for i in range(n)])
+    r = _capi.Result(text="xin chào".encode("utf-8"), json=b'{"text": "xin"}', tokens=toks, token_ids=ids, timestamps=ts, frames=frames,
+                     ys_log_probs=lps, tsallis=tsl, margin=mg, entropy=en, top1=t1, count=n, num_frames=248, duration=10.0)
+    res = result_from_struct(r)
+    assert res.text == "xin chào" and res.tokens == ["▁t%d" % i for i in range(n)] and str(res) == '{"text": "xin"}'
+    assert res.token_ids == [ids[i] for i in range(n)] and all(type(x) is int for x in res.token_ids)
+    assert res.frames == list(range(3, 3 + n)) and res.num_frames == 248 and res.duration == 10.0
+    for got, src in ((res.timestamps, ts), (res.ys_log_probs, lps), (res.tsallis, tsl), (res.margin, mg), (res.entropy, en), (res.top1, t1)):
+        assert got == [src[i] for i in range(n)] and all(type(x) is float for x in got)
+    empty = result_from_struct(_capi.Result(count=0))
+    assert empty.token_ids == [] and empty.text == "" and empty.tokens == [] and empty.timestamps == []
