@@ -48,3 +48,17 @@ def test_transcribe_recording_without_vad_uses_the_whole_recording():
     given = pipeline.transcribe_recording(None, audio, vad_segments=[(0, 16000 * 10), (16000 * 12, len(audio))], skip_preprocessing=True,
                                           decode_chunks=_fake_decode)
     assert given["vad_segments"] == [(0, len(audio))]                  # 2 s gap: merged by the 5 s rule
+
+
+def test_vad_failure_falls_back_to_silence_chunking():
+    """core/asr_engine.py:2171-2204: any error in the VAD phase -> the whole recording, chunked at silences."""
+    audio = cc.silence_audio(23, 70.0)
+
+    def broken(rows):
+        raise RuntimeError("VAD model missing")
+
+    res = pipeline.transcribe_recording(None, audio, vad_prob_fn=broken, decode_chunks=_fake_decode)
+    base = pipeline.transcribe_recording(None, audio, decode_chunks=_fake_decode)
+    assert "VAD model missing" in res["vad_error"] and base["vad_error"] is None
+    assert res["vad_segments"] is None and res["chunk_plan"] == base["chunk_plan"] and res["text"] == base["text"]
+    assert set(res["timing"]) == {"vad_preprocess", "transcription", "postprocess"} and all(v >= 0 for v in res["timing"].values())
