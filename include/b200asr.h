@@ -165,6 +165,14 @@ B200ASR_API int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *
 B200ASR_API double B200AsrContextForwardOneStep(const B200AsrOfflineRecognizer *r, int32_t state, int32_t token, int32_t *next_state);
 B200ASR_API double B200AsrContextFinalize(const B200AsrOfflineRecognizer *r, int32_t state);
 B200ASR_API int32_t B200AsrContextNumNodes(const B200AsrOfflineRecognizer *r);
+/* The same automaton without a recognizer or a GPU (host only): build from token-id phrases (phrase p =
+ * tokens[offsets[p] .. offsets[p+1]), per-phrase scores), step and finalize exactly as the search kernel does. Lets the
+ * hotword graph be checked against core/hotword_context.py:17-184 on any machine. Create returns NULL on failure. */
+B200ASR_API void *B200AsrHotwordGraphCreate(const int32_t *tokens, const int32_t *offsets, const float *scores, int32_t n_phrases);
+B200ASR_API void B200AsrHotwordGraphDestroy(void *graph);
+B200ASR_API int32_t B200AsrHotwordGraphNumNodes(const void *graph);
+B200ASR_API double B200AsrHotwordGraphStep(const void *graph, int32_t state, int32_t token, int32_t *next_state);
+B200ASR_API double B200AsrHotwordGraphFinalize(const void *graph, int32_t state);
 
 /* ---- device-resident benchmarking hooks (inputs staged once, timed region touches HBM only) ---- */
 /* Stages a ragged batch of PCM in HBM; returns a handle (>=0). */

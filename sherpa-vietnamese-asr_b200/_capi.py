@@ -76,6 +76,11 @@ SYMBOLS = {
     "B200AsrContextForwardOneStep": (C.c_double, [_P, C.c_int32, C.c_int32, _I32]),
     "B200AsrContextFinalize": (C.c_double, [_P, C.c_int32]),
     "B200AsrContextNumNodes": (C.c_int32, [_P]),
+    "B200AsrHotwordGraphCreate": (_P, [_I32, _I32, _F, C.c_int32]),
+    "B200AsrHotwordGraphDestroy": (None, [_P]),
+    "B200AsrHotwordGraphNumNodes": (C.c_int32, [_P]),
+    "B200AsrHotwordGraphStep": (C.c_double, [_P, C.c_int32, C.c_int32, _I32]),
+    "B200AsrHotwordGraphFinalize": (C.c_double, [_P, C.c_int32]),
     "B200AsrStageBatch": (C.c_int32, [_P, _F, _I64, C.c_int32]),
     "B200AsrRunStagedBatch": (C.c_int32, [_P, C.c_int32, _I32]),
     "B200AsrReleaseBatch": (C.c_int32, [_P, C.c_int32]),

@@ -126,3 +126,37 @@ void ContextGraphHost::build(const int32_t *tokens, const int32_t *offsets, cons
 }
 
 }  // namespace b200asr
+
+// ---- stand-alone host handle on the automaton (no recognizer, no CUDA): the same build and the same inline step function
+// the search kernel runs, so the product's hotword graph can be held to the reference on a machine without a GPU
+#include "../../include/b200asr.h"
+
+extern "C" {
+
+void *B200AsrHotwordGraphCreate(const int32_t *tokens, const int32_t *offsets, const float *scores, int32_t n_phrases) {
+  if (n_phrases < 0 || (n_phrases > 0 && (!tokens || !offsets || !scores))) return nullptr;
+  try {
+    auto *g = new b200asr::ContextGraphHost();
+    g->build(tokens, offsets, scores, n_phrases);
+    return g;
+  } catch (...) {
+    return nullptr;
+  }
+}
+void B200AsrHotwordGraphDestroy(void *g) { delete static_cast<b200asr::ContextGraphHost *>(g); }
+int32_t B200AsrHotwordGraphNumNodes(const void *g) { return g ? static_cast<const b200asr::ContextGraphHost *>(g)->n_nodes() : -1; }
+double B200AsrHotwordGraphStep(const void *g, int32_t state, int32_t token, int32_t *next_state) {
+  const auto *h = static_cast<const b200asr::ContextGraphHost *>(g);
+  if (!h || state < 0 || state >= h->n_nodes()) { if (next_state) *next_state = 0; return 0.0; }
+  int nxt = 0;
+  const double d = b200asr::cg_forward_one_step(h->view(), state, token, &nxt);
+  if (next_state) *next_state = nxt;
+  return d;
+}
+double B200AsrHotwordGraphFinalize(const void *g, int32_t state) {
+  const auto *h = static_cast<const b200asr::ContextGraphHost *>(g);
+  if (!h || state < 0 || state >= h->n_nodes()) return 0.0;
+  return b200asr::cg_finalize(h->view(), state);
+}
+
+}  // extern "C"

@@ -165,3 +165,72 @@ def test_chunk_plan_partitions_any_recording(total, raw_regions):
         assert s1 + o1 == e0 and 0 <= o1 <= ck.OVERLAP_SAMPLES and e1 > e0
     for s, e, o in plan[:-1]:
         assert e - s - o > 20 * 16000
+
+
+# ----------------------------------------------------------------------------- the product's automaton (csrc/context_graph.cpp) on the host
+class ProductGraph:
+    """B200AsrHotwordGraph*: the flattened automaton and the inline step function the CUDA search uses, run on the host."""
+
+    def __init__(self, seqs, scores):
+        import ctypes as C
+        from sherpa_vietnamese_asr_b200 import _capi
+        self.lib, self.C = _capi.lib(), C
+        flat = np.array([t for s in seqs for t in s] or [0], dtype=np.int32)
+        offs = np.zeros(len(seqs) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+        sc = np.array(list(scores) or [0.0], dtype=np.float32)
+        self.h = self.lib.B200AsrHotwordGraphCreate(_capi.i32ptr(flat), _capi.i32ptr(offs), _capi.fptr(sc), len(seqs))
+        assert self.h
+
+    def step(self, state, tok):
+        nxt = self.C.c_int32(0)
+        d = self.lib.B200AsrHotwordGraphStep(self.h, state, tok, self.C.byref(nxt))
+        return d, nxt.value
+
+    def finalize(self, state):
+        return self.lib.B200AsrHotwordGraphFinalize(self.h, state)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.B200AsrHotwordGraphDestroy(self.h)
+            self.h = None
+
+
+@settings(max_examples=300, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(phrases, tokens)
+def test_product_hotword_graph_equals_oracle(ps, toks):
+    """Mixed scores on shared prefixes, nested and repeated phrases: deltas and finalize values bit-equal to the oracle's
+    (itself pinned to core/hotword_context.py), step by step."""
+    seqs, scores = [p for p, _ in ps], [s for _, s in ps]
+    og, pg = _graph(ps), ProductGraph(seqs, scores)
+    os_, st_ = og.root, 0
+    for t in toks:
+        d1, os_ = og.forward_one_step(os_, t)
+        d2, st_ = pg.step(st_, t)
+        assert d1 == d2
+        assert og.finalize(os_) == pg.finalize(st_)
+        assert (os_ is og.root) == (st_ == 0)
+
+
+def test_product_hotword_graph_c3_configuration():
+    """BASELINE config C3's 500-phrase graph (2-8 tokens over a 2000-piece vocabulary, boosted and prefix-sharing phrases)."""
+    from sherpa_vietnamese_asr_b200 import synth
+    for vocab, seed in ((2000, 500), (40, 7)):
+        seqs, scores = synth.random_hotwords(500, vocab, seed)
+        og = sr.ContextGraph()
+        og.build(seqs, scores)
+        pg = ProductGraph(seqs, scores)
+        rng = np.random.default_rng(seed)
+        stream = []
+        for _ in range(400):                                   # phrase fragments glued with random tokens: matches, fails, restarts
+            s = seqs[int(rng.integers(len(seqs)))]
+            stream += s[: int(rng.integers(1, len(s) + 1))] + [int(rng.integers(3, vocab))]
+        os_, st_, fired = og.root, 0, 0
+        for t in stream:
+            d1, os_ = og.forward_one_step(os_, int(t))
+            d2, st_ = pg.step(st_, int(t))
+            assert d1 == d2 and og.finalize(os_) == pg.finalize(st_)
+            fired += d1 != 0
+        assert fired > 200
+    empty = ProductGraph([], [])
+    assert empty.step(0, 5) == (0.0, 0) and empty.finalize(0) == 0.0 and empty.lib.B200AsrHotwordGraphNumNodes(empty.h) == 1
