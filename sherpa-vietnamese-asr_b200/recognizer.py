@@ -194,6 +194,9 @@ class OfflineRecognizer:
                 if len(parts) >= 2:
                     self.id2token[int(parts[-1])] = parts[0]
         self._sp = None
+        if not bpe_model and bpe_vocab:        # get_hotwords_config hands over bpe.vocab; the model it was written from sits beside it
+            beside = os.path.join(os.path.dirname(os.path.abspath(bpe_vocab)), "bpe.model")
+            bpe_model = beside if os.path.exists(beside) else ""
         if bpe_model and os.path.exists(bpe_model):
             import sentencepiece as spm
             self._sp = spm.SentencePieceProcessor()

@@ -150,3 +150,77 @@ def test_result_marshalling_from_the_c_struct():
         assert got == [src[i] for i in range(n)] and all(type(x) is float for x in got)
     empty = result_from_struct(_capi.Result(count=0))
     assert empty.token_ids == [] and empty.text == "" and empty.tokens == [] and empty.timestamps == []
+
+
+# ----------------------------------------------------------------------------- hotword configuration (core/config.py:283-414)
+HOTWORD_TXT = """# tên riêng
+Hồ Chí Minh :2.5
+  thành phố hà nội
+trí tuệ nhân tạo:2.0
+tỷ lệ 3:1
+
+#bỏ qua
+chat gpt : abc
+"""
+
+
+def _tiny_sentencepiece(model_dir):
+    spm = pytest.importorskip("sentencepiece")
+    corpus = os.path.join(model_dir, "corpus.txt")
+    with open(corpus, "w", encoding="utf-8") as f:
+        for i in range(200):
+            f.write("XIN CHÀO CÁC BẠN HÔM NAY CHÚNG TA NÓI VỀ THÀNH PHỐ HỒ CHÍ MINH VÀ HÀ NỘI TRÍ TUỆ NHÂN TẠO %d\n" % i)
+    spm.SentencePieceTrainer.train(input=corpus, model_prefix=os.path.join(model_dir, "bpe"), vocab_size=60, model_type="bpe",
+                                   minloglevel=2)
+    os.remove(os.path.join(model_dir, "bpe.vocab"))      # the trainer writes one too; ensure_bpe_vocab has to create it
+
+
+def test_hotword_config_matches_reference(tmp_path):
+    from sherpa_vietnamese_asr_b200 import hotwords_config as hw
+    base = tmp_path / "app"
+    base.mkdir()
+    (base / "hotword.txt").write_text(HOTWORD_TXT, encoding="utf-8")
+    want_lines = ["HỒ CHÍ MINH :2.5", "THÀNH PHỐ HÀ NỘI", "TRÍ TUỆ NHÂN TẠO :2.0", "TỶ LỆ 3 :1", "CHAT GPT : ABC"]
+    assert hw.clean_hotword_lines(HOTWORD_TXT) == want_lines
+    cleaned = hw.prepare_hotwords_file("", str(base))
+    assert os.path.basename(cleaned).startswith("asr_hotword_") and open(cleaned, encoding="utf-8").read() == "\n".join(want_lines)
+    # what the cleaned file means to the recognizer: phrase + score pairs
+    assert recognizer.parse_hotwords_text(open(cleaned, encoding="utf-8").read()) == [
+        ("HỒ CHÍ MINH", 2.5), ("THÀNH PHỐ HÀ NỘI", 1.5), ("TRÍ TUỆ NHÂN TẠO", 2.0), ("TỶ LỆ 3", 1.0), ("CHAT GPT : ABC", 1.5)]
+    assert hw.prepare_hotwords_file("", str(tmp_path / "nowhere")) == ""
+    (base / "empty.txt").write_text("# only comments\n\n", encoding="utf-8")
+    assert hw.prepare_hotwords_file(str(base / "empty.txt"), str(base)) == ""
+
+    models = {}
+    for tag in ("ours", "ref"):
+        d = tmp_path / f"model_{tag}"
+        d.mkdir()
+        _tiny_sentencepiece(str(d))
+        models[tag] = str(d)
+    assert hw.ensure_bpe_vocab(str(tmp_path / "nowhere")) == ""
+    cfg = hw.get_hotwords_config(models["ours"], str(base))
+    assert set(cfg) == {"hotwords_file", "hotwords_score", "modeling_unit", "bpe_vocab"}
+    assert cfg["hotwords_score"] == 1.5 and cfg["modeling_unit"] == "bpe" and cfg["bpe_vocab"] == os.path.join(models["ours"], "bpe.vocab")
+    vocab_lines = open(cfg["bpe_vocab"], encoding="utf-8").read().splitlines()
+    assert len(vocab_lines) == 60 and all(len(l.split("\t")) == 2 for l in vocab_lines)
+    assert hw.get_hotwords_config(models["ours"], str(tmp_path / "nowhere")) == {}
+    no_model = tmp_path / "model_none"
+    no_model.mkdir()
+    assert set(hw.get_hotwords_config(str(no_model), str(base))) == {"hotwords_file", "hotwords_score"}
+
+    if not os.path.isdir("/root/reference/core"):
+        return
+    import io, sys
+    from contextlib import redirect_stdout
+    sys.dont_write_bytecode = True
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    with redirect_stdout(io.StringIO()):
+        import core.config as rc
+        ref_clean = rc.prepare_hotwords_file("", str(base))
+        ref_cfg = rc.get_hotwords_config(models["ref"], str(base))
+        assert rc.prepare_hotwords_file(str(base / "empty.txt"), str(base)) == ""
+    assert open(ref_clean, encoding="utf-8").read() == open(cleaned, encoding="utf-8").read()
+    assert set(ref_cfg) == set(cfg) and ref_cfg["hotwords_score"] == cfg["hotwords_score"] and ref_cfg["modeling_unit"] == cfg["modeling_unit"]
+    assert open(ref_cfg["bpe_vocab"], encoding="utf-8").read() == open(cfg["bpe_vocab"], encoding="utf-8").read()
+    assert open(ref_cfg["hotwords_file"], encoding="utf-8").read() == open(cfg["hotwords_file"], encoding="utf-8").read()
