@@ -234,3 +234,48 @@ def test_product_hotword_graph_c3_configuration():
         assert fired > 200
     empty = ProductGraph([], [])
     assert empty.step(0, 5) == (0.0, 0) and empty.finalize(0) == 0.0 and empty.lib.B200AsrHotwordGraphNumNodes(empty.h) == 1
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "hotword.txt")), reason="/root/reference not present (GPU box)")
+def test_real_hotword_file_through_the_whole_chain(tmp_path):
+    """Row a7 end to end on the reference's own hotword.txt (252 phrases): the reference's build_context_graph
+    (core/hotword_context.py:222-259: parse -> SentencePiece ids -> ContextGraph) beside ours (parse_hotwords_text ->
+    SentencePiece ids -> the product's flattened automaton), walked over streams of phrase fragments."""
+    spm = pytest.importorskip("sentencepiece")
+    from sherpa_vietnamese_asr_b200 import recognizer
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with redirect_stdout(io.StringIO()):
+        import core.hotword_context as hc
+    path = os.path.join(REF, "hotword.txt")
+    text = open(path, encoding="utf-8").read()
+    phrases = recognizer.parse_hotwords_text(text, 1.5)
+    assert phrases == hc.parse_hotwords_file(path, 1.5) and len(phrases) > 200
+    corpus = tmp_path / "corpus.txt"
+    corpus.write_text("\n".join(p for p, _ in phrases for _ in range(3)), encoding="utf-8")
+    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(tmp_path / "bpe"), vocab_size=400, model_type="bpe",
+                                   minloglevel=2, hard_vocab_limit=False)
+    sp = spm.SentencePieceProcessor()
+    sp.load(str(tmp_path / "bpe.model"))
+    with redirect_stdout(io.StringIO()):
+        rg = hc.build_context_graph(path, str(tmp_path / "bpe.model"), 1.5)
+    seqs, scores = [], []
+    for phrase, score in phrases:
+        ids = list(sp.encode(phrase, out_type=int))
+        if ids:
+            seqs.append(ids)
+            scores.append(score)
+    assert rg.n_phrases == len(seqs)
+    pg = ProductGraph(seqs, scores)
+    rng = np.random.default_rng(0)
+    rs, st_, fired = rg.root, 0, 0
+    for _ in range(1500):
+        s = seqs[int(rng.integers(len(seqs)))]
+        frag = s[: int(rng.integers(1, len(s) + 1))] + ([int(rng.integers(3, sp.get_piece_size()))] if rng.uniform() < 0.5 else [])
+        for t in frag:
+            d1, rs = rg.forward_one_step(rs, int(t))
+            d2, st_ = pg.step(st_, int(t))
+            assert d1 == d2 and rg.finalize(rs) == pg.finalize(st_)
+            fired += d1 > 0
+    assert fired > 1000
