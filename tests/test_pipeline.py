@@ -62,3 +62,47 @@ def test_vad_failure_falls_back_to_silence_chunking():
     assert "VAD model missing" in res["vad_error"] and base["vad_error"] is None
     assert res["vad_segments"] is None and res["chunk_plan"] == base["chunk_plan"] and res["text"] == base["text"]
     assert set(res["timing"]) == {"vad_preprocess", "transcription", "postprocess"} and all(v >= 0 for v in res["timing"].values())
+
+
+def test_rover_mode_merges_per_chunk_in_recording_time_and_flags_disagreement():
+    """ROVER (core/asr_engine.py:2333-2369, :2469-2486, :2556-2566): both models over the same chunks, word times mapped to
+    the recording before the per-chunk merge, disagreeing words end up flagged as suspects."""
+    from sherpa_vietnamese_asr_b200 import asr_engine
+    audio = cc.silence_audio(24, 50.0)
+    vad_segments = [(16000, 16000 * 20), (16000 * 28, 16000 * 49)]
+    seen = []
+
+    def decode(rec, chunks, offsets):
+        seen.append(rec)
+        out = []
+        for c, off in zip(chunks, offsets):
+            ws = []
+            for i in range(len(c) // 8000):
+                text = ["xin", "chào", "bạn"][i % 3]
+                if rec == "B" and i % 7 == 3:
+                    text = "khác"                                   # model B hears another word here
+                ws.append({"text": text, "start": off + 0.5 * i, "end": off + 0.5 * i + 0.3, "local_start": 0.5 * i,
+                           "local_end": 0.5 * i + 0.3, "prob": 0.9 if rec == "A" else 0.6, "tsallis_max": 0.0, "margin_min": 1.0})
+            out.append(ws)
+        return out
+
+    res = pipeline.transcribe_recording("A", audio, vad_segments=vad_segments, rover_recognizer="B", skip_preprocessing=True,
+                                        decode_chunks=decode)
+    assert seen == ["A", "B"]
+    single = pipeline.transcribe_recording("A", audio, vad_segments=vad_segments, skip_preprocessing=True, decode_chunks=decode)
+    assert res["chunk_plan"] == single["chunk_plan"]
+    assert any(w.get("_suspect_level") for w in res["words"]) and not any(w.get("_suspect_level") for w in single["words"])
+    assert all("_disagree" not in w for w in res["words"])
+    # every chunk is the product's rover_merge_words (itself pinned to the reference's) of the two decodes
+    a, b = decode("A", *_chunks(res, audio, vad_segments)), decode("B", *_chunks(res, audio, vad_segments))
+    n_dis = 0
+    for wa, wb, got in zip(a, b, res["chunk_results"]):
+        merged, dis = asr_engine.rover_merge_words(wa, wb)
+        assert [w["text"] for w in merged] == [w["text"] for w in got["words"]]
+        n_dis += len(dis)
+    assert n_dis > 0 and "khác" in res["text"].lower()
+
+
+def _chunks(res, audio, vad_segments):
+    speech, _ = chunking.concat_vad_speech(audio, vad.merge_close_segments(vad_segments, vad.MAX_VAD_GAP, True))
+    return [speech[s:e] for s, e, _ in res["chunk_plan"]], [s / 16000.0 for s, _, _ in res["chunk_plan"]]
