@@ -127,8 +127,15 @@ def compute_fbank_ort(recognizer: Recognizer, audio, sr: int = 16000) -> np.ndar
 
 
 # ----------------------------------------------------------------------------- tokens -> words
-def _round4(x: float) -> float:
-    return round(float(x), 4)
+def _mean_like_numpy(xs: List[float]) -> float:
+    """np.mean of a short list of Python floats, bit for bit: NumPy adds fewer than 8 values left to right (its pairwise
+    scheme starts at 8), which is what a plain loop does; longer lists go to NumPy itself."""
+    if len(xs) < 8:
+        acc = 0.0
+        for x in xs:
+            acc += x
+        return acc / len(xs)
+    return float(np.mean(xs))
 
 
 def words_from_result(res, id2token: Dict[int, str], n_samples: int, time_offset: float = 0.0) -> List[dict]:
@@ -141,8 +148,10 @@ def words_from_result(res, id2token: Dict[int, str], n_samples: int, time_offset
     dur = n_samples / 16000.0
     ts = [f / res.num_frames * dur for f in res.frames]
     step = (ts[-1] - ts[0]) / (len(ts) - 1) if len(ts) >= 2 else 0.08
-    ents = [{"tsallis_norm": _round4(a), "margin": _round4(b), "entropy_norm": _round4(c), "top1_prob": float(d)}
-            for a, b, c, d in zip(res.tsallis, res.margin, res.entropy, res.top1)]
+    # per-token statistics rounded to 4 decimals as _compute_token_entropy returns them (:1176-1181); tuples, not dicts:
+    # this loop runs once per token of every chunk
+    ents = [(round(float(a), 4), round(float(b), 4), round(float(c), 4))
+            for a, b, c in zip(res.tsallis, res.margin, res.entropy)]
     words: List[dict] = []
     for j, piece in enumerate(pieces):
         text = piece.lower()
@@ -163,10 +172,10 @@ def words_from_result(res, id2token: Dict[int, str], n_samples: int, time_offset
     for i, w in enumerate(words):
         probs, es = w.pop("_probs"), w.pop("_ents")
         w["prob"] = sum(probs) / len(probs)
-        w["tsallis_max"] = _round4(max(e["tsallis_norm"] for e in es))
-        w["margin_min"] = _round4(min(e["margin"] for e in es))
-        w["entropy_norm"] = _round4(np.mean([e["entropy_norm"] for e in es]))
-        w["_conf"] = _round4(sum(e["margin"] * (1.0 - e["tsallis_norm"]) for e in es) / len(es))
+        w["tsallis_max"] = round(max(e[0] for e in es), 4)
+        w["margin_min"] = round(min(e[1] for e in es), 4)
+        w["entropy_norm"] = round(_mean_like_numpy([e[2] for e in es]), 4)
+        w["_conf"] = round(sum(e[1] * (1.0 - e[0]) for e in es) / len(es), 4)
     words[0]["_chunk_bpe_tokens"] = list(pieces)
     words[0]["_chunk_bpe_timestamps_local"] = list(ts)
     for i, w in enumerate(words):
