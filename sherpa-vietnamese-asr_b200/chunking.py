@@ -24,7 +24,7 @@ import math
 import re
 import unicodedata
 from difflib import SequenceMatcher
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -238,6 +238,54 @@ def merge_chunks_with_overlap(chunk_results: Sequence[dict], overlap_duration_se
     return merged, " ".join(w["text"] for w in merged)
 
 
+class RecordingPlan:
+    """What has to be decoded for one recording, and what is needed to put the answers back together."""
+
+    def __init__(self, speech: np.ndarray, offset_map, plan: List[Tuple[int, int, int]], overlap_samples: int):
+        self.speech, self.offset_map, self.plan, self.overlap_samples = speech, offset_map, plan, overlap_samples
+
+    @property
+    def chunks(self) -> List[np.ndarray]:
+        return [self.speech[s:e] for s, e, _ in self.plan]
+
+    @property
+    def offsets(self) -> List[float]:
+        return [s / 16000.0 for s, _, _ in self.plan]
+
+
+def plan_recording(audio: np.ndarray, vad_segments: Sequence[Tuple[int, int]] = (), device_id: Optional[int] = None,
+                   segment_samples: int = SEGMENT_SAMPLES, overlap_samples: int = OVERLAP_SAMPLES) -> RecordingPlan:
+    """Speech-only concatenation of the VAD segments and the silence-aligned chunk plan over it
+    (core/asr_engine.py:2130-2161). `device_id` not None: the energy scan runs on that GPU (csrc/energy.cu, same flags as
+    NumPy); None keeps it on the host."""
+    audio = np.ascontiguousarray(audio, dtype=np.float32)
+    speech, offset_map = concat_vad_speech(audio, list(vad_segments))
+    regions = find_silent_regions(speech) if device_id is None else find_silent_regions_gpu(speech, device_id=device_id)
+    return RecordingPlan(speech, offset_map, plan_chunks(len(speech), regions, segment_samples, overlap_samples), overlap_samples)
+
+
+def finish_recording(rp: RecordingPlan, per_chunk: List[List[dict]], per_chunk_rover: Optional[List[List[dict]]] = None,
+                     hotword_phrases: Sequence[str] = ()) -> Dict[str, object]:
+    """Word times back to the original recording, ROVER per chunk when a second model's words are given (combined in
+    recording time, :2352-2357, :2469-2486), per-chunk results, overlap stitch (:2488-2494)."""
+    to_original = ConcatTimeMap(rp.offset_map)
+    for decoded in (per_chunk, per_chunk_rover or []):
+        for words in decoded:
+            for w in words:
+                w["start"], w["end"] = to_original(w["start"]), to_original(w["end"])
+    if per_chunk_rover is not None:
+        from .asr_engine import rover_merge_words
+        per_chunk = [rover_merge_words(a, b, hotword_phrases)[0] for a, b in zip(per_chunk, per_chunk_rover)]
+    results = [{"text": " ".join(w["text"] for w in words), "words": words, "audio_start_abs": s / 16000.0,
+                "audio_end_abs": e / 16000.0, "overlap_sec": o / 16000.0, "vad_group": 0}
+               for words, (s, e, o) in zip(per_chunk, rp.plan)]
+    if len(results) == 1:
+        words = list(results[0]["words"])
+    else:
+        words, _ = merge_chunks_with_overlap(results, rp.overlap_samples / 16000.0)
+    return {"words": words, "text": " ".join(w["text"] for w in words), "chunk_plan": rp.plan, "chunk_results": results}
+
+
 def transcribe_long(recognizer, audio: np.ndarray, vad_segments: Sequence[Tuple[int, int]] = (), decode_chunks=None,
                     rover_recognizer=None, hotword_phrases: Sequence[str] = (), segment_samples: int = SEGMENT_SAMPLES,
                     overlap_samples: int = OVERLAP_SAMPLES) -> Dict[str, object]:
@@ -245,37 +293,11 @@ def transcribe_long(recognizer, audio: np.ndarray, vad_segments: Sequence[Tuple[
     speech-only concatenation of the VAD segments, silence-aligned 30 s chunks with 3 s overlap, word times mapped back to
     the original recording, per-chunk word lists stitched. The per-chunk worker loop becomes ONE ragged GPU batch.
     Returns {"words", "text", "chunk_plan", "chunk_results"}."""
-    audio = np.ascontiguousarray(audio, dtype=np.float32)
-    speech, offset_map = concat_vad_speech(audio, list(vad_segments))
-    # real engine -> the energy scan runs on the GPU as well (same flags as NumPy, csrc/energy.cu); an injected decoder
-    # (tests on CPU) keeps the host scan
-    if decode_chunks is not None:
-        regions = find_silent_regions(speech)
-    else:
-        regions = find_silent_regions_gpu(speech, device_id=int(recognizer.engine.device_id))
-    plan = plan_chunks(len(speech), regions, segment_samples, overlap_samples)
-    chunks = [speech[s:e] for s, e, _ in plan]
-    offsets = [s / 16000.0 for s, _, _ in plan]
+    # real engine -> the energy scan runs on the GPU as well; an injected decoder (tests on CPU) keeps the host scan
+    device_id = None if decode_chunks is not None else int(recognizer.engine.device_id)
+    rp = plan_recording(audio, vad_segments, device_id, segment_samples, overlap_samples)
     if decode_chunks is None:
         from .asr_engine import decode_chunks
-    to_original = ConcatTimeMap(offset_map)
-
-    def decode_mapped(rec):
-        per_chunk = decode_chunks(rec, chunks, offsets)
-        for words in per_chunk:
-            for w in words:
-                w["start"], w["end"] = to_original(w["start"]), to_original(w["end"])
-        return per_chunk
-
-    per_chunk = decode_mapped(recognizer)
-    if rover_recognizer is not None:      # both hypotheses are combined in original-recording time (:2352-2357, :2469-2486)
-        from .asr_engine import rover_merge_words
-        per_chunk = [rover_merge_words(a, b, hotword_phrases)[0] for a, b in zip(per_chunk, decode_mapped(rover_recognizer))]
-    results = [{"text": " ".join(w["text"] for w in words), "words": words, "audio_start_abs": s / 16000.0,
-                "audio_end_abs": e / 16000.0, "overlap_sec": o / 16000.0, "vad_group": 0}
-               for words, (s, e, o) in zip(per_chunk, plan)]
-    if len(results) == 1:
-        words = list(results[0]["words"])
-    else:
-        words, _ = merge_chunks_with_overlap(results, overlap_samples / 16000.0)
-    return {"words": words, "text": " ".join(w["text"] for w in words), "chunk_plan": plan, "chunk_results": results}
+    per_chunk = decode_chunks(recognizer, rp.chunks, rp.offsets)
+    per_chunk_rover = decode_chunks(rover_recognizer, rp.chunks, rp.offsets) if rover_recognizer is not None else None
+    return finish_recording(rp, per_chunk, per_chunk_rover, hotword_phrases)

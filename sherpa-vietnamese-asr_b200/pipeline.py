@@ -54,3 +54,61 @@ def transcribe_recording(recognizer, audio: np.ndarray, vad_prob_fn: Optional[va
     timing["postprocess"] = time.perf_counter() - t0
     return {"words": words, "text": text, "vad_segments": vad_segments, "chunk_plan": res["chunk_plan"],
             "chunk_results": res["chunk_results"], "timing": timing, "vad_error": vad_error}
+
+
+def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments: Optional[Sequence[Optional[Sequence[Tuple[int, int]]]]] = None,
+                      rover_recognizer=None, hotword_phrases: Sequence[str] = (), rank: int = 0, world_size: int = 1,
+                      max_batch_seconds: float = 3000.0, decode_chunks=None, gather=None):
+    """Many recordings at once (BASELINE config C5: a 10 h corpus of 15-minute files). The frame loop of the search costs
+    the same ~27 ms whether a batch holds 30 chunks or 256, so chunks are pooled ACROSS recordings: every recording is
+    planned, the chunks of this rank's recordings are sorted by length into batches of up to `max_batch_seconds` of audio,
+    each batch is one ragged GPU pass, and the words go back to their recording for time mapping, stitching and the
+    post-ASR steps. Recordings are dealt to ranks by duration (sharding.partition_by_duration); only the finished
+    transcripts travel to rank 0 (`gather`, default torch.distributed.gather_object) - no data-path collective.
+    Returns, on rank 0, one result dict per recording in input order (None on other ranks)."""
+    from . import sharding
+    if decode_chunks is None:
+        from .asr_engine import decode_chunks
+        device_id = int(recognizer.engine.device_id)
+    else:
+        device_id = None
+    segs = list(vad_segments) if vad_segments is not None else [None] * len(recordings)
+    mine = sharding.partition_by_duration([len(a) for a in recordings], world_size)[rank]
+    plans = {i: chunking.plan_recording(recordings[i], segs[i] or (), device_id) for i in mine}
+    pool = [(i, k) for i in mine for k in range(len(plans[i].plan))]                 # (recording, chunk)
+    lengths = [plans[i].plan[k][1] - plans[i].plan[k][0] for i, k in pool]
+    chunk_audio = {i: plans[i].chunks for i in mine}
+    chunk_offsets = {i: plans[i].offsets for i in mine}
+    decoded = {"a": {}, "b": {}}
+    for batch in sharding.batches_by_length(range(len(pool)), lengths, max_batch_seconds):
+        audio_b = [chunk_audio[pool[j][0]][pool[j][1]] for j in batch]
+        offs_b = [chunk_offsets[pool[j][0]][pool[j][1]] for j in batch]
+        for j, words in zip(batch, decode_chunks(recognizer, audio_b, offs_b)):
+            decoded["a"][pool[j]] = words
+        if rover_recognizer is not None:
+            for j, words in zip(batch, decode_chunks(rover_recognizer, audio_b, offs_b)):
+                decoded["b"][pool[j]] = words
+    local = {}
+    for i in mine:
+        n = len(plans[i].plan)
+        per_chunk = [decoded["a"][(i, k)] for k in range(n)]
+        per_rover = [decoded["b"][(i, k)] for k in range(n)] if rover_recognizer is not None else None
+        res = chunking.finish_recording(plans[i], per_chunk, per_rover, hotword_phrases)
+        words, text = postprocess.finish_transcript(res["words"], recordings[i], is_rover=rover_recognizer is not None)
+        local[i] = {"words": words, "text": text, "chunk_plan": res["chunk_plan"]}
+    if world_size == 1:
+        return [local[i] for i in range(len(recordings))]
+    if gather is None:
+        import torch.distributed as dist
+
+        def gather(obj):
+            out = [None] * world_size if rank == 0 else None
+            dist.gather_object(obj, out, dst=0)
+            return out
+    parts = gather(local)
+    if rank != 0:
+        return None
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return [merged[i] for i in range(len(recordings))]

@@ -106,3 +106,38 @@ def test_rover_mode_merges_per_chunk_in_recording_time_and_flags_disagreement():
 def _chunks(res, audio, vad_segments):
     speech, _ = chunking.concat_vad_speech(audio, vad.merge_close_segments(vad_segments, vad.MAX_VAD_GAP, True))
     return [speech[s:e] for s, e, _ in res["chunk_plan"]], [s / 16000.0 for s, _, _ in res["chunk_plan"]]
+
+
+def test_transcribe_corpus_pools_chunks_across_recordings_and_ranks():
+    """C5 shape in miniature: several recordings, chunks pooled across them into length-sorted batches; every recording's
+    result equals its own transcribe_recording; two ranks (recordings dealt by duration) give the same answers."""
+    recs = [cc.silence_audio(40 + i, sec) for i, sec in enumerate([75.0, 12.0, 140.0, 33.0, 0.5])]
+    batches = []
+
+    def decode(rec, chunks, offsets):
+        batches.append([len(c) for c in chunks])
+        return _fake_decode(rec, chunks, offsets)
+
+    got = pipeline.transcribe_corpus(None, recs, max_batch_seconds=120.0, decode_chunks=decode)
+    assert len(got) == len(recs)
+    for audio, g in zip(recs, got):
+        want = pipeline.transcribe_recording(None, audio, decode_chunks=_fake_decode)
+        assert g["chunk_plan"] == want["chunk_plan"] and g["text"] == want["text"]
+        assert [(w["text"], w["start"]) for w in g["words"]] == [(w["text"], w["start"]) for w in want["words"]]
+    n_chunks = sum(len(g["chunk_plan"]) for g in got)
+    assert sum(len(b) for b in batches) == n_chunks and len(batches) < n_chunks          # pooled, not one pass per chunk
+    assert all(sum(b) / 16000.0 <= 120.0 + 35.0 for b in batches)
+    flat = [x for b in batches for x in b]
+    assert flat == sorted(flat, reverse=True)                                          # longest chunks first, across recordings
+    # two ranks, gathered in-process
+    parts = [None, None]
+    outs = []
+    for rank in (1, 0):
+        def gather(obj, rank=rank):
+            parts[rank] = obj
+            return parts if rank == 0 else None
+        outs.append(pipeline.transcribe_corpus(None, recs, rank=rank, world_size=2, max_batch_seconds=120.0, decode_chunks=_fake_decode,
+                                               gather=gather))
+    assert outs[0] is None
+    assert [g["text"] for g in outs[1]] == [g["text"] for g in got]
+    assert all(p for p in parts) and set(parts[0]) | set(parts[1]) == set(range(len(recs))) and not set(parts[0]) & set(parts[1])
