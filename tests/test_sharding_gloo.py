@@ -35,7 +35,15 @@ def _worker(rank, world, port, q):
         seen.extend(int(a[0]) for a in batch)
         return [(int(a[0]), len(a), rank) for a in batch]
     out = sharding.transcribe_sharded(decode, audios, rank, world)
-    q.put((rank, out, seen))
+    # the corpus driver over the same process group: recordings dealt to ranks, transcripts gathered on rank 0
+    from oracle import chunk_cases as cc
+    from sherpa_vietnamese_asr_b200 import pipeline
+    recs = [cc.silence_audio(60 + i, sec) for i, sec in enumerate([40.0, 65.0, 8.0, 33.0])]
+
+    def fake_decode(rec, chunks, offsets):
+        return [[{"text": f"r{rank}", "start": o, "end": o + 0.2, "local_start": 0.0, "local_end": 0.2, "prob": 0.9}] for o in offsets]
+    corpus = pipeline.transcribe_corpus(None, recs, rank=rank, world_size=world, decode_chunks=fake_decode)
+    q.put((rank, out, seen, None if corpus is None else [(c["text"], len(c["chunk_plan"])) for c in corpus]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,10 +58,11 @@ def test_two_rank_gloo_gather():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = {}
+    got, corpora = {}, {}
     for _ in range(2):
-        rank, out, seen = q.get(timeout=120)
+        rank, out, seen, corpus = q.get(timeout=120)
         got[rank] = (out, seen)
+        corpora[rank] = corpus
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -63,3 +72,7 @@ def test_two_rank_gloo_gather():
     assert [o[0] for o in out0] == list(range(23))
     assert set(seen0).isdisjoint(seen1) and len(seen0) + len(seen1) == 23
     assert {o[2] for o in out0} == {0, 1}
+    # transcribe_corpus: rank 1 returns nothing, rank 0 has every recording in input order, decoded on both ranks
+    assert corpora[1] is None and len(corpora[0]) == 4
+    assert [n for _, n in corpora[0]] == [2, 3, 1, 2]
+    assert {t.split()[0] for t, _ in corpora[0]} == {"R0", "R1"}
