@@ -141,3 +141,38 @@ def test_transcribe_corpus_pools_chunks_across_recordings_and_ranks():
     assert outs[0] is None
     assert [g["text"] for g in outs[1]] == [g["text"] for g in got]
     assert all(p for p in parts) and set(parts[0]) | set(parts[1]) == set(range(len(recs))) and not set(parts[0]) & set(parts[1])
+
+
+def test_real_engine_branch_wiring(monkeypatch):
+    """The branch taken with a real recognizer (no injected decoder): the energy scan goes to the recognizer's GPU and the
+    chunks to asr_engine.decode_chunks. Both are replaced here by host stand-ins, so only the wiring is under test."""
+    from sherpa_vietnamese_asr_b200 import asr_engine
+    calls = {"scan": [], "decode": 0}
+
+    def scan(audio, sample_rate=16000, threshold=0.01, min_silence_duration=0.3, device_id=0):
+        calls["scan"].append(device_id)
+        return chunking.find_silent_regions(audio, sample_rate, threshold, min_silence_duration)
+
+    def decode(rec, chunks, offsets=None):
+        calls["decode"] += 1
+        return _fake_decode(rec, chunks, offsets)
+
+    monkeypatch.setattr(chunking, "find_silent_regions_gpu", scan)
+    monkeypatch.setattr(asr_engine, "decode_chunks", decode)
+
+    class Engine:
+        device_id = 3
+
+    class Rec(dict):
+        engine = Engine()
+
+    audio = cc.silence_audio(25, 70.0)
+    want = pipeline.transcribe_recording(None, audio, decode_chunks=_fake_decode)
+    got = pipeline.transcribe_recording(Rec(), audio)
+    assert calls["scan"] == [3] and calls["decode"] == 1
+    assert got["text"] == want["text"] and got["chunk_plan"] == want["chunk_plan"]
+    calls["scan"].clear()
+    corpus = pipeline.transcribe_corpus(Rec(), [audio, audio[: 16000 * 20]])
+    assert calls["scan"] == [3, 3] and corpus[0]["text"] == want["text"]
+    long = chunking.transcribe_long(Rec(), audio, rover_recognizer=Rec())
+    assert long["chunk_plan"] == want["chunk_plan"]
