@@ -147,6 +147,16 @@ B200ASR_API int32_t B200AsrEncoderTap(const B200AsrOfflineRecognizer *r, const c
 B200ASR_API int32_t B200AsrDecoder(const B200AsrOfflineRecognizer *r, const int64_t *y, int32_t m, float *out);
 /* joi_sess.run (core/asr_engine.py:1092): enc[m*512], dec[m*512] -> logits[m*V] */
 B200ASR_API int32_t B200AsrJoiner(const B200AsrOfflineRecognizer *r, const float *enc, const float *dec, int32_t m, float *logits);
+/* The two kernels a frame step of the device search runs, on caller rows (the parity tests pin them directly):
+ * B200AsrDecoderJoinerInput = dec_sess.run for contexts y[m*2] followed by the joiner's input activation,
+ *   dec_out[m*512] = decoder(y) and x_out[m*512] = tanh(enc + dec) (enc may be NULL = zeros), core/asr_engine.py:1072-1093;
+ * B200AsrJoinerRecords = joi_sess.run's output_linear on x[m*512] with the log-softmax / top-k / entropy reduction of
+ *   core/asr_engine.py:1096-1106,1159-1181 folded into its epilogue: per row and per 32-column part a record of 4 + 2*kb
+ *   floats {max, sum e^(x-max), sum e^(x-max)(x-max), sum e^((x-max)/3), kb best values (descending), kb columns (int bits,
+ *   -1 = none)}. Returns floats per row (ceil(V/32) * (4 + 2*kb)); `records` may be NULL to query it. kb in {4, 8, 16}. */
+B200ASR_API int32_t B200AsrDecoderJoinerInput(const B200AsrOfflineRecognizer *r, const int64_t *y, const float *enc, int32_t m,
+                                              float *dec_out, float *x_out);
+B200ASR_API int32_t B200AsrJoinerRecords(const B200AsrOfflineRecognizer *r, const float *x, int32_t m, int32_t kb, float *records);
 /* _ort_beam_search from encoder_out on (core/asr_engine.py:1051-1153), batch of n utterances with packed
  * enc_out and lens; method 0 = greedy, 1 = modified beam search. Results are returned per utterance into
  * caller arrays of capacity max_tokens each: tokens, frames, tok_logprobs, stats[4] (tsallis, margin,
@@ -181,6 +191,14 @@ B200ASR_API int32_t B200AsrStageBatch(const B200AsrOfflineRecognizer *r, const f
  * copied back (n_tokens may be NULL). */
 B200ASR_API int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle, int32_t *n_tokens);
 B200ASR_API int32_t B200AsrReleaseBatch(const B200AsrOfflineRecognizer *r, int32_t handle);
+/* Token ids / frames of utterance u of the last staged run or decode pass (bench.py's parity self-check against the
+ * oracle's `_ort_beam_search` output, core/asr_engine.py:1143-1153). Returns the token count or <0. */
+B200ASR_API int32_t B200AsrLastPassTokens(const B200AsrOfflineRecognizer *r, int32_t u, int32_t *tokens, int32_t *frames, int32_t cap);
+/* Shape of the last pass: a batch is split into length-sorted groups whose searches run on their own streams beside the
+ * encoder of the following groups (where the reference splits chunks over two worker threads, core/asr_engine.py:2384-2397).
+ * n_groups, the sum of the groups' search times and each one's (ms, lane_ms8[8]), and the device->host result bytes. */
+B200ASR_API int32_t B200AsrLastPipelineStats(const B200AsrOfflineRecognizer *r, int32_t *n_groups, float *search_busy_ms,
+                                             float *lane_ms8, int64_t *d2h_bytes);
 /* Per-stage device times (ms, CUDA events on the engine's stream) of the last decode / staged run:
  * out[0]=fbank, [1]=encoder, [2]=search, [3]=total, [4]=H2D, [5]=D2H; and kernel launch count. */
 B200ASR_API int32_t B200AsrLastTimings(const B200AsrOfflineRecognizer *r, float *out6, int64_t *n_launches);

@@ -71,6 +71,8 @@ SYMBOLS = {
     "B200AsrEncoderTap": (C.c_int32, [_P, C.c_char_p, _F, _I32]),
     "B200AsrDecoder": (C.c_int32, [_P, _I64, C.c_int32, _F]),
     "B200AsrJoiner": (C.c_int32, [_P, _F, _F, C.c_int32, _F]),
+    "B200AsrDecoderJoinerInput": (C.c_int32, [_P, _I64, _F, C.c_int32, _F, _F]),
+    "B200AsrJoinerRecords": (C.c_int32, [_P, _F, C.c_int32, C.c_int32, _F]),
     "B200AsrBeamSearch": (C.c_int32, [_P, _F, _I32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _I32, _I32, _F, _F, _I32]),
     "B200AsrGemm": (C.c_int32, [_P, _F, _F, _F, _F, _F, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F]),
     "B200AsrContextForwardOneStep": (C.c_double, [_P, C.c_int32, C.c_int32, _I32]),
@@ -84,6 +86,8 @@ SYMBOLS = {
     "B200AsrStageBatch": (C.c_int32, [_P, _F, _I64, C.c_int32]),
     "B200AsrRunStagedBatch": (C.c_int32, [_P, C.c_int32, _I32]),
     "B200AsrReleaseBatch": (C.c_int32, [_P, C.c_int32]),
+    "B200AsrLastPassTokens": (C.c_int32, [_P, C.c_int32, _I32, _I32, C.c_int32]),
+    "B200AsrLastPipelineStats": (C.c_int32, [_P, _I32, _F, _F, _I64]),
     "B200AsrLastTimings": (C.c_int32, [_P, _F, _I64]),
     "B200AsrLastGemmStats": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _I64]),
     "B200AsrSetProfiling": (C.c_int32, [_P, C.c_int32]),

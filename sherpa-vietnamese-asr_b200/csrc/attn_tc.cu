@@ -319,7 +319,7 @@ void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st) {
   p.mapsVlo = reinterpret_cast<const CUtensorMap *>(a.split3 ? a.mapsVlo : a.mapsV);
   p.tile_off = a.tile_off; p.len = a.len; p.off = a.off; p.n_utt = a.n_utt; p.n_tiles = a.n_tiles;
   p.single_head = a.single_head; p.C = a.C; p.dv = a.dv; p.Y = a.Y; p.ldy = a.ldy; p.out = a.out; p.ldo = a.ldo;
-  const unsigned grid = (unsigned)std::min(a.n_tiles, n_sms);
+  const unsigned grid = (unsigned)std::min(a.n_tiles, persistent_grid_limit(n_sms));
   if (a.single_head) {
     if (a.split3) attn_apply_tcgen05_kernel<64, true><<<grid, 320, attn_smem(64, true), st>>>(p);
     else attn_apply_tcgen05_kernel<64, false><<<grid, 192, attn_smem(64, false), st>>>(p);

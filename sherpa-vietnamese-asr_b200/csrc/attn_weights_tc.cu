@@ -321,7 +321,7 @@ void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float
   AwParams p{};
   p.proj = proj; p.ldp = ldp; p.len = r.len; p.off = r.off; p.tile_off = tile_off; p.aoff = aoff; p.n_utt = r.n; p.n_tiles = n_tiles;
   p.H = H; p.Lmax = r.max_len; p.A = A;
-  const unsigned grid = (unsigned)std::min(n_tiles, n_sms);
+  const unsigned grid = (unsigned)std::min(n_tiles, persistent_grid_limit(n_sms));
   if (split3) attn_weights_tcgen05_kernel<true><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
   else attn_weights_tcgen05_kernel<false><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
   count_launch();

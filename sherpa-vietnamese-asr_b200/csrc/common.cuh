@@ -46,6 +46,13 @@ void set_max_dynamic_smem_impl(const void *func, int bytes);
 template <typename F>
 inline void set_max_dynamic_smem(F *func, size_t bytes) { set_max_dynamic_smem_impl(reinterpret_cast<const void *>(func), (int)bytes); }
 
+// Persistent kernels (tcgen05 GEMM, attention) size their grid to the SM count. While the search of an earlier sub-batch runs
+// beside the encoder of the next one (engine.cu, pipelined decode) the encoder's launches leave `reserve` SMs free for it:
+// a persistent CTA holds its SM for the whole kernel, so without the reservation the search's small kernels would wait
+// for encoder kernel boundaries. Thread-local (one decode call = one host thread).
+void set_sm_reserve(int reserve);
+int persistent_grid_limit(int n_sms);
+
 // Global launch counter (host side) so bench.py can report `gpu_launches`.
 extern long long g_launches;
 inline void count_launch(int n = 1) { g_launches += n; }
@@ -209,6 +216,24 @@ struct SearchResultHost {
 };
 void run_search(SearchState *s, const SearchModel &m, const ContextGraphDev *g, const float *enc, const int *h_lens, int n_utts,
                 int method, int beam, float blank_penalty, SearchResultHost *out, cudaStream_t st);
+// The same in two halves, for callers that overlap several searches (engine.cu): search_issue enqueues everything on `st`
+// (device->host result copies included) without synchronising; once `st` has been synchronised the results are read through
+// search_view (packed per utterance: off[u] = sum of T' of the utterances before u) or scattered with search_collect.
+void search_issue(SearchState *s, const SearchModel &m, const ContextGraphDev *g, const float *enc, const int *h_lens, int n_utts,
+                  int method, int beam, float blank_penalty, cudaStream_t st);
+struct SearchView {
+  int n;
+  const int *n_tokens;      // [n]
+  const long long *off;     // [n+1]
+  const int *tokens, *frames;
+  const float *tok_lp, *stats;   // stats [slots][4]
+};
+SearchView search_view(const SearchState *s);
+void search_collect(SearchState *s, SearchResultHost *out);
+long long search_result_bytes(const SearchState *s);   // device->host bytes the last issued search copies
+void launch_decoder_product_rows(const SearchModel &m, const long long *y, const float *enc, int rows, float *dec_out, float *x_out,
+                                 cudaStream_t st);
+void launch_joiner_records(SearchState *s, const SearchModel &m, const float *X, int rows, int kb, float *records, cudaStream_t st);
 void launch_decoder_rows(const SearchModel &m, const long long *y, int rows, float *out, cudaStream_t st);
 void launch_joiner_rows(const SearchModel &m, const float *enc, const float *dec, int rows, float *tmp, float *logits,
                         cudaStream_t st);

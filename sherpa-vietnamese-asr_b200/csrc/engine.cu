@@ -89,6 +89,19 @@ struct StackW {
 
 struct Timings { float fbank = 0, encoder = 0, search = 0, total = 0, h2d = 0, d2h = 0; };
 
+// One search in flight: its own stream (high priority), search state and encoder_out buffer. A decode pass splits its batch
+// into length-sorted groups; group g's search runs on lane g while the main stream already encodes group g + 1.
+constexpr int kMaxLanes = 8;
+struct Lane {
+  cudaStream_t st = nullptr;
+  SearchState *search = nullptr;
+  DevBuf enc, soff;
+  cudaEvent_t f0 = nullptr, f1 = nullptr, e1 = nullptr, s0 = nullptr, s1 = nullptr;
+  std::vector<int> members;   // original utterance indices of the group this lane holds
+  std::vector<int> Tp;
+  int steps = 0;
+};
+
 }  // namespace
 
 struct Stream;
@@ -351,7 +364,13 @@ struct Engine {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8]{};
   cudaEvent_t ev_copy = nullptr;   // marks the accept-time uploads a pass has to wait for
-  SearchState *search = nullptr;
+  SearchState *search = nullptr;   // lane 0's (also used by the raw B200AsrBeamSearch entry point)
+  Lane lanes[kMaxLanes];
+  int n_groups_last = 1;
+  float search_busy_ms = 0, lane_ms[kMaxLanes] = {0};
+  std::vector<int> lane_of, idx_of;   // last pass: utterance -> (lane, index inside the lane's group)
+  double kappa = 50.0;                // search ms per second of utterance length / encoder ms per audio-second (adapted per pass)
+  long long d2h_bytes_last = 0;
   SearchModel sm{};
   ContextGraphHost cg_host;
   ContextGraphDev cg_dev;
@@ -401,7 +420,9 @@ struct Engine {
   // h_len[u] = samples of utterance u; d_slen null = packed PCM (lengths from consecutive offsets)
   void run_fbank(const float *d_pcm, const long long *d_soff, const long long *d_slen, const std::vector<long long> &h_len, int n,
                  float **d_feats, std::vector<int> *T);
-  void run_encoder(const float *d_feats, const std::vector<int> &T, float **d_enc, std::vector<int> *Tp);
+  void run_encoder(const float *d_feats, const std::vector<int> &T, DevBuf &enc_buf, float **d_enc, std::vector<int> *Tp);
+  Lane &lane(int i);
+  std::vector<std::vector<int>> plan_groups(const std::vector<long long> &h_len) const;
   struct AttnPlan {   // tensor-core attention application: per-stack maps / offsets (valid for every layer of the stack)
     bool use = false;
     const void *mapsA = nullptr, *mapsV12 = nullptr, *mapsV12lo = nullptr, *mapsVh = nullptr, *mapsVhlo = nullptr;
@@ -420,8 +441,12 @@ struct Engine {
   void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
                  const AttnPlan &pl);
   void decode(Stream *const *ss, int n);
-  void decode_pcm_device(const float *d_pcm, const long long *d_soff, const long long *d_slen, const std::vector<long long> &h_len,
-                         int n, SearchResultHost *res, std::vector<int> *Tp);
+  // h_soff[u] = first sample of utterance u relative to d_pcm, h_len[u] = its samples. Results stay in the lanes' search
+  // states (lane_of / idx_of map utterances to them) until the next pass.
+  void decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
+                         std::vector<int> *Tp);
+  struct UttResult { int n_tokens; const int *tokens, *frames; const float *tok_lp, *stats; };
+  UttResult result_of(int u) const;
   void collect_gemm_times();
 };
 
@@ -443,6 +468,13 @@ Engine::~Engine() {
   for (auto &kv : tensors) if (kv.second.dev) cudaFree(kv.second.dev);
   for (float *p : owned) cudaFree(p);
   if (fb.window) fbank_tables_destroy(&fb);
+  for (int i = 0; i < kMaxLanes; ++i) {
+    Lane &l = lanes[i];
+    if (l.search && l.search != search) search_state_destroy(l.search);
+    cudaEvent_t evs[] = {l.f0, l.f1, l.e1, l.s0, l.s1};
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    if (l.st) cudaStreamDestroy(l.st);
+  }
   if (search) search_state_destroy(search);
   for (auto &e : ev) if (e) cudaEventDestroy(e);
   if (ev_copy) cudaEventDestroy(ev_copy);
@@ -956,7 +988,7 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   launch_biasnorm_bypass(w1, src, M, D, w.norm_bias, w.norm_log_scale, w.bypass, src, st);
 }
 
-void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float **d_enc, std::vector<int> *Tp) {
+void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, DevBuf &enc_buf, float **d_enc, std::vector<int> *Tp) {
   const int n = (int)T.size();
   last_n = n;
   h_T = T;
@@ -1032,7 +1064,7 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
   for (size_t i = 0; i < ns; ++i)
     CUDA_CHECK(cudaMemcpyAsync(d_aoff + i * (n + 1), aoffs[i].data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
   b_A.get<float>((size_t)maxA);
-  float *enc = b_enc.get<float>((size_t)std::max(Mr[1], 1) * join_dim);
+  float *enc = enc_buf.get<float>((size_t)std::max(Mr[1], 1) * join_dim);
   *d_enc = enc;
   if (M1 <= 0) {
     keep(std::move(foff)); keep(std::move(c0off)); keep(std::move(c1off)); keep(std::move(Tclamped)); keep(std::move(dwt));
@@ -1111,30 +1143,186 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, float 
 }
 
 // ------------------------------------------------------------------ full pipeline on device-resident PCM
-void Engine::decode_pcm_device(const float *d_pcm, const long long *d_soff, const long long *d_slen,
-                               const std::vector<long long> &h_len, int n, SearchResultHost *res, std::vector<int> *Tp) {
+Lane &Engine::lane(int i) {
+  Lane &l = lanes[i];
+  if (!l.st) {
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
+    CUDA_CHECK(cudaStreamCreateWithPriority(&l.st, cudaStreamNonBlocking, hi));
+    cudaEvent_t *evs[] = {&l.f0, &l.f1, &l.e1, &l.s0, &l.s1};
+    for (cudaEvent_t *e : evs) CUDA_CHECK(cudaEventCreate(e));
+    if (i == 0) l.search = search;
+    else {
+      l.search = search_state_create();
+      search_set_gemm(l.search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32), precision != 2);
+    }
+  }
+  return l;
+}
+
+// Split of a batch into groups that are encoded one after the other (longest utterances first) while the searches of the
+// groups already encoded run beside the encoder on their own streams. The search is T' dependent frame steps - its time
+// is set by the longest utterance of its group, not by the group's size - so: the last group holds the shortest
+// utterances (its search is the only one nothing can hide), and going backwards each earlier group may hold utterances
+// longer by what the encoder time of the groups after it can cover: L(g-1) <= L(g) + audio(g) / kappa, where
+// kappa = (search ms per second of utterance length) / (encoder ms per audio-second), measured on the previous passes.
+// B200ASR_PIPELINE=0 turns the split off; B200ASR_GROUPS="27,100,78" fixes the group sizes (longest first, rest last).
+std::vector<std::vector<int>> Engine::plan_groups(const std::vector<long long> &h_len) const {
+  const int n = (int)h_len.size();
+  std::vector<std::vector<int>> single(1);
+  single[0].resize(n);
+  for (int u = 0; u < n; ++u) single[0][u] = u;
+  static const bool off = getenv("B200ASR_PIPELINE") && atoi(getenv("B200ASR_PIPELINE")) == 0;
+  if (off || profiling || n < 16) return single;
+  std::vector<int> asc(n);
+  for (int u = 0; u < n; ++u) asc[u] = u;
+  std::stable_sort(asc.begin(), asc.end(), [&](int a, int b) { return h_len[a] < h_len[b]; });
+  std::vector<std::vector<int>> rev;   // shortest group first
+  if (const char *e = getenv("B200ASR_GROUPS")) {
+    std::vector<int> counts = parse_int_list(e);   // longest first
+    int hiu = n;
+    std::vector<std::vector<int>> fwd;
+    for (int c : counts) {
+      if ((int)fwd.size() + 1 >= kMaxLanes || c <= 0 || hiu <= 0) break;
+      const int lo = std::max(0, hiu - c);
+      fwd.emplace_back(asc.begin() + lo, asc.begin() + hiu);
+      hiu = lo;
+    }
+    if (hiu > 0) fwd.emplace_back(asc.begin(), asc.begin() + hiu);
+    for (auto &g : fwd) std::reverse(g.begin(), g.end());
+    return fwd.empty() ? single : fwd;
+  }
+  double total = 0;
+  for (long long v : h_len) total += (double)v / 16000.0;
+  static const double min_audio = getenv("B200ASR_PIPE_MIN_AUDIO") ? atof(getenv("B200ASR_PIPE_MIN_AUDIO")) : 150.0;
+  static const double kappa_env = getenv("B200ASR_PIPE_KAPPA") ? atof(getenv("B200ASR_PIPE_KAPPA")) : 0.0;
+  static const int max_groups = std::min(kMaxLanes, getenv("B200ASR_PIPE_MAX_GROUPS") ? atoi(getenv("B200ASR_PIPE_MAX_GROUPS")) : 6);
+  if (total < 3.0 * min_audio || max_groups < 2) return single;
+  const double kap = kappa_env > 0 ? kappa_env : kappa;
+  int i = 0;
+  double prevL = 0, prevA = 0;
+  while (i < n) {
+    std::vector<int> g;
+    double A = 0;
+    const bool last_slot = (int)rev.size() + 1 >= max_groups;
+    const double Llim = rev.empty() ? 0.0 : prevL + prevA / kap;
+    while (i < n) {
+      const double L = (double)h_len[asc[i]] / 16000.0;
+      if (!last_slot && A >= min_audio && L > Llim) break;
+      g.push_back(asc[i]);
+      A += L;
+      ++i;
+    }
+    prevL = (double)h_len[g.back()] / 16000.0;
+    prevA = A;
+    rev.push_back(std::move(g));
+  }
+  if (rev.size() >= 2) {   // a sliver of long utterances at the front would only add launches
+    double A = 0;
+    for (int u : rev.back()) A += (double)h_len[u] / 16000.0;
+    if (A < min_audio) {
+      auto tail = std::move(rev.back());
+      rev.pop_back();
+      rev.back().insert(rev.back().end(), tail.begin(), tail.end());
+    }
+  }
+  if (rev.size() < 2) return single;
+  std::vector<std::vector<int>> fwd(rev.rbegin(), rev.rend());
+  for (auto &g : fwd) std::reverse(g.begin(), g.end());   // longest first inside a group as well
+  return fwd;
+}
+
+Engine::UttResult Engine::result_of(int u) const {
+  const SearchView v = search_view(lanes[lane_of[u]].search);
+  const int i = idx_of[u];
+  const long long o = v.off[i];
+  return UttResult{v.n_tokens[i], v.tokens + o, v.frames + o, v.tok_lp + o, v.stats + 4 * o};
+}
+
+void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
+                               std::vector<int> *Tp) {
   gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
-  CUDA_CHECK(cudaEventRecord(ev[0], st));
-  float *d_feats = nullptr, *d_enc = nullptr;
-  std::vector<int> T;
-  run_fbank(d_pcm, d_soff, d_slen, h_len, n, &d_feats, &T);
-  CUDA_CHECK(cudaEventRecord(ev[1], st));
-  run_encoder(d_feats, T, &d_enc, Tp);
-  CUDA_CHECK(cudaEventRecord(ev[2], st));
-  int max_tokens = 1;
-  for (int v : *Tp) max_tokens = std::max(max_tokens, v);
-  res->n_utts = n;
-  res->max_tokens = max_tokens;
+  const std::vector<std::vector<int>> groups = plan_groups(h_len);
+  const int G = (int)groups.size();
+  static const int reserve = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
   const int method = decoding_method == "greedy_search" ? 0 : 1;
-  run_search(search, sm, has_graph ? &cg_dev : nullptr, d_enc, Tp->data(), n, method, max_active_paths, blank_penalty, res, st);
+  Tp->assign(n, 0);
+  lane_of.assign(n, 0); idx_of.assign(n, 0);
+  CUDA_CHECK(cudaEventRecord(ev[0], st));
+  // Issue order: encoder of group g + 1 goes to the main stream before the (long) launch sequence of group g's search, so
+  // the GPU never waits for the host between two encoders.
+  auto issue_encoder = [&](int g) {
+    Lane &l = lane(g);
+    const std::vector<int> &mem = groups[g];
+    const int ng = (int)mem.size();
+    l.members = mem;
+    std::vector<long long> off_len(2 * (size_t)ng + 1, 0), glen(ng);
+    for (int i = 0; i < ng; ++i) {
+      off_len[i] = h_soff[mem[i]];
+      off_len[ng + 1 + i] = glen[i] = h_len[mem[i]];
+      lane_of[mem[i]] = g; idx_of[mem[i]] = i;
+    }
+    long long *d_sl = l.soff.get<long long>(off_len.size());
+    CUDA_CHECK(cudaMemcpyAsync(d_sl, keep(std::move(off_len)), (2 * (size_t)ng + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    set_sm_reserve(g > 0 ? reserve : 0);   // from the second group on a search runs beside the encoder
+    CUDA_CHECK(cudaEventRecord(l.f0, st));
+    float *d_feats = nullptr, *d_enc = nullptr;
+    std::vector<int> T;
+    run_fbank(d_pcm, d_sl, d_sl + ng + 1, glen, ng, &d_feats, &T);
+    CUDA_CHECK(cudaEventRecord(l.f1, st));
+    run_encoder(d_feats, T, l.enc, &d_enc, &l.Tp);
+    CUDA_CHECK(cudaEventRecord(l.e1, st));
+    set_sm_reserve(0);
+    for (int i = 0; i < ng; ++i) (*Tp)[mem[i]] = l.Tp[i];
+  };
+  auto issue_search = [&](int g) {
+    Lane &l = lane(g);
+    cudaStream_t ss = G == 1 ? st : l.st;
+    if (G > 1) CUDA_CHECK(cudaStreamWaitEvent(ss, l.e1, 0));
+    CUDA_CHECK(cudaEventRecord(l.s0, ss));
+    l.steps = 0;
+    for (int v : l.Tp) l.steps = std::max(l.steps, v);
+    search_issue(l.search, sm, has_graph ? &cg_dev : nullptr, l.enc.ptr<float>(), l.Tp.data(), (int)l.members.size(), method,
+                 max_active_paths, blank_penalty, ss);
+    CUDA_CHECK(cudaEventRecord(l.s1, ss));
+  };
+  issue_encoder(0);
+  for (int g = 0; g < G; ++g) {
+    if (g + 1 < G) issue_encoder(g + 1);
+    issue_search(g);
+  }
+  if (G > 1)   // the pass ends (ev[3] on the main stream) after every search
+    for (int g = 0; g < G; ++g) CUDA_CHECK(cudaStreamWaitEvent(st, lanes[g].s1, 0));
   CUDA_CHECK(cudaEventRecord(ev[3], st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&tm.fbank, ev[0], ev[1]);
-  cudaEventElapsedTime(&tm.encoder, ev[1], ev[2]);
-  cudaEventElapsedTime(&tm.search, ev[2], ev[3]);
+  n_groups_last = G;
+  tm.fbank = tm.encoder = 0;
+  search_busy_ms = 0;
+  d2h_bytes_last = 0;
+  double steps_ms = 0, steps_len = 0;
+  for (int g = 0; g < G; ++g) {
+    Lane &l = lanes[g];
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, l.f0, l.f1);
+    cudaEventElapsedTime(&b, l.f1, l.e1);
+    cudaEventElapsedTime(&c, l.s0, l.s1);
+    tm.fbank += a; tm.encoder += b; search_busy_ms += c; lane_ms[g] = c;
+    d2h_bytes_last += search_result_bytes(l.search);
+    if (l.steps > 0) { steps_ms += c; steps_len += l.steps / 25.0; }
+  }
   cudaEventElapsedTime(&tm.total, ev[0], ev[3]);
+  tm.search = std::max(0.f, tm.total - tm.fbank - tm.encoder);   // the part of the searches no encoder hid
+  // adapt the planner's ratio: search ms per second of utterance length over encoder ms per audio-second
+  {
+    double audio = 0;
+    for (long long v : h_len) audio += (double)v / 16000.0;
+    if (n >= 16 && audio > 100.0 && tm.encoder > 0.f && steps_len > 0 && !profiling) {
+      const double k_now = (steps_ms / steps_len) / ((double)(tm.fbank + tm.encoder) / audio);
+      if (k_now > 1.0 && k_now < 1000.0) kappa = 0.5 * kappa + 0.5 * k_now;
+    }
+  }
   launches_last = g_launches - l0;
   if (profiling) collect_gemm_times();
 }
@@ -1198,16 +1386,12 @@ void Engine::decode(Stream *const *ss, int n) {
       if (!s->samples.empty() && !(s->samples.on_device() && s->samples.device == device)) { resident = false; break; }
     }
     float *d_pcm = b_pcm.get<float>((size_t)std::max<long long>(resident ? 1 : soff[nb], 1));
-    long long *d_soff = b_soff.get<long long>(2 * (size_t)nb + 1);
-    long long *d_slen = nullptr;
     CUDA_CHECK(cudaEventRecord(ev[4], st));
     if (resident) {
       for (int i = 0; i < nb; ++i) {
         const float *dp = ss[begin + i]->samples.empty() ? d_pcm : ss[begin + i]->samples.d;
         soff[i] = (long long)((reinterpret_cast<intptr_t>(dp) - reinterpret_cast<intptr_t>(d_pcm)) / (intptr_t)sizeof(float));
       }
-      d_slen = d_soff + nb + 1;
-      CUDA_CHECK(cudaMemcpyAsync(d_slen, slen.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, st));
       // the pass must see the uploads accept_waveform queued on the device's copy stream
       CUDA_CHECK(cudaEventRecord(ev_copy, DevicePcmPool::get(device).stream()));
       CUDA_CHECK(cudaStreamWaitEvent(st, ev_copy, 0));
@@ -1218,39 +1402,27 @@ void Engine::decode(Stream *const *ss, int n) {
           CUDA_CHECK(cudaMemcpyAsync(d_pcm + soff[i], ss[begin + i]->samples.data(), ss[begin + i]->samples.size() * sizeof(float),
                                      cudaMemcpyHostToDevice, st));
     }
-    CUDA_CHECK(cudaMemcpyAsync(d_soff, soff.data(), (nb + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaEventRecord(ev[5], st));
-    // results
     std::vector<int> Tp;
-    SearchResultHost res{};
-    int cap = 1;
-    for (int i = 0; i < nb; ++i) {
-      const long long ns = slen[i];
-      const int T = (int)((ns + 80) / 160);
-      const int T1 = T >= 9 ? (T - 7) / 2 : 0;
-      cap = std::max(cap, (T1 + 1) / 2);
-    }
-    std::vector<int> ntok(nb), toks((size_t)nb * cap), frm((size_t)nb * cap);
-    std::vector<float> lp((size_t)nb * cap), stt((size_t)nb * cap * 4);
-    res.n_tokens = ntok.data(); res.tokens = toks.data(); res.frames = frm.data(); res.tok_lp = lp.data(); res.stats = stt.data();
+    soff.resize(nb);
     const auto hp1 = std::chrono::steady_clock::now();
-    decode_pcm_device(d_pcm, d_soff, d_slen, slen, nb, &res, &Tp);
+    decode_pcm_device(d_pcm, soff, slen, nb, &Tp);
     const auto hp2 = std::chrono::steady_clock::now();
     cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
     for (int i = 0; i < nb; ++i) {
       Stream *s = ss[begin + i];
-      const int cnt = std::min(ntok[i], res.max_tokens);
+      const UttResult r = result_of(i);
+      const int cnt = std::max(0, std::min(r.n_tokens, Tp[i]));
       const float dur = (float)s->samples.size() / 16000.0f;
-      s->token_ids.assign(toks.begin() + (size_t)i * res.max_tokens, toks.begin() + (size_t)i * res.max_tokens + cnt);
-      s->frames.assign(frm.begin() + (size_t)i * res.max_tokens, frm.begin() + (size_t)i * res.max_tokens + cnt);
-      s->lps.assign(lp.begin() + (size_t)i * res.max_tokens, lp.begin() + (size_t)i * res.max_tokens + cnt);
+      s->token_ids.assign(r.tokens, r.tokens + cnt);
+      s->frames.assign(r.frames, r.frames + cnt);
+      s->lps.assign(r.tok_lp, r.tok_lp + cnt);
       s->timestamps.resize(cnt); s->tsallis.resize(cnt); s->margin.resize(cnt); s->entropy.resize(cnt); s->top1.resize(cnt);
       s->tok_str.resize(cnt); s->tok_ptr.resize(cnt);
       s->text.clear();
       for (int j = 0; j < cnt; ++j) {
-        const size_t o = (size_t)i * res.max_tokens + j;
         s->timestamps[j] = Tp[i] > 0 ? (float)((double)s->frames[j] / (double)Tp[i] * (double)dur) : 0.f;
-        s->tsallis[j] = stt[o * 4]; s->margin[j] = stt[o * 4 + 1]; s->entropy[j] = stt[o * 4 + 2]; s->top1[j] = stt[o * 4 + 3];
+        s->tsallis[j] = r.stats[j * 4]; s->margin[j] = r.stats[j * 4 + 1]; s->entropy[j] = r.stats[j * 4 + 2]; s->top1[j] = r.stats[j * 4 + 3];
         const int id = s->token_ids[j];
         s->tok_str[j] = (id >= 0 && id < V) ? id2token[id] : "";
         s->text += s->tok_str[j];
@@ -1473,7 +1645,7 @@ int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, co
   std::vector<int> Tp;
   e->gemm_flops = 0; e->gemm_launches = 0; e->gemm_ev_used = 0;
   e->host_keep.clear();
-  e->run_encoder(d_feats, T, &d_enc, &Tp);
+  e->run_encoder(d_feats, T, e->b_enc, &d_enc, &Tp);
   CUDA_CHECK(cudaMemcpyAsync(out, d_enc, (size_t)totp * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
   return (int32_t)totp;
@@ -1533,6 +1705,47 @@ int32_t B200AsrJoiner(const B200AsrOfflineRecognizer *r, const float *enc, const
   CUDA_CHECK(cudaMemcpyAsync(logits, d_lg, (size_t)m * e->V * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
   return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrDecoderJoinerInput(const B200AsrOfflineRecognizer *r, const int64_t *y, const float *enc, int32_t m, float *dec_out,
+                                  float *x_out) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (m <= 0) return 0;
+  for (int i = 0; i < 2 * m; ++i) if (y[i] >= e->V) throw std::runtime_error("decoder: token id out of range");
+  const size_t jd = e->join_dim;
+  long long *dy = e->b_tmp.get<long long>((size_t)2 * m + 3 * (size_t)m * jd);
+  float *d_enc = reinterpret_cast<float *>(dy + 2 * m), *d_dec = d_enc + m * jd, *d_x = d_dec + m * jd;
+  CUDA_CHECK(cudaMemcpyAsync(dy, y, (size_t)2 * m * sizeof(long long), cudaMemcpyHostToDevice, e->st));
+  if (enc) CUDA_CHECK(cudaMemcpyAsync(d_enc, enc, m * jd * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  launch_decoder_product_rows(e->sm, dy, enc ? d_enc : nullptr, m, d_dec, d_x, e->st);
+  if (dec_out) CUDA_CHECK(cudaMemcpyAsync(dec_out, d_dec, m * jd * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  if (x_out) CUDA_CHECK(cudaMemcpyAsync(x_out, d_x, m * jd * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  return 0;
+  API_CATCH(-1)
+}
+
+int32_t B200AsrJoinerRecords(const B200AsrOfflineRecognizer *r, const float *x, int32_t m, int32_t kb, float *records) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (kb != 4 && kb != 8 && kb != 16) throw std::runtime_error("kb must be 4, 8 or 16");
+  const int P = (e->V + kPartCols - 1) / kPartCols, REC = part_rec_floats(kb);
+  if (m <= 0) return P * REC;
+  if (!records) return P * REC;
+  const size_t jd = e->join_dim;
+  float *buf = e->b_tmp.get<float>((size_t)m * jd + (size_t)m * P * REC + 16);
+  float *d_x = buf, *d_rec = buf + (((size_t)m * jd + 3) & ~size_t(3));
+  CUDA_CHECK(cudaMemcpyAsync(d_x, x, m * jd * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  launch_joiner_records(e->search, e->sm, d_x, m, kb, d_rec, e->st);
+  CUDA_CHECK(cudaMemcpyAsync(records, d_rec, (size_t)m * P * REC * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  return P * REC;
   API_CATCH(-1)
 }
 
@@ -1636,15 +1849,41 @@ int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle,
   auto it = e->staged.find(handle);
   if (it == e->staged.end()) throw std::runtime_error("no such staged batch");
   const Engine::Staged &sgd = it->second;
-  std::vector<int> Tp, ntok(sgd.n);
-  SearchResultHost res{};
-  res.n_tokens = ntok.data();   // token arrays stay on the device; only counts come back
-  std::vector<long long> slen(sgd.n);
+  std::vector<int> Tp;
+  std::vector<long long> slen(sgd.n), soff(sgd.h_soff.begin(), sgd.h_soff.begin() + sgd.n);
   for (int i = 0; i < sgd.n; ++i) slen[i] = sgd.h_soff[i + 1] - sgd.h_soff[i];
-  e->decode_pcm_device(sgd.pcm, sgd.soff, nullptr, slen, sgd.n, &res, &Tp);
-  if (n_tokens) memcpy(n_tokens, ntok.data(), sgd.n * sizeof(int));
+  e->decode_pcm_device(sgd.pcm, soff, slen, sgd.n, &Tp);
+  if (n_tokens) for (int i = 0; i < sgd.n; ++i) n_tokens[i] = e->result_of(i).n_tokens;
   return 0;
   API_CATCH(-1)
+}
+
+/* Token ids of utterance u of the last staged run / decode pass (bench.py's parity self-check). Returns the count. */
+int32_t B200AsrLastPassTokens(const B200AsrOfflineRecognizer *r, int32_t u, int32_t *tokens, int32_t *frames, int32_t cap) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (u < 0 || u >= (int)e->lane_of.size()) throw std::runtime_error("no such utterance in the last pass");
+  const Engine::UttResult res = e->result_of(u);
+  for (int j = 0; j < res.n_tokens && j < cap; ++j) {
+    if (tokens) tokens[j] = res.tokens[j];
+    if (frames) frames[j] = res.frames[j];
+  }
+  return res.n_tokens;
+  API_CATCH(-1)
+}
+
+/* Pipeline shape of the last pass: number of groups, per-group search time (ms, on its own stream), their sum, and the
+ * device->host result bytes. */
+int32_t B200AsrLastPipelineStats(const B200AsrOfflineRecognizer *r, int32_t *n_groups, float *search_busy_ms, float *lane_ms8,
+                                 int64_t *d2h_bytes) {
+  if (!r) return -1;
+  const Engine &e = r->eng;
+  if (n_groups) *n_groups = e.n_groups_last;
+  if (search_busy_ms) *search_busy_ms = e.search_busy_ms;
+  if (lane_ms8) for (int i = 0; i < kMaxLanes; ++i) lane_ms8[i] = i < e.n_groups_last ? e.lane_ms[i] : 0.f;
+  if (d2h_bytes) *d2h_bytes = e.d2h_bytes_last;
+  return 0;
 }
 
 int32_t B200AsrReleaseBatch(const B200AsrOfflineRecognizer *r, int32_t handle) {

@@ -16,6 +16,10 @@ namespace b200asr {
 
 long long g_launches = 0;
 
+namespace { thread_local int tl_sm_reserve = 0; }
+void set_sm_reserve(int reserve) { tl_sm_reserve = reserve > 0 ? reserve : 0; }
+int persistent_grid_limit(int n_sms) { return n_sms - tl_sm_reserve > 8 ? n_sms - tl_sm_reserve : (n_sms < 8 ? n_sms : 8); }
+
 void set_max_dynamic_smem_impl(const void *func, int bytes) {
   static std::mutex mu;
   static std::set<std::pair<const void *, int>> done;   // (function, device)

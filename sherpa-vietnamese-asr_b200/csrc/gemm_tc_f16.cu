@@ -78,7 +78,9 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uin
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kF16Threads, 1)
 gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
-                             const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+                             const __grid_constant__ CUtensorMap map_wlo, TcParams p, int variant) {
+  // `variant` (B200ASR_F16_VARIANT, hardware bring-up only): 1 / 2 / 4 drop the lo*hi / hi*lo / hi*hi term, 8 swaps the two
+  // half-words of a packed A column, 16 makes lo fp16 too (all three MMAs f16 x f16)
   constexpr int NS = f16_stages(BN);
   constexpr uint32_t kTmemACol = 256;                         // A stages at columns 256 + 64 s (hi, 32 columns) / + 32 (lo)
   constexpr uint32_t kTmemCols = 512;
@@ -100,7 +102,7 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 0);
-  const int nk = p.K / FBK;                                 // the launcher only takes K % 64 == 0
+  const int nk = (p.K + FBK - 1) / FBK;                     // a ragged last block is zero-filled by TMA (A: columns >= K; W: padded to ld, then OOB)
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + TBM - 1) / TBM;
   const int n_tiles = tiles_m * tiles_n;
@@ -146,8 +148,9 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   } else if (warp == 1) {
     // ===== MMA issuer: per K = 16 step  A_lo(bf16) * W_hi(fp16)  +  A_hi(fp16) * W_lo(bf16)  +  A_hi * W_hi, small terms first
     if (lane == 0) {
-      constexpr uint32_t idesc_lh = make_idesc16(TBM, BN, 1, 0);
-      constexpr uint32_t idesc_hl = make_idesc16(TBM, BN, 0, 1);
+      const int lo_bf16 = (variant & 16) ? 0 : 1;
+      const uint32_t idesc_lh = make_idesc16(TBM, BN, lo_bf16, 0);
+      const uint32_t idesc_hl = make_idesc16(TBM, BN, 0, lo_bf16);
       constexpr uint32_t idesc_hh = make_idesc16(TBM, BN, 0, 0);
       int it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
@@ -168,9 +171,10 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
           for (int k = 0; k < FBK / UMMA_K16; ++k) {
             const uint64_t o = (uint64_t)(k * 2);             // +32 bytes inside the 128-byte swizzle row, in 16-byte units
             const uint32_t c = (uint32_t)(k * (UMMA_K16 / 2));   // 16 packed elements = 8 columns
-            umma_f16_ta(tmem_d, ta_lo + c, dwh + o, idesc_lh, (kb | k) ? 1u : 0u);
-            umma_f16_ta(tmem_d, ta_hi + c, dwl + o, idesc_hl, 1u);
-            umma_f16_ta(tmem_d, ta_hi + c, dwh + o, idesc_hh, 1u);
+            uint32_t accum = (kb | k) ? 1u : 0u;
+            if (!(variant & 1)) { umma_f16_ta(tmem_d, ta_lo + c, dwh + o, idesc_lh, accum); accum = 1u; }   // small terms first
+            if (!(variant & 2)) { umma_f16_ta(tmem_d, ta_hi + c, dwl + o, idesc_hl, accum); accum = 1u; }
+            if (!(variant & 4)) { umma_f16_ta(tmem_d, ta_hi + c, dwh + o, idesc_hh, accum); }
           }
           umma_commit(&empty_bar[s]);
         }
@@ -199,6 +203,17 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
             split_pair(v.z, v.w, hi[b * 16 + 2 * c + 1], lo[b * 16 + 2 * c + 1]);
           }
         }
+        if (variant & 24) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (variant & 16) {   // lo as fp16: re-round the bf16 pair (bring-up only; bf16 -> fp16 of a 2^-11-scale value is exact enough to tell)
+              const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162 *>(&lo[j]);
+              const __half2 h = __floats2half2_rn(__low2float(l), __high2float(l));
+              lo[j] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+            if (variant & 8) { hi[j] = (hi[j] >> 16) | (hi[j] << 16); lo[j] = (lo[j] >> 16) | (lo[j] << 16); }
+          }
+        }
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemACol + (uint32_t)(s * 64);
         tmem_st_32x32(ta, hi);
         tmem_st_32x32(ta + 32, lo);
@@ -222,32 +237,34 @@ constexpr size_t f16_smem_bytes(int BN) {
 }
 
 // ---- pre-split 16-bit copies of a weight matrix, made on first use and kept for the life of the process
-__global__ void split_w16_kernel(const float *__restrict__ w, __half *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int N, int K, int ld) {
+__global__ void split_w16_kernel(const float *__restrict__ w, __half *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int N, int K, int ld,
+                                 int lo_f16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * ld) return;
   const int n = (int)(i / ld), k = (int)(i % ld);
   const float x = k < K ? w[(long long)n * K + k] : 0.f;
   const __half h = __float2half_rn(clamp_f16(x));
   hi[i] = h;
-  lo[i] = __float2bfloat16_rn(x - __half2float(h));
+  if (lo_f16) reinterpret_cast<__half *>(lo)[i] = __float2half_rn(x - __half2float(h));   // bring-up variant 16
+  else lo[i] = __float2bfloat16_rn(x - __half2float(h));
 }
 
 struct W16 { __half *hi; __nv_bfloat16 *lo; int ld; };
 std::mutex g_w16_mu;
-std::map<std::tuple<const float *, int, int, int>, W16> g_w16;     // (pointer, N, K, device)
+std::map<std::tuple<const float *, int, int, int>, W16> g_w16;     // (pointer, N, K, device + 64 * lo_f16)
 
-W16 w16_for(const float *W, int N, int K, cudaStream_t st) {
+W16 w16_for(const float *W, int N, int K, cudaStream_t st, bool lo_f16 = false) {
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_w16_mu);
-  const auto key = std::make_tuple(W, N, K, dev);
+  const auto key = std::make_tuple(W, N, K, dev + (lo_f16 ? 64 : 0));
   auto it = g_w16.find(key);
   if (it != g_w16.end()) return it->second;
   W16 w{nullptr, nullptr, (K + 7) & ~7};
   const size_t n = (size_t)N * w.ld;
   CUDA_CHECK(cudaMalloc(&w.hi, n * sizeof(__half)));
   CUDA_CHECK(cudaMalloc(&w.lo, n * sizeof(__nv_bfloat16)));
-  split_w16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, w.hi, w.lo, N, K, w.ld);
+  split_w16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, w.hi, w.lo, N, K, w.ld, lo_f16 ? 1 : 0);
   count_launch();
   KERNEL_CHECK();
   g_w16.emplace(key, w);
@@ -260,7 +277,7 @@ W16 w16_for(const float *W, int N, int K, cudaStream_t st) {
 bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return true;
   if (!tc_init()) return false;
-  if ((g.K % FBK) || (g.lda & 3) || (reinterpret_cast<uintptr_t>(g.A) & 15)) return false;
+  if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<uintptr_t>(g.A) & 15)) return false;
   const bool joiner = g.act == ACT_JOINER;
   if (joiner) {
     if (!g.partials || !g.bias || (g.part_kb != 4 && g.part_kb != 8 && g.part_kb != 16) ||
@@ -277,19 +294,20 @@ bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
   }
   int BN = g.N > 64 ? 128 : 64;
   if (joiner && (long long)((g.M + TBM - 1) / TBM) * ((g.N + 63) / 64) <= n_sms) BN = 64;
-  const W16 w = w16_for(g.W, g.N, g.K, st);
+  const int variant = getenv("B200ASR_F16_VARIANT") ? atoi(getenv("B200ASR_F16_VARIANT")) : 0;
+  const W16 w = w16_for(g.W, g.N, g.K, st, (variant & 16) != 0);
   CUtensorMap ma, mwh, mwl;
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_16(&mwh, w.hi, false, g.N, w.ld, w.ld, BN);
   make_map_16(&mwl, w.lo, true, g.N, w.ld, w.ld, BN);
   TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
-  const unsigned grid = (unsigned)std::min<long long>(n_tiles, n_sms);
+  const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
 #define B200_F16_LAUNCH(BN_, EPI_)                                                                                        \
   do {                                                                                                                    \
     set_max_dynamic_smem(gemm_f16split_tcgen05_kernel<BN_, EPI_>, f16_smem_bytes(BN_));                                   \
     launch_pdl(gemm_f16split_tcgen05_kernel<BN_, EPI_>, dim3(grid), dim3(kF16Threads), f16_smem_bytes(BN_), st, g.pdl != 0, ma, mwh, \
-               mwl, p);                                                                                                   \
+               mwl, p, variant);                                                                                          \
   } while (0)
 #define B200_F16_BN(EPI_)                                                                          \
   do {                                                                                             \

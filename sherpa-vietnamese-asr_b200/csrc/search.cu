@@ -792,7 +792,7 @@ __global__ void bias_penalty_kernel(const float *__restrict__ b, int V, int blan
   if (i < V) out[i] = b[i] - (i == blank_id ? penalty : 0.f);
 }
 
-__global__ void init_search_kernel(SearchModel m, SearchDev d) {
+__global__ void init_search_kernel(SearchModel m, SearchDev d, int n_pos) {
   const int s = blockIdx.x;
   if (threadIdx.x == 0) {
     HypSlot h;
@@ -801,20 +801,24 @@ __global__ void init_search_kernel(SearchModel m, SearchDev d) {
     d.hyp_count[s] = 1;
     d.hyp_count[d.n + s] = 0;
     d.node_count[s] = 0;
-    d.chg_list[s] = make_int2(s * d.beam, (int)d.enc_off[s]);   // frame 0: every utterance's first row needs its decoder output
-    if (s == 0) { d.chg_count[0] = d.n; d.chg_count[1] = 0; }
+    // frame 0: the first row of every utterance that has frames needs its decoder output (longest first: those are a
+    // prefix; an empty utterance has no encoder row to pair it with)
+    if (s < n_pos) d.chg_list[s] = make_int2(s * d.beam, (int)d.enc_off[s]);
+    if (s == 0) { d.chg_count[0] = n_pos; d.chg_count[1] = 0; }
   }
   if ((int)threadIdx.x < d.beam) {
-    d.rowdesc[(size_t)s * d.beam + threadIdx.x] = make_int2(threadIdx.x == 0 ? -1 : -2, (int)d.enc_off[s]);
+    d.rowdesc[(size_t)s * d.beam + threadIdx.x] = make_int2((threadIdx.x == 0 && s < n_pos) ? -1 : -2, (int)d.enc_off[s]);
     d.rowdesc[(size_t)(d.n + s) * d.beam + threadIdx.x] = make_int2(-2, 0);
   }
   for (int o = threadIdx.x; o < m.dd; o += blockDim.x)   // context [0, 0]
     d.E[((long long)s * d.beam) * m.dd + o] = fmaxf(__ldg(m.conv_p0 + o) + __ldg(m.conv_p1 + o), 0.f);
 }
 
-// finalize (:1143-1153): subtract unfinished hotword score, pick first max of log_prob/len(ys), unroll the chain
+// finalize (:1143-1153): subtract unfinished hotword score, pick first max of log_prob/len(ys), unroll the chain.
+// Results are packed per utterance at out_off[u] (= sum of T' of the utterances before u in the caller's order; an
+// utterance emits at most one token per frame, so T' slots always suffice).
 __global__ void finalize_kernel(SearchDev d, ContextGraphView g, int has_graph, const int *__restrict__ final_buf,
-                                const int *__restrict__ orig_index, int max_tokens, int *__restrict__ n_tokens,
+                                const int *__restrict__ orig_index, const long long *__restrict__ out_off, int *__restrict__ n_tokens,
                                 int *__restrict__ tokens, int *__restrict__ frames, float *__restrict__ tok_lp,
                                 float *__restrict__ stats) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -833,16 +837,16 @@ __global__ void finalize_kernel(SearchDev d, ContextGraphView g, int has_graph, 
   const int u = orig_index[s];
   if (best < 0) { n_tokens[u] = 0; return; }
   const ArenaNode *arena = d.arena + d.arena_off[s];
-  int len = hy[best].len;
+  const int len = hy[best].len, cap = d.lens[s];
   n_tokens[u] = len;
   int node = hy[best].node;
+  const long long base = out_off[u];
   for (int i = len - 1; i >= 0 && node >= 0; --i) {
     const ArenaNode &nd = arena[node];
-    if (i < max_tokens) {
-      const long long o = (long long)u * max_tokens + i;
+    if (i < cap) {
+      const long long o = base + i;
       tokens[o] = nd.token; frames[o] = nd.frame; tok_lp[o] = nd.tok_lp;
-      stats[o * 4 + 0] = nd.stats[0]; stats[o * 4 + 1] = nd.stats[1];
-      stats[o * 4 + 2] = nd.stats[2]; stats[o * 4 + 3] = nd.stats[3];
+      reinterpret_cast<float4 *>(stats)[o] = make_float4(nd.stats[0], nd.stats[1], nd.stats[2], nd.stats[3]);
     }
     node = nd.parent;
   }
@@ -883,8 +887,18 @@ struct SearchState {
   int *o_frm = nullptr; size_t of_cap = 0;
   float *o_lp = nullptr; size_t ol_cap = 0;
   float *o_st = nullptr; size_t os_cap = 0;
+  long long *o_off = nullptr; size_t oo_cap = 0;
   void (*gemm)(const GemmArgs &, cudaStream_t) = launch_gemm_fp32;
   bool fused_partials = false;
+  // results of the last issued search: pinned host copies in the packed layout (h_off[u] = sum of T' before u)
+  void *h_pinned = nullptr; size_t h_cap = 0;
+  int *h_ntok = nullptr, *h_tok = nullptr, *h_frm = nullptr;
+  float *h_lp = nullptr, *h_st = nullptr;
+  std::vector<long long> h_off;
+  int n_last = 0;
+  long long *d_prof = nullptr;
+  unsigned long long *d_trace = nullptr;
+  int prof_steps = 0;
 };
 
 SearchState *search_state_create() { return new SearchState(); }
@@ -898,12 +912,14 @@ void search_state_destroy(SearchState *s) {
   cudaFree(s->X); cudaFree(s->logits); cudaFree(s->partials); cudaFree(s->bias_pen); cudaFree(s->chg_list); cudaFree(s->rowdesc); cudaFree(s->chg_count);
   cudaFree(s->enc_off); cudaFree(s->arena_off); cudaFree(s->lens);
   cudaFree(s->orig); cudaFree(s->final_buf); cudaFree(s->o_ntok); cudaFree(s->o_tok); cudaFree(s->o_frm);
-  cudaFree(s->o_lp); cudaFree(s->o_st);
+  cudaFree(s->o_lp); cudaFree(s->o_st); cudaFree(s->o_off);
+  if (s->h_pinned) cudaFreeHost(s->h_pinned);
   delete s;
 }
 
-void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, const float *enc, const int *h_lens, int n,
-                int method, int beam, float blank_penalty, SearchResultHost *out, cudaStream_t st) {
+void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g, const float *enc, const int *h_lens, int n,
+                  int method, int beam, float blank_penalty, cudaStream_t st) {
+  S->n_last = 0;
   if (n <= 0) return;
   const int greedy = (method == 0);
   if (greedy) beam = 1;
@@ -951,12 +967,29 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
   ensure(S->lens, S->ln_cap, (size_t)n);
   ensure(S->orig, S->og_cap, (size_t)n);
   ensure(S->final_buf, S->fb_cap, (size_t)n);
-  const int max_tokens = out->max_tokens;
+  const size_t slots = (size_t)std::max<long long>(off_orig[n], 1);
   ensure(S->o_ntok, S->ont_cap, (size_t)n);
-  ensure(S->o_tok, S->ot_cap, (size_t)n * max_tokens);
-  ensure(S->o_frm, S->of_cap, (size_t)n * max_tokens);
-  ensure(S->o_lp, S->ol_cap, (size_t)n * max_tokens);
-  ensure(S->o_st, S->os_cap, (size_t)n * max_tokens * 4);
+  ensure(S->o_tok, S->ot_cap, slots);
+  ensure(S->o_frm, S->of_cap, slots);
+  ensure(S->o_lp, S->ol_cap, slots);
+  ensure(S->o_st, S->os_cap, slots * 4);
+  ensure(S->o_off, S->oo_cap, (size_t)n);
+  {
+    // pinned host mirror: [n] counts, then tokens / frames / log-probs [slots] each, then stats [slots][4] (16-byte aligned)
+    const size_t n4 = ((size_t)n + 3) & ~size_t(3), s4 = (slots + 3) & ~size_t(3);
+    const size_t need = (n4 + 3 * s4 + 4 * s4) * 4;
+    if (need > S->h_cap) {
+      if (S->h_pinned) CUDA_CHECK(cudaFreeHost(S->h_pinned));
+      S->h_pinned = nullptr;
+      S->h_cap = need + need / 4;
+      CUDA_CHECK(cudaHostAlloc(&S->h_pinned, S->h_cap, cudaHostAllocPortable));
+    }
+    int *base = reinterpret_cast<int *>(S->h_pinned);
+    S->h_ntok = base; S->h_tok = base + n4; S->h_frm = S->h_tok + s4;
+    S->h_lp = reinterpret_cast<float *>(S->h_frm + s4); S->h_st = S->h_lp + s4;
+  }
+  S->h_off.assign(off_orig.begin(), off_orig.end());
+  CUDA_CHECK(cudaMemcpyAsync(S->o_off, off_orig.data(), n * sizeof(long long), cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(S->enc_off, enc_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(S->arena_off, arena_off.data(), n * sizeof(long long), cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaMemcpyAsync(S->lens, lens.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -970,6 +1003,8 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
   d.n = n; d.beam = beam;
   d.prof = nullptr;
   static const bool want_prof = getenv("B200ASR_SEARCH_PROF") != nullptr;
+  if (S->d_prof) { cudaFree(S->d_prof); S->d_prof = nullptr; }
+  if (S->d_trace) { cudaFree(S->d_trace); S->d_trace = nullptr; }
   long long *d_prof = nullptr;
   if (want_prof) {
     CUDA_CHECK(cudaMalloc(&d_prof, 8 * sizeof(long long)));
@@ -983,6 +1018,7 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
     CUDA_CHECK(cudaMemsetAsync(d_trace, 0, (size_t)std::max(max_len, 1) * 16 * sizeof(unsigned long long), st));
     d.trace = d_trace;
   }
+  S->d_prof = d_prof; S->d_trace = d_trace; S->prof_steps = max_len;
   ContextGraphView gv{};
   const int has_graph = (g && g->n_nodes > 1 && !greedy) ? 1 : 0;
   if (has_graph)
@@ -998,7 +1034,9 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
   }
   set_max_dynamic_smem(decoder_joinin_kernel, kDjSmem);
   if (!m.conv_p0 || !m.conv_p1) throw CudaError("beam search: decoder convolution tables are missing");
-  init_search_kernel<<<n, 128, 0, st>>>(m, d);
+  int n_pos = n;
+  while (n_pos > 0 && lens[n_pos - 1] <= 0) --n_pos;
+  init_search_kernel<<<n, 128, 0, st>>>(m, d, n_pos);
   count_launch(); KERNEL_CHECK();
   // the joiner epilogue takes the blank penalty folded into its bias
   const float *join_bias = m.join_b;
@@ -1051,30 +1089,48 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
   }
   KERNEL_CHECK();
   // Utterances that stopped at step T' hold their final state in buffer (T' & 1): select writes to cur^1 = (t+1)&1.
-  finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, gv, has_graph, S->final_buf, S->orig, max_tokens, S->o_ntok, S->o_tok,
-                                                   S->o_frm, S->o_lp, S->o_st);
+  finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(d, gv, has_graph, S->final_buf, S->orig, S->o_off, S->o_ntok, S->o_tok, S->o_frm,
+                                                   S->o_lp, S->o_st);
   count_launch(); KERNEL_CHECK();
-  CUDA_CHECK(cudaMemcpyAsync(out->n_tokens, S->o_ntok, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (out->tokens) {
-    CUDA_CHECK(cudaMemcpyAsync(out->tokens, S->o_tok, (size_t)n * max_tokens * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(out->frames, S->o_frm, (size_t)n * max_tokens * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(out->tok_lp, S->o_lp, (size_t)n * max_tokens * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(out->stats, S->o_st, (size_t)n * max_tokens * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
-  CUDA_CHECK(cudaStreamSynchronize(st));
-  if (d_prof) {
+  CUDA_CHECK(cudaMemcpyAsync(S->h_ntok, S->o_ntok, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(S->h_tok, S->o_tok, slots * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(S->h_frm, S->o_frm, slots * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(S->h_lp, S->o_lp, slots * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaMemcpyAsync(S->h_st, S->o_st, slots * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  S->n_last = n;
+}
+
+long long search_result_bytes(const SearchState *S) {
+  if (!S || S->n_last <= 0) return 0;
+  const long long slots = S->h_off.empty() ? 0 : S->h_off.back();
+  return (long long)S->n_last * 4 + slots * 28;
+}
+
+// Valid once the stream search_issue ran on has been synchronised.
+SearchView search_view(const SearchState *S) {
+  SearchView v{};
+  v.n = S->n_last;
+  if (v.n <= 0) return v;
+  v.n_tokens = S->h_ntok; v.off = S->h_off.data(); v.tokens = S->h_tok; v.frames = S->h_frm; v.tok_lp = S->h_lp; v.stats = S->h_st;
+  return v;
+}
+
+static void search_print_prof(SearchState *S) {
+  if (S->d_prof) {
     long long h[8];
-    CUDA_CHECK(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
-    cudaFree(d_prof);
+    CUDA_CHECK(cudaMemcpy(h, S->d_prof, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(S->d_prof); S->d_prof = nullptr;
+    const int max_len = S->prof_steps;
     const char *names[8] = {"load", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "-", "-", "decoder pre-activation"};
     fprintf(stderr, "[b200asr search prof] CTA0 cycles over %d steps:", max_len);
     for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f/step", names[i], (double)h[i] / std::max(max_len, 1));
     fprintf(stderr, "\n");
   }
-  if (d_trace) {
+  if (S->d_trace) {
+    const int max_len = S->prof_steps;
     std::vector<unsigned long long> h((size_t)max_len * 16);
-    CUDA_CHECK(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    cudaFree(d_trace);
+    CUDA_CHECK(cudaMemcpy(h.data(), S->d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(S->d_trace); S->d_trace = nullptr;
     // average timeline of a step (CTA 0 of each kernel), microseconds relative to decoder_joinin's entry
     const char *names[16] = {"dj.in", "dj.out", "gemm.in", "gemm.out", "gemm.prologue", "gemm.first_operands", "gemm.acc_done",
                              "gemm.epilogue_done", "sel.in", "sel.out", "dj.issued", "dj.rows", "dj.landed", "dj.mma", "dj.tile0", ""};
@@ -1097,6 +1153,91 @@ void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, 
       fprintf(stderr, " next_step=%.2f\n", step / cnt / 1e3);
     }
   }
+}
+
+// Scatter of the packed results into caller arrays of pitch max_tokens (the raw B200AsrBeamSearch layout).
+void search_collect(SearchState *S, SearchResultHost *out) {
+  search_print_prof(S);
+  const SearchView v = search_view(S);
+  for (int u = 0; u < v.n; ++u) {
+    out->n_tokens[u] = v.n_tokens[u];
+    if (!out->tokens) continue;
+    const int cnt = std::min(v.n_tokens[u], out->max_tokens);
+    const long long o = v.off[u], q = (long long)u * out->max_tokens;
+    for (int j = 0; j < cnt; ++j) {
+      out->tokens[q + j] = v.tokens[o + j]; out->frames[q + j] = v.frames[o + j]; out->tok_lp[q + j] = v.tok_lp[o + j];
+      for (int c = 0; c < 4; ++c) out->stats[(q + j) * 4 + c] = v.stats[(o + j) * 4 + c];
+    }
+  }
+}
+
+void run_search(SearchState *S, const SearchModel &m, const ContextGraphDev *g, const float *enc, const int *h_lens, int n,
+                int method, int beam, float blank_penalty, SearchResultHost *out, cudaStream_t st) {
+  if (n <= 0) return;
+  search_issue(S, m, g, enc, h_lens, n, method, beam, blank_penalty, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  search_collect(S, out);
+}
+
+// ---- the product's per-step kernels on caller-supplied rows (parity tests call them through the C-ABI) ----
+namespace {
+__global__ void prep_product_rows_kernel(SearchModel m, SearchDev d, const long long *__restrict__ y, int rows) {
+  const int i = blockIdx.x;
+  if (i >= rows) return;
+  const int y0 = (int)max(0LL, y[2 * i]), y1 = (int)max(0LL, y[2 * i + 1]);
+  for (int o = threadIdx.x; o < m.dd; o += blockDim.x)
+    d.E[(long long)i * m.dd + o] = fmaxf(__ldg(m.conv_p0 + (long long)y0 * m.dd + o) + __ldg(m.conv_p1 + (long long)y1 * m.dd + o), 0.f);
+  if (threadIdx.x == 0) {
+    d.chg_list[i] = make_int2(i, i);
+    d.rowdesc[i] = make_int2(-1, i);
+    if (i == 0) { d.chg_count[0] = rows; d.chg_count[1] = 0; }
+  }
+}
+}  // namespace
+
+// decoder_joinin_kernel exactly as a frame step launches it, with every row in the recompute list: dec = decoder_proj(relu(conv
+// (emb[y0], emb[y1]))) and X = tanh(enc + dec). enc may be null (zeros). All pointers device.
+void launch_decoder_product_rows(const SearchModel &m, const long long *y, const float *enc, int rows, float *dec_out, float *x_out,
+                                 cudaStream_t st) {
+  if (rows <= 0) return;
+  if (!m.conv_p0 || !m.conv_p1) throw CudaError("decoder convolution tables are missing");
+  float *E = nullptr, *dec = nullptr, *X = nullptr, *zero = nullptr;
+  int2 *lists = nullptr;
+  int *cnt = nullptr;
+  CUDA_CHECK(cudaMalloc(&E, (size_t)rows * m.dd * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&dec, 2 * (size_t)rows * m.jd * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&X, (size_t)rows * m.jd * sizeof(float)));
+  CUDA_CHECK(cudaMalloc(&lists, 4 * (size_t)rows * sizeof(int2)));
+  CUDA_CHECK(cudaMalloc(&cnt, 2 * sizeof(int)));
+  if (!enc) {
+    CUDA_CHECK(cudaMalloc(&zero, ((size_t)rows + 1) * m.jd * sizeof(float)));
+    CUDA_CHECK(cudaMemsetAsync(zero, 0, ((size_t)rows + 1) * m.jd * sizeof(float), st));
+  }
+  SearchDev d{};
+  d.enc = enc ? enc : zero; d.E = E; d.dec = dec; d.X = X; d.chg_list = lists; d.rowdesc = lists + 2 * (size_t)rows; d.chg_count = cnt;
+  d.n = rows; d.beam = 1; d.trace = nullptr; d.prof = nullptr;
+  prep_product_rows_kernel<<<rows, 128, 0, st>>>(m, d, y, rows);
+  count_launch(); KERNEL_CHECK();
+  set_max_dynamic_smem(decoder_joinin_kernel, kDjSmem);
+  const int ntn = (m.jd + DJ_TN - 1) / DJ_TN;
+  const int grid = std::min(296, std::max(((rows + DJ_TM - 1) / DJ_TM) * ntn, 1));
+  launch_pdl(decoder_joinin_kernel, dim3(grid), dim3(DJ_THREADS), kDjSmem, st, false, m, d, 0, rows);
+  count_launch(); KERNEL_CHECK();
+  CUDA_CHECK(cudaMemcpyAsync(dec_out, dec, (size_t)rows * m.jd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(x_out, X, (size_t)rows * m.jd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(E); cudaFree(dec); cudaFree(X); cudaFree(lists); cudaFree(cnt); cudaFree(zero);
+}
+
+// The joiner GEMM exactly as a frame step launches it (ACT_JOINER: per row and 32-column part a softmax / top-kb record, no
+// logits stored). X [rows, jd] -> records [rows, ceil(V/32), 4 + 2 kb]. Device pointers.
+void launch_joiner_records(SearchState *S, const SearchModel &m, const float *X, int rows, int kb, float *records, cudaStream_t st) {
+  if (rows <= 0) return;
+  if (!S->fused_partials) throw CudaError("this precision mode has no record epilogue (CUDA-core GEMM selects from full logits)");
+  GemmArgs ga{};
+  ga.A = X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = nullptr;
+  ga.ldc = m.V; ga.M = rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_JOINER; ga.partials = records; ga.part_kb = kb; ga.pdl = 0;
+  S->gemm(ga, st);
 }
 
 void launch_decoder_rows(const SearchModel &m, const long long *y, int rows, float *out, cudaStream_t st) {

@@ -345,6 +345,31 @@ class OfflineRecognizer:
             raise RuntimeError(_capi.last_error())
         return out
 
+    def decoder_joiner_input(self, y, enc=None):
+        """The search's decoder kernel on rows y[m,2]: (decoder_out[m,512], tanh(enc + decoder_out)[m,512])."""
+        y = np.ascontiguousarray(y, dtype=np.int64).reshape(-1, 2)
+        m = y.shape[0]
+        dec = np.empty((m, self.joiner_dim), dtype=np.float32)
+        x = np.empty((m, self.joiner_dim), dtype=np.float32)
+        e = np.ascontiguousarray(enc, dtype=np.float32) if enc is not None else None
+        rc = _capi.lib().B200AsrDecoderJoinerInput(self._h, _capi.i64ptr(y), _capi.fptr(e) if e is not None else None, m,
+                                                   _capi.fptr(dec), _capi.fptr(x))
+        if rc != 0:
+            raise RuntimeError(_capi.last_error())
+        return dec, x
+
+    def joiner_records(self, x, kb: int = 4) -> np.ndarray:
+        """The search's joiner GEMM on rows x[m,512]: records [m, ceil(V/32), 4 + 2*kb] (see include/b200asr.h)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        m = x.shape[0]
+        per_row = _capi.lib().B200AsrJoinerRecords(self._h, None, 0, kb, None)
+        if per_row < 0:
+            raise RuntimeError(_capi.last_error())
+        out = np.empty((m, per_row // (4 + 2 * kb), 4 + 2 * kb), dtype=np.float32)
+        if _capi.lib().B200AsrJoinerRecords(self._h, _capi.fptr(x), m, kb, _capi.fptr(out)) < 0:
+            raise RuntimeError(_capi.last_error())
+        return out
+
     def gemm(self, A, W, bias=None, R=None, act: int = 0, impl: str = "fp32", reps: int = 1):
         """One Linear: act(A W^T + bias) (+ R) through the selected kernel. Returns (C, ms_per_launch)."""
         A = np.ascontiguousarray(A, dtype=np.float32)
@@ -398,6 +423,22 @@ class OfflineRecognizer:
         if _capi.lib().B200AsrRunStagedBatch(self._h, handle, _capi.i32ptr(ntok)) != 0:
             raise RuntimeError(_capi.last_error())
         return ntok
+
+    def last_pass_tokens(self, u: int, cap: int = 4096):
+        """(token ids, frames) of utterance u of the last staged run / decode pass."""
+        toks = np.zeros(cap, dtype=np.int32)
+        frames = np.zeros(cap, dtype=np.int32)
+        n = _capi.lib().B200AsrLastPassTokens(self._h, int(u), _capi.i32ptr(toks), _capi.i32ptr(frames), cap)
+        if n < 0:
+            raise RuntimeError(_capi.last_error())
+        return toks[:n].tolist(), frames[:n].tolist()
+
+    def last_pipeline_stats(self) -> dict:
+        ng, busy, d2h = C.c_int32(0), C.c_float(0), C.c_int64(0)
+        lanes = (C.c_float * 8)()
+        _capi.lib().B200AsrLastPipelineStats(self._h, C.byref(ng), C.byref(busy), lanes, C.byref(d2h))
+        return {"groups": ng.value, "search_busy_ms": busy.value, "lane_ms": [lanes[i] for i in range(ng.value)],
+                "d2h_bytes": d2h.value}
 
     def release_batch(self, handle: int) -> None:
         _capi.lib().B200AsrReleaseBatch(self._h, handle)

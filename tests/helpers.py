@@ -36,3 +36,24 @@ def rel_err(a, b):
     if a.size == 0:
         return 0.0
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
+
+
+def rel_l2(a, b):
+    """||a - b|| / ||b|| — the output-difference metric of the reference's own CPU-vs-GPU gate
+    (/root/reference core/calibration.py:1057-1090 `_output_diff`)."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    if a.size == 0:
+        return 0.0
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-12))
+
+
+def row_err(a, b):
+    """Largest per-row error relative to that row's own scale: a localised fault cannot hide behind the tensor's global maximum."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    a = a.reshape(-1, a.shape[-1])
+    b = b.reshape(-1, b.shape[-1])
+    return float((np.abs(a - b).max(axis=1) / (np.abs(b).max(axis=1) + 1e-6)).max())
