@@ -37,7 +37,9 @@ def parse_args():
     ap.add_argument("--segments", type=int, default=256)
     ap.add_argument("--model", default="zipformer-68m")
     ap.add_argument("--beam", type=int, default=4)
-    ap.add_argument("--precision", default=os.environ.get("B200ASR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("B200ASR_PRECISION", "fp32"), choices=["fp32", "tf32"],
+                    help="fp32 = the token-exact mode (headline); tf32 = single-pass TF32 operands (labelled as such, never the headline)")
+    ap.add_argument("--parity-segments", type=int, default=8, help="segments whose tokens are compared with the oracle outside the timed region")
     ap.add_argument("--cpu-sample", type=int, default=24, help="segments in the bounded CPU sample (~7 s of CPU work per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -120,25 +122,54 @@ def encoder_flops(cfg, T: int) -> float:
     return 2.0 * macs
 
 
-def cpu_reference_pass(cfg, paths, audios, beam, threads):
+def cpu_reference_pass(cfg, paths, audios, beam, threads, workers=1):
     """The reference CPU path restated (oracle): NumPy fbank + PyTorch-CPU fp32 encoder/decoder/joiner driving the
-    restated `_ort_beam_search`, batch 1 per segment as core/asr_engine.py:1045-1047 does. Returns seconds."""
+    restated `_ort_beam_search`, batch 1 per segment as core/asr_engine.py:1045-1047 does; `workers` threads take the
+    even / odd segments as the reference's two-worker split does (core/asr_engine.py:2384-2397), each with its own
+    recognizer copy (private decoder cache, :2302-2315). Returns (seconds, tokens)."""
     import torch
 
     from oracle import fbank_ref, search_ref, zipformer_ref
     from sherpa_vietnamese_asr_b200 import weights
-    torch.set_num_threads(threads)
+    torch.set_num_threads(max(1, threads))
     tensors = {}
     for part in ("encoder", "decoder", "joiner"):
         tensors.update(weights.load_container(paths[part])[1])
-    rec = zipformer_ref.make_recognizer(tensors, cfg, max_active_paths=beam)
+    recs = [zipformer_ref.make_recognizer(tensors, cfg, max_active_paths=beam, batched_rows=True) for _ in range(workers)]
+    ntok = [0] * workers
+
+    def work(w):
+        rec = recs[w]
+        for a in audios[w::workers]:
+            feats = fbank_ref.fbank(a, np.float32)
+            rec["dec_cache"].clear()
+            ntok[w] += len(search_ref.modified_beam_search(rec, feats, beam)[0])
+
     t0 = time.perf_counter()
-    ntok = 0
-    for a in audios:
-        feats = fbank_ref.fbank(a, np.float32)
-        rec["dec_cache"].clear()
-        ntok += len(search_ref.modified_beam_search(rec, feats, beam)[0])
-    return time.perf_counter() - t0, ntok
+    if workers == 1:
+        work(0)
+    else:
+        ths = [threading.Thread(target=work, args=(w,)) for w in range(workers)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    return time.perf_counter() - t0, sum(ntok)
+
+
+def calibrate_cpu(cfg, paths, audios, beam, cores):
+    """The CPU arm's best (intra-op threads, workers) on this host, picked on a short sample: torch's intra-op scaling on a
+    batch-1 encoder saturates well below a big host's core count, and the launch environment (torchrun exports OMP_NUM_THREADS=1)
+    must not decide the number."""
+    sample = sorted(audios, key=len)[len(audios) // 2:][:2] * 2     # four mid-length segments
+    cands = sorted({(cores, 1), (max(1, cores // 2), 2), (min(cores, 8), 1), (min(max(1, cores // 2), 8), 2)})
+    best, best_rate = (cores, 1), 0.0
+    for th, w in cands:
+        dt, _ = cpu_reference_pass(cfg, paths, sample, beam, th, w)
+        rate = sum(len(a) for a in sample) / 16000.0 / dt
+        if rate > best_rate:
+            best, best_rate = (th, w), rate
+    return best
 
 
 def physical_cores() -> int:
@@ -157,11 +188,10 @@ def run_reference(args, rank, world):
     audios = workload(args, 0)[: args.cpu_sample]
     audio_s = sum(len(a) for a in audios) / 16000.0
     cores = min(physical_cores(), 32)
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_pass(cfg, paths, audios[:1], args.beam, cores)
+    threads, workers = calibrate_cpu(cfg, paths, audios, args.beam, cores)     # doubles as the warm-up
     times = []
     for _ in range(args.steps):
-        dt, _ = cpu_reference_pass(cfg, paths, audios, args.beam, cores)
+        dt, _ = cpu_reference_pass(cfg, paths, audios, args.beam, threads, workers)
         times.append(dt)
     ms = 1000.0 * float(np.mean(times))
     val = audio_s / (ms / 1000.0)
@@ -169,11 +199,33 @@ def run_reference(args, rank, world):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C2: {args.model} modified_beam_search beam {args.beam}, bounded sample = first "
-                                   f"{len(audios)} of {args.segments} VAD-like segments ({audio_s:.1f} audio-s), batch 1 per segment"},
-            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                   f"{len(audios)} of {args.segments} VAD-like segments ({audio_s:.1f} audio-s), batch 1 per segment, "
+                                   f"{workers} worker(s) x {threads} intra-op threads (best of a calibration sweep)"},
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": threads * workers, "kind": "port",
                              "sample": f"first {len(audios)} segments of C2 ({audio_s:.1f} audio-s) per step"},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def parity_check(rec, cfg, paths, audios, beam, k):
+    """Outside the timed region: the tokens and frames the engine produced for the first k segments of the (already decoded)
+    staged batch against the oracle's fbank -> encoder -> modified_beam_search on the same PCM and weights."""
+    from oracle import fbank_ref, search_ref, zipformer_ref
+    from sherpa_vietnamese_asr_b200 import weights
+    tensors = {}
+    for part in ("encoder", "decoder", "joiner"):
+        tensors.update(weights.load_container(paths[part])[1])
+    orec = zipformer_ref.make_recognizer(tensors, cfg, max_active_paths=beam)
+    n_tok, bad = 0, []
+    for u in range(min(k, len(audios))):
+        feats = fbank_ref.fbank(audios[u], np.float64)
+        orec["dec_cache"].clear()
+        toks, frames = search_ref.modified_beam_search(orec, feats, beam)[:2]
+        got_t, got_f = rec.last_pass_tokens(u)
+        if got_t != list(toks) or got_f != list(frames):
+            bad.append(u)
+        n_tok += len(toks)
+    return {"parity_checked": not bad, "parity_segments": min(k, len(audios)), "parity_tokens": n_tok, "parity_mismatches": bad}
 
 
 def main():
@@ -229,6 +281,8 @@ def main():
     wall_ms = 1000.0 * (time.perf_counter() - t0)
     clocks = sampler.stop()
     ms_dev = dev_ms / args.steps
+    pipe = rec.last_pipeline_stats()
+    parity = parity_check(rec, cfg, paths, audios, args.beam, args.parity_segments) if (rank == 0 and args.parity_segments > 0) else {}
 
     # ---------------- end to end through the recognizer surface (host buffers)
     def e2e_step():
@@ -247,7 +301,7 @@ def main():
         ss = e2e_step()
     barrier()
     e2e_ms = 1000.0 * (time.perf_counter() - t0) / args.steps
-    d2h_bytes = int(sum(len(s.result.token_ids) for s in ss) * (4 + 4 + 4 + 16) + 4 * len(ss))
+    d2h_bytes = int(rec.last_pipeline_stats()["d2h_bytes"])     # what the searches of the pass copied back (counts + packed slots)
 
     # ---------------- dominant kernel (GEMM) timed live with CUDA events around every launch
     rec.set_profiling(True)
@@ -296,12 +350,17 @@ def main():
     line = {
         "metric": "RTFx (audio-s/s) Zipformer-68M batch ASR", "value": total_audio / (ms_dev * 1e-3), "unit": "audio-s/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
         "config": {"workload": f"C2: {args.model} random-init, modified_beam_search beam {args.beam}, {args.segments} VAD-like "
                                f"segments/GPU clip(lognormal(ln 9 s, 0.7), 1, 30) = {audio_s:.0f} audio-s/GPU; "
                                f"utterance-sharded, no collective",
                    "l2": f"inputs larger than L2 ({pcm_bytes / 1e6:.0f} MB PCM, multi-GB activations per step)",
                    "precision": args.precision, "wall_ms_per_step": wall_step,
+                   "pipeline": {"groups": pipe["groups"], "search_ms_per_group": [round(x, 3) for x in pipe["lane_ms"]],
+                                "search_busy_ms": pipe["search_busy_ms"],
+                                "note": "length-sorted groups; group g's search runs on its own stream beside the encoder of group g+1; "
+                                        "stage_ms.search_ms is the part no encoder hid"},
+                   **parity,
                    "stage_ms": {k: v / args.steps for k, v in stage.items()},
                    "encoder_algorithmic_tflop_per_step": enc_fl / 1e12,
                    "stage_rooflines": {
@@ -310,7 +369,7 @@ def main():
                        "encoder": {"bound": "tensor", "achieved_tflops": enc_fl / 1e12 / (stage["encoder_ms"] / args.steps * 1e-3),
                                    "peak_tflops": peak_tf, "frac": enc_fl / 1e12 / (stage["encoder_ms"] / args.steps * 1e-3) / peak_tf},
                        "beam_search": {"bound": "latency", "frame_steps": n_steps,
-                                       "us_per_frame_step": 1e3 * stage["search_ms"] / args.steps / max(n_steps, 1)}}},
+                                       "us_per_frame_step": 1e3 * (pipe["lane_ms"][0] if pipe["lane_ms"] else 0.0) / max(n_steps, 1)}}},
         "clocks": clocks,
         "e2e": {"value": total_audio / (e2e_ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": pcm_bytes,
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
@@ -324,11 +383,12 @@ def main():
     if not args.no_cpu_baseline and world == 1:   # the bounded CPU sample is an N=1 figure (rank 0's host cores)
         cores = min(physical_cores(), 32)
         sample = audios[: args.cpu_sample]
-        dt, _ = cpu_reference_pass(cfg, paths, sample, args.beam, cores)
+        threads, workers = calibrate_cpu(cfg, paths, sample, args.beam, cores)
+        dt, _ = cpu_reference_pass(cfg, paths, sample, args.beam, threads, workers)
         sa = sum(len(a) for a in sample) / 16000.0
-        line["cpu_baseline"] = {"value": sa / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
+        line["cpu_baseline"] = {"value": sa / dt, "unit": "audio-s/s", "cores": threads * workers, "kind": "port",
                                 "sample": f"first {len(sample)} segments of C2 ({sa:.1f} audio-s), oracle = reference CPU path restated "
-                                          f"(sherpa-onnx/onnxruntime unavailable offline)"}
+                                          f"(sherpa-onnx/onnxruntime unavailable offline), {workers} worker(s) x {threads} threads"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -245,10 +245,13 @@ class EncoderSession:
 
 
 class DecoderSession:
-    def __init__(self, W, cfg):
-        self.W, self.cfg = W, cfg
+    def __init__(self, W, cfg, batched=False):
+        self.W, self.cfg, self.batched = W, cfg, batched
 
     def run(self, _, feeds):
+        if self.batched:      # one call for all rows, as onnxruntime runs it (timing runs; results may differ in the last bits)
+            with torch.no_grad():
+                return [decoder(self.W, self.cfg, np.asarray(feeds["y"])).to(torch.float32).numpy()]
         # row by row: BLAS results depend on the batch shape in the last bits, and the reference's memo
         # (core/asr_engine.py:1072-1088) batches whatever contexts happen to miss; per-row evaluation makes
         # a context's decoder output a pure function of the context.
@@ -259,8 +262,8 @@ class DecoderSession:
 
 
 class JoinerSession:
-    def __init__(self, W, cfg):
-        self.W, self.cfg = W, cfg
+    def __init__(self, W, cfg, batched=False):
+        self.W, self.cfg, self.batched = W, cfg, batched
 
     def get_outputs(self):
         return [_Out(["N", self.cfg.vocab_size])]
@@ -269,17 +272,21 @@ class JoinerSession:
         with torch.no_grad():
             e = torch.from_numpy(np.ascontiguousarray(feeds["encoder_out"])).to(self.W.dtype)
             d = torch.from_numpy(np.ascontiguousarray(feeds["decoder_out"])).to(self.W.dtype)
+            if self.batched:
+                return [joiner(self.W, e, d).to(torch.float32).numpy()]
             rows = [joiner(self.W, e[i:i + 1], d[i:i + 1]).to(torch.float32).numpy() for i in range(e.shape[0])]
             return [np.concatenate(rows, axis=0)]
 
 
 def make_recognizer(tensors: dict, cfg, id2token=None, max_active_paths=4, context_graph=None,
-                    dtype=torch.float32):
-    """Builds the dict `create_recognizer` returns (core/asr_engine.py:1005-1012) over oracle sessions."""
+                    dtype=torch.float32, batched_rows=False):
+    """Builds the dict `create_recognizer` returns (core/asr_engine.py:1005-1012) over oracle sessions. batched_rows: the
+    decoder / joiner sessions evaluate all rows of a call at once like onnxruntime does (the CPU timing arm); the parity
+    tests keep the row-by-row default, which makes every row a pure function of its inputs."""
     W = Weights(tensors, dtype)
     return {
-        "enc_sess": EncoderSession(W, cfg), "dec_sess": DecoderSession(W, cfg),
-        "joi_sess": JoinerSession(W, cfg), "id2token": id2token or {}, "vocab_size": cfg.vocab_size,
+        "enc_sess": EncoderSession(W, cfg), "dec_sess": DecoderSession(W, cfg, batched_rows),
+        "joi_sess": JoinerSession(W, cfg, batched_rows), "id2token": id2token or {}, "vocab_size": cfg.vocab_size,
         "max_active_paths": max_active_paths, "model_path": "", "dec_cache": {},
         "context_graph": context_graph, "provider_info": {},
     }

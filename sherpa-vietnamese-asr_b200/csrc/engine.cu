@@ -31,6 +31,7 @@ namespace b200asr {
 void launch_gemm_tc(const GemmArgs &g, cudaStream_t st);    // gemm_tc.cu: tcgen05, TF32 operands
 void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st);   // gemm_tc.cu: tcgen05, error-compensated 3xTF32 (fp32-grade)
 bool gemm_tc_available();
+void gemm_f16split_forget(const float *W);                   // gemm_tc_f16.cu
 
 namespace {
 
@@ -1799,6 +1800,7 @@ int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const flo
   CUDA_CHECK(cudaEventRecord(e->ev[7], e->st));
   CUDA_CHECK(cudaMemcpyAsync(C, dC, nC * 4, cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
+  gemm_f16split_forget(dW);   // dW is scratch: the next call may put other weights at the same address
   if (ms_per_launch) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]);

@@ -273,6 +273,16 @@ W16 w16_for(const float *W, int N, int K, cudaStream_t st, bool lo_f16 = false) 
 
 }  // namespace
 
+// Drops the cached 16-bit copies of a weight matrix (callers that reuse a scratch pointer for different weights: B200AsrGemm).
+// The stream that used them must have been synchronised.
+void gemm_f16split_forget(const float *W) {
+  std::lock_guard<std::mutex> lk(g_w16_mu);
+  for (auto it = g_w16.begin(); it != g_w16.end();) {
+    if (std::get<0>(it->first) == W) { cudaFree(it->second.hi); cudaFree(it->second.lo); it = g_w16.erase(it); }
+    else ++it;
+  }
+}
+
 // Returns false when the shape is outside what this variant takes (the caller then runs the 3xTF32 kernel).
 bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return true;

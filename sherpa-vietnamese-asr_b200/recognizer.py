@@ -176,7 +176,10 @@ class OfflineRecognizer:
         cfg.hotwords_score = hotwords_score
         cfg.blank_penalty = blank_penalty
         cfg.device_id = device_id
-        cfg.precision = {"fp32": 0, "tf32": 1, "bf16": 1, "fp32_simt": 2}[precision]
+        modes = {"fp32": 0, "tf32": 1, "fp32_simt": 2, "bf16": 3}
+        if precision not in modes:
+            raise ValueError(f"precision must be one of {sorted(modes)}")
+        cfg.precision = modes[precision]
         self._cfg = cfg
         self._h = _capi.lib().B200AsrCreateOfflineRecognizer(C.byref(cfg))
         if not self._h:

@@ -529,12 +529,12 @@ def test_gemm_kernels_match_numpy(tiny, impl, M, N, K):
 
 
 def test_tensor_core_mode_end_to_end(model_dirs):
-    """precision='bf16' slot = tensor-core mode (tcgen05, TF32 operands): encoder within 1e-2 relative of the
-    oracle, token edit distance vs the FP32 oracle decode small."""
+    """precision='tf32' = single-pass TF32 operands on tcgen05 (not the BF16 mode, see test_bf16_mode_*): encoder within
+    2e-2 relative of the oracle, token edit distance vs the FP32 oracle decode small."""
     from oracle import fbank_ref, search_ref as sr
     from sherpa_vietnamese_asr_b200 import synth
     cfg, paths, d = model_dirs("zipformer-30m", 30)
-    rec = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4, precision="bf16")
+    rec = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4, precision="tf32")
     orec, ocfg, _ = oracle_recognizer(paths, beam=4)
     audios = [synth.speech_like(n, 900 + i) for i, n in enumerate([16000 * 5, 16000 * 8 + 1234, 16000 * 3])]
     import torch
