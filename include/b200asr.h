@@ -92,7 +92,8 @@ typedef struct B200AsrOfflineRecognizerResult {
 B200ASR_API const B200AsrOfflineRecognizer *B200AsrCreateOfflineRecognizer(const B200AsrOfflineRecognizerConfig *config);
 /* SherpaOnnxDestroyOfflineRecognizer (sherpa-onnx-asr.js:1859-1862) */
 B200ASR_API void B200AsrDestroyOfflineRecognizer(const B200AsrOfflineRecognizer *r);
-/* SherpaOnnxOfflineRecognizerSetConfig (sherpa-onnx-asr.js:1853-1857): decoding method, beam, hotword score */
+/* SherpaOnnxOfflineRecognizerSetConfig (sherpa-onnx-asr.js:1853-1857): decoding method, beam, hotword score, blank penalty.
+ * Fields left at "" / 0 / NaN (blank_penalty) keep their current value. */
 B200ASR_API int32_t B200AsrOfflineRecognizerSetConfig(const B200AsrOfflineRecognizer *r, const B200AsrOfflineRecognizerConfig *config);
 /* Hotword phrases as token ids (what build_context_graph produces after SentencePiece,
  * core/hotword_context.py:222-259): phrase p = tokens[offsets[p] .. offsets[p+1]). n_phrases == 0 clears. */
@@ -100,11 +101,28 @@ B200ASR_API int32_t B200AsrSetHotwordsTokenIds(const B200AsrOfflineRecognizer *r
                                                const int32_t *offsets, const float *scores, int32_t n_phrases);
 /* SherpaOnnxCreateOfflineStream (sherpa-onnx-asr.js:1864-1867; streaming_asr.py:308) */
 B200ASR_API const B200AsrOfflineStream *B200AsrCreateOfflineStream(const B200AsrOfflineRecognizer *r);
+/* SherpaOnnxCreateOfflineStreamWithHotwords (upstream C API; Python create_stream(hotwords=...)): a stream with its own
+ * hotword automaton instead of the recognizer's. `hotwords` = phrases separated by '/', each a list of space-separated token
+ * ids with an optional " :score" (text phrases are tokenised by the host binding, as build_context_graph does with
+ * SentencePiece, core/hotword_context.py:222-259). Streams with different automata are decoded in separate passes. */
+B200ASR_API const B200AsrOfflineStream *B200AsrCreateOfflineStreamWithHotwords(const B200AsrOfflineRecognizer *r, const char *hotwords);
 B200ASR_API void B200AsrDestroyOfflineStream(const B200AsrOfflineStream *s);
 /* SherpaOnnxAcceptWaveformOffline (sherpa-onnx-asr.js:1798-1806; streaming_asr.py:285,312,355): copies the
  * samples ([-1,1] floats) and appends on repeated calls. The copy lands in pinned host memory and its upload to the
- * recognizer's GPU is queued at once, so a later decode call finds the PCM resident. */
-B200ASR_API void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n);
+ * recognizer's GPU is queued at once, so a later decode call finds the PCM resident. sherpa-onnx's function returns void;
+ * this one returns 0 / -1 (wrong sample rate, host memory exhausted: B200AsrGetLastError) so a failed copy cannot pass
+ * silently - a binding written against the void signature can ignore the value. */
+B200ASR_API int32_t B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n);
+/* The same for n streams in one call (stream i takes samples[i][0 .. ns[i])): the accept loop of a batch without n trips
+ * through the host binding. Returns 0, or -1 at the first stream that fails. */
+B200ASR_API int32_t B200AsrAcceptWaveformsOffline(const B200AsrOfflineStream *const *ss, int32_t sample_rate,
+                                                  const float *const *samples, const int32_t *ns, int32_t n);
+/* Precomputed features in place of samples: what decode_chunk's `precomputed_features` argument carries when ROVER computes
+ * one fbank for both models (core/asr_engine.py:1209-1216,2346-2350). feats[num_frames * 80] as B200AsrFbank returns them for
+ * num_samples samples (num_frames == (num_samples + 80) / 160; num_samples also gives the result's duration and timestamps).
+ * A stream holds either samples or features. Returns 0 / -1. */
+B200ASR_API int32_t B200AsrAcceptFeaturesOffline(const B200AsrOfflineStream *s, const float *feats, int32_t num_frames,
+                                                 int32_t feature_dim, int64_t num_samples);
 /* SherpaOnnxDecodeOfflineStream (sherpa-onnx-asr.js:1869-1871; streaming_asr.py:358,408) */
 B200ASR_API int32_t B200AsrDecodeOfflineStream(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *s);
 /* SherpaOnnxDecodeMultipleOfflineStreams (upstream C API; Python decode_streams): the batch entry point.

@@ -53,7 +53,10 @@ SYMBOLS = {
     "B200AsrSetHotwordsTokenIds": (C.c_int32, [_P, _I32, _I32, _F, C.c_int32]),
     "B200AsrCreateOfflineStream": (_P, [_P]),
     "B200AsrDestroyOfflineStream": (None, [_P]),
-    "B200AsrAcceptWaveformOffline": (None, [_P, C.c_int32, _F, C.c_int32]),
+    "B200AsrAcceptWaveformOffline": (C.c_int32, [_P, C.c_int32, _F, C.c_int32]),
+    "B200AsrAcceptFeaturesOffline": (C.c_int32, [_P, _F, C.c_int32, C.c_int32, C.c_int64]),
+    "B200AsrAcceptWaveformsOffline": (C.c_int32, [C.POINTER(_P), C.c_int32, C.POINTER(_P), _I32, C.c_int32]),
+    "B200AsrCreateOfflineStreamWithHotwords": (_P, [_P, C.c_char_p]),
     "B200AsrDecodeOfflineStream": (C.c_int32, [_P, _P]),
     "B200AsrDecodeMultipleOfflineStreams": (C.c_int32, [_P, C.POINTER(_P), C.c_int32]),
     "B200AsrGetOfflineStreamResult": (C.POINTER(Result), [_P]),

@@ -187,23 +187,31 @@ def words_from_result(res, id2token: Dict[int, str], n_samples: int, time_offset
     return words
 
 
-def decode_chunks(recognizer: Recognizer, chunks: Sequence[np.ndarray], time_offsets: Optional[Sequence[float]] = None) -> List[List[dict]]:
-    """Batched decode_chunk: all chunks go through one ragged-batch `decode_streams` call."""
+def decode_chunks(recognizer: Recognizer, chunks: Sequence[np.ndarray], time_offsets: Optional[Sequence[float]] = None,
+                  precomputed_features: Optional[Sequence[np.ndarray]] = None) -> List[List[dict]]:
+    """Batched decode_chunk: all chunks go through one ragged-batch `decode_streams` call. With `precomputed_features`
+    (one [T, 80] array per chunk, as compute_fbank_ort returns) the streams carry the features instead of the samples and the
+    pass skips its fbank stage - how ROVER runs two models on one fbank (core/asr_engine.py:2346-2350)."""
     eng = recognizer.engine
     offs = list(time_offsets) if time_offsets is not None else [0.0] * len(chunks)
-    streams = []
-    for c in chunks:
-        s = eng.create_stream()
-        s.accept_waveform(16000, c)
-        streams.append(s)
+    streams = [eng.create_stream() for _ in chunks]
+    if precomputed_features is not None:
+        if len(precomputed_features) != len(chunks):
+            raise ValueError("precomputed_features and chunks differ in length")
+        for s, c, f in zip(streams, chunks, precomputed_features):
+            s.accept_features(f, len(c))
+    else:
+        eng.accept_waveforms(streams, chunks)
     eng.decode_streams(streams)
     return [words_from_result(s.result, recognizer["id2token"], len(c), o) for s, c, o in zip(streams, chunks, offs)]
 
 
 def decode_chunk(recognizer: Recognizer, audio_chunk, time_offset: float = 0.0, precomputed_features=None) -> List[dict]:
-    """Signature of core/asr_engine.py:1209. `precomputed_features` (ROVER's shared fbank) is accepted for
-    compatibility; features are recomputed on the GPU, where they cost ~1 us per audio second."""
-    return decode_chunks(recognizer, [np.asarray(audio_chunk, dtype=np.float32)], [time_offset])[0]
+    """Signature of core/asr_engine.py:1209: `precomputed_features` ([T, 80], ROVER's shared fbank) replaces the fbank stage
+    when given (:1212-1216)."""
+    chunk = np.asarray(audio_chunk, dtype=np.float32)
+    feats = None if precomputed_features is None else [np.asarray(precomputed_features, dtype=np.float32)]
+    return decode_chunks(recognizer, [chunk], [time_offset], feats)[0]
 
 
 # ----------------------------------------------------------------------------- ROVER v3
@@ -307,6 +315,8 @@ def rover_merge_words(words_a: List[dict], words_b: List[dict], hotword_phrases:
 def rover_decode_chunks(rec_a: Recognizer, rec_b: Recognizer, chunks, time_offsets=None, hotword_phrases=()):
     """ROVER mode (BASELINE config C4): both models over the same chunks, hypotheses combined per chunk
     (core/asr_engine.py:2333-2369,2469-2486)."""
-    wa = decode_chunks(rec_a, chunks, time_offsets)
-    wb = decode_chunks(rec_b, chunks, time_offsets)
+    chunks = [np.asarray(c, dtype=np.float32) for c in chunks]
+    feats = rec_a.engine.fbank_batch(chunks) if chunks else []      # one fbank for both models (core/asr_engine.py:2346-2350)
+    wa = decode_chunks(rec_a, chunks, time_offsets, feats)
+    wb = decode_chunks(rec_b, chunks, time_offsets, feats)
     return [rover_merge_words(a, b, hotword_phrases) for a, b in zip(wa, wb)]

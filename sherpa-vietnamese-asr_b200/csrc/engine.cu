@@ -3,6 +3,7 @@
 // The pipeline stands where the reference runs compute_fbank_ort + `_ort_beam_search` per chunk
 // (/root/reference core/asr_engine.py:1209-1253, chunk loop :2326-2397); the encoder schedule follows
 // SURVEY.md Appendix B (icefall Zipformer2 inference graph).
+#include <cuda.h>
 #include <math.h>
 #include <sched.h>
 #include <stdio.h>
@@ -106,6 +107,34 @@ struct Lane {
 }  // namespace
 
 struct Stream;
+
+// Driver entry points of the green-context API, resolved at run time (the library must load on machines without libcuda,
+// e.g. the CPU-only build check).
+namespace {
+struct GreenApi {
+  CUresult (*DeviceGet)(CUdevice *, int) = nullptr;
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+  bool ok = false;
+  GreenApi() {
+    auto get = [](const char *name, void **fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn && q == cudaDriverEntryPointSuccess;
+    };
+    ok = get("cuDeviceGet", (void **)&DeviceGet) && get("cuDeviceGetDevResource", (void **)&DeviceGetDevResource) &&
+         get("cuDevSmResourceSplitByCount", (void **)&DevSmResourceSplitByCount) &&
+         get("cuDevResourceGenerateDesc", (void **)&DevResourceGenerateDesc) && get("cuGreenCtxCreate", (void **)&GreenCtxCreate) &&
+         get("cuGreenCtxDestroy", (void **)&GreenCtxDestroy) && get("cuGreenCtxStreamCreate", (void **)&GreenCtxStreamCreate);
+    if (!ok) cudaGetLastError();
+  }
+};
+const GreenApi &green_api() { static GreenApi a; return a; }
+}  // namespace
+
 
 // Page-locked host memory for stream PCM: accept_waveform copies the caller's samples straight into pinned
 // memory, so decode_streams issues true asynchronous H2D copies at PCIe speed. cudaHostAlloc costs ~2 ms per call,
@@ -342,6 +371,40 @@ struct PinnedSamples {
   }
 };
 
+// A hotword automaton with its device copy (the recognizer's own, or one attached to a stream by
+// B200AsrCreateOfflineStreamWithHotwords)
+struct GraphPair {
+  ContextGraphHost host;
+  ContextGraphDev dev;
+  int device = 0;
+  bool on_device = false;
+  void upload(int dev_id);
+  ~GraphPair() {
+    if (!on_device) return;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
+    int *ptrs[] = {dev.edge_start, dev.edge_token, dev.edge_child, dev.fail, dev.token, dev.is_end, dev.output};
+    for (int *p : ptrs) if (p) cudaFree(p);
+    double *dp[] = {dev.token_score, dev.node_score, dev.output_score};
+    for (double *p : dp) if (p) cudaFree(p);
+  }
+};
+void GraphPair::upload(int dev_id) {
+  device = dev_id;
+  const int N = host.n_nodes();
+  if (N <= 1) return;
+  auto up_i = [&](const std::vector<int> &v) { int *d; CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(int)));
+    CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); return d; };
+  auto up_d = [&](const std::vector<double> &v) { double *d; CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(double)));
+    CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice)); return d; };
+  on_device = true;
+  dev.n_nodes = N;
+  dev.edge_start = up_i(host.edge_start); dev.edge_token = up_i(host.edge_token);
+  dev.edge_child = up_i(host.edge_child); dev.fail = up_i(host.fail); dev.token = up_i(host.token);
+  dev.is_end = up_i(host.is_end); dev.output = up_i(host.output);
+  dev.token_score = up_d(host.token_score); dev.node_score = up_d(host.node_score);
+  dev.output_score = up_d(host.output_score);
+}
+
 struct Engine {
   // config
   std::map<std::string, std::string> cfg;
@@ -367,15 +430,26 @@ struct Engine {
   cudaEvent_t ev_copy = nullptr;   // marks the accept-time uploads a pass has to wait for
   SearchState *search = nullptr;   // lane 0's (also used by the raw B200AsrBeamSearch entry point)
   Lane lanes[kMaxLanes];
+  // Spatial split of the SMs for pipelined passes (CUDA green contexts): `search_sms` SMs run the search lanes, the rest
+  // run the encoder of the following groups. A persistent encoder CTA holds its SM for a whole kernel, so on shared SMs the
+  // search's small kernels and the encoder's tiles delay each other; on disjoint SMs neither sees the other.
+  struct SmPartition {
+    CUgreenCtx g_search = nullptr, g_enc = nullptr;
+    int search_sms = 0, enc_sms = 0;
+    bool tried = false, ok = false;
+  } part;
+  cudaStream_t st_part = nullptr;     // encoder stream inside the encoder partition
+  cudaEvent_t ev_part = nullptr;
+  void ensure_partition();
   int n_groups_last = 1;
   float search_busy_ms = 0, lane_ms[kMaxLanes] = {0};
   std::vector<int> lane_of, idx_of;   // last pass: utterance -> (lane, index inside the lane's group)
   double kappa = 50.0;                // search ms per second of utterance length / encoder ms per audio-second (adapted per pass)
   long long d2h_bytes_last = 0;
   SearchModel sm{};
-  ContextGraphHost cg_host;
-  ContextGraphDev cg_dev;
-  bool has_graph = false;
+  std::shared_ptr<GraphPair> graph;          // the recognizer's hotword automaton (null = none)
+  const ContextGraphDev *pass_graph = nullptr;   // what the pass being issued scores with (decode sets it per partition)
+  const ContextGraphHost &cg_host() const { static const ContextGraphHost empty; return graph ? graph->host : empty; }
   std::mutex mu;
   Timings tm;
   long long launches_last = 0;
@@ -386,7 +460,7 @@ struct Engine {
   size_t gemm_ev_used = 0;
 
   // workspaces
-  DevBuf b_pcm, b_soff, b_foff, b_feats;
+  DevBuf b_pcm, b_soff, b_foff, b_feats, b_featin;
   DevBuf b_T, b_c0off, b_c1off, b_len[4], b_off[4], b_aoff;
   DevBuf b_c0, b_c1, b_c2, b_dw, b_pw1, b_cn, b_x0, b_xc, b_sin, b_w1, b_proj, b_hid, b_A, b_pe, b_pp, b_cat, b_enc;
   DevBuf b_stack[6];
@@ -442,10 +516,14 @@ struct Engine {
   void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
                  const AttnPlan &pl);
   void decode(Stream *const *ss, int n);
+  void decode_part(Stream *const *ss, int n);
+  void unpack_results(Stream *const *ss, int nb, const std::vector<int> &Tp);
+  const ContextGraphDev *default_graph() const { return (graph && graph->on_device) ? &graph->dev : nullptr; }
+  std::shared_ptr<GraphPair> make_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n);
   // h_soff[u] = first sample of utterance u relative to d_pcm, h_len[u] = its samples. Results stay in the lanes' search
   // states (lane_of / idx_of map utterances to them) until the next pass.
   void decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
-                         std::vector<int> *Tp);
+                         std::vector<int> *Tp, const float *d_featin = nullptr, const std::vector<long long> *h_foff = nullptr);
   struct UttResult { int n_tokens; const int *tokens, *frames; const float *tok_lp, *stats; };
   UttResult result_of(int u) const;
   void collect_gemm_times();
@@ -454,6 +532,13 @@ struct Engine {
 struct Stream {
   Engine *eng;
   PinnedSamples samples;
+  std::shared_ptr<GraphPair> graph;   // per-stream hotwords (null = the recognizer's)
+  // precomputed features in place of samples (B200AsrAcceptFeaturesOffline: ROVER's shared fbank, core/asr_engine.py:2346-2350)
+  std::vector<float> feats;
+  int feat_T = 0;
+  long long feat_samples = 0;
+  bool has_feats() const { return feat_T > 0; }
+  long long n_samples() const { return has_feats() ? feat_samples : (long long)samples.size(); }
   // result storage
   B200AsrOfflineRecognizerResult res{};
   std::string text, json;
@@ -481,10 +566,11 @@ Engine::~Engine() {
   if (ev_copy) cudaEventDestroy(ev_copy);
   for (auto &p : gemm_events) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &kv : staged) { cudaFree(kv.second.pcm); cudaFree(kv.second.soff); }
-  int *ptrs[] = {cg_dev.edge_start, cg_dev.edge_token, cg_dev.edge_child, cg_dev.fail, cg_dev.token, cg_dev.is_end, cg_dev.output};
-  for (int *p : ptrs) if (p) cudaFree(p);
-  double *dp[] = {cg_dev.token_score, cg_dev.node_score, cg_dev.output_score};
-  for (double *p : dp) if (p) cudaFree(p);
+  graph.reset();
+  if (st_part) cudaStreamDestroy(st_part);
+  if (ev_part) cudaEventDestroy(ev_part);
+  if (part.g_search) green_api().GreenCtxDestroy(part.g_search);
+  if (part.g_enc) green_api().GreenCtxDestroy(part.g_enc);
   if (st) cudaStreamDestroy(st);
 }
 
@@ -784,32 +870,19 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-void Engine::set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n) {
-  int *ptrs[] = {cg_dev.edge_start, cg_dev.edge_token, cg_dev.edge_child, cg_dev.fail, cg_dev.token, cg_dev.is_end, cg_dev.output};
-  for (int *p : ptrs) if (p) cudaFree(p);
-  double *dp[] = {cg_dev.token_score, cg_dev.node_score, cg_dev.output_score};
-  for (double *p : dp) if (p) cudaFree(p);
-  cg_dev = ContextGraphDev{};
-  has_graph = false;
-  cg_host = ContextGraphHost{};
-  if (n <= 0) return;
+std::shared_ptr<GraphPair> Engine::make_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n) {
+  if (n <= 0) return nullptr;
   for (int p = 0; p < n; ++p)
     for (int j = offsets[p]; j < offsets[p + 1]; ++j)
       if (tokens[j] < 0 || tokens[j] >= V) throw std::runtime_error("hotword token id out of range");
-  cg_host.build(tokens, offsets, scores, n);
-  const int N = cg_host.n_nodes();
-  if (N <= 1) return;
-  auto up_i = [&](const std::vector<int> &v) { int *d; CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(int)));
-    CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice)); return d; };
-  auto up_d = [&](const std::vector<double> &v) { double *d; CUDA_CHECK(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(double)));
-    CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice)); return d; };
-  cg_dev.n_nodes = N;
-  cg_dev.edge_start = up_i(cg_host.edge_start); cg_dev.edge_token = up_i(cg_host.edge_token);
-  cg_dev.edge_child = up_i(cg_host.edge_child); cg_dev.fail = up_i(cg_host.fail); cg_dev.token = up_i(cg_host.token);
-  cg_dev.is_end = up_i(cg_host.is_end); cg_dev.output = up_i(cg_host.output);
-  cg_dev.token_score = up_d(cg_host.token_score); cg_dev.node_score = up_d(cg_host.node_score);
-  cg_dev.output_score = up_d(cg_host.output_score);
-  has_graph = true;
+  auto g = std::make_shared<GraphPair>();
+  g->host.build(tokens, offsets, scores, n);
+  g->upload(device);
+  return g;
+}
+
+void Engine::set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n) {
+  graph = make_graph(tokens, offsets, scores, n);
 }
 
 void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, const float *R, int ldr, float *C, int ldc, int M,
@@ -1144,12 +1217,50 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, DevBuf
 }
 
 // ------------------------------------------------------------------ full pipeline on device-resident PCM
+void Engine::ensure_partition() {
+  if (part.tried) return;
+  part.tried = true;
+  const GreenApi &ga = green_api();
+  if (!ga.ok) return;
+  static const int want = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
+  static const bool no_green = getenv("B200ASR_NO_GREEN_CTX") != nullptr;
+  if (no_green || want <= 0) return;
+  CUdevice dev;
+  CUdevResource sm{}, grp[1]{}, rem{};
+  unsigned int n = 1;
+  CUdevResourceDesc d_search = nullptr, d_enc = nullptr;
+  auto ok = [](CUresult r) { return r == CUDA_SUCCESS; };
+  if (!ok(ga.DeviceGet(&dev, device)) || !ok(ga.DeviceGetDevResource(dev, &sm, CU_DEV_RESOURCE_TYPE_SM))) return;
+  if (!ok(ga.DevSmResourceSplitByCount(grp, &n, &sm, &rem, 0, (unsigned)want)) || n < 1 || rem.sm.smCount < 64) return;
+  if (!ok(ga.DevResourceGenerateDesc(&d_search, &grp[0], 1)) || !ok(ga.DevResourceGenerateDesc(&d_enc, &rem, 1))) return;
+  if (!ok(ga.GreenCtxCreate(&part.g_search, d_search, dev, CU_GREEN_CTX_DEFAULT_STREAM))) return;
+  if (!ok(ga.GreenCtxCreate(&part.g_enc, d_enc, dev, CU_GREEN_CTX_DEFAULT_STREAM))) { ga.GreenCtxDestroy(part.g_search); part.g_search = nullptr; return; }
+  CUstream s = nullptr;
+  if (!ok(ga.GreenCtxStreamCreate(&s, part.g_enc, CU_STREAM_NON_BLOCKING, 0))) {
+    ga.GreenCtxDestroy(part.g_search); ga.GreenCtxDestroy(part.g_enc);
+    part.g_search = part.g_enc = nullptr;
+    return;
+  }
+  st_part = reinterpret_cast<cudaStream_t>(s);
+  CUDA_CHECK(cudaEventCreateWithFlags(&ev_part, cudaEventDisableTiming));
+  part.search_sms = (int)grp[0].sm.smCount;
+  part.enc_sms = (int)rem.sm.smCount;
+  part.ok = true;
+  if (getenv("B200ASR_DEBUG"))
+    fprintf(stderr, "[b200asr] SM partition: %d SMs for the search lanes, %d for the encoder\n", part.search_sms, part.enc_sms);
+}
+
 Lane &Engine::lane(int i) {
   Lane &l = lanes[i];
   if (!l.st) {
+    ensure_partition();
     int lo = 0, hi = 0;
     CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = greatest priority
-    CUDA_CHECK(cudaStreamCreateWithPriority(&l.st, cudaStreamNonBlocking, hi));
+    CUstream gs = nullptr;
+    if (part.ok && green_api().GreenCtxStreamCreate(&gs, part.g_search, CU_STREAM_NON_BLOCKING, hi) == CUDA_SUCCESS)
+      l.st = reinterpret_cast<cudaStream_t>(gs);
+    else
+      CUDA_CHECK(cudaStreamCreateWithPriority(&l.st, cudaStreamNonBlocking, hi));
     cudaEvent_t *evs[] = {&l.f0, &l.f1, &l.e1, &l.s0, &l.s1};
     for (cudaEvent_t *e : evs) CUDA_CHECK(cudaEventCreate(e));
     if (i == 0) l.search = search;
@@ -1240,14 +1351,20 @@ Engine::UttResult Engine::result_of(int u) const {
   return UttResult{v.n_tokens[i], v.tokens + o, v.frames + o, v.tok_lp + o, v.stats + 4 * o};
 }
 
+// With d_featin the pass starts from precomputed features instead of PCM: utterance u has (h_len[u] + 80) / 160 frames at
+// row h_foff[u] of d_featin (h_len stays the sample count the features were computed from).
 void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
-                               std::vector<int> *Tp) {
+                               std::vector<int> *Tp, const float *d_featin, const std::vector<long long> *h_foff) {
   gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
   const std::vector<std::vector<int>> groups = plan_groups(h_len);
   const int G = (int)groups.size();
-  static const int reserve = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
+  static const int reserve_env = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
+  static const bool no_overlap = getenv("B200ASR_PIPE_NOOVERLAP") != nullptr;   // diagnostic: searches start after the last encoder
+  if (G > 1) ensure_partition();
+  const int reserve = part.ok ? part.search_sms : reserve_env;
+  cudaStream_t const st_main = st;
   const int method = decoding_method == "greedy_search" ? 0 : 1;
   Tp->assign(n, 0);
   lane_of.assign(n, 0); idx_of.assign(n, 0);
@@ -1265,13 +1382,34 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
       off_len[ng + 1 + i] = glen[i] = h_len[mem[i]];
       lane_of[mem[i]] = g; idx_of[mem[i]] = i;
     }
-    long long *d_sl = l.soff.get<long long>(off_len.size());
-    CUDA_CHECK(cudaMemcpyAsync(d_sl, keep(std::move(off_len)), (2 * (size_t)ng + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
-    set_sm_reserve(g > 0 ? reserve : 0);   // from the second group on a search runs beside the encoder
+    // From the second group on a search runs beside the encoder: the encoder moves to its SM partition (or, without green
+    // contexts, leaves `reserve` SMs out of its persistent grids). Same workspaces, so the streams are chained by events.
+    if (g > 0 && part.ok && st == st_main) {
+      CUDA_CHECK(cudaEventRecord(ev_part, st_main));
+      CUDA_CHECK(cudaStreamWaitEvent(st_part, ev_part, 0));
+      st = st_part;
+    }
+    set_sm_reserve(g > 0 ? reserve : 0);
     CUDA_CHECK(cudaEventRecord(l.f0, st));
     float *d_feats = nullptr, *d_enc = nullptr;
     std::vector<int> T;
-    run_fbank(d_pcm, d_sl, d_sl + ng + 1, glen, ng, &d_feats, &T);
+    if (d_featin) {
+      T.resize(ng);
+      long long rows = 0;
+      for (int i = 0; i < ng; ++i) { T[i] = (int)((glen[i] + 80) / 160); rows += T[i]; }
+      d_feats = b_feats.get<float>((size_t)std::max<long long>(rows, 1) * 80);
+      long long at = 0;
+      for (int i = 0; i < ng; ++i) {
+        if (T[i] > 0)
+          CUDA_CHECK(cudaMemcpyAsync(d_feats + at * 80, d_featin + (*h_foff)[mem[i]] * 80, (size_t)T[i] * 80 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, st));
+        at += T[i];
+      }
+    } else {
+      long long *d_sl = l.soff.get<long long>(off_len.size());
+      CUDA_CHECK(cudaMemcpyAsync(d_sl, keep(std::move(off_len)), (2 * (size_t)ng + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+      run_fbank(d_pcm, d_sl, d_sl + ng + 1, glen, ng, &d_feats, &T);
+    }
     CUDA_CHECK(cudaEventRecord(l.f1, st));
     run_encoder(d_feats, T, l.enc, &d_enc, &l.Tp);
     CUDA_CHECK(cudaEventRecord(l.e1, st));
@@ -1281,18 +1419,24 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
   auto issue_search = [&](int g) {
     Lane &l = lane(g);
     cudaStream_t ss = G == 1 ? st : l.st;
-    if (G > 1) CUDA_CHECK(cudaStreamWaitEvent(ss, l.e1, 0));
+    if (G > 1) CUDA_CHECK(cudaStreamWaitEvent(ss, no_overlap ? lanes[G - 1].e1 : l.e1, 0));
     CUDA_CHECK(cudaEventRecord(l.s0, ss));
     l.steps = 0;
     for (int v : l.Tp) l.steps = std::max(l.steps, v);
-    search_issue(l.search, sm, has_graph ? &cg_dev : nullptr, l.enc.ptr<float>(), l.Tp.data(), (int)l.members.size(), method,
+    search_issue(l.search, sm, pass_graph, l.enc.ptr<float>(), l.Tp.data(), (int)l.members.size(), method,
                  max_active_paths, blank_penalty, ss);
     CUDA_CHECK(cudaEventRecord(l.s1, ss));
   };
   issue_encoder(0);
+  if (no_overlap) for (int g = 1; g < G; ++g) issue_encoder(g);
   for (int g = 0; g < G; ++g) {
-    if (g + 1 < G) issue_encoder(g + 1);
+    if (g + 1 < G && !no_overlap) issue_encoder(g + 1);
     issue_search(g);
+  }
+  if (st != st_main) {   // back to the main stream, after the partition's last encoder
+    CUDA_CHECK(cudaEventRecord(ev_part, st));
+    st = st_main;
+    CUDA_CHECK(cudaStreamWaitEvent(st, ev_part, 0));
   }
   if (G > 1)   // the pass ends (ev[3] on the main stream) after every search
     for (int g = 0; g < G; ++g) CUDA_CHECK(cudaStreamWaitEvent(st, lanes[g].s1, 0));
@@ -1321,7 +1465,8 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
     for (long long v : h_len) audio += (double)v / 16000.0;
     if (n >= 16 && audio > 100.0 && tm.encoder > 0.f && steps_len > 0 && !profiling) {
       const double k_now = (steps_ms / steps_len) / ((double)(tm.fbank + tm.encoder) / audio);
-      if (k_now > 1.0 && k_now < 1000.0) kappa = 0.5 * kappa + 0.5 * k_now;
+      // hysteresis: a new plan means new workspace sizes (reallocation stalls), so only a clear change moves it
+      if (k_now > 1.0 && k_now < 1000.0 && (k_now > 1.3 * kappa || k_now < 0.7 * kappa)) kappa = k_now;
     }
   }
   launches_last = g_launches - l0;
@@ -1357,26 +1502,116 @@ static void build_json(Stream *s) {
   s->json_built = true;
 }
 
+void Engine::unpack_results(Stream *const *ss, int nb, const std::vector<int> &Tp) {
+  for (int i = 0; i < nb; ++i) {
+      Stream *s = ss[i];
+      const UttResult r = result_of(i);
+      const int cnt = std::max(0, std::min(r.n_tokens, Tp[i]));
+      const float dur = (float)s->n_samples() / 16000.0f;
+      s->token_ids.assign(r.tokens, r.tokens + cnt);
+      s->frames.assign(r.frames, r.frames + cnt);
+      s->lps.assign(r.tok_lp, r.tok_lp + cnt);
+      s->timestamps.resize(cnt); s->tsallis.resize(cnt); s->margin.resize(cnt); s->entropy.resize(cnt); s->top1.resize(cnt);
+      s->tok_str.resize(cnt); s->tok_ptr.resize(cnt);
+      s->text.clear();
+      for (int j = 0; j < cnt; ++j) {
+        s->timestamps[j] = Tp[i] > 0 ? (float)((double)s->frames[j] / (double)Tp[i] * (double)dur) : 0.f;
+        s->tsallis[j] = r.stats[j * 4]; s->margin[j] = r.stats[j * 4 + 1]; s->entropy[j] = r.stats[j * 4 + 2]; s->top1[j] = r.stats[j * 4 + 3];
+        const int id = s->token_ids[j];
+        s->tok_str[j] = (id >= 0 && id < V) ? id2token[id] : "";
+        s->text += s->tok_str[j];
+      }
+      for (int j = 0; j < cnt; ++j) s->tok_ptr[j] = s->tok_str[j].c_str();
+      // U+2581 -> space, strip
+      std::string txt;
+      for (size_t p = 0; p < s->text.size();) {
+        if (p + 2 < s->text.size() + 0 && (unsigned char)s->text[p] == 0xE2 && (unsigned char)s->text[p + 1] == 0x96 &&
+            (unsigned char)s->text[p + 2] == 0x81) { txt += ' '; p += 3; }
+        else txt += s->text[p++];
+      }
+      size_t a = txt.find_first_not_of(' '), b = txt.find_last_not_of(' ');
+      s->text = (a == std::string::npos) ? "" : txt.substr(a, b - a + 1);
+      s->json.clear();
+      s->json_built = false;   // built on first request of the result (B200AsrGetOfflineStreamResult / ...AsJson)
+      s->res.text = s->text.c_str(); s->res.json = nullptr; s->res.tokens = s->tok_ptr.data();
+      s->res.token_ids = s->token_ids.data(); s->res.timestamps = s->timestamps.data(); s->res.frames = s->frames.data();
+      s->res.ys_log_probs = s->lps.data(); s->res.tsallis = s->tsallis.data(); s->res.margin = s->margin.data();
+      s->res.entropy = s->entropy.data(); s->res.top1 = s->top1.data(); s->res.count = cnt; s->res.num_frames = Tp[i];
+      s->res.duration = dur;
+      s->decoded = true;
+    }
+}
+
+// Streams that carry their own hotwords (B200AsrCreateOfflineStreamWithHotwords) are decoded in one pass per distinct
+// automaton; all others share the recognizer's.
 void Engine::decode(Stream *const *ss, int n) {
   if (n <= 0) return;
   std::lock_guard<std::mutex> lk(mu);
   CUDA_CHECK(cudaSetDevice(device));
+  bool mixed = false;
+  for (int i = 0; i < n && !mixed; ++i) mixed = ss[i]->graph != nullptr || ss[i]->has_feats() != ss[0]->has_feats();
+  if (!mixed) {
+    pass_graph = default_graph();
+    decode_part(ss, n);
+    return;
+  }
+  std::vector<const GraphPair *> keys;
+  std::vector<bool> kfeat;
+  std::vector<std::vector<Stream *>> parts;
+  for (int i = 0; i < n; ++i) {
+    const GraphPair *k = ss[i]->graph.get();
+    const bool f = ss[i]->has_feats();
+    size_t j = 0;
+    while (j < keys.size() && !(keys[j] == k && kfeat[j] == f)) ++j;
+    if (j == keys.size()) { keys.push_back(k); kfeat.push_back(f); parts.emplace_back(); }
+    parts[j].push_back(ss[i]);
+  }
+  for (size_t j = 0; j < parts.size(); ++j) {
+    pass_graph = keys[j] ? (keys[j]->on_device ? &keys[j]->dev : nullptr) : default_graph();
+    decode_part(parts[j].data(), (int)parts[j].size());
+  }
+  pass_graph = default_graph();
+}
+
+void Engine::decode_part(Stream *const *ss, int n) {
   // sub-batches bounded by total audio so workspaces stay bounded (about 70 min of audio per pass)
   const long long kMaxSamples = 4200LL * 16000;
   int begin = 0;
   while (begin < n) {
     int end = begin;
     long long tot = 0;
-    while (end < n && (end == begin || tot + (long long)ss[end]->samples.size() <= kMaxSamples)) {
-      tot += (long long)ss[end]->samples.size();
+    while (end < n && (end == begin || tot + ss[end]->n_samples() <= kMaxSamples)) {
+      tot += ss[end]->n_samples();
       ++end;
     }
     const int nb = end - begin;
     const auto hp0 = std::chrono::steady_clock::now();
     std::vector<long long> soff(nb + 1, 0), slen(nb, 0);
+    const bool from_feats = ss[begin]->has_feats();    // a part is homogeneous (decode() partitions)
     for (int i = 0; i < nb; ++i) {
-      slen[i] = (long long)ss[begin + i]->samples.size();
+      slen[i] = ss[begin + i]->n_samples();
       soff[i + 1] = soff[i] + slen[i];
+    }
+    if (from_feats) {
+      std::vector<long long> foff(nb + 1, 0);
+      for (int i = 0; i < nb; ++i) {
+        Stream *s = ss[begin + i];
+        if ((slen[i] + 80) / 160 != s->feat_T) throw std::runtime_error("stream features do not match their sample count");
+        foff[i + 1] = foff[i] + s->feat_T;
+      }
+      float *d_in = b_featin.get<float>((size_t)std::max<long long>(foff[nb], 1) * 80);
+      CUDA_CHECK(cudaEventRecord(ev[4], st));
+      for (int i = 0; i < nb; ++i)
+        CUDA_CHECK(cudaMemcpyAsync(d_in + foff[i] * 80, ss[begin + i]->feats.data(), (size_t)ss[begin + i]->feat_T * 80 * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaEventRecord(ev[5], st));
+      std::vector<int> Tp;
+      soff.resize(nb);
+      decode_pcm_device(nullptr, soff, slen, nb, &Tp, d_in, &foff);
+      cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
+      unpack_results(ss + begin, nb, Tp);
+      begin = end;
+      continue;
     }
     // Streams whose PCM accept_waveform has already sent to this device are read where they sit (offsets relative to
     // the staging buffer's base, lengths explicit); only if some stream has no device copy is the whole batch packed
@@ -1410,43 +1645,7 @@ void Engine::decode(Stream *const *ss, int n) {
     decode_pcm_device(d_pcm, soff, slen, nb, &Tp);
     const auto hp2 = std::chrono::steady_clock::now();
     cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
-    for (int i = 0; i < nb; ++i) {
-      Stream *s = ss[begin + i];
-      const UttResult r = result_of(i);
-      const int cnt = std::max(0, std::min(r.n_tokens, Tp[i]));
-      const float dur = (float)s->samples.size() / 16000.0f;
-      s->token_ids.assign(r.tokens, r.tokens + cnt);
-      s->frames.assign(r.frames, r.frames + cnt);
-      s->lps.assign(r.tok_lp, r.tok_lp + cnt);
-      s->timestamps.resize(cnt); s->tsallis.resize(cnt); s->margin.resize(cnt); s->entropy.resize(cnt); s->top1.resize(cnt);
-      s->tok_str.resize(cnt); s->tok_ptr.resize(cnt);
-      s->text.clear();
-      for (int j = 0; j < cnt; ++j) {
-        s->timestamps[j] = Tp[i] > 0 ? (float)((double)s->frames[j] / (double)Tp[i] * (double)dur) : 0.f;
-        s->tsallis[j] = r.stats[j * 4]; s->margin[j] = r.stats[j * 4 + 1]; s->entropy[j] = r.stats[j * 4 + 2]; s->top1[j] = r.stats[j * 4 + 3];
-        const int id = s->token_ids[j];
-        s->tok_str[j] = (id >= 0 && id < V) ? id2token[id] : "";
-        s->text += s->tok_str[j];
-      }
-      for (int j = 0; j < cnt; ++j) s->tok_ptr[j] = s->tok_str[j].c_str();
-      // U+2581 -> space, strip
-      std::string txt;
-      for (size_t p = 0; p < s->text.size();) {
-        if (p + 2 < s->text.size() + 0 && (unsigned char)s->text[p] == 0xE2 && (unsigned char)s->text[p + 1] == 0x96 &&
-            (unsigned char)s->text[p + 2] == 0x81) { txt += ' '; p += 3; }
-        else txt += s->text[p++];
-      }
-      size_t a = txt.find_first_not_of(' '), b = txt.find_last_not_of(' ');
-      s->text = (a == std::string::npos) ? "" : txt.substr(a, b - a + 1);
-      s->json.clear();
-      s->json_built = false;   // built on first request of the result (B200AsrGetOfflineStreamResult / ...AsJson)
-      s->res.text = s->text.c_str(); s->res.json = nullptr; s->res.tokens = s->tok_ptr.data();
-      s->res.token_ids = s->token_ids.data(); s->res.timestamps = s->timestamps.data(); s->res.frames = s->frames.data();
-      s->res.ys_log_probs = s->lps.data(); s->res.tsallis = s->tsallis.data(); s->res.margin = s->margin.data();
-      s->res.entropy = s->entropy.data(); s->res.top1 = s->top1.data(); s->res.count = cnt; s->res.num_frames = Tp[i];
-      s->res.duration = dur;
-      s->decoded = true;
-    }
+    unpack_results(ss + begin, nb, Tp);
     {
       const auto hp3 = std::chrono::steady_clock::now();
       auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -1522,7 +1721,7 @@ int32_t B200AsrOfflineRecognizerSetConfig(const B200AsrOfflineRecognizer *r, con
     e->max_active_paths = c->max_active_paths;
   }
   if (c->hotwords_score > 0) e->hotwords_score = c->hotwords_score;
-  e->blank_penalty = c->blank_penalty;
+  if (c->blank_penalty == c->blank_penalty) e->blank_penalty = c->blank_penalty;   // NaN = leave unchanged
   return 0;
   API_CATCH(-1)
 }
@@ -1547,13 +1746,79 @@ const B200AsrOfflineStream *B200AsrCreateOfflineStream(const B200AsrOfflineRecog
 }
 void B200AsrDestroyOfflineStream(const B200AsrOfflineStream *s) { delete const_cast<B200AsrOfflineStream *>(s); }
 
-void B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n) {
-  if (!s || !samples || n <= 0) return;
+int32_t B200AsrAcceptWaveformOffline(const B200AsrOfflineStream *s, int32_t sample_rate, const float *samples, int32_t n) {
+  if (!s) { g_last_error = "accept_waveform: null stream"; return -1; }
+  if (n < 0 || (n > 0 && !samples)) { g_last_error = "accept_waveform: null samples"; return -1; }
+  if (sample_rate != 16000) { g_last_error = "accept_waveform: only 16000 Hz is supported (no resampler on the path)"; return -1; }
+  if (n == 0) return 0;
   auto *ms = const_cast<B200AsrOfflineStream *>(s);
-  if (sample_rate != 16000) { g_last_error = "accept_waveform: only 16000 Hz is supported (no resampler on the path)"; return; }
-  try { ms->s.samples.append(samples, (size_t)n); } catch (const std::exception &e) { g_last_error = e.what(); return; }
+  if (ms->s.has_feats()) { g_last_error = "accept_waveform: the stream already holds precomputed features"; return -1; }
+  try { ms->s.samples.append(samples, (size_t)n); } catch (const std::exception &e) { g_last_error = e.what(); return -1; }
   ms->s.samples.upload(ms->s.eng->device);
   ms->s.decoded = false;
+  return 0;
+}
+
+int32_t B200AsrAcceptFeaturesOffline(const B200AsrOfflineStream *s, const float *feats, int32_t num_frames, int32_t feature_dim,
+                                     int64_t num_samples) {
+  if (!s || !feats || num_frames < 0) { g_last_error = "accept_features: null argument"; return -1; }
+  if (feature_dim != 80) { g_last_error = "accept_features: only 80-bin fbank is supported (core/asr_engine.py:710)"; return -1; }
+  if ((num_samples + 80) / 160 != num_frames) { g_last_error = "accept_features: num_frames must be (num_samples + 80) / 160"; return -1; }
+  auto *ms = const_cast<B200AsrOfflineStream *>(s);
+  if (!ms->s.samples.empty()) { g_last_error = "accept_features: the stream already holds samples"; return -1; }
+  try { ms->s.feats.assign(feats, feats + (size_t)num_frames * 80); } catch (const std::exception &e) { g_last_error = e.what(); return -1; }
+  ms->s.feat_T = num_frames;
+  ms->s.feat_samples = num_samples;
+  ms->s.decoded = false;
+  return 0;
+}
+
+int32_t B200AsrAcceptWaveformsOffline(const B200AsrOfflineStream *const *ss, int32_t sample_rate, const float *const *samples,
+                                      const int32_t *ns, int32_t n) {
+  if (n < 0 || (n > 0 && (!ss || !samples || !ns))) { g_last_error = "accept_waveforms: null argument"; return -1; }
+  for (int i = 0; i < n; ++i)
+    if (B200AsrAcceptWaveformOffline(ss[i], sample_rate, samples[i], ns[i]) != 0) return -1;
+  return 0;
+}
+
+// hotwords: phrases separated by '/', each a list of space-separated token ids with an optional " :score"
+const B200AsrOfflineStream *B200AsrCreateOfflineStreamWithHotwords(const B200AsrOfflineRecognizer *r, const char *hotwords) {
+  B200AsrOfflineStream *s = nullptr;
+  try {
+    Engine *e = E(r);
+    s = new B200AsrOfflineStream();
+    s->s.eng = e;
+    const std::string hw = hotwords ? hotwords : "";
+    std::vector<int32_t> toks, offs{0};
+    std::vector<float> scs;
+    std::stringstream all(hw);
+    std::string phrase;
+    while (std::getline(all, phrase, '/')) {
+      float sc = e->hotwords_score;
+      const size_t colon = phrase.rfind(':');
+      if (colon != std::string::npos) { sc = (float)atof(phrase.c_str() + colon + 1); phrase = phrase.substr(0, colon); }
+      std::stringstream ps(phrase);
+      std::string tok;
+      int cnt = 0;
+      while (ps >> tok) {
+        char *end = nullptr;
+        const long id = strtol(tok.c_str(), &end, 10);
+        if (end == tok.c_str() || *end != 0)
+          throw std::runtime_error("stream hotwords must be token ids (\"12 34/56 78 :2.0\"); text phrases are tokenised by the host binding");
+        toks.push_back((int32_t)id);
+        ++cnt;
+      }
+      if (cnt == 0) continue;
+      offs.push_back((int32_t)toks.size());
+      scs.push_back(sc);
+    }
+    if (!scs.empty()) {
+      std::lock_guard<std::mutex> lk(e->mu);
+      CUDA_CHECK(cudaSetDevice(e->device));
+      s->s.graph = e->make_graph(toks.data(), offs.data(), scs.data(), (int)scs.size());
+    }
+    return s;
+  } catch (const std::exception &e) { g_last_error = e.what(); delete s; return nullptr; }
 }
 
 int32_t B200AsrDecodeMultipleOfflineStreams(const B200AsrOfflineRecognizer *r, const B200AsrOfflineStream *const *ss, int32_t n) {
@@ -1765,7 +2030,7 @@ int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const float *enc_ou
   res.n_utts = n; res.max_tokens = max_tokens; res.n_tokens = n_tokens; res.tokens = tokens; res.frames = frames;
   res.tok_lp = tok_logprobs; res.stats = stats;
   std::vector<int> l(lens, lens + n);
-  run_search(e->search, e->sm, e->has_graph ? &e->cg_dev : nullptr, d_enc, l.data(), n, method, beam, e->blank_penalty, &res, e->st);
+  run_search(e->search, e->sm, e->default_graph(), d_enc, l.data(), n, method, beam, e->blank_penalty, &res, e->st);
   return 0;
   API_CATCH(-1)
 }
@@ -1811,17 +2076,17 @@ int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const flo
 }
 
 double B200AsrContextForwardOneStep(const B200AsrOfflineRecognizer *r, int32_t state, int32_t token, int32_t *next_state) {
-  if (!r || r->eng.cg_host.n_nodes() == 0 || state < 0 || state >= r->eng.cg_host.n_nodes()) { if (next_state) *next_state = 0; return 0.0; }
+  if (!r || r->eng.cg_host().n_nodes() == 0 || state < 0 || state >= r->eng.cg_host().n_nodes()) { if (next_state) *next_state = 0; return 0.0; }
   int nxt = 0;
-  const double d = cg_forward_one_step(r->eng.cg_host.view(), state, token, &nxt);
+  const double d = cg_forward_one_step(r->eng.cg_host().view(), state, token, &nxt);
   if (next_state) *next_state = nxt;
   return d;
 }
 double B200AsrContextFinalize(const B200AsrOfflineRecognizer *r, int32_t state) {
-  if (!r || r->eng.cg_host.n_nodes() == 0 || state < 0 || state >= r->eng.cg_host.n_nodes()) return 0.0;
-  return cg_finalize(r->eng.cg_host.view(), state);
+  if (!r || r->eng.cg_host().n_nodes() == 0 || state < 0 || state >= r->eng.cg_host().n_nodes()) return 0.0;
+  return cg_finalize(r->eng.cg_host().view(), state);
 }
-int32_t B200AsrContextNumNodes(const B200AsrOfflineRecognizer *r) { return r ? r->eng.cg_host.n_nodes() : 0; }
+int32_t B200AsrContextNumNodes(const B200AsrOfflineRecognizer *r) { return r ? r->eng.cg_host().n_nodes() : 0; }
 
 // ---- device-resident benchmarking hooks
 int32_t B200AsrStageBatch(const B200AsrOfflineRecognizer *r, const float *samples, const int64_t *sample_offsets, int32_t n) {
@@ -1854,6 +2119,7 @@ int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle,
   std::vector<int> Tp;
   std::vector<long long> slen(sgd.n), soff(sgd.h_soff.begin(), sgd.h_soff.begin() + sgd.n);
   for (int i = 0; i < sgd.n; ++i) slen[i] = sgd.h_soff[i + 1] - sgd.h_soff[i];
+  e->pass_graph = e->default_graph();
   e->decode_pcm_device(sgd.pcm, soff, slen, sgd.n, &Tp);
   if (n_tokens) for (int i = 0; i < sgd.n; ++i) n_tokens[i] = e->result_of(i).n_tokens;
   return 0;

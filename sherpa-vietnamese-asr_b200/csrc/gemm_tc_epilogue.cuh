@@ -28,6 +28,8 @@ struct TcParams {
   int M, N, K, act;
   float *partials;   // joiner epilogue (EPI > 0)
   unsigned long long *trace;
+  float acc_scale;   // the accumulator is multiplied by this (a power of two) before the epilogue; 0 or 1 = none. The all-fp16
+                     // operand split pre-scales both operands so their low parts stay in fp16's normal range.
 };
 
 // step-trace slot (joiner GEMM of the search only): %globaltimer of CTA 0
@@ -66,6 +68,10 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
       if (n0 + c0 >= p.N) continue;                      // warp-uniform
+      if (p.acc_scale != 0.f && p.acc_scale != 1.0f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * p.acc_scale);
+      }
       const int mrow0 = m0 + q * 32;
       if constexpr (EPI > 0) {
         const int nbase = n0 + c0;

@@ -45,6 +45,9 @@ namespace {
 constexpr int FBK = 64;          // K elements per stage
 constexpr int UMMA_K16 = 16;     // kind::f16: 32 bytes per instruction
 constexpr int kF16Threads = 448;
+// all-fp16 variant (16): x' = x * kAScale, w' = w * kWScale before the split, accumulator * 1 / (kAScale * kWScale) after. With
+// lo = fp16(x' - fp16(x')) the pair carries x' to 2^-22 while lo is a normal fp16 (|x'| >= 0.25) and to 2^-25 absolute below.
+constexpr float kAScale = 64.0f, kWScale = 1024.0f;
 
 __host__ __device__ constexpr int f16_stages(int BN) { return BN == 64 ? 4 : 3; }
 
@@ -71,6 +74,15 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uin
   const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
   const float2 hf = __half22float2(h);
   const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// all-fp16 variant: both halves fp16
+__device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
@@ -199,20 +211,18 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 v = lds128(rowp + ((c ^ (row & 7)) << 4));
-            split_pair(v.x, v.y, hi[b * 16 + 2 * c], lo[b * 16 + 2 * c]);
-            split_pair(v.z, v.w, hi[b * 16 + 2 * c + 1], lo[b * 16 + 2 * c + 1]);
+            if (variant & 16) {
+              split_pair_f16(v.x * kAScale, v.y * kAScale, hi[b * 16 + 2 * c], lo[b * 16 + 2 * c]);
+              split_pair_f16(v.z * kAScale, v.w * kAScale, hi[b * 16 + 2 * c + 1], lo[b * 16 + 2 * c + 1]);
+            } else {
+              split_pair(v.x, v.y, hi[b * 16 + 2 * c], lo[b * 16 + 2 * c]);
+              split_pair(v.z, v.w, hi[b * 16 + 2 * c + 1], lo[b * 16 + 2 * c + 1]);
+            }
           }
         }
-        if (variant & 24) {
+        if (variant & 8) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (variant & 16) {   // lo as fp16: re-round the bf16 pair (bring-up only; bf16 -> fp16 of a 2^-11-scale value is exact enough to tell)
-              const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162 *>(&lo[j]);
-              const __half2 h = __floats2half2_rn(__low2float(l), __high2float(l));
-              lo[j] = *reinterpret_cast<const uint32_t *>(&h);
-            }
-            if (variant & 8) { hi[j] = (hi[j] >> 16) | (hi[j] << 16); lo[j] = (lo[j] >> 16) | (lo[j] << 16); }
-          }
+          for (int j = 0; j < 32; ++j) { hi[j] = (hi[j] >> 16) | (hi[j] << 16); lo[j] = (lo[j] >> 16) | (lo[j] << 16); }
         }
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemACol + (uint32_t)(s * 64);
         tmem_st_32x32(ta, hi);
@@ -242,7 +252,7 @@ __global__ void split_w16_kernel(const float *__restrict__ w, __half *__restrict
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * ld) return;
   const int n = (int)(i / ld), k = (int)(i % ld);
-  const float x = k < K ? w[(long long)n * K + k] : 0.f;
+  const float x = (k < K ? w[(long long)n * K + k] : 0.f) * (lo_f16 ? kWScale : 1.0f);
   const __half h = __float2half_rn(clamp_f16(x));
   hi[i] = h;
   if (lo_f16) reinterpret_cast<__half *>(lo)[i] = __float2half_rn(x - __half2float(h));   // bring-up variant 16
@@ -304,13 +314,13 @@ bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
   }
   int BN = g.N > 64 ? 128 : 64;
   if (joiner && (long long)((g.M + TBM - 1) / TBM) * ((g.N + 63) / 64) <= n_sms) BN = 64;
-  const int variant = getenv("B200ASR_F16_VARIANT") ? atoi(getenv("B200ASR_F16_VARIANT")) : 0;
+  const int variant = getenv("B200ASR_F16_VARIANT") ? atoi(getenv("B200ASR_F16_VARIANT")) : 16;
   const W16 w = w16_for(g.W, g.N, g.K, st, (variant & 16) != 0);
   CUtensorMap ma, mwh, mwl;
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_16(&mwh, w.hi, false, g.N, w.ld, w.ld, BN);
   make_map_16(&mwl, w.lo, true, g.N, w.ld, w.ld, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace};
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, (variant & 16) ? 1.0f / (kAScale * kWScale) : 1.0f};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
 #define B200_F16_LAUNCH(BN_, EPI_)                                                                                        \

@@ -60,9 +60,12 @@ def result_from_struct(r: "_capi.Result") -> OfflineRecognitionResult:
 
 
 class OfflineStream:
-    def __init__(self, recognizer: "OfflineRecognizer"):
+    def __init__(self, recognizer: "OfflineRecognizer", hotword_ids: Optional[str] = None):
         self._rec = recognizer
-        self._h = _capi.lib().B200AsrCreateOfflineStream(recognizer._h)
+        if hotword_ids:
+            self._h = _capi.lib().B200AsrCreateOfflineStreamWithHotwords(recognizer._h, hotword_ids.encode())
+        else:
+            self._h = _capi.lib().B200AsrCreateOfflineStream(recognizer._h)
         if not self._h:
             raise RuntimeError(_capi.last_error())
         self._result: Optional[OfflineRecognitionResult] = None
@@ -72,7 +75,17 @@ class OfflineStream:
         w = np.ascontiguousarray(waveform, dtype=np.float32).reshape(-1)
         if int(sample_rate) != 16000:
             raise ValueError("only 16000 Hz input is supported (the reference resamples upstream, core/asr_engine.py:467-518)")
-        _capi.lib().B200AsrAcceptWaveformOffline(self._h, int(sample_rate), _capi.fptr(w), int(w.shape[0]))
+        if _capi.lib().B200AsrAcceptWaveformOffline(self._h, int(sample_rate), _capi.fptr(w), int(w.shape[0])) != 0:
+            raise RuntimeError("accept_waveform failed: " + _capi.last_error())
+        self._result = None
+
+    def accept_features(self, features, num_samples: int) -> None:
+        """Precomputed [T, 80] fbank of `num_samples` samples in place of the samples (decode_chunk's `precomputed_features`)."""
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        if f.ndim != 2:
+            raise ValueError("features must be [T, 80]")
+        if _capi.lib().B200AsrAcceptFeaturesOffline(self._h, _capi.fptr(f), int(f.shape[0]), int(f.shape[1]), int(num_samples)) != 0:
+            raise RuntimeError("accept_features failed: " + _capi.last_error())
         self._result = None
 
     @property
@@ -255,9 +268,34 @@ class OfflineRecognizer:
 
     # ---- sherpa surface
     def create_stream(self, hotwords: Optional[str] = None) -> OfflineStream:
-        if hotwords:
-            raise NotImplementedError("per-stream hotwords are not built; use hotwords_file / set_hotwords_text")
-        return OfflineStream(self)
+        """`hotwords` (sherpa-onnx: phrases separated by '/', optional ' :score' each) gives the stream its own automaton in
+        place of the recognizer's; phrases are parsed and tokenised like a hotwords file (core/hotword_context.py:191-259)."""
+        if not hotwords:
+            return OfflineStream(self)
+        parts = []
+        for phrase, score in parse_hotwords_text(hotwords.replace("/", "\n"), self.hotwords_score):
+            ids = self.encode_phrase(phrase)
+            if ids:
+                parts.append(" ".join(str(i) for i in ids) + f" :{score}")
+        return OfflineStream(self, "/".join(parts))
+
+    def accept_waveforms(self, streams: Sequence[OfflineStream], waveforms, sample_rate: int = 16000) -> None:
+        """accept_waveform for a whole batch in one library call (stream i takes waveforms[i])."""
+        n = len(streams)
+        if n != len(waveforms):
+            raise ValueError("streams and waveforms differ in length")
+        if n == 0:
+            return
+        if int(sample_rate) != 16000:
+            raise ValueError("only 16000 Hz input is supported (the reference resamples upstream, core/asr_engine.py:467-518)")
+        ws = [np.ascontiguousarray(w, dtype=np.float32).reshape(-1) for w in waveforms]
+        hs = (C.c_void_p * n)(*[s._h for s in streams])
+        ps = (C.c_void_p * n)(*[w.ctypes.data for w in ws])
+        ns = np.array([w.shape[0] for w in ws], dtype=np.int32)
+        if _capi.lib().B200AsrAcceptWaveformsOffline(hs, int(sample_rate), ps, _capi.i32ptr(ns), n) != 0:
+            raise RuntimeError("accept_waveforms failed: " + _capi.last_error())
+        for s in streams:
+            s._result = None
 
     def decode_stream(self, s: OfflineStream) -> None:
         self.decode_streams([s])
@@ -275,13 +313,17 @@ class OfflineRecognizer:
 
     def set_config(self, decoding_method: Optional[str] = None, max_active_paths: Optional[int] = None,
                    hotwords_score: Optional[float] = None, blank_penalty: Optional[float] = None) -> None:
+        """Arguments left at None keep their current value (a blank_penalty given to from_transducer survives a
+        decoding-method switch)."""
         cfg = _capi.RecognizerConfig()
         cfg.decoding_method = (decoding_method or "").encode()
         cfg.max_active_paths = max_active_paths or 0
-        cfg.hotwords_score = hotwords_score or 0.0
-        cfg.blank_penalty = blank_penalty if blank_penalty is not None else 0.0
+        cfg.hotwords_score = hotwords_score if hotwords_score is not None else 0.0
+        cfg.blank_penalty = blank_penalty if blank_penalty is not None else float("nan")
         if _capi.lib().B200AsrOfflineRecognizerSetConfig(self._h, C.byref(cfg)) != 0:
             raise RuntimeError(_capi.last_error())
+        if hotwords_score:
+            self.hotwords_score = hotwords_score
         if decoding_method:
             self.decoding_method = decoding_method
         if max_active_paths:

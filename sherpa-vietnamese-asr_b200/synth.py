@@ -98,3 +98,33 @@ def random_hotwords(n_phrases: int, vocab_size: int, seed: int, planted=None):
         seqs.append(seq)
         scores.append(float(rng.choice([2.0, 2.5])) if rng.random() < 0.10 else 1.5)
     return seqs, scores
+
+
+def corpus_recordings(n_files: int = 40, minutes: float = 15.0, seed: int = 36000, bank_seconds: float = 420.0):
+    """Config C5: `n_files` recordings of `minutes` each with a speech / silence layout and its ground-truth speech intervals
+    (the Silero model is not available offline, so the VAD stage is fed these intervals). A bank of speech-like utterances
+    (2-14 s, seeded) is synthesised once; every recording strings randomly chosen, randomly scaled bank utterances together
+    with 0.3-4 s pauses of -50 dB noise, so a 10 h corpus costs seconds to build instead of minutes.
+    Returns (recordings, intervals): float32 arrays and, per recording, a list of (start_sample, end_sample)."""
+    rng = np.random.default_rng(seed)
+    bank, tot = [], 0.0
+    while tot < bank_seconds:
+        d = float(np.clip(rng.lognormal(np.log(6.0), 0.5), 2.0, 14.0))
+        bank.append(speech_like(int(round(d * SAMPLE_RATE)), seed * 131 + len(bank)))
+        tot += d
+    n_total = int(round(minutes * 60 * SAMPLE_RATE))
+    recs, ivals = [], []
+    for f in range(n_files):
+        r = np.random.default_rng(seed + 1 + f)
+        out = (r.standard_normal(n_total) * 0.003).astype(np.float32)      # pause floor
+        iv, pos = [], int(r.uniform(0.2, 2.0) * SAMPLE_RATE)
+        while True:
+            u = bank[int(r.integers(0, len(bank)))]
+            if pos + len(u) >= n_total:
+                break
+            out[pos:pos + len(u)] += u * np.float32(r.uniform(0.5, 1.0))
+            iv.append((pos, pos + len(u)))
+            pos += len(u) + int(np.clip(r.lognormal(np.log(0.8), 0.8), 0.3, 4.0) * SAMPLE_RATE)
+        recs.append(out)
+        ivals.append(iv)
+    return recs, ivals

@@ -241,7 +241,8 @@ def test_product_decoder_and_joiner_record_kernels(m30, kb):
     got_dec, got_x = rec.decoder_joiner_input(y, enc)
     assert row_err(got_dec, want_dec) <= 2e-5
     want_x = np.tanh(enc.astype(np.float64) + want_dec.astype(np.float64))
-    assert np.abs(got_x - want_x).max() <= 2e-6
+    assert np.abs(got_x - np.tanh(enc.astype(np.float64) + got_dec.astype(np.float64))).max() <= 1e-6    # the activation itself
+    assert np.abs(got_x - want_x).max() <= 3e-5                                                          # decoder error carried through
     recs = rec.joiner_records(want_x.astype(np.float32), kb)
     P = (V + 31) // 32
     assert recs.shape == (m, P, 4 + 2 * kb)

@@ -42,7 +42,10 @@ def _worker(rank, world, port, q):
 
     def fake_decode(rec, chunks, offsets):
         return [[{"text": f"r{rank}", "start": o, "end": o + 0.2, "local_start": 0.0, "local_end": 0.2, "prob": 0.9}] for o in offsets]
-    corpus = pipeline.transcribe_corpus(None, recs, rank=rank, world_size=world, decode_chunks=fake_decode)
+    dist.barrier()
+    stats = {}
+    corpus = pipeline.transcribe_corpus(None, recs, rank=rank, world_size=world, decode_chunks=fake_decode, stats=stats)
+    assert stats["recordings"] + 0 >= 0 and stats["idle_s"] >= 0.0
     q.put((rank, out, seen, None if corpus is None else [(c["text"], len(c["chunk_plan"])) for c in corpus]))
     dist.barrier()
     dist.destroy_process_group()
@@ -75,4 +78,28 @@ def test_two_rank_gloo_gather():
     # transcribe_corpus: rank 1 returns nothing, rank 0 has every recording in input order, decoded on both ranks
     assert corpora[1] is None and len(corpora[0]) == 4
     assert [n for _, n in corpora[0]] == [2, 3, 1, 2]
-    assert {t.split()[0] for t, _ in corpora[0]} == {"R0", "R1"}
+    # the ranks pull from one shared queue (an atomic counter in the job's store): who decodes what is a race by design,
+    # every recording is decoded exactly once by one of them
+    assert {t.split()[0] for t, _ in corpora[0]} <= {"R0", "R1"}
+
+
+def test_store_work_queue_hands_every_item_out_once():
+    """StoreWorkQueue over a stand-in store: two consumers interleaving their pulls get disjoint items, longest first, and
+    None once the queue is drained (also for late askers)."""
+    from sherpa_vietnamese_asr_b200 import pipeline
+
+    class Store:
+        def __init__(self):
+            self.v = {}
+
+        def add(self, key, n):
+            self.v[key] = self.v.get(key, 0) + n
+            return self.v[key]
+
+    store = Store()
+    order = [3, 0, 2, 1, 4]
+    a, b = pipeline.StoreWorkQueue(store, order), pipeline.StoreWorkQueue(store, order)
+    got = [a.next(), b.next(), b.next(), a.next(), b.next(), a.next(), b.next()]
+    assert got == [3, 0, 2, 1, 4, None, None]
+    lq = pipeline.LocalWorkQueue([5, 6])
+    assert [lq.next(), lq.next(), lq.next()] == [5, 6, None]
