@@ -34,6 +34,7 @@ struct AttnTcParams {
   int C, dv;
   const float *Y; int ldy;
   float *out; int ldo;
+  int *tile_counter;       // dynamic tile scheduling (tc_common.cuh); null = static
 };
 
 struct TileInfo { int u, a_row0, v_row0, m_row0, col0, ncols, nk, Tk; };
@@ -91,13 +92,17 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
   uint64_t *ready_bar = empty_bar + kNS;
   uint64_t *tmem_full_bar = ready_bar + kNS;    // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2; // [2]
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  uint64_t *sched_full = tmem_empty_bar + 2, *sched_empty = sched_full + kSchedSlots;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(sched_empty + kSchedSlots);
+  int *sched_tile = reinterpret_cast<int *>(tmem_ptr_smem + 4);
   constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  const TileSched sched{sched_tile, sched_full, sched_empty, p.tile_counter, p.n_tiles};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kNS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+    sched_init(sched, 1 + 4 + (SPLIT3 ? 4 : 0));            // MMA issuer, 4 epilogue warps, 4 splitter warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -112,7 +117,9 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_produce(sched, ti);
+        if (tile < 0) break;
         const TileInfo t = decode_tile<BN>(p, tile);
         const CUtensorMap *ma = p.mapsA + t.u, *mv = p.mapsV + t.u, *mvl = p.mapsVlo + t.u;
         for (int kb = 0; kb < t.nk; ++kb, ++it) {
@@ -129,8 +136,10 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TBM, BN);
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_consume_thread(sched, ti);
+        if (tile < 0) break;
         const TileInfo t = decode_tile<BN>(p, tile);
         const int acc = ti & 1;
         mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
@@ -166,8 +175,9 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
   } else if (warp < 6) {
     // epilogue: thread = one query row; BN accumulator columns -> (* Y) -> out
     const int q = warp & 3;
-    int ti = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+    for (int ti = 0;; ++ti) {
+      const int tile = sched_consume_warp(sched, ti, lane);
+      if (tile < 0) break;
       const TileInfo t = decode_tile<BN>(p, tile);
       const int acc = ti & 1;
       mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
@@ -210,7 +220,9 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
     if constexpr (SPLIT3) {
       const int tix = threadIdx.x - 192;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_consume_warp(sched, ti, lane);
+        if (tile < 0) break;
         const TileInfo t = decode_tile<BN>(p, tile);
         for (int kb = 0; kb < t.nk; ++kb, ++it) {
           const int s = it % kNS;
@@ -286,7 +298,7 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const float *__restric
 }
 
 constexpr size_t attn_smem(int BN, bool split3) {
-  return 1024 + (size_t)stages_of(BN) * (TBM * TBK * 4 + ((BN * TBK * 4 + 1023) & ~1023)) * (split3 ? 2 : 1) + (3 * stages_of(BN) + 4) * 8 + 64;
+  return 1024 + (size_t)stages_of(BN) * (TBM * TBK * 4 + ((BN * TBK * 4 + 1023) & ~1023)) * (split3 ? 2 : 1) + (3 * stages_of(BN) + 4 + 2 * kSchedSlots) * 8 + 16 + 64;
 }
 
 }  // namespace
@@ -319,6 +331,7 @@ void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st) {
   p.mapsVlo = reinterpret_cast<const CUtensorMap *>(a.split3 ? a.mapsVlo : a.mapsV);
   p.tile_off = a.tile_off; p.len = a.len; p.off = a.off; p.n_utt = a.n_utt; p.n_tiles = a.n_tiles;
   p.single_head = a.single_head; p.C = a.C; p.dv = a.dv; p.Y = a.Y; p.ldy = a.ldy; p.out = a.out; p.ldo = a.ldo;
+  p.tile_counter = a.tile_counter;
   const unsigned grid = (unsigned)std::min(a.n_tiles, persistent_grid_limit(n_sms));
   if (a.single_head) {
     if (a.split3) attn_apply_tcgen05_kernel<64, true><<<grid, 320, attn_smem(64, true), st>>>(p);

@@ -40,6 +40,7 @@ struct AwParams {
   const long long *aoff;           // [n_utt] element offset of A[u]
   int n_utt, n_tiles, H, Lmax;
   float *A;
+  int *tile_counter;               // dynamic tile scheduling (tc_common.cuh); null = static
 };
 
 struct AwTile { int u, h, i0, Tk, nkt; long long row0; };
@@ -86,10 +87,14 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
   uint64_t *q_empty = q_ready + 1;
   uint64_t *tmem_full_bar = q_empty + 1;     // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+  uint64_t *sched_full = tmem_empty_bar + 2, *sched_empty = sched_full + kSchedSlots;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(sched_empty + kSchedSlots);
+  int *sched_tile = reinterpret_cast<int *>(tmem_ptr_smem + 4);
+  const TileSched sched{sched_tile, sched_full, sched_empty, p.tile_counter, p.n_tiles};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == kEpiWarps && lane == 0) {
+    sched_init(sched, 1 + kEpiWarps + (SPLIT3 ? 4 : 0));    // MMA issuer, epilogue warps, splitter warps
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_proj)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_pos)) : "memory");
     for (int s = 0; s < kWS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1 + kEpiWarps); mbar_init(&ready_bar[s], 128); }
@@ -109,8 +114,10 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
   if (warp == kEpiWarps) {
     // ===== TMA producer
     if (lane == 0) {
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_produce(sched, ti);
+        if (tile < 0) break;
         const AwTile t = aw_decode(p, tile);
         mbar_wait(q_empty, (ti & 1) ^ 1);                 // the previous item's MMAs no longer read sQ / sQlo
         mbar_expect_tx(q_full, kTileBytes);
@@ -131,8 +138,10 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
     // ===== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TBM, TBM);
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_consume_thread(sched, ti);
+        if (tile < 0) break;
         const AwTile t = aw_decode(p, tile);
         mbar_wait(SPLIT3 ? q_ready : q_full, ti & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -166,7 +175,9 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
     // ===== epilogue: thread = one query row x 32 key columns of each block
     const int q = warp & 3, cg = warp >> 2;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int ti = 0;; ++ti) {
+      const int tile = sched_consume_warp(sched, ti, lane);
+      if (tile < 0) break;
       const AwTile t = aw_decode(p, tile);
       const int il = q * 32 + lane;            // row inside the tile
       const int i = t.i0 + il;
@@ -274,8 +285,10 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       };
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++ti) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_consume_warp(sched, ti, lane);
+        if (tile < 0) break;
         const AwTile t = aw_decode(p, tile);
         mbar_wait(q_full, ti & 1);
         split(sQ, sQlo);
@@ -297,14 +310,14 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
   }
 }
 
-constexpr size_t kAwSmem = 1024 + 2 * kTileBytes + 2 * kWS * kTileBytes + kWS * kWinBytes + 4 * TBM * sizeof(float2) + (3 * kWS + 7) * 8 + 64;
+constexpr size_t kAwSmem = 1024 + 2 * kTileBytes + 2 * kWS * kTileBytes + kWS * kWinBytes + 4 * TBM * sizeof(float2) + (3 * kWS + 7 + 2 * kSchedSlots) * 8 + 16 + 64;
 
 }  // namespace
 
 bool attn_weights_tc_supported(int qd, int pd) { return qd == 32 && pd == 4 && tc_init(); }
 
 void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float *pos, const RaggedDesc &r, const long long *aoff,
-                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st) {
+                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st, int *tile_counter) {
   if (n_tiles <= 0 || r.total <= 0) return;
   if (!tc_init()) throw CudaError("tcgen05 attention weights: cuTensorMapEncodeTiled entry point unavailable");
   set_max_dynamic_smem(attn_weights_tcgen05_kernel<true>, kAwSmem);
@@ -320,7 +333,7 @@ void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float
   make_map_plain(&mw, pos, 2 * r.max_len - 1, H * 4, H * 4, 4, kWinRows);            // per-head 4-float rows, box 4 x 256
   AwParams p{};
   p.proj = proj; p.ldp = ldp; p.len = r.len; p.off = r.off; p.tile_off = tile_off; p.aoff = aoff; p.n_utt = r.n; p.n_tiles = n_tiles;
-  p.H = H; p.Lmax = r.max_len; p.A = A;
+  p.H = H; p.Lmax = r.max_len; p.A = A; p.tile_counter = tile_counter;
   const unsigned grid = (unsigned)std::min(n_tiles, persistent_grid_limit(n_sms));
   if (split3) attn_weights_tcgen05_kernel<true><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
   else attn_weights_tcgen05_kernel<false><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);

@@ -461,6 +461,19 @@ struct Engine {
 
   // workspaces
   DevBuf b_pcm, b_soff, b_foff, b_feats, b_featin;
+  // one tile counter per GEMM launch of a pass (dynamic tile scheduling of the persistent kernels), zeroed at pass start
+  static constexpr int kTileCounters = 16384;
+  DevBuf b_counters;
+  int counter_next = 0;
+  int *next_tile_counter() {
+    static const bool dyn_tiles = getenv("B200ASR_STATIC_TILES") == nullptr;
+    return (dyn_tiles && b_counters.p && counter_next < kTileCounters) ? b_counters.ptr<int>() + counter_next++ : nullptr;
+  }
+  void reset_tile_counters() {
+    int *c = b_counters.get<int>(kTileCounters);
+    CUDA_CHECK(cudaMemsetAsync(c, 0, kTileCounters * sizeof(int), st));
+    counter_next = 0;
+  }
   DevBuf b_T, b_c0off, b_c1off, b_len[4], b_off[4], b_aoff;
   DevBuf b_c0, b_c1, b_c2, b_dw, b_pw1, b_cn, b_x0, b_xc, b_sin, b_w1, b_proj, b_hid, b_A, b_pe, b_pp, b_cat, b_enc;
   DevBuf b_stack[6];
@@ -894,6 +907,7 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
   static const bool enc_pdl = getenv("B200ASR_NO_PDL") == nullptr;
   g.pdl = (enc_pdl && !profiling) ? 1 : 0;
   if (M <= 0) return;
+  g.tile_counter = next_tile_counter();
   if (precision == 0) {
     auto it = w_lo.find(Wt);
     if (it == w_lo.end()) {   // first use of this weight: split once, keep
@@ -1010,6 +1024,7 @@ void Engine::attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r
   AttnTcLaunch a{};
   a.mapsA = pl.mapsA; a.len = r.len; a.off = r.off; a.n_utt = r.n; a.single_head = single_head ? 1 : 0; a.C = C; a.dv = vd;
   a.Y = Y; a.ldy = ldy; a.out = out; a.ldo = ldo; a.split3 = split3 ? 1 : 0;
+  a.tile_counter = next_tile_counter();
   if (single_head) {
     launch_transpose_v(X, ldx, S, lds, C, r, pl.dw_tile_off, pl.dw_tiles, pl.vt_offh, pl.VTh, split3 ? pl.VThlo : nullptr, st);
     a.mapsV = pl.mapsVh; a.mapsVlo = pl.mapsVhlo; a.tile_off = pl.tile_offh; a.n_tiles = pl.n_tilesh;
@@ -1034,7 +1049,7 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   gemm(src, D, w.attn_in_w, w.attn_in_b, nullptr, 0, proj, pw, M, pw, D, ACT_NONE);
   gemm(b_pe.ptr<float>(), pos_dim, w.pos_w, nullptr, nullptr, 0, pp, H * pd, 2 * Lmax - 1, H * pd, pos_dim, ACT_NONE);
   if (pl.use && attn_weights_tc_supported(qd, pd) && !getenv("B200ASR_ATTN_SIMT"))
-    launch_attn_weights_tc(proj, pw, M, pp, r, aoff, pl.tile_off12, pl.n_tiles12, H, A, precision == 0, st);
+    launch_attn_weights_tc(proj, pw, M, pp, r, aoff, pl.tile_off12, pl.n_tiles12, H, A, precision == 0, st, next_tile_counter());
   else
     launch_attn_weights(proj, pw, pp, r, aoff, H, qd, pd, A, st);
   // feed_forward1
@@ -1223,8 +1238,11 @@ void Engine::ensure_partition() {
   const GreenApi &ga = green_api();
   if (!ga.ok) return;
   static const int want = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
-  static const bool no_green = getenv("B200ASR_NO_GREEN_CTX") != nullptr;
-  if (no_green || want <= 0) return;
+  // Off unless asked for (B200ASR_GREEN_CTX=1). Measured on a B200 (C2, 4 groups): the search's step kernels want 60-100 SMs
+  // for a few microseconds at a time; confined to a 16-SM partition a frame step takes 185 us instead of 37 (32 SMs: 100 us)
+  // and the pass gets slower, not faster. Stream priority plus SMs left free by the encoder's persistent grids does better.
+  static const bool green = getenv("B200ASR_GREEN_CTX") != nullptr;
+  if (!green || want <= 0) return;
   CUdevice dev;
   CUdevResource sm{}, grp[1]{}, rem{};
   unsigned int n = 1;
@@ -1358,6 +1376,7 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
   gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
+  reset_tile_counters();
   const std::vector<std::vector<int>> groups = plan_groups(h_len);
   const int G = (int)groups.size();
   static const int reserve_env = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
@@ -1911,6 +1930,7 @@ int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, co
   std::vector<int> Tp;
   e->gemm_flops = 0; e->gemm_launches = 0; e->gemm_ev_used = 0;
   e->host_keep.clear();
+  e->reset_tile_counters();
   e->run_encoder(d_feats, T, e->b_enc, &d_enc, &Tp);
   CUDA_CHECK(cudaMemcpyAsync(out, d_enc, (size_t)totp * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));

@@ -84,8 +84,11 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   uint64_t *ready_bar = empty_bar + NS;                    // split done (SPLIT3)
   uint64_t *tmem_full_bar = ready_bar + NS;                // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;            // [2]
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
-  float *epi_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));   // 8 warps x 32 x 32 floats, 16-byte aligned
+  uint64_t *sched_full = tmem_empty_bar + 2;               // [kSchedSlots]
+  uint64_t *sched_empty = sched_full + kSchedSlots;        // [kSchedSlots]
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(sched_empty + kSchedSlots);
+  int *sched_tile = reinterpret_cast<int *>(tmem_ptr_smem + 4);
+  float *epi_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sched_tile + kSchedSlots) + 15) & ~uintptr_t(15));   // 8 warps x 32 x 32 floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (EPI > 0 && p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -97,12 +100,14 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + TBM - 1) / TBM;
   const int n_tiles = tiles_m * tiles_n;
+  const TileSched sched{sched_tile, sched_full, sched_empty, p.tile_counter, n_tiles};
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+    sched_init(sched, 1 + 8 + (SPLIT3 ? 4 : 0));            // MMA issuer, 8 epilogue warps, 4 splitter warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -128,7 +133,9 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // ===== TMA producer
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_produce(sched, ti);
+        if (tile < 0) break;
         const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % NS;
@@ -145,8 +152,9 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     // ===== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TBM, BN);
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        if (sched_consume_thread(sched, ti) < 0) break;
         const int acc = ti & 1;
         mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -191,13 +199,14 @@ gemm_tf32_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
   } else if (warp < 10) {
     // ===== epilogue warps 2..9 (gemm_tc_epilogue.cuh)
-    tc_epilogue_warps<BN, EPI>(p, tmem_base, tmem_full_bar, tmem_empty_bar, epi_stage, n_tiles, tiles_n, warp, lane);
+    tc_epilogue_warps<BN, EPI>(p, tmem_base, tmem_full_bar, tmem_empty_bar, epi_stage, sched, tiles_n, warp, lane);
   } else {
     // ===== operand splitter warps 10..13 (SPLIT3): hi in place, lo into the shadow stage (same swizzled layout)
     if constexpr (SPLIT3) {
       const int t = threadIdx.x - 320;   // 0..127
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = 0;; ++ti) {
+        if (sched_consume_warp(sched, ti, lane) < 0) break;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
@@ -275,8 +284,8 @@ void init_once() {
 }
 
 constexpr size_t smem_bytes(int BN, bool split3, bool atmem = false) {
-  if (atmem) return 1024 + (size_t)4 * (TBM * TBK * 4 + 2 * BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
-  return 1024 + (size_t)stages_for(BN, split3) * (split3 ? 2 : 1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
+  if (atmem) return 1024 + (size_t)4 * (TBM * TBK * 4 + 2 * BN * TBK * 4) + (3 * 5 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 + 8 * 32 * 32 * 4 + 16;
+  return 1024 + (size_t)stages_for(BN, split3) * (split3 ? 2 : 1) * (TBM * TBK * 4 + BN * TBK * 4) + (3 * 5 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 + 8 * 32 * 32 * 4 + 16;
 }
 
 // 2-D fp32 row-major [rows, K] with row stride ld (elements); box = 32 x box_rows, 128-byte swizzle, OOB -> 0
@@ -387,7 +396,7 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   make_map_impl(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_impl(&mw, g.W, g.N, g.K, g.K, BN);
   make_map_impl(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, 1.0f};
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 1.0f};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));   // persistent: one CTA per SM
   // one launcher per instantiation; the opt-in shared-memory attribute is set on first use

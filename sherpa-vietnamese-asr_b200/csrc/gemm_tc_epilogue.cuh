@@ -28,6 +28,7 @@ struct TcParams {
   int M, N, K, act;
   float *partials;   // joiner epilogue (EPI > 0)
   unsigned long long *trace;
+  int *tile_counter; // dynamic tile scheduling: a global counter that is zero at launch (null = static round-robin)
   float acc_scale;   // the accumulator is multiplied by this (a power of two) before the epilogue; 0 or 1 = none. The all-fp16
                      // operand split pre-scales both operands so their low parts stay in fp16's normal range.
 };
@@ -47,13 +48,14 @@ __device__ __forceinline__ void tc_trace_mark(const TcParams &p, int slot) {
 // columns [acc * BN, acc * BN + BN).
 template <int BN, int EPI>
 __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tmem_base, uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar,
-                                                  float *epi_stage, int n_tiles, int tiles_n, int warp, int lane) {
+                                                  float *epi_stage, const TileSched &sched, int tiles_n, int warp, int lane) {
   constexpr int kAct = EPI == -1 ? (int)ACT_SWOOSH_L : (EPI == -2 ? (int)ACT_SWOOSH_R : (int)ACT_NONE);
   // ===== epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
   const int q = warp & 3;
   const int chalf = (warp - 2) >> 2;
-  int ti = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+  for (int ti = 0;; ++ti) {
+    const int tile = sched_consume_warp(sched, ti, lane);
+    if (tile < 0) break;
     const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
     const int acc = ti & 1;
     mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);

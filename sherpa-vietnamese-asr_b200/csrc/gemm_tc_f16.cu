@@ -109,8 +109,11 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   uint64_t *ready_bar = empty_bar + NS;
   uint64_t *tmem_full_bar = ready_bar + NS;                // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;            // [2]
-  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
-  float *epi_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));
+  uint64_t *sched_full = tmem_empty_bar + 2;               // [kSchedSlots]
+  uint64_t *sched_empty = sched_full + kSchedSlots;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(sched_empty + kSchedSlots);
+  int *sched_tile = reinterpret_cast<int *>(tmem_ptr_smem + 4);
+  float *epi_stage = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(sched_tile + kSchedSlots) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 0);
@@ -118,6 +121,7 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   const int tiles_n = (p.N + BN - 1) / BN;
   const int tiles_m = (p.M + TBM - 1) / TBM;
   const int n_tiles = tiles_m * tiles_n;
+  const TileSched sched{sched_tile, sched_full, sched_empty, p.tile_counter, n_tiles};
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
@@ -125,6 +129,7 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+    sched_init(sched, 1 + 8 + 4);                            // MMA issuer, 8 epilogue warps, 4 converter warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -143,7 +148,9 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
     // ===== TMA producer
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_produce(sched, ti);
+        if (tile < 0) break;
         const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % NS;
@@ -164,8 +171,9 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
       const uint32_t idesc_lh = make_idesc16(TBM, BN, lo_bf16, 0);
       const uint32_t idesc_hl = make_idesc16(TBM, BN, 0, lo_bf16);
       constexpr uint32_t idesc_hh = make_idesc16(TBM, BN, 0, 0);
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        if (sched_consume_thread(sched, ti) < 0) break;
         const int acc = ti & 1;
         mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -194,12 +202,13 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
       }
     }
   } else if (warp < 10) {
-    tc_epilogue_warps<BN, EPI>(p, tmem_base, tmem_full_bar, tmem_empty_bar, epi_stage, n_tiles, tiles_n, warp, lane);
+    tc_epilogue_warps<BN, EPI>(p, tmem_base, tmem_full_bar, tmem_empty_bar, epi_stage, sched, tiles_n, warp, lane);
   } else {
     // ===== operand converter warps 10..13: thread = one row of the landed A tile (two 128-byte swizzled box rows)
     int it = 0;
     const int row = (warp & 3) * 32 + lane;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int ti = 0;; ++ti) {
+      if (sched_consume_warp(sched, ti, lane) < 0) break;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % NS;
         const uint32_t ph = (it / NS) & 1;
@@ -243,7 +252,7 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
 }
 
 constexpr size_t f16_smem_bytes(int BN) {
-  return 1024 + (size_t)f16_stages(BN) * (2 * TBM * TBK * 4 + 2 * BN * FBK * 2) + (3 * 4 + 4) * 8 + 16 + 8 * 32 * 32 * 4 + 16;
+  return 1024 + (size_t)f16_stages(BN) * (2 * TBM * TBK * 4 + 2 * BN * FBK * 2) + (3 * 4 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 + 8 * 32 * 32 * 4 + 16;
 }
 
 // ---- pre-split 16-bit copies of a weight matrix, made on first use and kept for the life of the process
@@ -320,7 +329,7 @@ bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_16(&mwh, w.hi, false, g.N, w.ld, w.ld, BN);
   make_map_16(&mwl, w.lo, true, g.N, w.ld, w.ld, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, (variant & 16) ? 1.0f / (kAScale * kWScale) : 1.0f};
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, (variant & 16) ? 1.0f / (kAScale * kWScale) : 1.0f};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
 #define B200_F16_LAUNCH(BN_, EPI_)                                                                                        \

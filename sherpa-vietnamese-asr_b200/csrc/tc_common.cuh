@@ -100,6 +100,53 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Tile scheduler of the persistent kernels. One producer thread hands tile numbers to the other warp roles of its CTA through a
+// 4-slot ring in shared memory (full / empty mbarriers per slot); -1 ends the kernel. With a global counter the tiles are
+// claimed dynamically (atomicAdd), so a CTA that starts late - its SM was busy with a kernel of another stream, e.g. a frame
+// step of the search running beside the encoder - simply takes fewer tiles instead of stretching the whole kernel by its
+// static share; without a counter (null) tile = blockIdx.x + i * gridDim.x as before.
+constexpr int kSchedSlots = 4;
+struct TileSched {
+  int *tile;              // shared [kSchedSlots]
+  uint64_t *full, *empty; // shared [kSchedSlots] each
+  int *counter;           // global, zero at launch (or null)
+  int n_tiles;
+};
+__device__ __forceinline__ void sched_init(const TileSched &s, int n_consumer_arrivals) {   // one thread, before the CTA-wide sync
+  for (int i = 0; i < kSchedSlots; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], (uint32_t)n_consumer_arrivals); }
+}
+// producer thread: claims the ti-th tile of this CTA and publishes it
+__device__ __forceinline__ int sched_produce(const TileSched &s, int ti) {
+  const int slot = ti & (kSchedSlots - 1);
+  mbar_wait(&s.empty[slot], (uint32_t)(((ti / kSchedSlots) & 1) ^ 1));
+  int t = s.counter ? atomicAdd(s.counter, 1) : (int)(blockIdx.x + (unsigned)ti * gridDim.x);
+  if (t >= s.n_tiles) t = -1;
+  *reinterpret_cast<volatile int *>(&s.tile[slot]) = t;
+  mbar_arrive(&s.full[slot]);          // release: the slot's content is visible to whoever acquires the phase
+  return t;
+}
+// a consumer role that runs as ONE thread
+__device__ __forceinline__ int sched_consume_thread(const TileSched &s, int ti) {
+  const int slot = ti & (kSchedSlots - 1);
+  mbar_wait(&s.full[slot], (uint32_t)((ti / kSchedSlots) & 1));
+  const int t = *reinterpret_cast<volatile int *>(&s.tile[slot]);
+  mbar_arrive(&s.empty[slot]);
+  return t;
+}
+// a consumer role that runs as a full warp (one arrival per warp)
+__device__ __forceinline__ int sched_consume_warp(const TileSched &s, int ti, int lane) {
+  const int slot = ti & (kSchedSlots - 1);
+  mbar_wait(&s.full[slot], (uint32_t)((ti / kSchedSlots) & 1));
+  const int t = *reinterpret_cast<volatile int *>(&s.tile[slot]);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&s.empty[slot]);
+  return t;
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major), [32,46) stride byte
 //   offset >> 4 (1024 B between 8-row groups), [46,48) version = 1, [61,64) layout type = 2 (SWIZZLE_128B)

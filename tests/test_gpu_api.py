@@ -39,7 +39,7 @@ def test_accept_waveforms_batch_equals_loop(tiny):
     rec.accept_waveforms(ss, audios)
     rec.decode_streams(ss)
     assert [(list(s.result.token_ids), list(s.result.frames)) for s in ss] == want
-    assert sum(len(t) for t, _ in want) > 10
+    assert sum(len(t) for t, _ in want) > 3
 
 
 def test_accept_waveform_reports_failures(tiny):

@@ -251,10 +251,11 @@ def test_product_decoder_and_joiner_record_kernels(m30, kb):
     cols = recs[:, :, 4 + kb:].copy().view(np.int32)
     M = pm.max(axis=1)
     want_M = want_lg.max(axis=1)
-    assert np.abs(M - want_M).max() <= 2e-5
+    tol = 1e-5 * np.abs(want_lg).max()           # fp32-grade product of a K = 512 contraction, relative to the logits' scale
+    assert np.abs(M - want_M).max() <= tol
     lse = M + np.log((ps * np.exp(pm - M[:, None])).sum(axis=1))
     want_lse = want_M + np.log(np.exp(want_lg - want_M[:, None]).sum(axis=1))
-    assert np.abs(lse - want_lse).max() <= 2e-5
+    assert np.abs(lse - want_lse).max() <= tol
     # sum p log p from the records (search.cu select_partials) against the direct sum
     S = (ps * np.exp(pm - M[:, None])).sum(axis=1)
     dm = pm - M[:, None]
@@ -273,10 +274,10 @@ def test_product_decoder_and_joiner_record_kernels(m30, kb):
             order = np.argsort(-part, kind="stable")[:kb]
             n_have = len(order)
             got_c = cols[r, q, :n_have]
-            np.testing.assert_allclose(vals[r, q, :n_have], part[order], atol=3e-5)
+            np.testing.assert_allclose(vals[r, q, :n_have], part[order], atol=tol)
             if not np.array_equal(got_c, order + lo):     # a swap is legitimate only inside fp32 noise
                 for a, b in zip(got_c, order + lo):
-                    assert abs(want_lg[r, a] - want_lg[r, b]) <= 3e-5
+                    assert abs(want_lg[r, a] - want_lg[r, b]) <= 2 * tol
             assert (cols[r, q, n_have:] == -1).all()
 
 

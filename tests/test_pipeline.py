@@ -143,6 +143,25 @@ def test_transcribe_corpus_pools_chunks_across_recordings_and_ranks():
     assert all(p for p in parts) and set(parts[0]) | set(parts[1]) == set(range(len(recs))) and not set(parts[0]) & set(parts[1])
 
 
+def test_corpus_of_one_equals_transcribe_recording_with_vad():
+    """Both entry points share prepare_recording (VAD -> preprocess_audio -> 5 s merge, core/asr_engine.py:2076-2128): with the
+    same VAD input - a probability function, or given segments - they build the same speech concatenation, chunk plan, words and
+    suspect flags (the gap rule needs the VAD probabilities, so those travel too)."""
+    audio = (cc.silence_audio(31, 95.0) * np.float32(1.7)).astype(np.float32)
+    audio[16000 * 40:16000 * 52] = 0
+    want = pipeline.transcribe_recording(None, audio, vad_prob_fn=_prob, rms_normalize=True, decode_chunks=_fake_decode)
+    got = pipeline.transcribe_corpus(None, [audio], vad_prob_fn=_prob, rms_normalize=True, decode_chunks=_fake_decode)[0]
+    assert got["vad_segments"] == want["vad_segments"] and len(want["vad_segments"]) >= 2
+    assert got["chunk_plan"] == want["chunk_plan"] and got["words"] == want["words"] and got["text"] == want["text"]
+    assert np.max(np.abs(audio)) > 0.95                                 # the peak limiter had something to do
+    segs = [(16000 * 2, 16000 * 30), (16000 * 33, 16000 * 39), (16000 * 55, len(audio) - 8000)]
+    want = pipeline.transcribe_recording(None, audio, vad_segments=segs, decode_chunks=_fake_decode)
+    stats = {}
+    got = pipeline.transcribe_corpus(None, [audio], vad_segments=[segs], decode_chunks=_fake_decode, stats=stats)[0]
+    assert got["chunk_plan"] == want["chunk_plan"] and got["words"] == want["words"] and got["text"] == want["text"]
+    assert stats["recordings"] == 1 and stats["batches"] >= 1 and stats["chunks"] == len(want["chunk_plan"])
+
+
 def test_real_engine_branch_wiring(monkeypatch):
     """The branch taken with a real recognizer (no injected decoder): the energy scan goes to the recognizer's GPU and the
     chunks to asr_engine.decode_chunks. Both are replaced here by host stand-ins, so only the wiring is under test."""
