@@ -154,6 +154,23 @@ B200ASR_API int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const f
  * bit for bit). Needs no recognizer. `quiet` may be NULL to query the frame count n / 160. Returns the frame count or <0. */
 B200ASR_API int32_t B200AsrSilentFrames(const float *samples, int64_t n, int32_t sample_rate, float threshold, uint8_t *quiet,
                                         int32_t device_id);
+/* ---- voice-activity network (the step before the recognizer) ----
+ * Stands where the reference runs the Silero VAD ONNX session once per 512-sample window, carrying a 64-sample context and
+ * the LSTM state from call to call (core/vad_utils.py:62-118: `session.run(None, {'input','state','sr'})`, state reset per
+ * recording). Here all windows of all recordings of a batch go through the window-parallel part at once and one persistent
+ * CTA per recording runs the recurrence. `weights_path` = a `.b200w` container with the vad.* tensors (weights.save_vad).
+ * Create returns NULL on failure. Needs no recognizer. */
+B200ASR_API void *B200AsrVadCreate(const char *weights_path, int32_t device_id);
+B200ASR_API void B200AsrVadDestroy(void *vad);
+/* One recording: samples[n] (16 kHz, [-1, 1]) -> probs[n / 512] (a partial last window is dropped, core/vad_utils.py:84).
+ * `probs` may be NULL to query the window count. Returns the window count or <0. */
+B200ASR_API int32_t B200AsrVadProbs(void *vad, const float *samples, int64_t n, float *probs);
+/* A batch of recordings: recording r = samples[sample_offsets[r] .. sample_offsets[r+1]); probabilities packed, window
+ * offsets written to prob_offsets[n_rec + 1] (may be NULL). Each recording starts from a zero state. */
+B200ASR_API int32_t B200AsrVadProbsBatch(void *vad, const float *samples, const int64_t *sample_offsets, int32_t n_rec, float *probs,
+                                         int64_t *prob_offsets);
+/* Device times (ms, CUDA events) of the last call: window-parallel front end, recurrence. */
+B200ASR_API int32_t B200AsrVadLastTimings(void *vad, float *frontend_ms, float *recurrence_ms);
 /* enc_sess.run (core/asr_engine.py:1045-1049): packed features [sum T, 80] with x_lens[n] ->
  * packed encoder_out [sum T', 512], out_lens[n]. `out` may be NULL to query lengths only. */
 B200ASR_API int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, const int32_t *x_lens,

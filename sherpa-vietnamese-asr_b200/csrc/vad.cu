@@ -88,14 +88,17 @@ __device__ __forceinline__ int rec_of_window(const VadBatch &b, int g) {
   return lo;
 }
 
-constexpr size_t kFeSmem = (size_t)(kTW * kPadded + kTW * 4 * kMagLd + kTW * 4 * 128 + kTW * 2 * 64 + kTW * 64 + kTW * 128) * sizeof(float);
+// shared memory of a CTA: padded inputs (dead after the STFT, so conv0's output reuses the space), magnitudes, h1..h3 = 95 KB,
+// two CTAs per SM
+constexpr size_t kFeSmem = (size_t)(kTW * kPadded + kTW * 4 * kMagLd + kTW * 2 * 64 + kTW * 64 + kTW * 128) * sizeof(float);
+static_assert(kTW * kPadded >= kTW * 4 * 128, "h0 must fit in the input staging area");
 
 __global__ void __launch_bounds__(kFeThreads) vad_frontend_kernel(VadWeights W, VadBatch b, float *__restrict__ gx) {
   extern __shared__ __align__(16) float sm[];
   float *xin = sm;                          // [16][640]
+  float *h0 = sm;                           // [16][4][128], written after the last read of xin
   float *mag = xin + kTW * kPadded;         // [16][4][132]
-  float *h0 = mag + kTW * 4 * kMagLd;       // [16][4][128]
-  float *h1 = h0 + kTW * 4 * 128;           // [16][2][64]
+  float *h1 = mag + kTW * 4 * kMagLd;       // [16][2][64]
   float *h2 = h1 + kTW * 2 * 64;            // [16][1][64]
   float *h3 = h2 + kTW * 64;                // [16][1][128]
   const int tid = threadIdx.x;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kFeThreads) vad_frontend_kernel(VadWeights W, 
 
 // ---- recurrence: one CTA per recording, thread j = gate row j (PyTorch order i, f, g, o)
 constexpr int kLstmThreads = 512;
-constexpr size_t kLstmSmem = (size_t)(64 * 512 + 512 + 2 * 128) * sizeof(float);
+constexpr size_t kLstmSmem = (size_t)(64 * 512 + 512 + 2 * 128 + 4) * sizeof(float);
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) vad_lstm_kernel(VadWeights W,
   float *wsm = sm;                 // [64][512]: W_hh[j][64 + k] at wsm[k * 512 + j]
   float *gates = wsm + 64 * 512;   // [512]
   float *hbuf = gates + 512;       // [2][128]
+  float *psum = hbuf + 256;        // [4] per-warp partial sums of the output head
   const int j = threadIdx.x, r = blockIdx.x;
   float wreg[64];
 #pragma unroll
@@ -268,13 +272,11 @@ __global__ void __launch_bounds__(kLstmThreads, 1) vad_lstm_kernel(VadWeights W,
       float part = fmaxf(hv, 0.f) * wo;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      if ((j & 31) == 0) gates[j >> 5] = part;       // gates[0..3] are free again: every reader of this step has passed the barrier? no - see below
+      if ((j & 31) == 0) psum[j >> 5] = part;
     }
-    __syncthreads();
-    if (j == 0) probs[w] = sigmoidf_(gates[0] + gates[1] + gates[2] + gates[3] + W.bo);
-    // the next step's writers of gates[] run after its reads of h (no barrier needed before them) but thread 0's read of
-    // gates[0..3] must come first:
-    __syncthreads();
+    __syncthreads();     // h of this step and the partial sums are complete; gates[] may be rewritten by the next step
+    if (j == 0) probs[w] = sigmoidf_(psum[0] + psum[1] + psum[2] + psum[3] + W.bo);
+    // psum is rewritten only after the next step's first barrier, which thread 0 reaches after this read
   }
 }
 

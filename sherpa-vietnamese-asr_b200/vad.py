@@ -9,11 +9,13 @@ Host-side restatement (own code, same behaviour) of /root/reference:
   get_vad_segments              :158-263                    low-level boost to -23 dBFS, retry at 0.3, fallback, 1 s padding,
                                                             250 ms merge
   5 s gap merge                 core/asr_engine.py:2115-2128  `merge_close_segments`
-The Silero weights are not available offline, so no network ships here: `prob_fn(windows[n, 576]) -> probs[n]` is the seam.
+`prob_fn(windows[n, 576]) -> probs[n]` is the seam; `GpuVad` (csrc/vad.cu) is the network behind it on the GPU. The Silero
+weights are not available offline, so it runs seeded random tensors of that architecture (weights.init_vad_weights).
 Parity: tests/test_vad_logic.py drives the reference's functions and these with the same stand-in network.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -24,6 +26,67 @@ VAD_BOOST_TARGET = 0.071       # -23 dBFS (core/vad_utils.py:203)
 MAX_VAD_GAP = 5 * 16000        # core/asr_engine.py:2117
 
 ProbFn = Callable[[np.ndarray], np.ndarray]
+
+
+class GpuVad:
+    """The voice-activity network on the GPU (csrc/vad.cu through B200AsrVad*): all windows of a recording - or of a batch of
+    recordings - in one call, the LSTM state carried on the device, where the reference makes 31 sequential onnxruntime calls
+    per audio-second (core/vad_utils.py:97-104)."""
+
+    def __init__(self, weights_path: str, device_id: int = 0):
+        from . import _capi
+        self._capi = _capi
+        self._h = _capi.lib().B200AsrVadCreate(os.fsencode(weights_path), int(device_id))
+        if not self._h:
+            raise RuntimeError("B200AsrVadCreate failed: " + _capi.last_error())
+
+    def probs(self, audio: np.ndarray) -> np.ndarray:
+        """Speech probability of every 512-sample window of one recording (zero state at its start)."""
+        c = self._capi
+        x = np.ascontiguousarray(audio, dtype=np.float32).reshape(-1)
+        out = np.empty(len(x) // WINDOW, dtype=np.float32)
+        if out.size == 0:
+            return out
+        if c.lib().B200AsrVadProbs(self._h, c.fptr(x), len(x), c.fptr(out)) < 0:
+            raise RuntimeError(c.last_error())
+        return out
+
+    def probs_batch(self, recordings: Sequence[np.ndarray]) -> List[np.ndarray]:
+        c = self._capi
+        offs = np.zeros(len(recordings) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(r) for r in recordings])
+        x = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.float32).reshape(-1) for r in recordings])
+                                 if len(recordings) else np.zeros(0, np.float32))
+        poffs = np.zeros(len(recordings) + 1, dtype=np.int64)
+        n = c.lib().B200AsrVadProbsBatch(self._h, c.fptr(x), c.i64ptr(offs), len(recordings), None, c.i64ptr(poffs))
+        if n < 0:
+            raise RuntimeError(c.last_error())
+        out = np.empty(max(n, 0), dtype=np.float32)
+        if n and c.lib().B200AsrVadProbsBatch(self._h, c.fptr(x), c.i64ptr(offs), len(recordings), c.fptr(out), c.i64ptr(poffs)) < 0:
+            raise RuntimeError(c.last_error())
+        return [out[poffs[i]:poffs[i + 1]] for i in range(len(recordings))]
+
+    def prob_fn(self) -> "ProbFn":
+        """The `get_vad_segments(prob_fn=...)` seam: rows[n, 576] (context + window, one recording in order) -> probs[n]. The rows
+        overlap by construction (window_matrix), so the recording is rebuilt from their window parts."""
+        def fn(rows: np.ndarray) -> np.ndarray:
+            rows = np.asarray(rows, dtype=np.float32)
+            return self.probs(np.ascontiguousarray(rows[:, CONTEXT:]).reshape(-1))
+        return fn
+
+    def last_timings(self) -> dict:
+        import ctypes as C
+        a, b = C.c_float(0), C.c_float(0)
+        self._capi.lib().B200AsrVadLastTimings(self._h, C.byref(a), C.byref(b))
+        return {"frontend_ms": a.value, "recurrence_ms": b.value}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._capi.lib().B200AsrVadDestroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 def window_matrix(audio: np.ndarray) -> np.ndarray:

@@ -203,7 +203,7 @@ def save_container(path: str, cfg: ZipformerConfig, tensors: dict, prefix: str =
         off = (off + 255) // 256 * 256
         offs[n] = off
         off += tensors[n].nbytes
-    body = "".join(f"config {k} {v}\n" for k, v in config_items(cfg))
+    body = "".join(f"config {k} {v}\n" for k, v in (config_items(cfg) if cfg is not None else [("name", "vad")]))
     for n in names:
         a = tensors[n]
         dims = " ".join(str(d) for d in a.shape)
@@ -224,6 +224,44 @@ def save_container(path: str, cfg: ZipformerConfig, tensors: dict, prefix: str =
             f.write(b"\0" * (offs[n] - pos))
             f.write(tensors[n].tobytes())
             pos = offs[n] + tensors[n].nbytes
+
+
+def stft_basis() -> np.ndarray:
+    """[258, 256] Hann-windowed Fourier basis of the VAD front end: rows 0..128 real parts, 129..257 imaginary parts."""
+    n = np.arange(256, dtype=np.float64)
+    hann = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / 256.0)
+    ang = 2.0 * np.pi * np.arange(129, dtype=np.float64)[:, None] * n[None, :] / 256.0
+    return np.concatenate([np.cos(ang) * hann, -np.sin(ang) * hann], axis=0).astype(np.float32)
+
+
+def init_vad_weights(seed: int = 5) -> dict:
+    """Seeded random tensors of the voice-activity network (Silero VAD v5 topology, 16 kHz; the reference loads
+    `silero_vad.onnx`, core/vad_utils.py:31-52, which is not available offline): STFT basis, four Conv1d, LSTMCell(128, 128),
+    Conv1d(128 -> 1). Scales keep activations O(1) and the recurrence contractive."""
+    rng = np.random.default_rng(seed)
+    W = {"vad.stft.basis": stft_basis()}
+
+    def conv(name, co, ci, k, gain):
+        W[name + ".weight"] = (rng.standard_normal((co, ci, k)) * (gain / math.sqrt(ci * k))).astype(np.float32)
+        W[name + ".bias"] = (rng.standard_normal(co) * 0.05).astype(np.float32)
+
+    conv("vad.enc0", 128, 129, 3, 0.6)
+    conv("vad.enc1", 64, 128, 3, 1.4)
+    conv("vad.enc2", 64, 64, 3, 1.4)
+    conv("vad.enc3", 128, 64, 3, 1.4)
+    W["vad.lstm.weight_ih"] = (rng.standard_normal((512, 128)) * (1.0 / math.sqrt(128))).astype(np.float32)
+    W["vad.lstm.weight_hh"] = (rng.standard_normal((512, 128)) * (0.6 / math.sqrt(128))).astype(np.float32)
+    W["vad.lstm.bias_ih"] = (rng.standard_normal(512) * 0.05).astype(np.float32)
+    W["vad.lstm.bias_hh"] = (rng.standard_normal(512) * 0.05).astype(np.float32)
+    W["vad.out.weight"] = (rng.standard_normal((1, 128, 1)) * 0.8).astype(np.float32)
+    W["vad.out.bias"] = np.array([-0.3], dtype=np.float32)
+    return W
+
+
+def save_vad(path: str, tensors: dict) -> str:
+    """Writes the vad.* tensors as a `.b200w` container (no model config lines)."""
+    save_container(path, None, tensors, prefix="vad.")
+    return path
 
 
 def load_container(path: str):

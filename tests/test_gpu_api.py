@@ -142,3 +142,60 @@ def test_search_with_trailing_empty_utterance(tiny):
             orec["dec_cache"].clear()
             want = sr.modified_beam_search(orec, None, 4, enc_out=x)[0] if len(x) else []
             assert toks == list(want)
+
+
+# ----------------------------------------------------------------------------- voice-activity network
+@pytest.fixture(scope="module")
+def gpu_vad(tmp_path_factory):
+    from sherpa_vietnamese_asr_b200 import vad, weights
+    W = weights.init_vad_weights(5)
+    path = weights.save_vad(str(tmp_path_factory.mktemp("vad") / "silero_vad.b200w"), W)
+    return W, vad.GpuVad(path)
+
+
+def _vad_audio(seed, seconds):
+    """Speech-like bursts between near-silent pauses, so the probabilities move."""
+    from sherpa_vietnamese_asr_b200 import synth
+    rng = np.random.default_rng(seed)
+    a = synth.speech_like(int(16000 * seconds), seed)
+    t = 0
+    while t < len(a):
+        t += int(rng.uniform(0.8, 3.0) * 16000)
+        gap = int(rng.uniform(0.2, 1.2) * 16000)
+        a[t:t + gap] *= np.float32(0.003)
+        t += gap
+    return a
+
+
+def test_vad_network_matches_oracle(gpu_vad):
+    """csrc/vad.cu against oracle/silero_ref.py on the same seeded weights: probabilities of every 512-sample window within 1e-4
+    over a 40 s recording (1250 sequential LSTM steps), identical speech segments through get_vad_segments, and the window
+    matrix seam (`prob_fn`) equal to the direct call."""
+    from oracle import silero_ref
+    from sherpa_vietnamese_asr_b200 import vad
+    W, g = gpu_vad
+    audio = _vad_audio(11, 40.0)
+    got = g.probs(audio)
+    want = silero_ref.probs(W, vad.window_matrix(audio))
+    assert got.shape == want.shape == (len(audio) // 512,)
+    assert np.abs(got - want).max() <= 1e-4, np.abs(got - want).max()
+    assert want.std() > 0.02                                  # the network reacts to the input
+    np.testing.assert_array_equal(g.prob_fn()(vad.window_matrix(audio)), got)
+    thr = float(np.median(want))                              # a threshold in the middle of this (untrained) network's range
+    clear = np.abs(want - thr) > 1e-3                         # windows whose side of the threshold is not within the tolerance
+    assert ((got >= thr) == (want >= thr))[clear].all()
+    if clear.all():
+        assert vad.segments_from_probs(got, thr) == vad.segments_from_probs(want, thr)
+    print("vad timings:", g.last_timings())
+
+
+def test_vad_batch_of_recordings_equals_single(gpu_vad):
+    """Ragged batch: each recording starts from a zero state and a zero context; results equal the one-recording calls,
+    including a recording shorter than one window and one with a partial last window."""
+    W, g = gpu_vad
+    recs = [_vad_audio(20 + i, s) for i, s in enumerate([6.0, 0.02, 13.7, 1.0])]
+    batch = g.probs_batch(recs)
+    assert [len(b) for b in batch] == [len(r) // 512 for r in recs]
+    for r, b in zip(recs, batch):
+        np.testing.assert_array_equal(g.probs(r), b)
+    assert g.probs(np.zeros(100, np.float32)).shape == (0,)
