@@ -59,9 +59,11 @@ typedef struct B200AsrOfflineRecognizerConfig {
   float hotwords_score;        /* default boost 1.5 (core/config.py:405-412) */
   float blank_penalty;
   int32_t device_id;           /* CUDA device ordinal */
-  int32_t precision;           /* 0 = FP32 mode (token-exact): tcgen05 with error-compensated 3xTF32 operands;
-                                  1 = tensor-core fast mode: tcgen05, TF32 operands, FP32 accumulate;
-                                  2 = FP32 on CUDA cores (plain FFMA kernels, the cross-check of mode 0) */
+  int32_t precision;           /* 0 = FP32 mode (token-exact): tcgen05 with error-compensated operand splits (fp16 hi + lo x 3 MMAs;
+                                      3xTF32 for attention and for shapes the fp16 kernel does not take), fp32-grade products;
+                                  1 = tcgen05, TF32 operands in one pass, FP32 accumulate;
+                                  2 = FP32 on CUDA cores (plain FFMA kernels, the cross-check of mode 0);
+                                  3 = BF16 mode: bf16 weights, activations rounded to bf16 at every Linear, FP32 accumulate */
 } B200AsrOfflineRecognizerConfig;
 
 typedef struct B200AsrOfflineRecognizer B200AsrOfflineRecognizer;
@@ -154,6 +156,16 @@ B200ASR_API int32_t B200AsrFbankBatch(const B200AsrOfflineRecognizer *r, const f
  * bit for bit). Needs no recognizer. `quiet` may be NULL to query the frame count n / 160. Returns the frame count or <0. */
 B200ASR_API int32_t B200AsrSilentFrames(const float *samples, int64_t n, int32_t sample_rate, float threshold, uint8_t *quiet,
                                         int32_t device_id);
+/* ---- audio staging ----
+ * preprocess_audio (core/audio_preprocessing.py:251-292) over the uploaded PCM: optional per-segment RMS normalisation
+ * (:46-155: gain = median segment RMS / segment RMS clamped to +-20 dB, 5 ms linear fades at segment edges) then the peak
+ * limiter (:226-244: peak > 0.95 -> scaled to 0.95); `boost_low_volume` != 0 first applies the load step's boost
+ * (core/asr_engine.py:512-516: 0 < peak < 0.5 -> audio / peak * 0.95). Segments are [start, end) sample ranges of the VAD.
+ * samples[n] -> out[n] (host pointers; may alias). Bit-equal to the NumPy code except that segment RMS values are
+ * accumulated in float64 (gains agree to ~1e-7 relative). Needs no recognizer. Returns 0 / -1. */
+B200ASR_API int32_t B200AsrPreprocessAudio(const float *samples, int64_t n, const int64_t *seg_starts, const int64_t *seg_ends,
+                                           int32_t n_seg, int32_t enable_rms_normalize, int32_t boost_low_volume, int32_t sample_rate,
+                                           float *out, int32_t device_id);
 /* ---- voice-activity network (the step before the recognizer) ----
  * Stands where the reference runs the Silero VAD ONNX session once per 512-sample window, carrying a 64-sample context and
  * the LSTM state from call to call (core/vad_utils.py:62-118: `session.run(None, {'input','state','sr'})`, state reset per
@@ -201,7 +213,8 @@ B200ASR_API int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const f
                                       float *tok_logprobs, float *stats, int32_t *n_tokens);
 /* One dense Linear as the encoder/joiner graphs run it (onnxruntime MatMul+Add inside enc_sess/joi_sess,
  * core/asr_engine.py:1047,1092): C[M,N] = act(A[M,K] W[N,K]^T + bias) (+ R). Host pointers; act 0/1/2 = none/SwooshL/
- * SwooshR; impl 0 = FP32 CUDA-core kernel, 1 = tcgen05 TF32 kernel, 2 = tcgen05 3xTF32 kernel. reps > 1 repeats the launch and
+ * SwooshR; impl 0 = FP32 CUDA-core kernel, 1 = tcgen05 TF32, 2 = tcgen05 3xTF32, 3 = tcgen05 fp16 operand split (fp32-grade),
+ * 4 = tcgen05 BF16. reps > 1 repeats the launch and
  * writes the mean device time per launch (ms, CUDA events) to *ms_per_launch (may be NULL). */
 B200ASR_API int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const float *W, const float *bias, const float *R,
                                 float *C, int32_t M, int32_t N, int32_t K, int32_t act, int32_t impl, int32_t reps, float *ms_per_launch);

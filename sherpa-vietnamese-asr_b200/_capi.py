@@ -70,6 +70,7 @@ SYMBOLS = {
     "B200AsrFbank": (C.c_int32, [_P, _F, C.c_int32, _F]),
     "B200AsrFbankBatch": (C.c_int32, [_P, _F, _I64, C.c_int32, _F, _I64]),
     "B200AsrSilentFrames": (C.c_int32, [_F, C.c_int64, C.c_int32, C.c_float, C.POINTER(C.c_uint8), C.c_int32]),
+    "B200AsrPreprocessAudio": (C.c_int32, [_F, C.c_int64, _I64, _I64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _F, C.c_int32]),
     "B200AsrVadCreate": (_P, [C.c_char_p, C.c_int32]),
     "B200AsrVadDestroy": (None, [_P]),
     "B200AsrVadProbs": (C.c_int32, [_P, _F, C.c_int64, _F]),

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200asr.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["fbank.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc_f16.cu", "attn_tc.cu", "attn_weights_tc.cu", "encoder.cu", "search.cu", "energy.cu", "vad.cu", "engine.cu", "context_graph.cpp"]
+SOURCES = ["fbank.cu", "gemm.cu", "gemm_tc.cu", "gemm_tc_f16.cu", "attn_tc.cu", "attn_weights_tc.cu", "encoder.cu", "search.cu", "energy.cu", "vad.cu", "staging.cu", "engine.cu", "context_graph.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-diag-suppress", "177"]
 

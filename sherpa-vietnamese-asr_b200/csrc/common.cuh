@@ -88,6 +88,8 @@ struct GemmArgs {
   const float *A; int lda;
   const float *W;            // [N,K] row-major (ldw = K)
   const float *Wlo;          // W - trunc_tf32(W), needed by the 3xTF32 tensor-core kernel only (else null)
+  const void *W16hi, *W16lo; // 16-bit operand copies made by split_weights_16 (gemm_tc_f16.cu), row pitch w16_ld; else null
+  int w16_ld;
   const float *bias;         // [N] or null
   const float *R; int ldr;   // residual or null
   float *C; int ldc;
@@ -101,6 +103,10 @@ struct GemmArgs {
   int *tile_counter;         // tensor-core kernels: a device int that is zero at launch -> tiles are claimed dynamically (null: static)
 };
 void launch_gemm_fp32(const GemmArgs &g, cudaStream_t st);
+// gemm_tc_f16.cu: 16-bit tensor-core operands. split_weights_16 makes the copies of W[N, K] (caller frees hi / lo with cudaFree);
+// launch_gemm_16 returns false for shapes it does not take. bf16 = single-pass BF16 mode, else the fp32-grade fp16 split.
+void split_weights_16(const float *W, int N, int K, bool bf16, void **hi, void **lo, int *ld, cudaStream_t st);
+bool launch_gemm_16(const GemmArgs &g, bool bf16, cudaStream_t st);
 void launch_split_lo(const float *w, float *lo, long long n, cudaStream_t st);
 
 // ---------------------------------------------------------------- encoder kernels (encoder.cu)
@@ -195,6 +201,8 @@ struct SearchModel {
   const float *dec_proj_b;
   const float *join_w;     // [V, jd]
   const float *join_w_lo;  // low part for the 3xTF32 joiner GEMM (or null)
+  const void *join_w16hi, *join_w16lo;   // 16-bit operand copies for the joiner GEMM (or null)
+  int join_w16_ld;
   const float *join_b;
   int V, dd, jd;
   int blank_id, unk_id;

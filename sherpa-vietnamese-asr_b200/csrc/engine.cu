@@ -30,9 +30,9 @@
 namespace b200asr {
 
 void launch_gemm_tc(const GemmArgs &g, cudaStream_t st);    // gemm_tc.cu: tcgen05, TF32 operands
-void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st);   // gemm_tc.cu: tcgen05, error-compensated 3xTF32 (fp32-grade)
+void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st);   // gemm_tc.cu: fp32-grade on tcgen05 (fp16 operand split, or 3xTF32)
+void launch_gemm_bf16(const GemmArgs &g, cudaStream_t st);  // gemm_tc.cu: BF16 operands, FP32 accumulate
 bool gemm_tc_available();
-void gemm_f16split_forget(const float *W);                   // gemm_tc_f16.cu
 
 namespace {
 
@@ -423,6 +423,20 @@ struct Engine {
   float *w_conv0 = nullptr, *w_conv1 = nullptr, *w_conv2 = nullptr, *w_dw7 = nullptr, *w_out = nullptr;
   std::vector<float *> owned;   // extra device allocations to free
   std::map<const float *, const float *> w_lo;   // weight -> its pre-split low part (3xTF32 mode)
+  struct W16 { void *hi, *lo; int ld; };
+  std::map<const float *, W16> w16;              // weight -> its 16-bit operand copies (fp16 split of the FP32 mode, or bf16)
+  bool use_f16x3 = false;                        // FP32 mode on the fp16 operand split instead of 3xTF32
+  typedef void (*GemmFn)(const GemmArgs &, cudaStream_t);
+  GemmFn gemm_fn() const { return precision == 1 ? launch_gemm_tc : precision == 0 ? launch_gemm_tc3 : precision == 3 ? launch_gemm_bf16 : launch_gemm_fp32; }
+  const W16 &w16_for(const float *Wt, int N, int K) {
+    auto it = w16.find(Wt);
+    if (it == w16.end()) {
+      W16 w{nullptr, nullptr, 0};
+      split_weights_16(Wt, N, K, precision == 3, &w.hi, &w.lo, &w.ld, st);
+      it = w16.emplace(Wt, w).first;
+    }
+    return it->second;
+  }
 
   FbankTables fb{};
   cudaStream_t st = nullptr;
@@ -566,6 +580,7 @@ struct Stream {
 Engine::~Engine() {
   for (auto &kv : tensors) if (kv.second.dev) cudaFree(kv.second.dev);
   for (float *p : owned) cudaFree(p);
+  for (auto &kv : w16) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
   if (fb.window) fbank_tables_destroy(&fb);
   for (int i = 0; i < kMaxLanes; ++i) {
     Lane &l = lanes[i];
@@ -847,9 +862,16 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   blank_penalty = c->blank_penalty;
   fbank_tables_create(&fb);
   search = search_state_create();
-  if (precision < 0 || precision > 2) throw std::runtime_error("precision must be 0 (fp32 via 3xTF32 tcgen05), 1 (tf32 tcgen05) or 2 (fp32 CUDA cores)");
+  if (precision < 0 || precision > 3)
+    throw std::runtime_error("precision must be 0 (FP32 mode on tcgen05), 1 (TF32 tcgen05), 2 (FP32 CUDA cores) or 3 (BF16 tcgen05)");
+  // FP32 mode: the fp16 operand split (gemm_tc_f16.cu) unless B200ASR_GEMM_3XTF32 asks for the 3xTF32 kernel
+  use_f16x3 = precision == 0 && getenv("B200ASR_GEMM_3XTF32") == nullptr;
   if (precision != 2 && !gemm_tc_available()) throw std::runtime_error("tensor-core GEMM path unavailable (cuTensorMapEncodeTiled not found)");
-  search_set_gemm(search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32), precision != 2);
+  search_set_gemm(search, gemm_fn(), precision != 2);
+  if (use_f16x3 || precision == 3) {
+    const W16 &w = w16_for(sm.join_w, V, join_dim);
+    sm.join_w16hi = w.hi; sm.join_w16lo = w.lo; sm.join_w16_ld = w.ld;
+  }
   if (precision == 0) {
     float *lo;
     CUDA_CHECK(cudaMalloc(&lo, (size_t)V * join_dim * sizeof(float)));
@@ -919,6 +941,10 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
     }
     g.Wlo = it->second;
   }
+  if (use_f16x3 || precision == 3) {
+    const W16 &w = w16_for(Wt, N, K);
+    g.W16hi = w.hi; g.W16lo = w.lo; g.w16_ld = w.ld;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profiling) {
     if (gemm_ev_used >= gemm_events.size()) {
@@ -930,9 +956,7 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
     ++gemm_ev_used;
     CUDA_CHECK(cudaEventRecord(e0, st));
   }
-  if (precision == 1) launch_gemm_tc(g, st);
-  else if (precision == 0) launch_gemm_tc3(g, st);
-  else launch_gemm_fp32(g, st);
+  gemm_fn()(g, st);
   if (profiling) CUDA_CHECK(cudaEventRecord(e1, st));
   gemm_flops += 2.0 * (double)M * (double)N * (double)K;
   ++gemm_launches;
@@ -1284,7 +1308,7 @@ Lane &Engine::lane(int i) {
     if (i == 0) l.search = search;
     else {
       l.search = search_state_create();
-      search_set_gemm(l.search, precision == 1 ? launch_gemm_tc : (precision == 0 ? launch_gemm_tc3 : launch_gemm_fp32), precision != 2);
+      search_set_gemm(l.search, gemm_fn(), precision != 2);
     }
   }
   return l;
@@ -1302,7 +1326,11 @@ std::vector<std::vector<int>> Engine::plan_groups(const std::vector<long long> &
   std::vector<std::vector<int>> single(1);
   single[0].resize(n);
   for (int u = 0; u < n; ++u) single[0][u] = u;
-  static const bool off = getenv("B200ASR_PIPELINE") && atoi(getenv("B200ASR_PIPELINE")) == 0;
+  // Off unless B200ASR_PIPELINE=1. Measured on a B200 (C2, Zipformer-68M): the search's step kernels are wide and shallow - a
+  // frame step spreads 64-300 CTAs of 100-200 KB shared memory over the SMs for a few microseconds - so beside them the
+  // encoder's 200 KB CTAs find about half the SMs free; splitting the encoder into g groups also costs ~3.5 ms of launch-bound
+  // small kernels per group. 4 groups: 86 ms against 80 ms for the plain pass. Kept for a search kernel that fits few SMs.
+  static const bool off = !(getenv("B200ASR_PIPELINE") && atoi(getenv("B200ASR_PIPELINE")) != 0);
   if (off || profiling || n < 16) return single;
   std::vector<int> asc(n);
   for (int u = 0; u < n; ++u) asc[u] = u;
@@ -2072,20 +2100,31 @@ int32_t B200AsrGemm(const B200AsrOfflineRecognizer *r, const float *A, const flo
   GemmArgs g{};
   g.A = dA; g.lda = K; g.W = dW; g.bias = bias ? dB : nullptr; g.R = R ? dR : nullptr; g.ldr = N; g.C = dC; g.ldc = N;
   g.M = M; g.N = N; g.K = K; g.act = act;
-  if (impl == 2) {
+  if (impl == 2 || impl == 3) {
     float *dWlo = e->b_tmp2.get<float>(nW);
     launch_split_lo(dW, dWlo, (long long)nW, e->st);
     g.Wlo = dWlo;
   }
+  void *w16hi = nullptr, *w16lo = nullptr;
+  if (impl == 3 || impl == 4) {
+    int ld = 0;
+    split_weights_16(dW, N, K, impl == 4, &w16hi, &w16lo, &ld, e->st);
+    g.W16hi = w16hi; g.W16lo = w16lo; g.w16_ld = ld;
+  }
   if (reps < 1) reps = 1;
-  auto run = [&]() { if (impl == 1) launch_gemm_tc(g, e->st); else if (impl == 2) launch_gemm_tc3(g, e->st); else launch_gemm_fp32(g, e->st); };
+  auto run = [&]() {
+    if (impl == 1) launch_gemm_tc(g, e->st);
+    else if (impl == 2 || impl == 3) launch_gemm_tc3(g, e->st);      // 3 carries the 16-bit copies -> fp16 operand split
+    else if (impl == 4) launch_gemm_bf16(g, e->st);
+    else launch_gemm_fp32(g, e->st);
+  };
   run();   // warm-up / the checked result
   CUDA_CHECK(cudaEventRecord(e->ev[6], e->st));
   for (int i = 1; i < reps; ++i) run();
   CUDA_CHECK(cudaEventRecord(e->ev[7], e->st));
   CUDA_CHECK(cudaMemcpyAsync(C, dC, nC * 4, cudaMemcpyDeviceToHost, e->st));
   CUDA_CHECK(cudaStreamSynchronize(e->st));
-  gemm_f16split_forget(dW);   // dW is scratch: the next call may put other weights at the same address
+  cudaFree(w16hi); cudaFree(w16lo);
   if (ms_per_launch) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]);

@@ -456,14 +456,16 @@ void launch_split_lo(const float *w, float *lo, long long n, cudaStream_t st) {
 }
 
 void launch_gemm_tc(const GemmArgs &g, cudaStream_t st) { launch_tc_impl(g, st, false); }
-bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st);   // gemm_tc_f16.cu (experimental)
-// FP32-grade product on the tensor pipe (error-compensated 3xTF32)
+// FP32-grade product on the tensor pipe: the fp16 operand split (gemm_tc_f16.cu) when the caller supplies the 16-bit weight
+// copies, else (and for shapes that kernel does not take) error-compensated 3xTF32
 void launch_gemm_tc3(const GemmArgs &g, cudaStream_t st) {
-  // B200ASR_GEMM_F16SPLIT=1: the fp16-hi / bf16-lo operand split (experimental, see gemm_tc_f16.cu); shapes it does not take
-  // fall through to 3xTF32
-  static const bool f16split = getenv("B200ASR_GEMM_F16SPLIT") != nullptr;
-  if (f16split && launch_gemm_f16split(g, st)) return;
+  if (g.W16hi && g.W16lo && launch_gemm_16(g, false, st)) return;
   launch_tc_impl(g, st, true);
+}
+// BF16 operands, FP32 accumulate; shapes the 16-bit kernel does not take run as single-pass TF32
+void launch_gemm_bf16(const GemmArgs &g, cudaStream_t st) {
+  if (g.W16hi && launch_gemm_16(g, true, st)) return;
+  launch_tc_impl(g, st, false);
 }
 
 }  // namespace b200asr

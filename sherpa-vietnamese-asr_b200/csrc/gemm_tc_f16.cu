@@ -1,31 +1,31 @@
-// EXPERIMENTAL, off by default (B200ASR_GEMM_F16SPLIT=1 turns it on), NOT YET RUN ON HARDWARE when this was committed: the
-// FP32 (token-exact) GEMM mode on 16-bit tensor-core operands.
+// 16-bit tensor-core operands for the Linear layers (tcgen05 kind::f16, FP32 accumulation in TMEM), two modes:
 //
-// Today's FP32 mode is error-compensated 3xTF32 (gemm_tc.cu): three kind::tf32 MMAs per K step. tools/fp16_split_study.py
-// replays every Linear of the oracle encoder and shows that the split  x = hi + lo,  hi = fp16(x), lo = bf16(x - hi)  with
-//     A*W ~ A_lo*W_hi + A_hi*W_lo + A_hi*W_hi        (FP32 accumulation in TMEM, mixed a/b formats per MMA)
-// has the same error as 3xTF32 (9e-7 vs 7e-7 relative, native fp32 1.2e-6) and keeps the decoded token ids exact, while
-// kind::f16 runs at twice the TF32 rate and the weight tiles are half the bytes. Range: inside fp16's normal range
-// (6.1e-5 .. 65504) the two terms carry x to 2^-20; lo is bf16 (fp32's exponent), so under that range the pair degrades
-// smoothly - |x - (hi + lo)| <= max(2^-20 |x|, 6e-11), i.e. down to bf16 precision for |x| < 6e-8 - which is harmless next
-// to O(1) terms of the same dot product but would show if a whole operand were tiny (a power-of-two pre-scale of W would
-// remove that; not done); hi is clamped to +-65504, so values over the range also degrade to bf16 precision instead of
-// producing infinities. tests/test_kernel_math.py::test_f16_split_product_is_fp32_grade pins these statements on the CPU.
+// F16X3 - the FP32 (token-exact) mode on fp16 operands. Every operand is pre-scaled by a power of two and split
+//     x' = x * 2^s = hi + lo,   hi = fp16(x'), lo = fp16(x' - hi)
+// and each K step issues  A_lo*W_hi + A_hi*W_lo + A_hi*W_hi  into one FP32 accumulator, which the epilogue scales back by
+// 2^-(sA+sW). With hi and lo both fp16 the pair carries x' to 2^-22 while lo is a normal fp16 number (|x'| >= 0.25) and to
+// 2^-25 absolute below that; the scales (activations x 64, weights x 1024) put this network's operands there with a range of
+// +-1023 / +-63 before fp16 would overflow (hi is clamped, so larger values degrade to fp16 precision instead of producing
+// infinities). Products of fp16 numbers are exact in FP32, so the result is fp32-grade: measured on a B200 against a float64
+// product 4.7e-7 .. 2.2e-6 of the output scale for K = 64 .. 512 and 8.8e-6 at K = 2432 - the same as the 3xTF32 kernel
+// (gemm_tc.cu), at half the MMA issue time and half the weight-tile bytes. (An fp16-hi / bf16-lo split needs no scaling, but
+// tcgen05 traps with "illegal instruction" on kind::f16 MMAs whose a and b formats differ - measured, tools/f16_probe.py.)
 //
-// Same structure as the A-in-TMEM 3xTF32 kernel: persistent CTAs over 128 x BN tiles; warp 0 TMA producer, warp 1 MMA
-// issuer, warps 2..9 epilogue (gemm_tc_epilogue.cuh), warps 10..13 read the landed fp32 A tile once, convert it and store
-// packed hi / lo rows to tensor memory (two 16-bit K elements per 32-bit column, lane = row); the MMAs take A from there
-// and the pre-split 16-bit W tiles from shared memory. One stage = 64 K elements: two 128 x 32 fp32 boxes of A (32 KB) and
-// BN x 64 fp16 + BN x 64 bf16 of W (128-byte swizzled rows), 12 MMAs of K = 16.
+// BF16 - the reduced-precision mode the north star names: activations rounded to bf16 as they enter a GEMM, bf16 weights, one
+// MMA per K step, FP32 accumulation; the residual stream between layers stays fp32.
+//
+// Same structure as the A-in-TMEM 3xTF32 kernel: persistent CTAs over 128 x BN tiles claimed through the tile scheduler;
+// warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (gemm_tc_epilogue.cuh), warps 10..13 read the landed fp32 A
+// tile once, convert it and store packed 16-bit rows to tensor memory (two K elements per 32-bit column, lane = row; element
+// 2j in the low half-word - measured); the MMAs take A from there and the pre-converted W tiles from shared memory. One stage
+// = 64 K elements: two 128 x 32 fp32 boxes of A (32 KB) and BN x 64 16-bit weights per operand part (128-byte swizzled rows).
+// A ragged last K block is zero-filled by TMA.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include <algorithm>
-#include <map>
-#include <mutex>
-#include <tuple>
 
 #include "common.cuh"
 #include "gemm_tc_epilogue.cuh"
@@ -45,15 +45,14 @@ namespace {
 constexpr int FBK = 64;          // K elements per stage
 constexpr int UMMA_K16 = 16;     // kind::f16: 32 bytes per instruction
 constexpr int kF16Threads = 448;
-// all-fp16 variant (16): x' = x * kAScale, w' = w * kWScale before the split, accumulator * 1 / (kAScale * kWScale) after. With
-// lo = fp16(x' - fp16(x')) the pair carries x' to 2^-22 while lo is a normal fp16 (|x'| >= 0.25) and to 2^-25 absolute below.
 constexpr float kAScale = 64.0f, kWScale = 1024.0f;
 
-__host__ __device__ constexpr int f16_stages(int BN) { return BN == 64 ? 4 : 3; }
+__host__ __device__ constexpr int f16_stages(int BN, bool bf16) { return bf16 ? 4 : (BN == 64 ? 4 : 3); }
 
-// c_format F32 at [4,6); a_format / b_format at [7,10) / [10,13): 0 = F16, 1 = BF16; K-major both; N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc16(int M, int N, int a_bf16, int b_bf16) {
-  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// c_format F32 at [4,6); a_format / b_format at [7,10) / [10,13): 0 = F16, 1 = BF16 (must be equal); K-major both; N >> 3 at
+// [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc16(int M, int N, int bf16) {
+  return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // A from tensor memory: 128 lanes = rows, two 16-bit K elements per 32-bit column (16 elements = 8 columns per instruction)
@@ -69,16 +68,7 @@ __device__ __forceinline__ void umma_f16_ta(uint32_t tmem_d, uint32_t tmem_a, ui
 
 __device__ __forceinline__ float clamp_f16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }   // NaN stays NaN
 
-// (x0, x1) -> packed fp16 hi pair and packed bf16 lo pair; element 0 in the low half-word
-__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
-  const float2 hf = __half22float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t *>(&h);
-  lo = *reinterpret_cast<const uint32_t *>(&l);
-}
-
-// all-fp16 variant: both halves fp16
+// (x0, x1), already scaled -> packed fp16 hi pair and packed fp16 lo pair; element 0 in the low half-word
 __device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi, uint32_t &lo) {
   const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
   const float2 hf = __half22float2(h);
@@ -86,14 +76,16 @@ __device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi,
   hi = *reinterpret_cast<const uint32_t *>(&h);
   lo = *reinterpret_cast<const uint32_t *>(&l);
 }
+__device__ __forceinline__ uint32_t pack_bf16(float x0, float x1) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+  return *reinterpret_cast<const uint32_t *>(&b);
+}
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool BF16>
 __global__ void __launch_bounds__(kF16Threads, 1)
-gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
-                             const __grid_constant__ CUtensorMap map_wlo, TcParams p, int variant) {
-  // `variant` (B200ASR_F16_VARIANT, hardware bring-up only): 1 / 2 / 4 drop the lo*hi / hi*lo / hi*hi term, 8 swaps the two
-  // half-words of a packed A column, 16 makes lo fp16 too (all three MMAs f16 x f16)
-  constexpr int NS = f16_stages(BN);
+gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+                        const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+  constexpr int NS = f16_stages(BN, BF16);
   constexpr uint32_t kTmemACol = 256;                         // A stages at columns 256 + 64 s (hi, 32 columns) / + 32 (lo)
   constexpr uint32_t kTmemCols = 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,10 +93,11 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   constexpr int kABox = TBM * TBK * 4;     // one 128 x 32 fp32 box, 16 KB
   constexpr int kABytes = 2 * kABox;       // 64 K elements of A per stage
   constexpr int kWBytes = BN * FBK * 2;    // BN x 64 16-bit elements: 16 or 8 KB
+  constexpr int kWParts = BF16 ? 1 : 2;
   uint8_t *sA = smem;
   uint8_t *sWhi = sA + NS * kABytes;
-  uint8_t *sWlo = sWhi + NS * kWBytes;
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWlo + NS * kWBytes);
+  uint8_t *sWlo = sWhi + NS * kWBytes;     // not carved in the BF16 mode
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWhi + kWParts * NS * kWBytes);
   uint64_t *empty_bar = full_bar + NS;
   uint64_t *ready_bar = empty_bar + NS;
   uint64_t *tmem_full_bar = ready_bar + NS;                // [2]
@@ -126,7 +119,7 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
+    if constexpr (!BF16) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
     for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&ready_bar[s], 128); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
     sched_init(sched, 1 + 8 + 4);                            // MMA issuer, 8 epilogue warps, 4 converter warps
@@ -156,21 +149,18 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kABytes + 2 * kWBytes);
+          mbar_expect_tx(&full_bar[s], kABytes + kWParts * kWBytes);
           tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes, kb * FBK, m0);
           tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes + kABox, kb * FBK + TBK, m0);
           tma_load_2d(&map_whi, &full_bar[s], sWhi + s * kWBytes, kb * FBK, n0);
-          tma_load_2d(&map_wlo, &full_bar[s], sWlo + s * kWBytes, kb * FBK, n0);
+          if constexpr (!BF16) tma_load_2d(&map_wlo, &full_bar[s], sWlo + s * kWBytes, kb * FBK, n0);
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: per K = 16 step  A_lo(bf16) * W_hi(fp16)  +  A_hi(fp16) * W_lo(bf16)  +  A_hi * W_hi, small terms first
+    // ===== MMA issuer. F16X3: per K = 16 step  A_lo * W_hi + A_hi * W_lo + A_hi * W_hi, small terms first; BF16: one MMA
     if (lane == 0) {
-      const int lo_bf16 = (variant & 16) ? 0 : 1;
-      const uint32_t idesc_lh = make_idesc16(TBM, BN, lo_bf16, 0);
-      const uint32_t idesc_hl = make_idesc16(TBM, BN, 0, lo_bf16);
-      constexpr uint32_t idesc_hh = make_idesc16(TBM, BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc16(TBM, BN, BF16 ? 1 : 0);
       int it = 0;
       for (int ti = 0;; ++ti) {
         if (sched_consume_thread(sched, ti) < 0) break;
@@ -191,10 +181,13 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
           for (int k = 0; k < FBK / UMMA_K16; ++k) {
             const uint64_t o = (uint64_t)(k * 2);             // +32 bytes inside the 128-byte swizzle row, in 16-byte units
             const uint32_t c = (uint32_t)(k * (UMMA_K16 / 2));   // 16 packed elements = 8 columns
-            uint32_t accum = (kb | k) ? 1u : 0u;
-            if (!(variant & 1)) { umma_f16_ta(tmem_d, ta_lo + c, dwh + o, idesc_lh, accum); accum = 1u; }   // small terms first
-            if (!(variant & 2)) { umma_f16_ta(tmem_d, ta_hi + c, dwl + o, idesc_hl, accum); accum = 1u; }
-            if (!(variant & 4)) { umma_f16_ta(tmem_d, ta_hi + c, dwh + o, idesc_hh, accum); }
+            if constexpr (BF16) {
+              umma_f16_ta(tmem_d, ta_hi + c, dwh + o, idesc, (kb | k) ? 1u : 0u);
+            } else {
+              umma_f16_ta(tmem_d, ta_lo + c, dwh + o, idesc, (kb | k) ? 1u : 0u);
+              umma_f16_ta(tmem_d, ta_hi + c, dwl + o, idesc, 1u);
+              umma_f16_ta(tmem_d, ta_hi + c, dwh + o, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[s]);
         }
@@ -220,22 +213,18 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 v = lds128(rowp + ((c ^ (row & 7)) << 4));
-            if (variant & 16) {
+            if constexpr (BF16) {
+              hi[b * 16 + 2 * c] = pack_bf16(v.x, v.y);
+              hi[b * 16 + 2 * c + 1] = pack_bf16(v.z, v.w);
+            } else {
               split_pair_f16(v.x * kAScale, v.y * kAScale, hi[b * 16 + 2 * c], lo[b * 16 + 2 * c]);
               split_pair_f16(v.z * kAScale, v.w * kAScale, hi[b * 16 + 2 * c + 1], lo[b * 16 + 2 * c + 1]);
-            } else {
-              split_pair(v.x, v.y, hi[b * 16 + 2 * c], lo[b * 16 + 2 * c]);
-              split_pair(v.z, v.w, hi[b * 16 + 2 * c + 1], lo[b * 16 + 2 * c + 1]);
             }
           }
         }
-        if (variant & 8) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { hi[j] = (hi[j] >> 16) | (hi[j] << 16); lo[j] = (lo[j] >> 16) | (lo[j] << 16); }
-        }
         const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kTmemACol + (uint32_t)(s * 64);
         tmem_st_32x32(ta, hi);
-        tmem_st_32x32(ta + 32, lo);
+        if constexpr (!BF16) tmem_st_32x32(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
@@ -251,61 +240,51 @@ gemm_f16split_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __
   if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 1);
 }
 
-constexpr size_t f16_smem_bytes(int BN) {
-  return 1024 + (size_t)f16_stages(BN) * (2 * TBM * TBK * 4 + 2 * BN * FBK * 2) + (3 * 4 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 + 8 * 32 * 32 * 4 + 16;
+constexpr size_t f16_smem_bytes(int BN, bool bf16) {
+  return 1024 + (size_t)f16_stages(BN, bf16) * (2 * TBM * TBK * 4 + (bf16 ? 1 : 2) * BN * FBK * 2) + (3 * 4 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 +
+         8 * 32 * 32 * 4 + 16;
 }
 
-// ---- pre-split 16-bit copies of a weight matrix, made on first use and kept for the life of the process
-__global__ void split_w16_kernel(const float *__restrict__ w, __half *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int N, int K, int ld,
-                                 int lo_f16) {
+// 16-bit copies of a weight matrix [N, K] -> [N, ld] (ld = K rounded up to 8, zero padded)
+__global__ void split_w16_kernel(const float *__restrict__ w, uint16_t *__restrict__ hi, uint16_t *__restrict__ lo, int N, int K, int ld,
+                                 int bf16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * ld) return;
   const int n = (int)(i / ld), k = (int)(i % ld);
-  const float x = (k < K ? w[(long long)n * K + k] : 0.f) * (lo_f16 ? kWScale : 1.0f);
-  const __half h = __float2half_rn(clamp_f16(x));
-  hi[i] = h;
-  if (lo_f16) reinterpret_cast<__half *>(lo)[i] = __float2half_rn(x - __half2float(h));   // bring-up variant 16
-  else lo[i] = __float2bfloat16_rn(x - __half2float(h));
-}
-
-struct W16 { __half *hi; __nv_bfloat16 *lo; int ld; };
-std::mutex g_w16_mu;
-std::map<std::tuple<const float *, int, int, int>, W16> g_w16;     // (pointer, N, K, device + 64 * lo_f16)
-
-W16 w16_for(const float *W, int N, int K, cudaStream_t st, bool lo_f16 = false) {
-  int dev = 0;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(g_w16_mu);
-  const auto key = std::make_tuple(W, N, K, dev + (lo_f16 ? 64 : 0));
-  auto it = g_w16.find(key);
-  if (it != g_w16.end()) return it->second;
-  W16 w{nullptr, nullptr, (K + 7) & ~7};
-  const size_t n = (size_t)N * w.ld;
-  CUDA_CHECK(cudaMalloc(&w.hi, n * sizeof(__half)));
-  CUDA_CHECK(cudaMalloc(&w.lo, n * sizeof(__nv_bfloat16)));
-  split_w16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, w.hi, w.lo, N, K, w.ld, lo_f16 ? 1 : 0);
-  count_launch();
-  KERNEL_CHECK();
-  g_w16.emplace(key, w);
-  return w;
+  const float x = k < K ? w[(long long)n * K + k] : 0.f;
+  if (bf16) {
+    const __nv_bfloat16 b = __float2bfloat16_rn(x);
+    hi[i] = *reinterpret_cast<const uint16_t *>(&b);
+  } else {
+    const float xs = x * kWScale;
+    const __half h = __float2half_rn(clamp_f16(xs));
+    const __half l = __float2half_rn(xs - __half2float(h));
+    hi[i] = *reinterpret_cast<const uint16_t *>(&h);
+    lo[i] = *reinterpret_cast<const uint16_t *>(&l);
+  }
 }
 
 }  // namespace
 
-// Drops the cached 16-bit copies of a weight matrix (callers that reuse a scratch pointer for different weights: B200AsrGemm).
-// The stream that used them must have been synchronised.
-void gemm_f16split_forget(const float *W) {
-  std::lock_guard<std::mutex> lk(g_w16_mu);
-  for (auto it = g_w16.begin(); it != g_w16.end();) {
-    if (std::get<0>(it->first) == W) { cudaFree(it->second.hi); cudaFree(it->second.lo); it = g_w16.erase(it); }
-    else ++it;
-  }
+// Makes the 16-bit operand copies of W[N, K] the kernels below read (device memory owned by the caller: cudaFree both).
+// bf16: one bf16 copy (*lo = null); else the scaled fp16 hi / lo pair.
+void split_weights_16(const float *W, int N, int K, bool bf16, void **hi, void **lo, int *ld, cudaStream_t st) {
+  const int l = (K + 7) & ~7;
+  const size_t n = (size_t)N * l;
+  *hi = nullptr; *lo = nullptr; *ld = l;
+  CUDA_CHECK(cudaMalloc(hi, n * 2));
+  if (!bf16) CUDA_CHECK(cudaMalloc(lo, n * 2));
+  split_w16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(W, reinterpret_cast<uint16_t *>(*hi), reinterpret_cast<uint16_t *>(*lo), N, K, l, bf16 ? 1 : 0);
+  count_launch();
+  KERNEL_CHECK();
 }
 
-// Returns false when the shape is outside what this variant takes (the caller then runs the 3xTF32 kernel).
-bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
+// C = act(A W^T + bias) (+ R) on the 16-bit operand copies in g.W16hi / g.W16lo. Returns false when the shape is outside what
+// the kernel takes (the caller then runs a TF32 kernel).
+bool launch_gemm_16(const GemmArgs &g, bool bf16, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return true;
   if (!tc_init()) return false;
+  if (!g.W16hi || (!bf16 && !g.W16lo)) return false;
   if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<uintptr_t>(g.A) & 15)) return false;
   const bool joiner = g.act == ACT_JOINER;
   if (joiner) {
@@ -323,24 +302,23 @@ bool launch_gemm_f16split(const GemmArgs &g, cudaStream_t st) {
   }
   int BN = g.N > 64 ? 128 : 64;
   if (joiner && (long long)((g.M + TBM - 1) / TBM) * ((g.N + 63) / 64) <= n_sms) BN = 64;
-  const int variant = getenv("B200ASR_F16_VARIANT") ? atoi(getenv("B200ASR_F16_VARIANT")) : 16;
-  const W16 w = w16_for(g.W, g.N, g.K, st, (variant & 16) != 0);
   CUtensorMap ma, mwh, mwl;
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
-  make_map_16(&mwh, w.hi, false, g.N, w.ld, w.ld, BN);
-  make_map_16(&mwl, w.lo, true, g.N, w.ld, w.ld, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, (variant & 16) ? 1.0f / (kAScale * kWScale) : 1.0f};
+  make_map_16(&mwh, g.W16hi, bf16, g.N, g.w16_ld, g.w16_ld, BN);
+  make_map_16(&mwl, bf16 ? g.W16hi : g.W16lo, bf16, g.N, g.w16_ld, g.w16_ld, BN);
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, bf16 ? 1.0f : 1.0f / (kAScale * kWScale)};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
-#define B200_F16_LAUNCH(BN_, EPI_)                                                                                        \
+#define B200_F16_LAUNCH(BN_, EPI_, BF_)                                                                                   \
   do {                                                                                                                    \
-    set_max_dynamic_smem(gemm_f16split_tcgen05_kernel<BN_, EPI_>, f16_smem_bytes(BN_));                                   \
-    launch_pdl(gemm_f16split_tcgen05_kernel<BN_, EPI_>, dim3(grid), dim3(kF16Threads), f16_smem_bytes(BN_), st, g.pdl != 0, ma, mwh, \
-               mwl, p, variant);                                                                                          \
+    set_max_dynamic_smem(gemm_f16_tcgen05_kernel<BN_, EPI_, BF_>, f16_smem_bytes(BN_, BF_));                              \
+    launch_pdl(gemm_f16_tcgen05_kernel<BN_, EPI_, BF_>, dim3(grid), dim3(kF16Threads), f16_smem_bytes(BN_, BF_), st, g.pdl != 0, ma, \
+               mwh, mwl, p);                                                                                              \
   } while (0)
 #define B200_F16_BN(EPI_)                                                                          \
   do {                                                                                             \
-    if (BN == 128) B200_F16_LAUNCH(128, EPI_); else B200_F16_LAUNCH(64, EPI_);                     \
+    if (bf16) { if (BN == 128) B200_F16_LAUNCH(128, EPI_, true); else B200_F16_LAUNCH(64, EPI_, true); }    \
+    else { if (BN == 128) B200_F16_LAUNCH(128, EPI_, false); else B200_F16_LAUNCH(64, EPI_, false); }       \
   } while (0)
   if (joiner) {
     if (g.part_kb == 4) B200_F16_BN(4);

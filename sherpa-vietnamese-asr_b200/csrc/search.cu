@@ -1068,6 +1068,7 @@ void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g
     // joiner output_linear: logits = X * Wj^T + bj (+ partial records)
     GemmArgs ga{};
     ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
+    ga.W16hi = m.join_w16hi; ga.W16lo = m.join_w16lo; ga.w16_ld = m.join_w16_ld;
     ga.ldc = m.V; ga.M = act_rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE; ga.pdl = use_pdl ? 1 : 0;
     if (fused) {   // records only: nothing downstream reads the logits
       ga.act = ACT_JOINER; ga.C = nullptr; ga.partials = S->partials; ga.part_kb = KB; ga.bias = join_bias;
@@ -1236,6 +1237,7 @@ void launch_joiner_records(SearchState *S, const SearchModel &m, const float *X,
   if (!S->fused_partials) throw CudaError("this precision mode has no record epilogue (CUDA-core GEMM selects from full logits)");
   GemmArgs ga{};
   ga.A = X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = nullptr;
+  ga.W16hi = m.join_w16hi; ga.W16lo = m.join_w16lo; ga.w16_ld = m.join_w16_ld;
   ga.ldc = m.V; ga.M = rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_JOINER; ga.partials = records; ga.part_kb = kb; ga.pdl = 0;
   S->gemm(ga, st);
 }

@@ -24,12 +24,13 @@ from . import chunking, postprocess, staging, vad
 
 def prepare_recording(audio: np.ndarray, vad_prob_fn: Optional[vad.ProbFn] = None,
                       vad_segments: Optional[Sequence[Tuple[int, int]]] = None, skip_preprocessing: bool = False,
-                      rms_normalize: bool = False):
+                      rms_normalize: bool = False, device_id: Optional[int] = None):
     """The steps `_run_pipeline` takes before the chunk plan (core/asr_engine.py:2076-2128): VAD segments (computed from
     `vad_prob_fn` or given), preprocess_audio on the recording (peak limit, optional per-segment RMS normalisation; an error
     there is skipped, :2099-2113), the 5 s gap merge. With neither VAD input the whole recording is speech (:2085-2086); any
     VAD failure takes the same path (:2171-2204). One helper for every entry point, so a recording gets the same speech
-    concatenation and chunk plan however it is transcribed. Returns (audio, vad_segments or None, vad_probs or None, vad_error)."""
+    concatenation and chunk plan however it is transcribed. `device_id` not None: the preprocessing passes run on that GPU
+    (csrc/staging.cu). Returns (audio, vad_segments or None, vad_probs or None, vad_error)."""
     audio = np.ascontiguousarray(audio, dtype=np.float32)
     probs, vad_error = None, None
     try:
@@ -39,7 +40,10 @@ def prepare_recording(audio: np.ndarray, vad_prob_fn: Optional[vad.ProbFn] = Non
             vad_segments = list(vad_segments)
             if not skip_preprocessing:
                 try:
-                    audio = staging.preprocess_audio(audio, vad_segments, enable_rms_normalize=rms_normalize)
+                    if device_id is None:
+                        audio = staging.preprocess_audio(audio, vad_segments, enable_rms_normalize=rms_normalize)
+                    else:
+                        audio = staging.preprocess_audio_gpu(audio, vad_segments, enable_rms_normalize=rms_normalize, device_id=device_id)
                 except Exception as e:  # noqa: BLE001
                     vad_error = f"preprocess: {e!r}"
             vad_segments = vad.merge_close_segments(vad_segments, vad.MAX_VAD_GAP, inclusive=True)
@@ -57,7 +61,8 @@ def transcribe_recording(recognizer, audio: np.ndarray, vad_prob_fn: Optional[va
     spans the reference keeps in timing_details (:1969-1977)."""
     timing: Dict[str, float] = {}
     t0 = time.perf_counter()
-    audio, vad_segments, probs, vad_error = prepare_recording(audio, vad_prob_fn, vad_segments, skip_preprocessing, rms_normalize)
+    device_id = None if decode_chunks is not None else int(recognizer.engine.device_id)   # real engine: staging on its GPU too
+    audio, vad_segments, probs, vad_error = prepare_recording(audio, vad_prob_fn, vad_segments, skip_preprocessing, rms_normalize, device_id)
     timing["vad_preprocess"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     res = chunking.transcribe_long(recognizer, audio, vad_segments or (), decode_chunks=decode_chunks,
@@ -102,7 +107,7 @@ def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments
                       rover_recognizer=None, hotword_phrases: Sequence[str] = (), rank: int = 0, world_size: int = 1,
                       max_batch_seconds: float = 3000.0, decode_chunks=None, gather=None, vad_prob_fn: Optional[vad.ProbFn] = None,
                       skip_preprocessing: bool = False, rms_normalize: bool = False, work_queue=None, prefetch: int = 8,
-                      stats: Optional[dict] = None):
+                      stats: Optional[dict] = None, vad_prob_fns: Optional[Sequence[Optional[vad.ProbFn]]] = None):
     """Many recordings at once (BASELINE config C5: a 10 h corpus of 15-minute files), every rank pulling from one queue.
 
     * Queue: recordings, longest first. `work_queue.next()` hands each one out exactly once - LocalWorkQueue inside a
@@ -157,7 +162,8 @@ def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments
                 i = work_queue.next()
                 if i is None:
                     break
-                audio, vs, probs, err = prepare_recording(recordings[i], vad_prob_fn, segs[i], skip_preprocessing, rms_normalize)
+                pf = vad_prob_fns[i] if vad_prob_fns is not None else vad_prob_fn      # per-recording VAD, or one for all
+                audio, vs, probs, err = prepare_recording(recordings[i], pf, segs[i], skip_preprocessing, rms_normalize, device_id)
                 ready.put((i, audio, probs, err, vs, chunking.plan_recording(audio, vs or (), device_id)))
         except BaseException as e:  # noqa: BLE001   surfaces in the consumer
             ready.put(e)

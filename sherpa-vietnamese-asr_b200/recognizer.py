@@ -427,7 +427,7 @@ class OfflineRecognizer:
         ms = C.c_float(0)
         rc = _capi.lib().B200AsrGemm(self._h, _capi.fptr(A), _capi.fptr(W), _capi.fptr(b) if b is not None else None,
                                     _capi.fptr(Rr) if Rr is not None else None, _capi.fptr(out), M, N, K, act,
-                                    {"fp32": 0, "tc": 1, "tc3": 2}[impl], reps, C.byref(ms))
+                                    {"fp32": 0, "tc": 1, "tc3": 2, "f16x3": 3, "bf16": 4}[impl], reps, C.byref(ms))
         if rc != 0:
             raise RuntimeError(_capi.last_error())
         return out, ms.value

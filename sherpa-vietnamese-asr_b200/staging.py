@@ -101,3 +101,20 @@ def preprocess_audio(audio: np.ndarray, vad_segments: Sequence[Tuple[int, int]],
     if enable_rms_normalize and len(vad_segments) > 0:
         out = per_segment_rms_normalize(out, vad_segments, sample_rate)
     return adaptive_peak_limit(out)
+
+
+def preprocess_audio_gpu(audio: np.ndarray, vad_segments: Sequence[Tuple[int, int]], sample_rate: int = 16000,
+                         enable_rms_normalize: bool = True, boost_low: bool = False, device_id: int = 0) -> np.ndarray:
+    """preprocess_audio on the GPU (csrc/staging.cu through B200AsrPreprocessAudio): the per-sample passes run over the
+    uploaded PCM, the host only sees a few numbers per VAD segment. `boost_low` also applies boost_low_volume first."""
+    from . import _capi
+    x = np.ascontiguousarray(audio, dtype=np.float32).reshape(-1)
+    out = np.empty_like(x)
+    seg = np.asarray(list(vad_segments), dtype=np.int64).reshape(-1, 2)
+    s = np.ascontiguousarray(seg[:, 0]) if len(seg) else np.zeros(1, np.int64)
+    e = np.ascontiguousarray(seg[:, 1]) if len(seg) else np.zeros(1, np.int64)
+    rc = _capi.lib().B200AsrPreprocessAudio(_capi.fptr(x), len(x), _capi.i64ptr(s), _capi.i64ptr(e), len(seg), int(bool(enable_rms_normalize)),
+                                            int(bool(boost_low)), int(sample_rate), _capi.fptr(out), int(device_id))
+    if rc != 0:
+        raise RuntimeError("B200AsrPreprocessAudio failed: " + _capi.last_error())
+    return out

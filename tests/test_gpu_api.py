@@ -199,3 +199,88 @@ def test_vad_batch_of_recordings_equals_single(gpu_vad):
     for r, b in zip(recs, batch):
         np.testing.assert_array_equal(g.probs(r), b)
     assert g.probs(np.zeros(100, np.float32)).shape == (0,)
+
+
+# ----------------------------------------------------------------------------- audio staging
+def _staging_case(seed, seconds, scale):
+    from oracle import chunk_cases as cc
+    rng = np.random.default_rng(seed)
+    audio = (cc.silence_audio(seed, seconds) * np.float32(scale)).astype(np.float32)
+    n = len(audio)
+    segs, t = [], int(rng.uniform(0, 0.5) * 16000)
+    while t < n - 2000:
+        ln = int(rng.choice([600, 2500, 9000, 40000, 120000]))       # incl. segments under the 100 ms minimum
+        e = min(n, t + ln)
+        segs.append((t, e))
+        audio[t:e] *= np.float32(rng.choice([0.05, 0.3, 1.0, 2.0]))   # loudness differs from segment to segment
+        t = e + int(rng.choice([0, 1, 50, 4000, 30000]))              # incl. touching segments (fade onto the neighbour's gain)
+    return audio, segs
+
+
+@pytest.mark.parametrize("seed,seconds,scale", [(1, 30.0, 1.0), (2, 95.0, 1.7), (3, 12.0, 0.2), (4, 0.5, 1.0)])
+def test_device_staging_matches_host_preprocess(seed, seconds, scale):
+    """csrc/staging.cu against staging.preprocess_audio (itself bit-equal to core/audio_preprocessing.py:46-292 in
+    tests/test_staging.py): peak limiter only -> bit-equal; with per-segment RMS normalisation -> 1e-6 of the peak (segment RMS is
+    accumulated in float64 on the device); with the load step's low-volume boost in front as well."""
+    from sherpa_vietnamese_asr_b200 import staging
+    audio, segs = _staging_case(seed, seconds, scale)
+    want = staging.preprocess_audio(audio, segs, enable_rms_normalize=False)
+    got = staging.preprocess_audio_gpu(audio, segs, enable_rms_normalize=False)
+    np.testing.assert_array_equal(got, want)
+    want = staging.preprocess_audio(audio, segs, enable_rms_normalize=True)
+    got = staging.preprocess_audio_gpu(audio, segs, enable_rms_normalize=True)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-6 * max(1.0, float(np.abs(want).max()))
+    assert np.abs(want - audio).max() > 1e-3 or seconds < 1.0          # the normalisation did something
+    boosted = staging.boost_low_volume(audio)
+    want = staging.preprocess_audio(boosted, segs, enable_rms_normalize=True)
+    got = staging.preprocess_audio_gpu(audio, segs, enable_rms_normalize=True, boost_low=True)
+    assert np.abs(got - want).max() <= 1e-6 * max(1.0, float(np.abs(want).max()))
+    np.testing.assert_array_equal(staging.preprocess_audio_gpu(audio, [], enable_rms_normalize=True),
+                                  staging.preprocess_audio(audio, [], enable_rms_normalize=True))
+
+
+# ----------------------------------------------------------------------------- the whole phase on real device statistics (SURVEY 8f rank 4)
+def test_pipeline_flags_from_device_statistics_equal_oracle_chain(model_dirs, gpu_vad):
+    """transcribe_recording on the real engine - GPU VAD probabilities, GPU staging, GPU energy scan, one ragged GPU decode whose
+    per-token tsallis / margin / entropy statistics come out of the joiner epilogue - against the same chain fed by the oracle:
+    oracle VAD probabilities and oracle decode_chunk (core/asr_engine.py:1209-1326) per chunk. Word texts, times, the suspect
+    flags of suspect_detect (:1711-1865) and the final text must agree; `_conf` / entropy features within the rounding of the
+    statistics (4 decimals)."""
+    from oracle import fbank_ref, search_ref as sr, silero_ref
+    from sherpa_vietnamese_asr_b200 import asr_engine, pipeline, synth
+    cfg, paths, d = model_dirs("zipformer-tiny", 3)
+    W, g = gpu_vad
+    rec = asr_engine.create_recognizer(d, max_active_paths=4)
+    orec = oracle_recognizer(paths, beam=4)[0]
+    audio = _vad_audio(77, 75.0)
+    thr = None
+
+    def oracle_decode(_rec, chunks, offsets, **kw):
+        out = []
+        for c, o in zip(chunks, offsets):
+            orec["dec_cache"].clear()
+            out.append(sr.decode_chunk(orec, c, o, precomputed_features=fbank_ref.fbank(c, np.float64)))
+        return out
+
+    # the (untrained) network's probabilities sit around 0.5: pick the segments once, from the oracle, so both chains get the
+    # same VAD segments and differ only in where the numbers after that come from
+    from sherpa_vietnamese_asr_b200 import vad as vadmod
+    segs, probs_o = vadmod.get_vad_segments(audio, silero_ref.prob_fn(W), threshold=0.5)
+    _, probs_g = vadmod.get_vad_segments(audio, g.prob_fn(), threshold=0.5)
+    assert np.abs(probs_o - probs_g).max() <= 1e-4
+    got = pipeline.transcribe_recording(rec, audio, vad_segments=segs, rms_normalize=True)
+    want = pipeline.transcribe_recording(None, audio, vad_segments=segs, rms_normalize=True, decode_chunks=oracle_decode)
+    assert got["chunk_plan"] == want["chunk_plan"] and len(want["chunk_plan"]) >= 2
+    assert got["text"] == want["text"] and len(want["words"]) > 20
+    n_flag = 0
+    for a, b in zip(got["words"], want["words"]):
+        assert a["text"] == b["text"]
+        assert abs(a["start"] - b["start"]) <= 1e-4 and abs(a["end"] - b["end"]) <= 1e-4
+        assert a.get("_suspect_level") == b.get("_suspect_level"), (a, b)
+        assert a.get("_suspect_reasons") == b.get("_suspect_reasons")
+        for k in ("tsallis_max", "margin_min", "entropy_norm", "_conf"):
+            if k in b:
+                assert abs(a[k] - b[k]) <= 2e-4, (k, a[k], b[k])
+        n_flag += bool(b.get("_suspect_level"))
+    print("suspect words:", n_flag, "of", len(want["words"]))

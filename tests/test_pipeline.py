@@ -162,6 +162,25 @@ def test_corpus_of_one_equals_transcribe_recording_with_vad():
     assert stats["recordings"] == 1 and stats["batches"] >= 1 and stats["chunks"] == len(want["chunk_plan"])
 
 
+def test_corpus_with_per_recording_vad_functions():
+    """vad_prob_fns: one probability function per recording (bench.py's C5 feeds ground-truth intervals this way)."""
+    recs = [cc.silence_audio(50 + i, sec) for i, sec in enumerate([48.0, 70.0])]
+
+    def gt(iv):
+        def fn(rows):
+            p = np.full(rows.shape[0], 0.02, dtype=np.float32)
+            for s, e in iv:
+                p[s // 512:(e + 511) // 512] = 0.95
+            return p
+        return fn
+    ivs = [[(16000 * 2, 16000 * 20), (16000 * 30, 16000 * 44)], [(16000 * 5, 16000 * 60)]]
+    got = pipeline.transcribe_corpus(None, recs, vad_prob_fns=[gt(iv) for iv in ivs], decode_chunks=_fake_decode)
+    for audio, iv, g in zip(recs, ivs, got):
+        want = pipeline.transcribe_recording(None, audio, vad_prob_fn=gt(iv), decode_chunks=_fake_decode)
+        assert g["vad_segments"] == want["vad_segments"] and g["words"] == want["words"]
+    assert got[0]["vad_segments"] != got[1]["vad_segments"]
+
+
 def test_real_engine_branch_wiring(monkeypatch):
     """The branch taken with a real recognizer (no injected decoder): the energy scan goes to the recognizer's GPU and the
     chunks to asr_engine.decode_chunks. Both are replaced here by host stand-ins, so only the wiring is under test."""
