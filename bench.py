@@ -39,8 +39,9 @@ def parse_args():
     ap.add_argument("--beam", type=int, default=4)
     ap.add_argument("--precision", default=os.environ.get("B200ASR_PRECISION", "fp32"), choices=["fp32", "tf32"],
                     help="fp32 = the token-exact mode (headline); tf32 = single-pass TF32 operands (labelled as such, never the headline)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2 = the headline batch of 256 VAD segments per GPU; c5 = the 10 h corpus of 15-minute recordings through "
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="c2 = the headline batch of 256 VAD segments per GPU; c3 = c2 with a 500-phrase hotword ContextGraph; c4 = ROVER: "
+                         "Zipformer-30M + 68M over the same segments, one fbank, hypotheses combined on the host; c5 = the 10 h corpus of 15-minute recordings through "
                          "VAD post-logic, staging, chunk planner, pooled ragged decodes and stitching, ranks pulling recordings from one queue")
     ap.add_argument("--files", type=int, default=40)
     ap.add_argument("--minutes", type=float, default=15.0)
@@ -212,7 +213,12 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def parity_check(rec, cfg, paths, audios, beam, k):
+def synth_mod():
+    from sherpa_vietnamese_asr_b200 import synth
+    return synth
+
+
+def parity_check(rec, cfg, paths, audios, beam, k, graph=None):
     """Outside the timed region: the tokens and frames the engine produced for the first k segments of the (already decoded)
     staged batch against the oracle's fbank -> encoder -> modified_beam_search on the same PCM and weights."""
     from oracle import fbank_ref, search_ref, zipformer_ref
@@ -220,7 +226,11 @@ def parity_check(rec, cfg, paths, audios, beam, k):
     tensors = {}
     for part in ("encoder", "decoder", "joiner"):
         tensors.update(weights.load_container(paths[part])[1])
-    orec = zipformer_ref.make_recognizer(tensors, cfg, max_active_paths=beam)
+    ctx = None
+    if graph is not None:
+        ctx = search_ref.ContextGraph()
+        ctx.build(*graph)
+    orec = zipformer_ref.make_recognizer(tensors, cfg, max_active_paths=beam, context_graph=ctx)
     n_tok, bad = 0, []
     for u in range(min(k, len(audios))):
         feats = fbank_ref.fbank(audios[u], np.float64)
@@ -231,6 +241,71 @@ def parity_check(rec, cfg, paths, audios, beam, k):
             bad.append(u)
         n_tok += len(toks)
     return {"parity_checked": not bad, "parity_segments": min(k, len(audios)), "parity_tokens": n_tok, "parity_mismatches": bad}
+
+
+def run_c4(args, rank, local_rank, world):
+    """BASELINE config C4 (ROVER): Zipformer-30M and Zipformer-68M over the same segments - one fbank for both
+    (core/asr_engine.py:2346-2350), two encoder + search passes, hypotheses combined per segment with rover_merge_words on the
+    host (:1446-1577). One step = both models + the merge over this rank's segments, host buffers in, word lists out."""
+    import torch
+    import torch.distributed as dist
+
+    from sherpa_vietnamese_asr_b200 import asr_engine
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    recs = []
+    for name, seed in (("zipformer-30m", 30), ("zipformer-68m", 68)):
+        cfg, paths = model_dir(name, seed)
+        recs.append(asr_engine.create_recognizer(os.path.dirname(paths["encoder"]), max_active_paths=args.beam, device_id=local_rank,
+                                                 precision=args.precision))
+    audios = workload(args, rank)
+    audio_s = sum(len(a) for a in audios) / 16000.0
+
+    def step():
+        return asr_engine.rover_decode_chunks(recs[0], recs[1], audios)
+
+    for _ in range(max(1, args.warmup)):
+        out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    dev = [0.0, 0.0]
+    for _ in range(args.steps):
+        out = step()
+        dev[0] += recs[0].engine.last_timings()["total_ms"]
+        dev[1] += recs[1].engine.last_timings()["total_ms"]
+    torch.cuda.synchronize()
+    ms = 1000.0 * (time.perf_counter() - t0) / args.steps
+    clocks = sampler.stop()
+    tot_audio = audio_s
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        a = torch.tensor([audio_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+        tot_audio = float(a.item())
+    if rank == 0:
+        n_words = sum(len(m) for m, _ in out)
+        n_dis = sum(len(d) for _, d in out)
+        line = {"metric": "RTFx (audio-s/s) Zipformer-68M batch ASR", "value": tot_audio / (ms * 1e-3), "unit": "audio-s/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
+                "config": {"workload": f"C4 (ROVER): zipformer-30m + zipformer-68m over the same {args.segments} VAD-like segments/GPU "
+                                       f"({audio_s:.0f} audio-s), one fbank, beam {args.beam}, rover_merge_words on the host",
+                           "device_ms_per_step": {"zipformer-30m": dev[0] / args.steps, "zipformer-68m": dev[1] / args.steps},
+                           "merged_words": n_words, "disagreements": n_dis,
+                           "note": "host-inclusive wall time through rover_decode_chunks (features computed once, two decodes, host merge)"},
+                "clocks": clocks,
+                "e2e": {"value": tot_audio / (ms * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": int(sum(len(a) for a in audios) * 4),
+                        "d2h_bytes_per_step": None, "ms_per_step": ms}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_c5(args, rank, local_rank, world):
@@ -325,6 +400,9 @@ def main():
     if args.workload == "c5":
         run_c5(args, rank, local_rank, world)
         return
+    if args.workload == "c4":
+        run_c4(args, rank, local_rank, world)
+        return
 
     import torch
     import torch.distributed as dist
@@ -343,6 +421,16 @@ def main():
     audios = workload(args, rank)
     audio_s = sum(len(a) for a in audios) / 16000.0
     pcm_bytes = sum(len(a) for a in audios) * 4
+    graph = None
+    if args.workload == "c3":
+        # BASELINE config C3: 500 phrases of 2-8 tokens, a quarter cut from this batch's own no-hotword decodes so boosts fire
+        h0 = rec.stage_batch(audios)
+        rec.run_staged(h0)
+        planted = [rec.last_pass_tokens(u)[0] for u in range(min(64, len(audios)))]
+        rec.release_batch(h0)
+        seqs, scores = synth_mod().random_hotwords(500, cfg.vocab_size, 500, planted=[p for p in planted if len(p) >= 2])
+        rec.set_hotwords_token_ids(seqs, scores)
+        graph = (seqs, scores)
 
     def barrier():
         torch.cuda.synchronize()
@@ -371,7 +459,19 @@ def main():
     clocks = sampler.stop()
     ms_dev = dev_ms / args.steps
     pipe = rec.last_pipeline_stats()
-    parity = parity_check(rec, cfg, paths, audios, args.beam, args.parity_segments) if (rank == 0 and args.parity_segments > 0) else {}
+    parity = parity_check(rec, cfg, paths, audios, args.beam, args.parity_segments, graph) if (rank == 0 and args.parity_segments > 0) else {}
+    # consecutive passes issued back to back (what a decode call with several batches does): search of pass k beside encoder of k + 1
+    chained = None
+    if os.environ.get("B200ASR_BENCH_CHAIN", "1") != "0":
+        reps = 4
+        rec.run_staged_chained(h, reps)
+        barrier()
+        tot_ms = 0.0
+        rounds = max(1, args.steps // reps)
+        for _ in range(rounds):
+            tot_ms += rec.run_staged_chained(h, reps)[1]
+        barrier()
+        chained = {"passes_per_call": reps, "ms_per_pass": tot_ms / (rounds * reps), "audio_s_per_s": audio_s / (tot_ms / (rounds * reps) * 1e-3)}
 
     # ---------------- end to end through the recognizer surface (host buffers)
     def e2e_step():
@@ -440,7 +540,7 @@ def main():
         "metric": "RTFx (audio-s/s) Zipformer-68M batch ASR", "value": total_audio / (ms_dev * 1e-3), "unit": "audio-s/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
-        "config": {"workload": f"C2: {args.model} random-init, modified_beam_search beam {args.beam}, {args.segments} VAD-like "
+        "config": {"workload": f"{'C3 (500-phrase hotword ContextGraph)' if args.workload == 'c3' else 'C2'}: {args.model} random-init, modified_beam_search beam {args.beam}, {args.segments} VAD-like "
                                f"segments/GPU clip(lognormal(ln 9 s, 0.7), 1, 30) = {audio_s:.0f} audio-s/GPU; "
                                f"utterance-sharded, no collective",
                    "l2": f"inputs larger than L2 ({pcm_bytes / 1e6:.0f} MB PCM, multi-GB activations per step)",
@@ -449,6 +549,7 @@ def main():
                                 "search_busy_ms": pipe["search_busy_ms"],
                                 "note": "length-sorted groups; group g's search runs on its own stream beside the encoder of group g+1; "
                                         "stage_ms.search_ms is the part no encoder hid"},
+                   "chained_passes": chained,
                    **parity,
                    "stage_ms": {k: v / args.steps for k, v in stage.items()},
                    "encoder_algorithmic_tflop_per_step": enc_fl / 1e12,

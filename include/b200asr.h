@@ -238,6 +238,11 @@ B200ASR_API int32_t B200AsrStageBatch(const B200AsrOfflineRecognizer *r, const f
 /* Runs fbank -> encoder -> search on a staged batch entirely on the device; token counts per utterance are
  * copied back (n_tokens may be NULL). */
 B200ASR_API int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle, int32_t *n_tokens);
+/* `reps` (1..8) passes over a staged batch issued back to back: the search of pass k runs on its own stream beside the fbank
+ * and encoder of pass k + 1, as consecutive batches of one long B200AsrDecodeMultipleOfflineStreams call do. Returns after the
+ * last search; total_ms = device time from the first launch to the end of the last search; n_tokens = counts of the last pass. */
+B200ASR_API int32_t B200AsrRunStagedBatchChained(const B200AsrOfflineRecognizer *r, int32_t handle, int32_t reps, int32_t *n_tokens,
+                                                 float *total_ms);
 B200ASR_API int32_t B200AsrReleaseBatch(const B200AsrOfflineRecognizer *r, int32_t handle);
 /* Token ids / frames of utterance u of the last staged run or decode pass (bench.py's parity self-check against the
  * oracle's `_ort_beam_search` output, core/asr_engine.py:1143-1153). Returns the token count or <0. */

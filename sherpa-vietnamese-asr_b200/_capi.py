@@ -94,6 +94,7 @@ SYMBOLS = {
     "B200AsrHotwordGraphFinalize": (C.c_double, [_P, C.c_int32]),
     "B200AsrStageBatch": (C.c_int32, [_P, _F, _I64, C.c_int32]),
     "B200AsrRunStagedBatch": (C.c_int32, [_P, C.c_int32, _I32]),
+    "B200AsrRunStagedBatchChained": (C.c_int32, [_P, C.c_int32, C.c_int32, _I32, _F]),
     "B200AsrReleaseBatch": (C.c_int32, [_P, C.c_int32]),
     "B200AsrLastPassTokens": (C.c_int32, [_P, C.c_int32, _I32, _I32, C.c_int32]),
     "B200AsrLastPipelineStats": (C.c_int32, [_P, _I32, _F, _F, _I64]),

@@ -550,7 +550,8 @@ struct Engine {
   // h_soff[u] = first sample of utterance u relative to d_pcm, h_len[u] = its samples. Results stay in the lanes' search
   // states (lane_of / idx_of map utterances to them) until the next pass.
   void decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
-                         std::vector<int> *Tp, const float *d_featin = nullptr, const std::vector<long long> *h_foff = nullptr);
+                         std::vector<int> *Tp, const float *d_featin = nullptr, const std::vector<long long> *h_foff = nullptr,
+                         const std::vector<std::vector<int>> *forced_groups = nullptr);
   struct UttResult { int n_tokens; const int *tokens, *frames; const float *tok_lp, *stats; };
   UttResult result_of(int u) const;
   void collect_gemm_times();
@@ -1399,15 +1400,20 @@ Engine::UttResult Engine::result_of(int u) const {
 
 // With d_featin the pass starts from precomputed features instead of PCM: utterance u has (h_len[u] + 80) / 160 frames at
 // row h_foff[u] of d_featin (h_len stays the sample count the features were computed from).
+// forced_groups: the caller's own split (consecutive batches of a long decode call, or repetitions of a staged batch): group g's
+// search runs on its lane beside the encoder of group g + 1 - the same mechanism as the length-sorted split, without cutting a
+// batch into smaller encoder passes.
 void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
-                               std::vector<int> *Tp, const float *d_featin, const std::vector<long long> *h_foff) {
+                               std::vector<int> *Tp, const float *d_featin, const std::vector<long long> *h_foff,
+                               const std::vector<std::vector<int>> *forced_groups) {
   gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
   reset_tile_counters();
-  const std::vector<std::vector<int>> groups = plan_groups(h_len);
+  const std::vector<std::vector<int>> groups = forced_groups ? *forced_groups : plan_groups(h_len);
   const int G = (int)groups.size();
-  static const int reserve_env = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 16;
+  if (G > kMaxLanes) throw std::runtime_error("too many groups in one pass");
+  static const int reserve_env = getenv("B200ASR_SM_RESERVE") ? atoi(getenv("B200ASR_SM_RESERVE")) : 8;
   static const bool no_overlap = getenv("B200ASR_PIPE_NOOVERLAP") != nullptr;   // diagnostic: searches start after the last encoder
   if (G > 1) ensure_partition();
   const int reserve = part.ok ? part.search_sms : reserve_env;
@@ -1510,7 +1516,7 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
   {
     double audio = 0;
     for (long long v : h_len) audio += (double)v / 16000.0;
-    if (n >= 16 && audio > 100.0 && tm.encoder > 0.f && steps_len > 0 && !profiling) {
+    if (!forced_groups && n >= 16 && audio > 100.0 && tm.encoder > 0.f && steps_len > 0 && !profiling) {
       const double k_now = (steps_ms / steps_len) / ((double)(tm.fbank + tm.encoder) / audio);
       // hysteresis: a new plan means new workspace sizes (reallocation stalls), so only a clear change moves it
       if (k_now > 1.0 && k_now < 1000.0 && (k_now > 1.3 * kappa || k_now < 0.7 * kappa)) kappa = k_now;
@@ -1621,20 +1627,29 @@ void Engine::decode(Stream *const *ss, int n) {
 }
 
 void Engine::decode_part(Stream *const *ss, int n) {
-  // sub-batches bounded by total audio so workspaces stay bounded (about 70 min of audio per pass)
+  // Batches bounded by total audio so workspaces stay bounded (about 70 min of audio per encoder pass). A call that needs
+  // several of them runs up to kMaxLanes as ONE pass with forced groups: the search of batch k (on its lane's stream) overlaps
+  // the fbank + encoder of batch k + 1.
   const long long kMaxSamples = 4200LL * 16000;
+  static const bool chain = !(getenv("B200ASR_CHAIN_BATCHES") && atoi(getenv("B200ASR_CHAIN_BATCHES")) == 0);
   int begin = 0;
   while (begin < n) {
+    std::vector<std::vector<int>> groups;
     int end = begin;
-    long long tot = 0;
-    while (end < n && (end == begin || tot + ss[end]->n_samples() <= kMaxSamples)) {
-      tot += ss[end]->n_samples();
-      ++end;
+    const bool from_feats = ss[begin]->has_feats();    // a part is homogeneous (decode() partitions)
+    while (end < n && (int)groups.size() < (chain && !from_feats ? kMaxLanes : 1)) {
+      std::vector<int> g;
+      long long tot = 0;
+      while (end < n && (g.empty() || tot + ss[end]->n_samples() <= kMaxSamples)) {
+        tot += ss[end]->n_samples();
+        g.push_back(end - begin);
+        ++end;
+      }
+      groups.push_back(std::move(g));
     }
     const int nb = end - begin;
     const auto hp0 = std::chrono::steady_clock::now();
     std::vector<long long> soff(nb + 1, 0), slen(nb, 0);
-    const bool from_feats = ss[begin]->has_feats();    // a part is homogeneous (decode() partitions)
     for (int i = 0; i < nb; ++i) {
       slen[i] = ss[begin + i]->n_samples();
       soff[i + 1] = soff[i] + slen[i];
@@ -1689,7 +1704,7 @@ void Engine::decode_part(Stream *const *ss, int n) {
     std::vector<int> Tp;
     soff.resize(nb);
     const auto hp1 = std::chrono::steady_clock::now();
-    decode_pcm_device(d_pcm, soff, slen, nb, &Tp);
+    decode_pcm_device(d_pcm, soff, slen, nb, &Tp, nullptr, nullptr, groups.size() > 1 ? &groups : nullptr);
     const auto hp2 = std::chrono::steady_clock::now();
     cudaEventElapsedTime(&tm.h2d, ev[4], ev[5]);
     unpack_results(ss + begin, nb, Tp);
@@ -1699,8 +1714,8 @@ void Engine::decode_part(Stream *const *ss, int n) {
       tm.d2h = (float)ms(hp2, hp3);   // host-side result unpacking
       static const bool host_prof = getenv("B200ASR_HOST_PROF") != nullptr;
       if (host_prof)
-        fprintf(stderr, "[b200asr host prof] %d streams: stage+enqueue H2D %.2f ms | device pass (wall) %.2f ms | unpack results %.2f ms\n",
-                nb, ms(hp0, hp1), ms(hp1, hp2), ms(hp2, hp3));
+        fprintf(stderr, "[b200asr host prof] %d streams in %d batch(es): stage+enqueue H2D %.2f ms | device pass (wall) %.2f ms | unpack results %.2f ms\n",
+                nb, (int)groups.size(), ms(hp0, hp1), ms(hp1, hp2), ms(hp2, hp3));
     }
     begin = end;
   }
@@ -2181,6 +2196,36 @@ int32_t B200AsrRunStagedBatch(const B200AsrOfflineRecognizer *r, int32_t handle,
   e->pass_graph = e->default_graph();
   e->decode_pcm_device(sgd.pcm, soff, slen, sgd.n, &Tp);
   if (n_tokens) for (int i = 0; i < sgd.n; ++i) n_tokens[i] = e->result_of(i).n_tokens;
+  return 0;
+  API_CATCH(-1)
+}
+
+/* `reps` passes over a staged batch issued back to back, the search of pass k (on its own stream) beside the encoder of pass
+ * k + 1; returns after the last search. total_ms = device time from the first fbank launch to the end of the last search.
+ * n_tokens (may be NULL) receives the token counts of the last pass. reps <= 8. */
+int32_t B200AsrRunStagedBatchChained(const B200AsrOfflineRecognizer *r, int32_t handle, int32_t reps, int32_t *n_tokens, float *total_ms) {
+  API_TRY
+  Engine *e = E(r);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_CHECK(cudaSetDevice(e->device));
+  auto it = e->staged.find(handle);
+  if (it == e->staged.end()) throw std::runtime_error("no such staged batch");
+  if (reps < 1 || reps > kMaxLanes) throw std::runtime_error("reps must be in [1, 8]");
+  const Engine::Staged &sgd = it->second;
+  const int n = sgd.n;
+  std::vector<long long> slen((size_t)n * reps), soff((size_t)n * reps);
+  std::vector<std::vector<int>> groups(reps);
+  for (int k = 0; k < reps; ++k)
+    for (int i = 0; i < n; ++i) {
+      soff[(size_t)k * n + i] = sgd.h_soff[i];
+      slen[(size_t)k * n + i] = sgd.h_soff[i + 1] - sgd.h_soff[i];
+      groups[k].push_back(k * n + i);
+    }
+  std::vector<int> Tp;
+  e->pass_graph = e->default_graph();
+  e->decode_pcm_device(sgd.pcm, soff, slen, n * reps, &Tp, nullptr, nullptr, reps > 1 ? &groups : nullptr);
+  if (n_tokens) for (int i = 0; i < n; ++i) n_tokens[i] = e->result_of((reps - 1) * n + i).n_tokens;
+  if (total_ms) *total_ms = e->tm.total;
   return 0;
   API_CATCH(-1)
 }

@@ -485,6 +485,15 @@ class OfflineRecognizer:
         return {"groups": ng.value, "search_busy_ms": busy.value, "lane_ms": [lanes[i] for i in range(ng.value)],
                 "d2h_bytes": d2h.value}
 
+    def run_staged_chained(self, handle: int, reps: int):
+        """`reps` (<= 8) passes over a staged batch back to back, each pass's search beside the next pass's encoder.
+        Returns (token counts of the last pass, device ms for all passes)."""
+        ntok = np.zeros(self._staged_n[handle], dtype=np.int32)
+        ms = C.c_float(0)
+        if _capi.lib().B200AsrRunStagedBatchChained(self._h, handle, int(reps), _capi.i32ptr(ntok), C.byref(ms)) != 0:
+            raise RuntimeError(_capi.last_error())
+        return ntok, ms.value
+
     def release_batch(self, handle: int) -> None:
         _capi.lib().B200AsrReleaseBatch(self._h, handle)
 

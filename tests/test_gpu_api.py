@@ -284,3 +284,23 @@ def test_pipeline_flags_from_device_statistics_equal_oracle_chain(model_dirs, gp
                 assert abs(a[k] - b[k]) <= 2e-4, (k, a[k], b[k])
         n_flag += bool(b.get("_suspect_level"))
     print("suspect words:", n_flag, "of", len(want["words"]))
+
+
+def test_one_decode_call_spanning_several_batches(tiny):
+    """A decode_streams call with more audio than one encoder pass takes (70 min) runs as chained batches - the search of batch k
+    beside the encoder of batch k + 1: results equal the stream-by-stream decode."""
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, d, rec = tiny
+    clips = [synth.speech_like(16000 * 30 + 37 * i, 9700 + i) for i in range(6)]
+    audios = [clips[i % 6][: len(clips[i % 6]) - 1000 * (i // 6)] for i in range(170)]       # 170 x ~30 s = 85 min, ragged
+    ss = [rec.create_stream() for _ in audios]
+    rec.accept_waveforms(ss, audios)
+    rec.decode_streams(ss)
+    st = rec.last_pipeline_stats()
+    print("chained batches:", st)
+    assert st["groups"] >= 2
+    for i in (0, 5, 77, 139, 140, 169):
+        s1 = rec.create_stream(); s1.accept_waveform(16000, audios[i]); rec.decode_stream(s1)
+        assert s1.result.token_ids == ss[i].result.token_ids and s1.result.frames == ss[i].result.frames
+    ntok = sum(len(s.result.token_ids) for s in ss)
+    assert ntok > 1000

@@ -20,9 +20,22 @@ rec = OfflineRecognizer.from_transducer(encoder=paths["encoder"], decoder=paths[
                                         precision=os.environ.get("PRECISION", "fp32"))
 h = rec.stage_batch(bench.workload(A, 0))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+chain = int(os.environ.get("CHAIN", "0"))
+if chain > 1:     # `chain` passes issued back to back: search of pass k beside the encoder of pass k + 1
+    for i in range(n):
+        ntok, ms = rec.run_staged_chained(h, chain)
+        print(f"chained x{chain}: {ms:.2f} ms total, {ms / chain:.2f} ms per pass", rec.last_pipeline_stats(), "tokens", int(ntok.sum()), flush=True)
+    sys.exit(0)
 tot = []
+prof = os.environ.get("PROFILE_LAST") is not None      # ncu --profile-from-start off: only the last pass is captured
+if prof:
+    from cuda import cuda as _cu
 for i in range(n):
+    if prof and i == n - 1:
+        _cu.cuProfilerStart()
     ntok = rec.run_staged(h)
+    if prof and i == n - 1:
+        _cu.cuProfilerStop()
     tm = rec.last_timings()
     tot.append(tm["total_ms"])
     if i >= n - 2:
