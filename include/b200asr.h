@@ -257,6 +257,8 @@ B200ASR_API int32_t B200AsrLastPipelineStats(const B200AsrOfflineRecognizer *r, 
 B200ASR_API int32_t B200AsrLastTimings(const B200AsrOfflineRecognizer *r, float *out6, int64_t *n_launches);
 /* Dominant-kernel timing: accumulated device time (ms) and FLOPs of all GEMM launches in the last run. */
 B200ASR_API int32_t B200AsrLastGemmStats(const B200AsrOfflineRecognizer *r, double *ms, double *flops, int64_t *launches);
+/* Algorithmic bytes of the same launches: 4 (M K + N K + M N [+ M N residual]) summed. */
+B200ASR_API double B200AsrLastGemmBytes(const B200AsrOfflineRecognizer *r);
 /* Enables per-GEMM CUDA-event timing (costs a little launch overhead); 0/1. */
 B200ASR_API int32_t B200AsrSetProfiling(const B200AsrOfflineRecognizer *r, int32_t on);
 

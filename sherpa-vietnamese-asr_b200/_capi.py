@@ -100,6 +100,7 @@ SYMBOLS = {
     "B200AsrLastPipelineStats": (C.c_int32, [_P, _I32, _F, _F, _I64]),
     "B200AsrLastTimings": (C.c_int32, [_P, _F, _I64]),
     "B200AsrLastGemmStats": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _I64]),
+    "B200AsrLastGemmBytes": (C.c_double, [_P]),
     "B200AsrSetProfiling": (C.c_int32, [_P, C.c_int32]),
 }
 

@@ -218,7 +218,8 @@ class ParallelCopy {
     int ranks = 1;
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
     const int share = std::max(1, hw / ranks);
-    int n = std::min(7, share / 2 - 1);                    // helpers besides the calling thread
+    int n = std::min(7, share - 1);                        // helpers besides the calling thread: copies come in short bursts, so a
+                                                           // rank may use its whole share of the cores for them
     if (const char *e = getenv("B200ASR_COPY_THREADS")) n = atoi(e) - 1;
     n_workers_ = std::max(0, std::min(n, share > 1 ? share - 1 : 0));
     for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this, i] { worker(i + 1); });
@@ -468,7 +469,7 @@ struct Engine {
   Timings tm;
   long long launches_last = 0;
   bool profiling = false;
-  double gemm_ms = 0, gemm_flops = 0;
+  double gemm_ms = 0, gemm_flops = 0, gemm_bytes = 0;
   long long gemm_launches = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
   size_t gemm_ev_used = 0;
@@ -960,6 +961,7 @@ void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, c
   gemm_fn()(g, st);
   if (profiling) CUDA_CHECK(cudaEventRecord(e1, st));
   gemm_flops += 2.0 * (double)M * (double)N * (double)K;
+  gemm_bytes += 4.0 * ((double)M * K + (double)N * K + (double)M * N * (R ? 2.0 : 1.0));   // operands once, result (+ residual)
   ++gemm_launches;
 }
 
@@ -1406,7 +1408,7 @@ Engine::UttResult Engine::result_of(int u) const {
 void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
                                std::vector<int> *Tp, const float *d_featin, const std::vector<long long> *h_foff,
                                const std::vector<std::vector<int>> *forced_groups) {
-  gemm_flops = 0; gemm_launches = 0; gemm_ev_used = 0;
+  gemm_flops = 0; gemm_bytes = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
   reset_tile_counters();
@@ -2284,6 +2286,7 @@ int32_t B200AsrLastGemmStats(const B200AsrOfflineRecognizer *r, double *ms, doub
   if (launches) *launches = r->eng.gemm_launches;
   return 0;
 }
+double B200AsrLastGemmBytes(const B200AsrOfflineRecognizer *r) { return r ? r->eng.gemm_bytes : -1.0; }
 int32_t B200AsrSetProfiling(const B200AsrOfflineRecognizer *r, int32_t on) {
   if (!r) return -1;
   const_cast<Engine &>(r->eng).profiling = on != 0;

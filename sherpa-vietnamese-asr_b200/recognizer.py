@@ -507,7 +507,7 @@ class OfflineRecognizer:
     def last_gemm_stats(self) -> dict:
         ms, fl, n = C.c_double(0), C.c_double(0), C.c_int64(0)
         _capi.lib().B200AsrLastGemmStats(self._h, C.byref(ms), C.byref(fl), C.byref(n))
-        return {"ms": ms.value, "flops": fl.value, "launches": n.value}
+        return {"ms": ms.value, "flops": fl.value, "launches": n.value, "bytes": _capi.lib().B200AsrLastGemmBytes(self._h)}
 
     def set_profiling(self, on: bool) -> None:
         _capi.lib().B200AsrSetProfiling(self._h, int(on))
