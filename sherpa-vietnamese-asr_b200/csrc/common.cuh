@@ -199,6 +199,8 @@ struct SearchModel {
   const float *conv_p1;    // ... and slot 1: relu(conv(emb[y0], emb[y1])) = relu(conv_p0[y0] + conv_p1[y1])
   const float *dec_proj_w; // [jd, dd]
   const float *dec_proj_b;
+  const float *dec_table;  // [V * V, jd] decoder output of every 2-token context (y0 * V + y1), built once by the engine; null = the
+                           // search computes decoder_proj on demand (decoder_joinin_kernel)
   const float *join_w;     // [V, jd]
   const float *join_w_lo;  // low part for the 3xTF32 joiner GEMM (or null)
   const void *join_w16hi, *join_w16lo;   // 16-bit operand copies for the joiner GEMM (or null)
@@ -245,6 +247,8 @@ void launch_decoder_product_rows(const SearchModel &m, const long long *y, const
                                  cudaStream_t st);
 void launch_joiner_records(SearchState *s, const SearchModel &m, const float *X, int rows, int kb, float *records, cudaStream_t st);
 void launch_decoder_rows(const SearchModel &m, const long long *y, int rows, float *out, cudaStream_t st);
+// E[r] = relu(conv_p0[y0] + conv_p1[y1]) for the contexts ctx0 + r = y0 * V + y1 (the decoder-table build, engine.cu)
+void launch_context_preactivations(const SearchModel &m, long long ctx0, int rows, float *E, cudaStream_t st);
 void launch_joiner_rows(const SearchModel &m, const float *enc, const float *dec, int rows, float *tmp, float *logits,
                         cudaStream_t st);
 

@@ -462,6 +462,10 @@ struct Engine {
   double kappa = 50.0;                // search ms per second of utterance length / encoder ms per audio-second (adapted per pass)
   long long d2h_bytes_last = 0;
   SearchModel sm{};
+  // Decoder outputs of all V^2 two-token contexts (the reference's dec_cache, core/asr_engine.py:1072-1088, filled completely
+  // and ahead of time): built on the first search when it fits comfortably, see ensure_dec_table()
+  bool dec_table_tried = false;
+  void ensure_dec_table();
   std::shared_ptr<GraphPair> graph;          // the recognizer's hotword automaton (null = none)
   const ContextGraphDev *pass_graph = nullptr;   // what the pass being issued scores with (decode sets it per partition)
   const ContextGraphHost &cg_host() const { static const ContextGraphHost empty; return graph ? graph->host : empty; }
@@ -916,6 +920,44 @@ std::shared_ptr<GraphPair> Engine::make_graph(const int32_t *tokens, const int32
   g->host.build(tokens, offsets, scores, n);
   g->upload(device);
   return g;
+}
+
+// The stateless decoder sees only the last two tokens, so decoder_proj(relu(conv(emb[y0], emb[y1]))) takes V^2 values. With the
+// whole table in HBM (V = 2000, jd = 512: 8.2 GB of the 180) a frame step of the search needs no decoder kernel at all: the
+// selection kernel reads the row of each new hypothesis and writes the joiner input directly. Built once per recognizer with
+// the Linear-layer GEMM of the recognizer's precision mode, in chunks of 128 K contexts (pre-activations from the per-token
+// convolution tables, then one GEMM). Skipped (the search then computes decoder rows on demand) in the CUDA-core cross-check
+// mode, with B200ASR_DEC_TABLE=0, or when the table would take more than a quarter of the free device memory.
+void Engine::ensure_dec_table() {
+  if (dec_table_tried) return;
+  dec_table_tried = true;
+  if (precision == 2) return;
+  if (const char *e = getenv("B200ASR_DEC_TABLE")) if (atoi(e) == 0) return;
+  const size_t n_ctx = (size_t)V * V;
+  const size_t bytes = n_ctx * join_dim * sizeof(float);
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  const int chunk = 128 * 1024;
+  if (bytes + (size_t)chunk * dec_dim * sizeof(float) > free_b / 4) return;
+  float *table = nullptr, *pre = nullptr;
+  if (cudaMalloc(&table, bytes) != cudaSuccess) { cudaGetLastError(); return; }
+  owned.push_back(table);
+  CUDA_CHECK(cudaMalloc(&pre, (size_t)chunk * dec_dim * sizeof(float)));
+  const double f0 = gemm_flops, b0 = gemm_bytes;
+  const long long n0 = gemm_launches;
+  const bool prof = profiling;
+  profiling = false;
+  reset_tile_counters();   // the GEMMs below claim tiles through counters that must be zero at launch
+  for (size_t c0 = 0; c0 < n_ctx; c0 += chunk) {
+    const int rows = (int)std::min<size_t>(chunk, n_ctx - c0);
+    launch_context_preactivations(sm, (long long)c0, rows, pre, st);
+    gemm(pre, dec_dim, sm.dec_proj_w, sm.dec_proj_b, nullptr, 0, table + c0 * join_dim, join_dim, rows, join_dim, dec_dim, ACT_NONE);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(cudaFree(pre));
+  profiling = prof;
+  gemm_flops = f0; gemm_bytes = b0; gemm_launches = n0;
+  sm.dec_table = table;
 }
 
 void Engine::set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n) {
@@ -1408,6 +1450,7 @@ Engine::UttResult Engine::result_of(int u) const {
 void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> &h_soff, const std::vector<long long> &h_len, int n,
                                std::vector<int> *Tp, const float *d_featin, const std::vector<long long> *h_foff,
                                const std::vector<std::vector<int>> *forced_groups) {
+  ensure_dec_table();
   gemm_flops = 0; gemm_bytes = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
@@ -2052,6 +2095,7 @@ int32_t B200AsrDecoderJoinerInput(const B200AsrOfflineRecognizer *r, const int64
   float *d_enc = reinterpret_cast<float *>(dy + 2 * m), *d_dec = d_enc + m * jd, *d_x = d_dec + m * jd;
   CUDA_CHECK(cudaMemcpyAsync(dy, y, (size_t)2 * m * sizeof(long long), cudaMemcpyHostToDevice, e->st));
   if (enc) CUDA_CHECK(cudaMemcpyAsync(d_enc, enc, m * jd * sizeof(float), cudaMemcpyHostToDevice, e->st));
+  e->ensure_dec_table();
   launch_decoder_product_rows(e->sm, dy, enc ? d_enc : nullptr, m, d_dec, d_x, e->st);
   if (dec_out) CUDA_CHECK(cudaMemcpyAsync(dec_out, d_dec, m * jd * sizeof(float), cudaMemcpyDeviceToHost, e->st));
   if (x_out) CUDA_CHECK(cudaMemcpyAsync(x_out, d_x, m * jd * sizeof(float), cudaMemcpyDeviceToHost, e->st));
@@ -2095,6 +2139,7 @@ int32_t B200AsrBeamSearch(const B200AsrOfflineRecognizer *r, const float *enc_ou
   res.n_utts = n; res.max_tokens = max_tokens; res.n_tokens = n_tokens; res.tokens = tokens; res.frames = frames;
   res.tok_lp = tok_logprobs; res.stats = stats;
   std::vector<int> l(lens, lens + n);
+  e->ensure_dec_table();
   run_search(e->search, e->sm, e->default_graph(), d_enc, l.data(), n, method, beam, e->blank_penalty, &res, e->st);
   return 0;
   API_CATCH(-1)

@@ -386,6 +386,7 @@ struct SelShared {
   unsigned long long win[kMaxBeam];
   NewNode nodes[kMaxBeam];
   int chg_pos[kMaxBeam];
+  int slot_of[kMaxBeam];        // winner r -> slot in the new beam, -1 if it merged into an earlier one (decoder-table mode)
   float rstats[kMaxBeam][4];   // per-row token statistics when they come from the partial records
   int n_new, n_nodes;
   int node_count0;             // arena fill of this utterance, fetched at kernel start (off the serial section)
@@ -397,9 +398,37 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
   const int V = m.V;
   ArenaNode *arena = d.arena + d.arena_off[s];
   const bool more = t + 1 < d.lens[s];      // another frame follows: the new beam needs joiner inputs
+  // Decoder-table mode: the joiner input of every new hypothesis is tanh(enc[t + 1] + table[y0, y1]), written here, so a frame
+  // step has no decoder kernel. Warps 1.. fetch the table and encoder rows of all k winners while thread 0 runs the serial
+  // expansion below (the context of winner r is known from its key; whether it survives the dedup is not, yet).
+  const bool table = m.dec_table != nullptr;
+  constexpr int kPf = 3;
+  constexpr int kPfThreads = kSelThreads - 32;
+  const int jd4 = m.jd >> 2;
+  const long long enc_next_row = d.enc_off[s] + t + 1;
+  float4 pf_t[kPf], pf_e[kPf];
+  if (table && more && warp > 0) {
+#pragma unroll
+    for (int i = 0; i < kPf; ++i) {
+      const int u = (tid - 32) + i * kPfThreads;
+      const int r = u / jd4, c = u - r * jd4;
+      pf_t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_e[i] = pf_t[i];
+      const unsigned long long key = r < k ? sh.win[r] : 0ULL;
+      if (key != 0ULL) {
+        const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
+        const int hi = idx / V, tok = idx - hi * V;
+        const bool blank = tok == m.blank_id;
+        const int y0 = blank ? sh.old_[hi].y0 : sh.old_[hi].y1, y1 = blank ? sh.old_[hi].y1 : tok;
+        pf_t[i] = __ldg(reinterpret_cast<const float4 *>(m.dec_table + ((long long)y0 * V + y1) * m.jd) + c);
+        pf_e[i] = __ldg(reinterpret_cast<const float4 *>(d.enc + enc_next_row * m.jd) + c);
+      }
+    }
+  }
   if (tid == 0) {
     int n_new = 0, n_nodes = 0;
     int node_count = sh.node_count0;
+    for (int r = 0; r < kMaxBeam; ++r) sh.slot_of[r] = -1;
     for (int r = 0; r < k; ++r) {
       const unsigned long long key = sh.win[r];
       if (key == 0ULL) break;
@@ -450,6 +479,7 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
         sh.nodes[n_nodes].row = hi;
         ++n_nodes;
       }
+      sh.slot_of[r] = n_new;
       sh.new_[n_new++] = c;
     }
     sh.n_new = n_new;
@@ -458,27 +488,55 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
     d.hyp_count[(cur ^ 1) * d.n + s] = n_new;
     // rows of the new beam whose decoder output has to be recomputed before the next joiner step, and the per-row
     // descriptors of the blank extensions (parent row to copy from); both carry the encoder_out row of frame t + 1
-    int n_chg = 0;
-    for (int q = 0; q < n_new; ++q) {
-      sh.chg_pos[q] = -1;
-      if (more && sh.new_[q].dec_src < 0) sh.chg_pos[q] = n_chg++;
-    }
-    const int enc_next = (int)d.enc_off[s] + t + 1;
-    int2 *rdesc = d.rowdesc + (size_t)((t + 1) & 1) * d.n * d.beam + (size_t)s * d.beam;
-    for (int q = 0; q < d.beam; ++q) {
-      int src = -2;
-      if (more && q < n_new) src = sh.new_[q].dec_src < 0 ? -1 : s * d.beam + sh.new_[q].dec_src;
-      rdesc[q] = make_int2(src, enc_next);
-    }
-    if (n_chg > 0) {
-      const int base = atomicAdd(&d.chg_count[(t + 1) & 1], n_chg);
-      int2 *list = d.chg_list + (size_t)((t + 1) & 1) * d.n * d.beam;
-      for (int q = 0; q < n_new; ++q)
-        if (sh.chg_pos[q] >= 0) list[base + sh.chg_pos[q]] = make_int2(s * d.beam + q, enc_next);
+    // (on-demand decoder only: with the table every row is written below)
+    if (!table) {
+      int n_chg = 0;
+      for (int q = 0; q < n_new; ++q) {
+        sh.chg_pos[q] = -1;
+        if (more && sh.new_[q].dec_src < 0) sh.chg_pos[q] = n_chg++;
+      }
+      const int enc_next = (int)d.enc_off[s] + t + 1;
+      int2 *rdesc = d.rowdesc + (size_t)((t + 1) & 1) * d.n * d.beam + (size_t)s * d.beam;
+      for (int q = 0; q < d.beam; ++q) {
+        int src = -2;
+        if (more && q < n_new) src = sh.new_[q].dec_src < 0 ? -1 : s * d.beam + sh.new_[q].dec_src;
+        rdesc[q] = make_int2(src, enc_next);
+      }
+      if (n_chg > 0) {
+        const int base = atomicAdd(&d.chg_count[(t + 1) & 1], n_chg);
+        int2 *list = d.chg_list + (size_t)((t + 1) & 1) * d.n * d.beam;
+        for (int q = 0; q < n_new; ++q)
+          if (sh.chg_pos[q] >= 0) list[base + sh.chg_pos[q]] = make_int2(s * d.beam + q, enc_next);
+      }
     }
   }
   __syncthreads();
   SEL_PROF(3);
+  if (table && more) {
+    auto tanh4 = [](const float4 &a, const float4 &b) {
+      return make_float4(tanhf(a.x + b.x), tanhf(a.y + b.y), tanhf(a.z + b.z), tanhf(a.w + b.w));
+    };
+    float *xs = d.X + (long long)s * d.beam * m.jd;
+    if (warp > 0) {
+#pragma unroll
+      for (int i = 0; i < kPf; ++i) {
+        const int u = (tid - 32) + i * kPfThreads;
+        const int r = u / jd4, c = u - r * jd4;
+        const int q = r < k ? sh.slot_of[r] : -1;
+        if (q >= 0) reinterpret_cast<float4 *>(xs + (long long)q * m.jd)[c] = tanh4(pf_e[i], pf_t[i]);
+      }
+    }
+    // winners past the prefetch window (beam > 4 or a wider joiner)
+    for (int u = kPf * kPfThreads + tid; u < k * jd4; u += kSelThreads) {
+      const int r = u / jd4, c = u - r * jd4;
+      const int q = sh.slot_of[r];
+      if (q < 0) continue;
+      const HypSlot &hs = sh.new_[q];
+      const float4 tv = __ldg(reinterpret_cast<const float4 *>(m.dec_table + ((long long)hs.y0 * V + hs.y1) * m.jd) + c);
+      const float4 ev = __ldg(reinterpret_cast<const float4 *>(d.enc + enc_next_row * m.jd) + c);
+      reinterpret_cast<float4 *>(xs + (long long)q * m.jd)[c] = tanh4(ev, tv);
+    }
+  }
 
   // per emitted token statistics from its logits row, one warp per token (full-logits selection only; the
   // partial-record selection has them per row already)
@@ -518,7 +576,7 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
 
   // decoder pre-activation for the hypotheses with a new context: E = relu(P0[y0] + P1[y1]), the grouped k=2
   // convolution split into its two per-token halves (tables built once at load)
-  if (more) {
+  if (more && !table) {
     const int dd4 = m.dd >> 2;
     for (int i = tid; i < n_new * dd4; i += kSelThreads) {
       const int q = i / dd4, c = i - q * dd4;
@@ -810,8 +868,41 @@ __global__ void init_search_kernel(SearchModel m, SearchDev d, int n_pos) {
     d.rowdesc[(size_t)s * d.beam + threadIdx.x] = make_int2((threadIdx.x == 0 && s < n_pos) ? -1 : -2, (int)d.enc_off[s]);
     d.rowdesc[(size_t)(d.n + s) * d.beam + threadIdx.x] = make_int2(-2, 0);
   }
+  if (m.dec_table) {   // joiner input of frame 0: context [0, 0] is row 0 of the decoder table
+    if (s < n_pos)
+      for (int o = threadIdx.x; o < m.jd; o += blockDim.x)
+        d.X[((long long)s * d.beam) * m.jd + o] = tanhf(__ldg(d.enc + d.enc_off[s] * m.jd + o) + __ldg(m.dec_table + o));
+    return;
+  }
   for (int o = threadIdx.x; o < m.dd; o += blockDim.x)   // context [0, 0]
     d.E[((long long)s * d.beam) * m.dd + o] = fmaxf(__ldg(m.conv_p0 + o) + __ldg(m.conv_p1 + o), 0.f);
+}
+
+// decoder-table build: pre-activations of the contexts ctx0 .. ctx0 + rows
+__global__ void context_pre_kernel(SearchModel m, long long ctx0, int rows, float *__restrict__ E) {
+  const int dd4 = m.dd >> 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * dd4) return;
+  const int r = (int)(i / dd4), c = (int)(i - (long long)r * dd4);
+  const long long ctx = ctx0 + r;
+  const int y0 = (int)(ctx / m.V), y1 = (int)(ctx - (long long)y0 * m.V);
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(m.conv_p0 + (long long)y0 * m.dd) + c);
+  const float4 b = __ldg(reinterpret_cast<const float4 *>(m.conv_p1 + (long long)y1 * m.dd) + c);
+  reinterpret_cast<float4 *>(E)[i] = make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
+}
+
+// decoder-table mode of the parity hook: dec = table[y0, y1], X = tanh(enc + dec)
+__global__ void table_rows_kernel(SearchModel m, const long long *__restrict__ y, const float *__restrict__ enc, int rows,
+                                  float *__restrict__ dec_out, float *__restrict__ x_out) {
+  const int i = blockIdx.x;
+  if (i >= rows) return;
+  const int y0 = (int)max(0LL, y[2 * i]), y1 = (int)max(0LL, y[2 * i + 1]);
+  const float *row = m.dec_table + ((long long)y0 * m.V + y1) * m.jd;
+  for (int o = threadIdx.x; o < m.jd; o += blockDim.x) {
+    const float v = __ldg(row + o);
+    dec_out[(long long)i * m.jd + o] = v;
+    x_out[(long long)i * m.jd + o] = tanhf((enc ? enc[(long long)i * m.jd + o] : 0.f) + v);
+  }
 }
 
 // finalize (:1143-1153): subtract unfinished hotword score, pick first max of log_prob/len(ys), unroll the chain.
@@ -899,6 +990,7 @@ struct SearchState {
   long long *d_prof = nullptr;
   unsigned long long *d_trace = nullptr;
   int prof_steps = 0;
+  bool table_mode = false;   // last issued search ran without decoder_joinin (decoder table)
 };
 
 SearchState *search_state_create() { return new SearchState(); }
@@ -1018,7 +1110,7 @@ void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g
     CUDA_CHECK(cudaMemsetAsync(d_trace, 0, (size_t)std::max(max_len, 1) * 16 * sizeof(unsigned long long), st));
     d.trace = d_trace;
   }
-  S->d_prof = d_prof; S->d_trace = d_trace; S->prof_steps = max_len;
+  S->d_prof = d_prof; S->d_trace = d_trace; S->prof_steps = max_len; S->table_mode = m.dec_table != nullptr;
   ContextGraphView gv{};
   const int has_graph = (g && g->n_nodes > 1 && !greedy) ? 1 : 0;
   if (has_graph)
@@ -1062,9 +1154,12 @@ void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g
     const int cur = t & 1;
     const int act_rows = n_active * beam;
     // decoder outputs for the changed contexts + joiner input X = tanh(enc_t + dec) for every live row
-    const int dj_grid = std::min(2 * n_sms, std::max(((act_rows + DJ_TM - 1) / DJ_TM) * ntn, 1));
-    launch_pdl(decoder_joinin_kernel, dim3(dj_grid), dim3(DJ_THREADS), kDjSmem, st, use_pdl, m, d, t, act_rows);
-    count_launch();
+    // (with the decoder table the previous selection - or init_search_kernel - has already written X)
+    if (!m.dec_table) {
+      const int dj_grid = std::min(2 * n_sms, std::max(((act_rows + DJ_TM - 1) / DJ_TM) * ntn, 1));
+      launch_pdl(decoder_joinin_kernel, dim3(dj_grid), dim3(DJ_THREADS), kDjSmem, st, use_pdl, m, d, t, act_rows);
+      count_launch();
+    }
     // joiner output_linear: logits = X * Wj^T + bj (+ partial records)
     GemmArgs ga{};
     ga.A = S->X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = S->logits;
@@ -1138,19 +1233,22 @@ static void search_print_prof(SearchState *S) {
     double acc[16] = {0};
     double step = 0;
     int cnt = 0;
+    // decoder-table mode: a step starts with the joiner GEMM (slot 2) and has no decoder_joinin marks
+    const int b0 = S->table_mode ? 2 : 0;
+    auto used = [&](int i) { return !S->table_mode || (i >= 2 && i <= 9); };
     for (int t = 1; t + 1 < max_len; ++t) {
       const unsigned long long *r = &h[(size_t)t * 16], *nx = &h[(size_t)(t + 1) * 16];
-      bool ok = nx[0] != 0;
-      for (int i = 0; i < 15; ++i) ok = ok && r[i] != 0;
+      bool ok = nx[b0] != 0;
+      for (int i = 0; i < 15; ++i) ok = ok && (!used(i) || r[i] != 0);
       if (!ok) continue;
-      for (int i = 0; i < 15; ++i) acc[i] += (double)((long long)(r[i] - r[0]));
-      step += (double)(nx[0] - r[0]);
+      for (int i = 0; i < 15; ++i) if (used(i)) acc[i] += (double)((long long)(r[i] - r[b0]));
+      step += (double)(nx[b0] - r[b0]);
       ++cnt;
     }
     if (cnt) {
       fprintf(stderr, "[b200asr search trace] %d steps, mean us from step start:", cnt);
       const int order[15] = {0, 10, 11, 12, 13, 14, 1, 2, 4, 5, 6, 7, 3, 8, 9};
-      for (int i : order) fprintf(stderr, " %s=%.2f", names[i], acc[i] / cnt / 1e3);
+      for (int i : order) if (used(i)) fprintf(stderr, " %s=%.2f", names[i], acc[i] / cnt / 1e3);
       fprintf(stderr, " next_step=%.2f\n", step / cnt / 1e3);
     }
   }
@@ -1201,6 +1299,12 @@ __global__ void prep_product_rows_kernel(SearchModel m, SearchDev d, const long 
 void launch_decoder_product_rows(const SearchModel &m, const long long *y, const float *enc, int rows, float *dec_out, float *x_out,
                                  cudaStream_t st) {
   if (rows <= 0) return;
+  if (m.dec_table) {   // what a frame step reads in decoder-table mode
+    table_rows_kernel<<<rows, 128, 0, st>>>(m, y, enc, rows, dec_out, x_out);
+    count_launch(); KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return;
+  }
   if (!m.conv_p0 || !m.conv_p1) throw CudaError("decoder convolution tables are missing");
   float *E = nullptr, *dec = nullptr, *X = nullptr, *zero = nullptr;
   int2 *lists = nullptr;
@@ -1240,6 +1344,13 @@ void launch_joiner_records(SearchState *S, const SearchModel &m, const float *X,
   ga.W16hi = m.join_w16hi; ga.W16lo = m.join_w16lo; ga.w16_ld = m.join_w16_ld;
   ga.ldc = m.V; ga.M = rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_JOINER; ga.partials = records; ga.part_kb = kb; ga.pdl = 0;
   S->gemm(ga, st);
+}
+
+void launch_context_preactivations(const SearchModel &m, long long ctx0, int rows, float *E, cudaStream_t st) {
+  if (rows <= 0) return;
+  const long long total = (long long)rows * (m.dd >> 2);
+  context_pre_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m, ctx0, rows, E);
+  count_launch(); KERNEL_CHECK();
 }
 
 void launch_decoder_rows(const SearchModel &m, const long long *y, int rows, float *out, cudaStream_t st) {

@@ -224,7 +224,9 @@ def test_decoder_joiner_rows(m30):
 @pytest.mark.parametrize("kb", [4, 8, 16])
 def test_product_decoder_and_joiner_record_kernels(m30, kb):
     """The kernels a frame step of the device search launches, pinned directly (not through downstream tokens):
-    decoder_joinin_kernel -> decoder_out and X = tanh(enc + dec) against the oracle decoder; the tcgen05 joiner GEMM with
+    the decoder rows a step reads (the V^2 context table built by the Linear-layer GEMM; decoder_joinin_kernel with
+    B200ASR_DEC_TABLE=0, test_on_demand_decoder_equals_decoder_table) -> decoder_out and X = tanh(enc + dec) against the
+    oracle decoder; the tcgen05 joiner GEMM with
     the record epilogue -> log-sum-exp, top-k and the entropy sums rebuilt from the records against the oracle's logits."""
     import torch
     from oracle import zipformer_ref as zr
@@ -356,6 +358,34 @@ def test_search_batch_spanning_several_row_tiles(m30):
     orec, ocfg, _ = oracle_recognizer(paths, beam=4)
     encs = _window_cases(orec, ocfg, 70)
     assert _search_case(rec, orec, encs, 4, "modified_beam_search") > 50
+
+
+def test_on_demand_decoder_equals_decoder_table(m30, monkeypatch):
+    """Frame steps read the decoder output of a context from the V^2 table the engine builds on its first search (the
+    reference's dec_cache filled ahead of time, core/asr_engine.py:1072-1088); B200ASR_DEC_TABLE=0 keeps the on-demand path
+    (decoder_joinin_kernel: decoder_proj only for changed contexts). Both are held to the oracle: identical tokens / frames,
+    decoder rows within 2e-5, and the two product paths agree with each other at fp32 rounding level."""
+    import torch
+    from oracle import zipformer_ref as zr
+    cfg, paths, rec_table = m30
+    monkeypatch.setenv("B200ASR_DEC_TABLE", "0")
+    rec = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+    orec, ocfg, tensors = oracle_recognizer(paths, beam=4)
+    encs = _window_cases(orec, ocfg, 40)
+    assert _search_case(rec, orec, encs, 4, "modified_beam_search") > 30      # the search issues decoder_joinin here
+    assert _search_case(rec, orec, encs[:9], 1, "greedy_search") > 5
+    rng = np.random.default_rng(5)
+    y = rng.integers(0, ocfg.vocab_size, (150, 2))
+    y[0] = (0, 0)
+    enc = rng.standard_normal((150, ocfg.joiner_dim)).astype(np.float32)
+    with torch.no_grad():
+        want_dec = zr.decoder(zr.Weights(tensors), ocfg, y).numpy()
+    dec_a, x_a = rec.decoder_joiner_input(y, enc)
+    monkeypatch.delenv("B200ASR_DEC_TABLE")
+    assert _search_case(rec_table, orec, encs, 4, "modified_beam_search") > 30
+    dec_b, x_b = rec_table.decoder_joiner_input(y, enc)
+    assert row_err(dec_a, want_dec) <= 2e-5 and row_err(dec_b, want_dec) <= 2e-5
+    assert row_err(dec_a, dec_b) <= 1e-5 and np.abs(x_a - x_b).max() <= 1e-5
 
 
 def test_search_cuda_core_mode_uses_full_logits_selection(model_dirs):
