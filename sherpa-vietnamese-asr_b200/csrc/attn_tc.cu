@@ -23,7 +23,7 @@ using namespace tc;
 namespace {
 
 // smem stages: the 12-wide value tiles are tiny, so the kernel is bound by how many bytes of A it keeps in flight
-constexpr int stages_of(int BN) { return BN <= 16 ? 4 : 4; }
+constexpr int stages_of(int BN) { return BN <= 16 ? 6 : 4; }   // 6 x 36 KB (A, A_lo, V, V_lo) / 4 x 48 KB of the 227 KB
 
 struct AttnTcParams {
   const CUtensorMap *mapsA, *mapsV, *mapsVlo;

@@ -25,7 +25,22 @@ struct CudaError : std::runtime_error {
 // kernel in the stream is still running; it must execute pdl_wait() before touching anything that kernel (or an
 // earlier one) produces, and it lets its own successor start launching with pdl_trigger(). Both are no-ops for
 // normal launches.
+// The fp16 operand split of the FP32 mode (gemm_tc_f16.cu): x' = x * scale = hi + lo with hi = fp16(x'), lo = fp16(x' - hi);
+// activations are scaled by 64, weights by 1024 (powers of two, undone in the epilogue).
+constexpr float kF16AScale = 64.0f, kF16WScale = 1024.0f;
 #ifdef __CUDACC__
+}  // namespace b200asr
+#include <cuda_fp16.h>
+namespace b200asr {
+__device__ __forceinline__ float clamp_f16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }   // NaN stays NaN
+// (x0, x1), already scaled -> packed fp16 hi pair and packed fp16 lo pair; element 0 in the low half-word
+__device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t *>(&h);
+  lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>
@@ -90,6 +105,8 @@ struct GemmArgs {
   const float *Wlo;          // W - trunc_tf32(W), needed by the 3xTF32 tensor-core kernel only (else null)
   const void *W16hi, *W16lo; // 16-bit operand copies made by split_weights_16 (gemm_tc_f16.cu), row pitch w16_ld; else null
   int w16_ld;
+  const void *A16hi, *A16lo; // the activation already in the same scaled fp16 hi / lo form ([M, K] each, row pitch a16_ld): the search's
+  int a16_ld, a16_rows;      // joiner input, written that way by the selection kernel (A may then be null; a16_rows = rows the planes hold, >= M, 0 = M); ACT_JOINER records only
   const float *bias;         // [N] or null
   const float *R; int ldr;   // residual or null
   float *C; int ldc;
@@ -242,6 +259,7 @@ struct SearchView {
 };
 SearchView search_view(const SearchState *s);
 void search_collect(SearchState *s, SearchResultHost *out);
+void search_print_prof(SearchState *s);   // B200ASR_SEARCH_PROF=1: phase counters / step timeline of the last issued search, to stderr
 long long search_result_bytes(const SearchState *s);   // device->host bytes the last issued search copies
 void launch_decoder_product_rows(const SearchModel &m, const long long *y, const float *enc, int rows, float *dec_out, float *x_out,
                                  cudaStream_t st);

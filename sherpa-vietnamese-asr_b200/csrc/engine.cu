@@ -522,6 +522,7 @@ struct Engine {
   float *upload(const std::vector<float> &h);
   void gemm(const float *A, int lda, const float *Wt, const float *bias, const float *R, int ldr, float *C, int ldc, int M, int N,
             int K, int act);
+  void feed_forward(const LayerW &w, int j, const float *x, const float *R, float *out, int M, int D, float *hidden);
   void set_graph(const int32_t *tokens, const int32_t *offsets, const float *scores, int n);
   // pipeline pieces (device pointers)
   // h_len[u] = samples of utterance u; d_slen null = packed PCM (lengths from consecutive offsets)
@@ -1104,6 +1105,24 @@ void Engine::attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r
   launch_attn_apply_tc(a, st);
 }
 
+// out = R + Linear(SwooshL(Linear(x))). The hidden activation [M, f] is the largest tensor of a layer (up to 5 D wide); walking
+// the rows in chunks whose hidden block stays in L2 keeps it out of HBM: the second GEMM of a chunk reads what the first has
+// just written, and the next chunk overwrites the same lines before they are evicted (B200ASR_FFN_CHUNK_MB, 0 = one pass).
+void Engine::feed_forward(const LayerW &w, int j, const float *x, const float *R, float *out, int M, int D, float *hidden) {
+  const int f = w.ff_dim[j];
+  static const long long chunk_mb = getenv("B200ASR_FFN_CHUNK_MB") ? atoll(getenv("B200ASR_FFN_CHUNK_MB")) : 0;
+  long long rows = M;
+  if (chunk_mb > 0) {
+    rows = std::max<long long>(128 * 148, ((chunk_mb << 20) / ((long long)f * 4)) / 128 * 128);
+    if (rows * 5 / 4 >= M) rows = M;      // no sliver at the end
+  }
+  for (long long m0 = 0; m0 < M; m0 += rows) {
+    const int mc = (int)std::min<long long>(rows, M - m0);
+    gemm(x + m0 * D, D, w.ff_in_w[j], w.ff_in_b[j], nullptr, 0, hidden, f, mc, f, D, ACT_SWOOSH_L);
+    gemm(hidden, f, w.ff_out_w[j], w.ff_out_b[j], R + m0 * D, D, out + m0 * D, D, mc, D, f, ACT_NONE);
+  }
+}
+
 void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
                        const AttnPlan &pl) {
   const int D = s.D, H = s.H, h = (3 * D) / 4;
@@ -1122,8 +1141,7 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   else
     launch_attn_weights(proj, pw, pp, r, aoff, H, qd, pd, A, st);
   // feed_forward1
-  gemm(src, D, w.ff_in_w[0], w.ff_in_b[0], nullptr, 0, proj, w.ff_dim[0], M, w.ff_dim[0], D, ACT_SWOOSH_L);
-  gemm(proj, w.ff_dim[0], w.ff_out_w[0], w.ff_out_b[0], src, D, w1, D, M, D, w.ff_dim[0], ACT_NONE);
+  feed_forward(w, 0, src, src, w1, M, D, proj);
   // nonlin attention (head 0)
   gemm(w1, D, w.nl_in_w, w.nl_in_b, nullptr, 0, proj, 3 * h, M, 3 * h, D, ACT_NONE);
   attn_apply(pl, s, r, aoff, proj + h, 3 * h, proj, 3 * h, proj + 2 * h, 3 * h, h, true, hid, h);
@@ -1138,9 +1156,7 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
     launch_glu_dwconv(proj, r, pl.dw_tile_off, pl.dw_tiles, D, s.k, w.cv_dw_w[j], w.cv_dw_b[j], hid, st);
     gemm(hid, D, w.cv_out_w[j], w.cv_out_b[j], w1, D, w1, D, M, D, D, ACT_NONE);
     // feed forward 2 / 3
-    const int f = w.ff_dim[j + 1];
-    gemm(w1, D, w.ff_in_w[j + 1], w.ff_in_b[j + 1], nullptr, 0, proj, f, M, f, D, ACT_SWOOSH_L);
-    gemm(proj, f, w.ff_out_w[j + 1], w.ff_out_b[j + 1], w1, D, w1, D, M, D, f, ACT_NONE);
+    feed_forward(w, j + 1, w1, w1, w1, M, D, proj);
     if (j == 0) launch_bypass(w1, src, M, D, w.bypass_mid, w1, st);
   }
   launch_biasnorm_bypass(w1, src, M, D, w.norm_bias, w.norm_log_scale, w.bypass, src, st);
@@ -1540,6 +1556,7 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
     for (int g = 0; g < G; ++g) CUDA_CHECK(cudaStreamWaitEvent(st, lanes[g].s1, 0));
   CUDA_CHECK(cudaEventRecord(ev[3], st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int g = 0; g < G; ++g) search_print_prof(lane(g).search);
   n_groups_last = G;
   tm.fbank = tm.encoder = 0;
   search_busy_ms = 0;

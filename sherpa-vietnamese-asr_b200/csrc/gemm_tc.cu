@@ -349,6 +349,15 @@ bool tc_init() { init_once(); return g_ok; }
 void make_map_16(CUtensorMap *map, const void *ptr, bool bf16, int rows, int K, int ld, int box_rows) {
   init_once();
   if (!g_ok) throw CudaError("cuTensorMapEncodeTiled entry point unavailable");
+  // same small per-thread cache as make_map: a frame step of the search uses four of these (pointer, shape) pairs T' times
+  struct Key { const void *p; int bf16, rows, K, ld, box; };
+  struct Ent { Key k; CUtensorMap m; };
+  static thread_local Ent cache[16];
+  static thread_local int n_cached = 0, next = 0;
+  for (int i = 0; i < n_cached; ++i) {
+    const Key &k = cache[i].k;
+    if (k.p == ptr && k.bf16 == (int)bf16 && k.rows == rows && k.K == K && k.ld == ld && k.box == box_rows) { *map = cache[i].m; return; }
+  }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
@@ -357,6 +366,11 @@ void make_map_16(CUtensorMap *map, const void *ptr, bool bf16, int rows, int K, 
                               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw CudaError("cuTensorMapEncodeTiled (16-bit) failed (" + std::to_string((int)r) + ")");
+  Ent &e = cache[next];
+  e.k = Key{ptr, (int)bf16, rows, K, ld, box_rows};
+  e.m = *map;
+  next = (next + 1) % 16;
+  if (n_cached < 16) ++n_cached;
 }
 }  // namespace tc
 

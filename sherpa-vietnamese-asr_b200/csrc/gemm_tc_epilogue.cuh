@@ -58,6 +58,16 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
     if (tile < 0) break;
     const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
     const int acc = ti & 1;
+    // joiner records: the bias of this warp's first 32 columns is fetched while the main loop runs (the step is latency-bound
+    // and the bias would otherwise cost an L2 round trip after the accumulator is complete)
+    float4 bias_pf[EPI > 0 ? 8 : 1];
+    if constexpr (EPI > 0) {
+      const int nb = n0 + chalf * (BN / 2);
+      if (nb + 32 <= p.N) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) bias_pf[j4] = __ldg(reinterpret_cast<const float4 *>(p.bias + nb) + j4);
+      }
+    }
     mbar_wait(&tmem_full_bar[acc], (ti >> 1) & 1);
     if (ti == 0 && warp == 2 && lane == 0) tc_trace_mark<EPI>(p, 4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -80,9 +90,10 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
         float mx = -INFINITY;
         if (nbase + 32 <= p.N) {                          // warp-uniform; only the last tile of a row is ragged
           const float4 *b4 = reinterpret_cast<const float4 *>(p.bias + nbase);   // bias is 16-byte aligned (checked on the host)
+          const bool first_chunk = c0 == chalf * (BN / 2);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 bq = __ldg(b4 + j4);
+            const float4 bq = first_chunk ? bias_pf[j4] : __ldg(b4 + j4);
             const float x0 = __uint_as_float(r[4 * j4]) + bq.x, x1 = __uint_as_float(r[4 * j4 + 1]) + bq.y;
             const float x2 = __uint_as_float(r[4 * j4 + 2]) + bq.z, x3 = __uint_as_float(r[4 * j4 + 3]) + bq.w;
             r[4 * j4] = __float_as_uint(x0); r[4 * j4 + 1] = __float_as_uint(x1);

@@ -45,7 +45,7 @@ namespace {
 constexpr int FBK = 64;          // K elements per stage
 constexpr int UMMA_K16 = 16;     // kind::f16: 32 bytes per instruction
 constexpr int kF16Threads = 448;
-constexpr float kAScale = 64.0f, kWScale = 1024.0f;
+constexpr float kAScale = kF16AScale, kWScale = kF16WScale;
 
 __host__ __device__ constexpr int f16_stages(int BN, bool bf16) { return bf16 ? 4 : (BN == 64 ? 4 : 3); }
 
@@ -66,16 +66,6 @@ __device__ __forceinline__ void umma_f16_ta(uint32_t tmem_d, uint32_t tmem_a, ui
       : "memory");
 }
 
-__device__ __forceinline__ float clamp_f16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }   // NaN stays NaN
-
-// (x0, x1), already scaled -> packed fp16 hi pair and packed fp16 lo pair; element 0 in the low half-word
-__device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t *>(&h);
-  lo = *reinterpret_cast<const uint32_t *>(&l);
-}
 __device__ __forceinline__ uint32_t pack_bf16(float x0, float x1) {
   const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
   return *reinterpret_cast<const uint32_t *>(&b);
@@ -240,6 +230,143 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Joiner step of the search with the activation already split: X arrives as scaled fp16 hi / lo planes (the selection kernel
+// writes them), so both operands go from TMA straight into the MMAs (shared-memory descriptors on both sides) - no converter
+// warps and no tensor-memory staging between the load and the first MMA. The frame step is a latency chain, and the conversion
+// stage was 2 of its ~12 us. Same three products per K = 16 step in the same order as the kernel above, so the records are
+// bit-identical to it. Records only (EPI > 0, no logits stored).
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+constexpr int kSsThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+__host__ __device__ constexpr int ss_stages(int BN) { return BN == 64 ? 4 : 3; }
+constexpr size_t ss_smem_bytes(int BN) {
+  return 1024 + (size_t)ss_stages(BN) * (2 * TBM * FBK * 2 + 2 * BN * FBK * 2) + (2 * 4 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 + 16;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kSsThreads, 1)
+joiner_f16ss_tcgen05_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
+                            const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo, TcParams p) {
+  static_assert(EPI > 0, "record epilogue only");
+  constexpr int NS = ss_stages(BN);
+  constexpr uint32_t kTmemCols = 2 * BN;                     // two accumulators: 128 or 256 columns
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kABytes = TBM * FBK * 2;   // 128 x 64 fp16: 16 KB per operand part
+  constexpr int kWBytes = BN * FBK * 2;
+  uint8_t *sAhi = smem;
+  uint8_t *sAlo = sAhi + NS * kABytes;
+  uint8_t *sWhi = sAlo + NS * kABytes;
+  uint8_t *sWlo = sWhi + NS * kWBytes;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sWlo + NS * kWBytes);
+  uint64_t *empty_bar = full_bar + NS;
+  uint64_t *tmem_full_bar = empty_bar + NS;                // [2]
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;            // [2]
+  uint64_t *sched_full = tmem_empty_bar + 2;               // [kSchedSlots]
+  uint64_t *sched_empty = sched_full + kSchedSlots;
+  uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(sched_empty + kSchedSlots);
+  int *sched_tile = reinterpret_cast<int *>(tmem_ptr_smem + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 0);
+  const int nk = (p.K + FBK - 1) / FBK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + TBM - 1) / TBM;
+  const int n_tiles = tiles_m * tiles_n;
+  const TileSched sched{sched_tile, sched_full, sched_empty, p.tile_counter, n_tiles};
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_ahi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_alo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_whi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_wlo)) : "memory");
+    for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+    sched_init(sched, 1 + 8);                                // MMA issuer, 8 epilogue warps
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 2);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        const int tile = sched_produce(sched, ti);
+        if (tile < 0) break;
+        const int m0 = (tile / tiles_n) * TBM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], 2 * kABytes + 2 * kWBytes);
+          tma_load_2d(&map_ahi, &full_bar[s], sAhi + s * kABytes, kb * FBK, m0);
+          tma_load_2d(&map_whi, &full_bar[s], sWhi + s * kWBytes, kb * FBK, n0);
+          tma_load_2d(&map_alo, &full_bar[s], sAlo + s * kABytes, kb * FBK, m0);
+          tma_load_2d(&map_wlo, &full_bar[s], sWlo + s * kWBytes, kb * FBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc16(TBM, BN, 0);
+      int it = 0;
+      for (int ti = 0;; ++ti) {
+        if (sched_consume_thread(sched, ti) < 0) break;
+        const int acc = ti & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((ti >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&full_bar[s], ph);
+          if (it == 0) tc_trace_mark<EPI>(p, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t dah = make_smem_desc(smem_u32(sAhi + s * kABytes)), dal = make_smem_desc(smem_u32(sAlo + s * kABytes));
+          const uint64_t dwh = make_smem_desc(smem_u32(sWhi + s * kWBytes)), dwl = make_smem_desc(smem_u32(sWlo + s * kWBytes));
+#pragma unroll
+          for (int k = 0; k < FBK / UMMA_K16; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);             // +32 bytes inside the 128-byte swizzle row, in 16-byte units
+            umma_f16_ss(tmem_d, dal + o, dwh + o, idesc, (kb | k) ? 1u : 0u);
+            umma_f16_ss(tmem_d, dah + o, dwl + o, idesc, 1u);
+            umma_f16_ss(tmem_d, dah + o, dwh + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    tc_epilogue_warps<BN, EPI>(p, tmem_base, tmem_full_bar, tmem_empty_bar, nullptr, sched, tiles_n, warp, lane);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+  if (threadIdx.x == 0) tc_trace_mark<EPI>(p, 1);
+}
+
 constexpr size_t f16_smem_bytes(int BN, bool bf16) {
   return 1024 + (size_t)f16_stages(BN, bf16) * (2 * TBM * TBK * 4 + (bf16 ? 1 : 2) * BN * FBK * 2) + (3 * 4 + 4 + 2 * kSchedSlots) * 8 + 16 + 16 +
          8 * 32 * 32 * 4 + 16;
@@ -285,12 +412,18 @@ bool launch_gemm_16(const GemmArgs &g, bool bf16, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return true;
   if (!tc_init()) return false;
   if (!g.W16hi || (!bf16 && !g.W16lo)) return false;
-  if ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<uintptr_t>(g.A) & 15)) return false;
   const bool joiner = g.act == ACT_JOINER;
+  const bool pre_split = g.A16hi != nullptr;
+  if (pre_split && (bf16 || !joiner || g.C || !g.A16lo || (g.a16_ld & 7) || (g.K & 7) ||
+                    ((reinterpret_cast<uintptr_t>(g.A16hi) | reinterpret_cast<uintptr_t>(g.A16lo)) & 15)))
+    throw CudaError("pre-split activations are taken by the joiner record GEMM of the fp16-split mode only");
+  if (!pre_split && ((g.K & 3) || (g.lda & 3) || (reinterpret_cast<uintptr_t>(g.A) & 15))) return false;
   if (joiner) {
     if (!g.partials || !g.bias || (g.part_kb != 4 && g.part_kb != 8 && g.part_kb != 16) ||
-        ((reinterpret_cast<uintptr_t>(g.partials) | reinterpret_cast<uintptr_t>(g.bias)) & 15))
+        ((reinterpret_cast<uintptr_t>(g.partials) | reinterpret_cast<uintptr_t>(g.bias)) & 15)) {
+      if (pre_split) throw CudaError("joiner record GEMM: unaligned records / bias");
       return false;
+    }
   } else if (g.act != ACT_NONE && g.act != ACT_SWOOSH_L && g.act != ACT_SWOOSH_R) {
     return false;
   }
@@ -303,6 +436,32 @@ bool launch_gemm_16(const GemmArgs &g, bool bf16, cudaStream_t st) {
   int BN = g.N > 64 ? 128 : 64;
   if (joiner && (long long)((g.M + TBM - 1) / TBM) * ((g.N + 63) / 64) <= n_sms) BN = 64;
   CUtensorMap ma, mwh, mwl;
+  if (pre_split) {
+    CUtensorMap mah, mal;
+    const int a_rows = g.a16_rows > g.M ? g.a16_rows : g.M;   // a constant row count keeps the tensor map cached across frame steps
+    make_map_16(&mah, g.A16hi, false, a_rows, g.K, g.a16_ld, TBM);
+    make_map_16(&mal, g.A16lo, false, a_rows, g.K, g.a16_ld, TBM);
+    make_map_16(&mwh, g.W16hi, false, g.N, g.w16_ld, g.w16_ld, BN);
+    make_map_16(&mwl, g.W16lo, false, g.N, g.w16_ld, g.w16_ld, BN);
+    TcParams p{g.bias, nullptr, 0, nullptr, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 1.0f / (kAScale * kWScale)};
+    const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
+    const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
+#define B200_SS_LAUNCH(BN_, EPI_)                                                                                          \
+  do {                                                                                                                     \
+    set_max_dynamic_smem(joiner_f16ss_tcgen05_kernel<BN_, EPI_>, ss_smem_bytes(BN_));                                      \
+    launch_pdl(joiner_f16ss_tcgen05_kernel<BN_, EPI_>, dim3(grid), dim3(kSsThreads), ss_smem_bytes(BN_), st, g.pdl != 0, mah, mal, \
+               mwh, mwl, p);                                                                                               \
+  } while (0)
+#define B200_SS_BN(EPI_) do { if (BN == 128) B200_SS_LAUNCH(128, EPI_); else B200_SS_LAUNCH(64, EPI_); } while (0)
+    if (g.part_kb == 4) B200_SS_BN(4);
+    else if (g.part_kb == 8) B200_SS_BN(8);
+    else B200_SS_BN(16);
+#undef B200_SS_BN
+#undef B200_SS_LAUNCH
+    count_launch();
+    KERNEL_CHECK();
+    return true;
+  }
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_16(&mwh, g.W16hi, bf16, g.N, g.w16_ld, g.w16_ld, BN);
   make_map_16(&mwl, bf16 ? g.W16hi : g.W16lo, bf16, g.N, g.w16_ld, g.w16_ld, BN);

@@ -66,6 +66,8 @@ struct SearchDev {
   float *E;                    // [n*beam, dd] relu(conv(embeddings)) of hypotheses whose context changed
   float *dec;                  // [2][n*beam, jd] decoder outputs, ping-pong by frame parity
   float *X;                    // [n*beam, jd] joiner input tanh(enc+dec)
+  uint2 *X16hi, *X16lo;        // the same as scaled fp16 hi / lo planes ([n*beam, jd] halves each) for the pre-split joiner GEMM, or
+                               // null (then X is written); decoder-table mode only
   float *logits;               // [n*beam, V]
   float *partials;             // [n*beam, ceil(V/32), 4+2*KB] records from the joiner epilogue (or null)
   int2 *chg_list;              // [2][n*beam] {row, encoder_out row of its next frame} of the hypotheses whose decoder
@@ -179,6 +181,19 @@ __device__ bool same_chain(const ArenaNode *arena, int a, int b) {
 }
 
 struct NewNode { int arena_idx; int row; };
+
+// joiner input of 4 consecutive columns: fp32, or the scaled fp16 hi / lo planes the pre-split joiner GEMM reads
+__device__ __forceinline__ void store_joiner_input(const SearchDev &d, long long row, int jd, int c4, const float4 &x) {
+  if (d.X16hi) {
+    uint2 hi, lo;
+    split_pair_f16(x.x * kF16AScale, x.y * kF16AScale, hi.x, lo.x);
+    split_pair_f16(x.z * kF16AScale, x.w * kF16AScale, hi.y, lo.y);
+    d.X16hi[row * (jd >> 2) + c4] = hi;
+    d.X16lo[row * (jd >> 2) + c4] = lo;
+  } else {
+    reinterpret_cast<float4 *>(d.X + row * jd)[c4] = x;
+  }
+}
 
 #define SEL_PROF(k)                                                               \
   do {                                                                            \
@@ -516,14 +531,14 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
     auto tanh4 = [](const float4 &a, const float4 &b) {
       return make_float4(tanhf(a.x + b.x), tanhf(a.y + b.y), tanhf(a.z + b.z), tanhf(a.w + b.w));
     };
-    float *xs = d.X + (long long)s * d.beam * m.jd;
+    const long long xrow0 = (long long)s * d.beam;
     if (warp > 0) {
 #pragma unroll
       for (int i = 0; i < kPf; ++i) {
         const int u = (tid - 32) + i * kPfThreads;
         const int r = u / jd4, c = u - r * jd4;
         const int q = r < k ? sh.slot_of[r] : -1;
-        if (q >= 0) reinterpret_cast<float4 *>(xs + (long long)q * m.jd)[c] = tanh4(pf_e[i], pf_t[i]);
+        if (q >= 0) store_joiner_input(d, xrow0 + q, m.jd, c, tanh4(pf_e[i], pf_t[i]));
       }
     }
     // winners past the prefetch window (beam > 4 or a wider joiner)
@@ -534,7 +549,7 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
       const HypSlot &hs = sh.new_[q];
       const float4 tv = __ldg(reinterpret_cast<const float4 *>(m.dec_table + ((long long)hs.y0 * V + hs.y1) * m.jd) + c);
       const float4 ev = __ldg(reinterpret_cast<const float4 *>(d.enc + enc_next_row * m.jd) + c);
-      reinterpret_cast<float4 *>(xs + (long long)q * m.jd)[c] = tanh4(ev, tv);
+      store_joiner_input(d, xrow0 + q, m.jd, c, tanh4(ev, tv));
     }
   }
 
@@ -870,8 +885,11 @@ __global__ void init_search_kernel(SearchModel m, SearchDev d, int n_pos) {
   }
   if (m.dec_table) {   // joiner input of frame 0: context [0, 0] is row 0 of the decoder table
     if (s < n_pos)
-      for (int o = threadIdx.x; o < m.jd; o += blockDim.x)
-        d.X[((long long)s * d.beam) * m.jd + o] = tanhf(__ldg(d.enc + d.enc_off[s] * m.jd + o) + __ldg(m.dec_table + o));
+      for (int c = threadIdx.x; c < (m.jd >> 2); c += blockDim.x) {
+        const float4 e = __ldg(reinterpret_cast<const float4 *>(d.enc + d.enc_off[s] * m.jd) + c);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(m.dec_table) + c);
+        store_joiner_input(d, (long long)s * d.beam, m.jd, c, make_float4(tanhf(e.x + v.x), tanhf(e.y + v.y), tanhf(e.z + v.z), tanhf(e.w + v.w)));
+      }
     return;
   }
   for (int o = threadIdx.x; o < m.dd; o += blockDim.x)   // context [0, 0]
@@ -962,6 +980,7 @@ struct SearchState {
   float *E = nullptr; size_t e_cap = 0;
   float *dec = nullptr; size_t dec_cap = 0;
   float *X = nullptr; size_t x_cap = 0;
+  uint2 *X16 = nullptr; size_t x16_cap = 0;   // hi plane then lo plane
   float *logits = nullptr; size_t lg_cap = 0;
   float *partials = nullptr; size_t pt_cap = 0;
   float *bias_pen = nullptr; size_t bp_cap = 0;
@@ -1001,7 +1020,7 @@ void search_set_gemm(SearchState *s, void (*fn)(const GemmArgs &, cudaStream_t),
 void search_state_destroy(SearchState *s) {
   if (!s) return;
   cudaFree(s->hyps); cudaFree(s->hyp_count); cudaFree(s->node_count); cudaFree(s->arena); cudaFree(s->E); cudaFree(s->dec);
-  cudaFree(s->X); cudaFree(s->logits); cudaFree(s->partials); cudaFree(s->bias_pen); cudaFree(s->chg_list); cudaFree(s->rowdesc); cudaFree(s->chg_count);
+  cudaFree(s->X); cudaFree(s->X16); cudaFree(s->logits); cudaFree(s->partials); cudaFree(s->bias_pen); cudaFree(s->chg_list); cudaFree(s->rowdesc); cudaFree(s->chg_count);
   cudaFree(s->enc_off); cudaFree(s->arena_off); cudaFree(s->lens);
   cudaFree(s->orig); cudaFree(s->final_buf); cudaFree(s->o_ntok); cudaFree(s->o_tok); cudaFree(s->o_frm);
   cudaFree(s->o_lp); cudaFree(s->o_st); cudaFree(s->o_off);
@@ -1049,6 +1068,11 @@ void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g
   ensure(S->E, S->e_cap, rows * m.dd);
   ensure(S->dec, S->dec_cap, 2 * rows * m.jd);
   ensure(S->X, S->x_cap, rows * m.jd);
+  // decoder-table mode on the fp16 operand split: the selection kernel writes the joiner input already split, and the joiner
+  // GEMM feeds both operands to the MMAs straight from TMA (B200ASR_JOINER_SS=0: fp32 X through the converting kernel)
+  static const bool ss_env = !(getenv("B200ASR_JOINER_SS") && atoi(getenv("B200ASR_JOINER_SS")) == 0);
+  const bool x16 = ss_env && fused && m.dec_table && m.join_w16hi && m.join_w16lo && (m.jd & 7) == 0;
+  if (x16) ensure(S->X16, S->x16_cap, 2 * rows * (size_t)(m.jd >> 2));
   if (!fused) ensure(S->logits, S->lg_cap, rows * m.V);
   if (fused) ensure(S->partials, S->pt_cap, rows * P * REC);
   ensure(S->chg_list, S->cl_cap, 2 * rows);
@@ -1091,6 +1115,7 @@ void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g
   SearchDev d;
   d.enc = enc; d.enc_off = S->enc_off; d.lens = S->lens; d.arena_off = S->arena_off; d.hyps = S->hyps;
   d.hyp_count = S->hyp_count; d.node_count = S->node_count; d.arena = S->arena; d.E = S->E; d.dec = S->dec; d.X = S->X;
+  d.X16hi = x16 ? S->X16 : nullptr; d.X16lo = x16 ? S->X16 + rows * (size_t)(m.jd >> 2) : nullptr;
   d.logits = S->logits; d.partials = fused ? S->partials : nullptr; d.chg_list = S->chg_list; d.chg_count = S->chg_count; d.rowdesc = S->rowdesc;
   d.n = n; d.beam = beam;
   d.prof = nullptr;
@@ -1167,6 +1192,7 @@ void search_issue(SearchState *S, const SearchModel &m, const ContextGraphDev *g
     ga.ldc = m.V; ga.M = act_rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_NONE; ga.pdl = use_pdl ? 1 : 0;
     if (fused) {   // records only: nothing downstream reads the logits
       ga.act = ACT_JOINER; ga.C = nullptr; ga.partials = S->partials; ga.part_kb = KB; ga.bias = join_bias;
+      if (x16) { ga.A = nullptr; ga.A16hi = d.X16hi; ga.A16lo = d.X16lo; ga.a16_ld = m.jd; ga.a16_rows = (int)rows; }
       ga.trace = d_trace ? d_trace + (size_t)t * 16 + 2 : nullptr;
     }
     S->gemm(ga, st);
@@ -1211,7 +1237,7 @@ SearchView search_view(const SearchState *S) {
   return v;
 }
 
-static void search_print_prof(SearchState *S) {
+void search_print_prof(SearchState *S) {
   if (S->d_prof) {
     long long h[8];
     CUDA_CHECK(cudaMemcpy(h, S->d_prof, sizeof h, cudaMemcpyDeviceToHost));
@@ -1244,6 +1270,22 @@ static void search_print_prof(SearchState *S) {
       for (int i = 0; i < 15; ++i) if (used(i)) acc[i] += (double)((long long)(r[i] - r[b0]));
       step += (double)(nx[b0] - r[b0]);
       ++cnt;
+    }
+    {
+      // the same per eighth of the search (the active set shrinks with t: early steps carry every utterance)
+      fprintf(stderr, "[b200asr search trace] step us by eighth of the %d steps (gemm, select, whole step):", max_len);
+      for (int b = 0; b < 8; ++b) {
+        double g = 0, sl = 0, w = 0;
+        int c = 0;
+        for (int t = std::max(1, b * max_len / 8); t < (b + 1) * max_len / 8 && t + 1 < max_len; ++t) {
+          const unsigned long long *r = &h[(size_t)t * 16], *nx = &h[(size_t)(t + 1) * 16];
+          if (!r[2] || !r[3] || !r[8] || !r[9] || !nx[b0] || !r[b0]) continue;
+          g += (double)((long long)(r[3] - r[2])); sl += (double)((long long)(r[9] - r[8])); w += (double)((long long)(nx[b0] - r[b0]));
+          ++c;
+        }
+        if (c) fprintf(stderr, " [%.1f %.1f %.1f]", g / c / 1e3, sl / c / 1e3, w / c / 1e3);
+      }
+      fprintf(stderr, "\n");
     }
     if (cnt) {
       fprintf(stderr, "[b200asr search trace] %d steps, mean us from step start:", cnt);
@@ -1336,13 +1378,34 @@ void launch_decoder_product_rows(const SearchModel &m, const long long *y, const
 
 // The joiner GEMM exactly as a frame step launches it (ACT_JOINER: per row and 32-column part a softmax / top-kb record, no
 // logits stored). X [rows, jd] -> records [rows, ceil(V/32), 4 + 2 kb]. Device pointers.
+namespace {
+__global__ void split_x16_kernel(const float *__restrict__ X, long long n4, uint2 *__restrict__ hi, uint2 *__restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 x = reinterpret_cast<const float4 *>(X)[i];
+  uint2 h, l;
+  split_pair_f16(x.x * kF16AScale, x.y * kF16AScale, h.x, l.x);
+  split_pair_f16(x.z * kF16AScale, x.w * kF16AScale, h.y, l.y);
+  hi[i] = h; lo[i] = l;
+}
+}  // namespace
+
 void launch_joiner_records(SearchState *S, const SearchModel &m, const float *X, int rows, int kb, float *records, cudaStream_t st) {
   if (rows <= 0) return;
   if (!S->fused_partials) throw CudaError("this precision mode has no record epilogue (CUDA-core GEMM selects from full logits)");
+  // the kernel a frame step launches: pre-split operands in the fp16-split mode (read at call time so a test can run both)
+  const bool ss = !(getenv("B200ASR_JOINER_SS") && atoi(getenv("B200ASR_JOINER_SS")) == 0) && m.join_w16hi && m.join_w16lo && (m.jd & 7) == 0;
+  if (ss) {
+    const size_t n4 = (size_t)rows * (m.jd >> 2);
+    ensure(S->X16, S->x16_cap, 2 * n4);
+    split_x16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(X, (long long)n4, S->X16, S->X16 + n4);
+    count_launch(); KERNEL_CHECK();
+  }
   GemmArgs ga{};
   ga.A = X; ga.lda = m.jd; ga.W = m.join_w; ga.Wlo = m.join_w_lo; ga.bias = m.join_b; ga.R = nullptr; ga.ldr = 0; ga.C = nullptr;
   ga.W16hi = m.join_w16hi; ga.W16lo = m.join_w16lo; ga.w16_ld = m.join_w16_ld;
   ga.ldc = m.V; ga.M = rows; ga.N = m.V; ga.K = m.jd; ga.act = ACT_JOINER; ga.partials = records; ga.part_kb = kb; ga.pdl = 0;
+  if (ss) { ga.A = nullptr; ga.A16hi = S->X16; ga.A16lo = S->X16 + (size_t)rows * (m.jd >> 2); ga.a16_ld = m.jd; }
   S->gemm(ga, st);
 }
 

@@ -222,7 +222,7 @@ def test_decoder_joiner_rows(m30):
 
 
 @pytest.mark.parametrize("kb", [4, 8, 16])
-def test_product_decoder_and_joiner_record_kernels(m30, kb):
+def test_product_decoder_and_joiner_record_kernels(m30, kb, monkeypatch):
     """The kernels a frame step of the device search launches, pinned directly (not through downstream tokens):
     the decoder rows a step reads (the V^2 context table built by the Linear-layer GEMM; decoder_joinin_kernel with
     B200ASR_DEC_TABLE=0, test_on_demand_decoder_equals_decoder_table) -> decoder_out and X = tanh(enc + dec) against the
@@ -250,6 +250,12 @@ def test_product_decoder_and_joiner_record_kernels(m30, kb):
     recs = rec.joiner_records(want_x.astype(np.float32), kb)
     P = (V + 31) // 32
     assert recs.shape == (m, P, 4 + 2 * kb)
+    # the frame step's joiner kernel takes X already split into fp16 hi / lo planes (both operands straight from TMA); the
+    # kernel that converts fp32 X on the fly issues the same products in the same order: identical records
+    monkeypatch.setenv("B200ASR_JOINER_SS", "0")
+    recs_conv = rec.joiner_records(want_x.astype(np.float32), kb)
+    monkeypatch.delenv("B200ASR_JOINER_SS")
+    np.testing.assert_array_equal(recs.view(np.int32), recs_conv.view(np.int32))
     pm, ps, pu, pt = (recs[:, :, i].astype(np.float64) for i in range(4))
     vals = recs[:, :, 4:4 + kb].astype(np.float64)
     cols = recs[:, :, 4 + kb:].copy().view(np.int32)
