@@ -35,11 +35,11 @@ namespace b200asr {
 __device__ __forceinline__ float clamp_f16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }   // NaN stays NaN
 // (x0, x1), already scaled -> packed fp16 hi pair and packed fp16 lo pair; element 0 in the low half-word
 __device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const __half2 h = __floats2half2_rn(clamp_f16(x0), clamp_f16(x1));
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-  hi = *reinterpret_cast<const uint32_t *>(&h);
-  lo = *reinterpret_cast<const uint32_t *>(&l);
+  // one F2FP.SATFINITE per pair (overflow -> +-65504, as clamp_f16 + round-to-nearest gives) instead of four FMNMX and an F2FP:
+  // the converter warps of the GEMM are its busiest role, every instruction per element counts
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

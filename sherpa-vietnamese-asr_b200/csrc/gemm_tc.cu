@@ -410,7 +410,7 @@ static void launch_tc_impl(const GemmArgs &g, cudaStream_t st, bool split3) {
   make_map_impl(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_impl(&mw, g.W, g.N, g.K, g.K, BN);
   make_map_impl(&mwl, split3 ? g.Wlo : g.W, g.N, g.K, g.K, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 1.0f};
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 0, 1.0f};
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));   // persistent: one CTA per SM
   // one launcher per instantiation; the opt-in shared-memory attribute is set on first use

@@ -29,6 +29,8 @@ struct TcParams {
   float *partials;   // joiner epilogue (EPI > 0)
   unsigned long long *trace;
   int *tile_counter; // dynamic tile scheduling: a global counter that is zero at launch (null = static round-robin)
+  int dbg;           // timing experiments only (B200ASR_DBG_GEMM): bit 0 = the W_lo tile is not loaded, bit 1 = half of the A tile is not
+                     // loaded (results are wrong; shows how the kernel's time depends on operand bytes per stage)
   float acc_scale;   // the accumulator is multiplied by this (a power of two) before the epilogue; 0 or 1 = none. The all-fp16
                      // operand split pre-scales both operands so their low parts stay in fp16's normal range.
 };

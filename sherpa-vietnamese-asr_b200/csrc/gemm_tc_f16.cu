@@ -139,11 +139,12 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           const int s = it % NS;
           const uint32_t ph = (it / NS) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kABytes + kWParts * kWBytes);
+          const bool no_wlo = BF16 || (p.dbg & 1), no_a2 = (p.dbg & 2) != 0;
+          mbar_expect_tx(&full_bar[s], (no_a2 ? kABox : kABytes) + (no_wlo ? 1 : 2) * kWBytes);
           tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes, kb * FBK, m0);
-          tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes + kABox, kb * FBK + TBK, m0);
+          if (!no_a2) tma_load_2d(&map_a, &full_bar[s], sA + s * kABytes + kABox, kb * FBK + TBK, m0);
           tma_load_2d(&map_whi, &full_bar[s], sWhi + s * kWBytes, kb * FBK, n0);
-          if constexpr (!BF16) tma_load_2d(&map_wlo, &full_bar[s], sWlo + s * kWBytes, kb * FBK, n0);
+          if (!no_wlo) tma_load_2d(&map_wlo, &full_bar[s], sWlo + s * kWBytes, kb * FBK, n0);
         }
       }
     }
@@ -443,7 +444,7 @@ bool launch_gemm_16(const GemmArgs &g, bool bf16, cudaStream_t st) {
     make_map_16(&mal, g.A16lo, false, a_rows, g.K, g.a16_ld, TBM);
     make_map_16(&mwh, g.W16hi, false, g.N, g.w16_ld, g.w16_ld, BN);
     make_map_16(&mwl, g.W16lo, false, g.N, g.w16_ld, g.w16_ld, BN);
-    TcParams p{g.bias, nullptr, 0, nullptr, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 1.0f / (kAScale * kWScale)};
+    TcParams p{g.bias, nullptr, 0, nullptr, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 0, 1.0f / (kAScale * kWScale)};
     const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
     const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
 #define B200_SS_LAUNCH(BN_, EPI_)                                                                                          \
@@ -465,7 +466,9 @@ bool launch_gemm_16(const GemmArgs &g, bool bf16, cudaStream_t st) {
   make_map(&ma, g.A, g.M, g.K, g.lda, TBM);
   make_map_16(&mwh, g.W16hi, bf16, g.N, g.w16_ld, g.w16_ld, BN);
   make_map_16(&mwl, bf16 ? g.W16hi : g.W16lo, bf16, g.N, g.w16_ld, g.w16_ld, BN);
-  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, bf16 ? 1.0f : 1.0f / (kAScale * kWScale)};
+  TcParams p{g.bias, g.R, g.ldr, g.C, g.ldc, g.M, g.N, g.K, g.act, g.partials, g.trace, g.tile_counter, 0, bf16 ? 1.0f : 1.0f / (kAScale * kWScale)};
+  static const int dbg = getenv("B200ASR_DBG_GEMM") ? atoi(getenv("B200ASR_DBG_GEMM")) : 0;
+  p.dbg = dbg;
   const long long n_tiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
   const unsigned grid = (unsigned)std::min<long long>(n_tiles, persistent_grid_limit(n_sms));
 #define B200_F16_LAUNCH(BN_, EPI_, BF_)                                                                                   \
