@@ -35,6 +35,7 @@ struct AttnTcParams {
   const float *Y; int ldy;
   float *out; int ldo;
   int *tile_counter;       // dynamic tile scheduling (tc_common.cuh); null = static
+  const float *Ls; int H;  // unnormalised weights (single-pass attn_weights): output row i of head h is divided by Ls[row, h]
 };
 
 struct TileInfo { int u, a_row0, v_row0, m_row0, col0, ncols, nk, Tk; };
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int i = t.m_row0 + q * 32 + lane;
       const long long grow = (long long)__ldg(p.off + t.u) + i;
+      float scale = 1.0f;
+      if (p.Ls && i < t.Tk) scale = 1.0f / __ldg(p.Ls + grow * p.H + (p.single_head ? 0 : t.col0 / p.dv));
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[16];
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (c0 + j + 3 < t.ncols && ((p.ldo & 3) == 0) && (((t.col0 + c0) & 3) == 0) && (!yrow || (p.ldy & 3) == 0)) {
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              float4 v = make_float4(__uint_as_float(r[j]) * scale, __uint_as_float(r[j + 1]) * scale, __uint_as_float(r[j + 2]) * scale,
+                                     __uint_as_float(r[j + 3]) * scale);
               if (yrow) {
                 const float4 y = *reinterpret_cast<const float4 *>(yrow + j);
                 v.x *= y.x; v.y *= y.y; v.z *= y.z; v.w *= y.w;
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 if (c0 + j + e < t.ncols) {
-                  float v = __uint_as_float(r[j + e]);
+                  float v = __uint_as_float(r[j + e]) * scale;
                   if (yrow) v *= yrow[j + e];
                   orow[j + e] = v;
                 }
@@ -331,7 +335,7 @@ void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st) {
   p.mapsVlo = reinterpret_cast<const CUtensorMap *>(a.split3 ? a.mapsVlo : a.mapsV);
   p.tile_off = a.tile_off; p.len = a.len; p.off = a.off; p.n_utt = a.n_utt; p.n_tiles = a.n_tiles;
   p.single_head = a.single_head; p.C = a.C; p.dv = a.dv; p.Y = a.Y; p.ldy = a.ldy; p.out = a.out; p.ldo = a.ldo;
-  p.tile_counter = a.tile_counter;
+  p.tile_counter = a.tile_counter; p.Ls = a.Ls; p.H = a.H;
   const unsigned grid = (unsigned)std::min(a.n_tiles, persistent_grid_limit(n_sms));
   if (a.single_head) {
     if (a.split3) attn_apply_tcgen05_kernel<64, true><<<grid, 320, attn_smem(64, true), st>>>(p);

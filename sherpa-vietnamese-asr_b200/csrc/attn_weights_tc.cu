@@ -13,6 +13,13 @@
 // K = 32) and writes exp(s - max) / sum. The kernel is bound by its epilogue (one shared-memory read, one ex2 and a
 // handful of FMAs per score) and by the single HBM write of A, 4*H*Tk^2 bytes per utterance.
 //
+// ONEPASS (the default on the tensor-core path): softmax is invariant to the shift, so the row's DIAGONAL score s_ii - one
+// 36-dim dot product per row, known before any block - takes the place of the row maximum, the pass writes the unnormalised
+// exp(s_ij - s_ii) and leaves the row sum in Ls[row][head]; the three consumers of A (attn_tc.cu) scale their output rows by
+// 1 / Ls in their epilogues, as a fused attention kernel would. Half the epilogue work of the two-pass form. exp(s_ij - s_ii)
+// overflows only if some score exceeds the diagonal one by more than ~80; a row sum that is not finite or beyond 1e36 raises a
+// device flag and the engine repeats the pass with the exact two-pass kernel (and keeps it for that recognizer).
+//
 // Warp roles (704 threads): warps 0..15 epilogue (TMEM lane quarter = warp % 4, 32-column group = warp / 4),
 // warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer, warps 18..21 hi/lo operand splitter (3xTF32 mode).
 #include <algorithm>
@@ -41,6 +48,9 @@ struct AwParams {
   int n_utt, n_tiles, H, Lmax;
   float *A;
   int *tile_counter;               // dynamic tile scheduling (tc_common.cuh); null = static
+  const float *pos;                // ONEPASS: the positional projection [2*Lmax-1, H*4] (row Lmax-1 = offset 0)
+  float *Ls;                       // ONEPASS: row sums [M, H]
+  int *overflow;                   // ONEPASS: set when a row sum leaves the safe range
 };
 
 struct AwTile { int u, h, i0, Tk, nkt; long long row0; };
@@ -68,7 +78,7 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <bool SPLIT3>
+template <bool SPLIT3, bool ONEPASS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const __grid_constant__ CUtensorMap map_pos, AwParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -92,6 +102,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
   int *sched_tile = reinterpret_cast<int *>(tmem_ptr_smem + 4);
   const TileSched sched{sched_tile, sched_full, sched_empty, p.tile_counter, p.n_tiles};
 
+  constexpr int kPasses = ONEPASS ? 1 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == kEpiWarps && lane == 0) {
     sched_init(sched, 1 + kEpiWarps + (SPLIT3 ? 4 : 0));    // MMA issuer, epilogue warps, splitter warps
@@ -122,7 +133,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
         mbar_wait(q_empty, (ti & 1) ^ 1);                 // the previous item's MMAs no longer read sQ / sQlo
         mbar_expect_tx(q_full, kTileBytes);
         tma_load_2d(&map_proj, q_full, sQ, t.h * 32, (int)t.row0 + t.i0);
-        for (int pass = 0; pass < 2; ++pass)
+        for (int pass = 0; pass < kPasses; ++pass)
           for (int kt = 0; kt < t.nkt; ++kt, ++it) {
             const int s = it % kWS;
             const uint32_t ph = (it / kWS) & 1;
@@ -146,7 +157,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
         mbar_wait(SPLIT3 ? q_ready : q_full, ti & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t dq = make_smem_desc(smem_u32(sQ)), dql = make_smem_desc(smem_u32(sQlo));
-        for (int blk = 0; blk < 2 * t.nkt; ++blk, ++it) {
+        for (int blk = 0; blk < kPasses * t.nkt; ++blk, ++it) {
           const int s = it % kWS, acc = it & 1;
           mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);
           mbar_wait(SPLIT3 ? &ready_bar[s] : &full_bar[s], (it / kWS) & 1);
@@ -188,7 +199,28 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
       float *arow = p.A + __ldg(p.aoff + t.u) + ((long long)t.h * t.Tk + i) * Tk4;
       float m = -INFINITY, l = 0.f, inv = 0.f;
       constexpr float kLog2e = 1.4426950408889634f;
-      for (int pass = 0; pass < 2; ++pass) {
+      if constexpr (ONEPASS) {
+        // the shift: this row's diagonal score q_i . k_i + p_i . pos[0] (the four column-group warps of a row compute the same
+        // sequence of operations on the same data, so they agree bit for bit)
+        m = 0.f;
+        inv = 1.0f;
+        if (row_ok) {
+          const float4 *qv = reinterpret_cast<const float4 *>(p.proj + (t.row0 + i) * p.ldp + t.h * 32);
+          const float4 *kv = reinterpret_cast<const float4 *>(p.proj + (t.row0 + i) * p.ldp + p.H * 32 + t.h * 32);
+          float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            const float4 qa = __ldg(qv + c), ka = __ldg(kv + c), qb = __ldg(qv + c + 1), kb = __ldg(kv + c + 1);
+            d0 = fmaf(qa.x, ka.x, d0); d0 = fmaf(qa.y, ka.y, d0); d0 = fmaf(qa.z, ka.z, d0); d0 = fmaf(qa.w, ka.w, d0);
+            d1 = fmaf(qb.x, kb.x, d1); d1 = fmaf(qb.y, kb.y, d1); d1 = fmaf(qb.z, kb.z, d1); d1 = fmaf(qb.w, kb.w, d1);
+          }
+          const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.pos + (long long)(p.Lmax - 1) * p.H * 4 + t.h * 4));
+          float ps = pi.x * w0.x;
+          ps = fmaf(pi.y, w0.y, ps); ps = fmaf(pi.z, w0.z, ps); ps = fmaf(pi.w, w0.w, ps);
+          m = (d0 + d1) + ps;
+        }
+      }
+      for (int pass = 0; pass < kPasses; ++pass) {
         for (int kt = 0; kt < t.nkt; ++kt, ++it) {
           const int s = it % kWS, acc = it & 1;
           mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
@@ -207,7 +239,31 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
               ps = fmaf(pi.y, w.y, ps); ps = fmaf(pi.z, w.z, ps); ps = fmaf(pi.w, w.w, ps);
               r[jj] = __float_as_uint(jj < nvalid ? __uint_as_float(r[jj]) + ps : -INFINITY);
             }
-            if (pass == 0) {
+            if constexpr (ONEPASS) {
+              const float mb = m * kLog2e;
+              float add0 = 0.f, add1 = 0.f;
+              float *dst = arow + j0;
+              if (nvalid == 32) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  float4 v;
+                  v.x = ex2f(fmaf(__uint_as_float(r[4 * j4]), kLog2e, -mb));
+                  v.y = ex2f(fmaf(__uint_as_float(r[4 * j4 + 1]), kLog2e, -mb));
+                  v.z = ex2f(fmaf(__uint_as_float(r[4 * j4 + 2]), kLog2e, -mb));
+                  v.w = ex2f(fmaf(__uint_as_float(r[4 * j4 + 3]), kLog2e, -mb));
+                  add0 += v.x + v.z; add1 += v.y + v.w;
+                  if (row_ok) *reinterpret_cast<float4 *>(dst + 4 * j4) = v;
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const float e = ex2f(fmaf(__uint_as_float(r[jj]), kLog2e, -mb));   // -inf past the keys: 0
+                  add0 += e;
+                  if (row_ok && jj < nvalid) dst[jj] = e;
+                }
+              }
+              l += add0 + add1;
+            } else if (pass == 0) {
               float cm = __uint_as_float(r[0]);
 #pragma unroll
               for (int jj = 1; jj < 32; ++jj) cm = fmaxf(cm, __uint_as_float(r[jj]));
@@ -248,7 +304,17 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");   // window consumed
           }
         }
-        if (pass == 0) {
+        if constexpr (ONEPASS) {
+          // row sum = the four column groups' partial sums (same shift); the consumers divide by it
+          sML[cg * TBM + il] = make_float2(m, l);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (cg == 0 && row_ok) {
+            const float L = (sML[il].y + sML[TBM + il].y) + (sML[2 * TBM + il].y + sML[3 * TBM + il].y);
+            p.Ls[(t.row0 + i) * p.H + t.h] = L;
+            if (!(L < 1e36f)) atomicOr(p.overflow, 1);          // inf / NaN / close to the fp32 range
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // sML may be rewritten by the next item
+        } else if (pass == 0) {
           // merge the four column groups' running (max, sum) of each row
           sML[cg * TBM + il] = make_float2(m, l);
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -293,7 +359,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
         mbar_wait(q_full, ti & 1);
         split(sQ, sQlo);
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(q_ready)) : "memory");
-        for (int blk = 0; blk < 2 * t.nkt; ++blk, ++it) {
+        for (int blk = 0; blk < kPasses * t.nkt; ++blk, ++it) {
           const int s = it % kWS;
           mbar_wait(&full_bar[s], (it / kWS) & 1);
           split(sK + s * kTileBytes, sKlo + s * kTileBytes);
@@ -317,11 +383,14 @@ constexpr size_t kAwSmem = 1024 + 2 * kTileBytes + 2 * kWS * kTileBytes + kWS * 
 bool attn_weights_tc_supported(int qd, int pd) { return qd == 32 && pd == 4 && tc_init(); }
 
 void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float *pos, const RaggedDesc &r, const long long *aoff,
-                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st, int *tile_counter) {
+                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st, int *tile_counter,
+                            float *Ls, int *overflow) {
   if (n_tiles <= 0 || r.total <= 0) return;
   if (!tc_init()) throw CudaError("tcgen05 attention weights: cuTensorMapEncodeTiled entry point unavailable");
-  set_max_dynamic_smem(attn_weights_tcgen05_kernel<true>, kAwSmem);
-  set_max_dynamic_smem(attn_weights_tcgen05_kernel<false>, kAwSmem);
+  set_max_dynamic_smem(attn_weights_tcgen05_kernel<true, false>, kAwSmem);
+  set_max_dynamic_smem(attn_weights_tcgen05_kernel<false, false>, kAwSmem);
+  set_max_dynamic_smem(attn_weights_tcgen05_kernel<true, true>, kAwSmem);
+  set_max_dynamic_smem(attn_weights_tcgen05_kernel<false, true>, kAwSmem);
   static int n_sms = 0;
   if (n_sms == 0) {
     int dev = 0;
@@ -334,9 +403,14 @@ void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float
   AwParams p{};
   p.proj = proj; p.ldp = ldp; p.len = r.len; p.off = r.off; p.tile_off = tile_off; p.aoff = aoff; p.n_utt = r.n; p.n_tiles = n_tiles;
   p.H = H; p.Lmax = r.max_len; p.A = A; p.tile_counter = tile_counter;
+  p.pos = pos; p.Ls = Ls; p.overflow = overflow;
   const unsigned grid = (unsigned)std::min(n_tiles, persistent_grid_limit(n_sms));
-  if (split3) attn_weights_tcgen05_kernel<true><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
-  else attn_weights_tcgen05_kernel<false><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
+  if (Ls) {   // single pass, unnormalised weights + row sums
+    if (!overflow) throw CudaError("single-pass attention weights need the overflow flag");
+    if (split3) attn_weights_tcgen05_kernel<true, true><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
+    else attn_weights_tcgen05_kernel<false, true><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
+  } else if (split3) attn_weights_tcgen05_kernel<true, false><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
+  else attn_weights_tcgen05_kernel<false, false><<<grid, kThreads, kAwSmem, st>>>(mp, mw, p);
   count_launch();
   KERNEL_CHECK();
 }

@@ -169,7 +169,8 @@ void launch_attn_weights(const float *proj, int ldp, const float *pos, const Rag
 // H * ceil(len / 128) per utterance, A row pitch (len + 3) & ~3
 bool attn_weights_tc_supported(int qd, int pd);
 void launch_attn_weights_tc(const float *proj, int ldp, int m_total, const float *pos, const RaggedDesc &r, const long long *aoff,
-                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st, int *tile_counter = nullptr);
+                            const int *tile_off, int n_tiles, int H, float *A, bool split3, cudaStream_t st, int *tile_counter = nullptr,
+                            float *Ls = nullptr, int *overflow = nullptr);   // Ls != null: single pass, unnormalised A + row sums [M, H]
 // out[i, c] = (sum_j A[h(c)][i][j] * V[j,c]) (* Y[i,c]);  V = X (* tanh(S) if S). head = c / dv_per_head (0 if single_head)
 void launch_attn_apply(const float *A, const long long *aoff, const RaggedDesc &r, const float *X, int ldx, const float *S, int lds,
                        const float *Y, int ldy, int C, int dv_per_head, int single_head, float *out, int ldo, cudaStream_t st);
@@ -184,6 +185,7 @@ struct AttnTcLaunch {
   float *out; int ldo;
   int split3;
   int *tile_counter;                     // dynamic tile scheduling: a device int that is zero at launch (null: static)
+  const float *Ls; int H;                // row sums [M, H] of unnormalised weights (single-pass attn_weights) or null
 };
 // tile_off = cumulative ceil(len / 128) per utterance
 void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C, const RaggedDesc &r, const int *tile_off, int n_tiles,

@@ -466,6 +466,14 @@ struct Engine {
   // and ahead of time): built on the first search when it fits comfortably, see ensure_dec_table()
   bool dec_table_tried = false;
   void ensure_dec_table();
+  // Single-pass attention weights (attn_weights_tc.cu ONEPASS): unnormalised weights + row sums, the consumers divide. A row
+  // sum outside the safe range raises sm_flag on the device; the pass is then repeated with the exact two-pass kernel, which
+  // the recognizer keeps from there on (B200ASR_SOFTMAX_2PASS=1 selects it from the start).
+  bool exact_softmax = false;
+  int *sm_flag = nullptr;        // device
+  int *sm_flag_host = nullptr;   // pinned mirror, copied at the end of every encoder run
+  DevBuf b_ls;
+  bool softmax_overflowed();
   std::shared_ptr<GraphPair> graph;          // the recognizer's hotword automaton (null = none)
   const ContextGraphDev *pass_graph = nullptr;   // what the pass being issued scores with (decode sets it per partition)
   const ContextGraphHost &cg_host() const { static const ContextGraphHost empty; return graph ? graph->host : empty; }
@@ -545,7 +553,7 @@ struct Engine {
   DevBuf b_maps, b_tileoff, b_vtoff, b_vt12, b_vt12lo, b_vth, b_vthlo;
   void build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const std::vector<long long> &aoff_host);
   void attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r, const long long *aoff, const float *X, int ldx,
-                  const float *S, int lds, const float *Y, int ldy, int C, bool single_head, float *out, int ldo);
+                  const float *S, int lds, const float *Y, int ldy, int C, bool single_head, float *out, int ldo, const float *Ls = nullptr);
   void run_layer(const StackW &s, const LayerW &w, float *src, const RaggedDesc &r, const long long *aoff, int M, int Lmax,
                  const AttnPlan &pl);
   void decode(Stream *const *ss, int n);
@@ -585,6 +593,8 @@ struct Stream {
 };
 
 Engine::~Engine() {
+  if (sm_flag) cudaFree(sm_flag);
+  if (sm_flag_host) cudaFreeHost(sm_flag_host);
   for (auto &kv : tensors) if (kv.second.dev) cudaFree(kv.second.dev);
   for (float *p : owned) cudaFree(p);
   for (auto &kv : w16) { cudaFree(kv.second.hi); cudaFree(kv.second.lo); }
@@ -707,6 +717,11 @@ void Engine::load(const B200AsrOfflineRecognizerConfig *c) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) throw std::runtime_error("libb200asr is built for sm_100a only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
   CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaMalloc(&sm_flag, sizeof(int)));
+  CUDA_CHECK(cudaMemset(sm_flag, 0, sizeof(int)));
+  CUDA_CHECK(cudaHostAlloc(&sm_flag_host, sizeof(int), cudaHostAllocPortable));
+  *sm_flag_host = 0;
+  exact_softmax = getenv("B200ASR_SOFTMAX_2PASS") != nullptr && atoi(getenv("B200ASR_SOFTMAX_2PASS")) != 0;
   for (auto &x : ev) CUDA_CHECK(cudaEventCreate(&x));
   CUDA_CHECK(cudaEventCreateWithFlags(&ev_copy, cudaEventDisableTiming));
 
@@ -929,6 +944,18 @@ std::shared_ptr<GraphPair> Engine::make_graph(const int32_t *tokens, const int32
 // the Linear-layer GEMM of the recognizer's precision mode, in chunks of 128 K contexts (pre-activations from the per-token
 // convolution tables, then one GEMM). Skipped (the search then computes decoder rows on demand) in the CUDA-core cross-check
 // mode, with B200ASR_DEC_TABLE=0, or when the table would take more than a quarter of the free device memory.
+// Call once the stream an encoder ran on has been synchronised. True: a softmax row left the safe range of the single-pass
+// form; the caller repeats its pass (exact_softmax is set, so the repeat and everything after it use the two-pass kernel).
+bool Engine::softmax_overflowed() {
+  if (exact_softmax || !sm_flag_host) return false;
+  if (getenv("B200ASR_DBG_FORCE_SOFTMAX_RETRY")) *sm_flag_host = 1;   // tests: take the retry path without a pathological model
+  if (*sm_flag_host == 0) return false;
+  *sm_flag_host = 0;
+  CUDA_CHECK(cudaMemset(sm_flag, 0, sizeof(int)));
+  exact_softmax = true;
+  return true;
+}
+
 void Engine::ensure_dec_table() {
   if (dec_table_tried) return;
   dec_table_tried = true;
@@ -1085,7 +1112,7 @@ void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const 
 }
 
 void Engine::attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r, const long long *aoff, const float *X, int ldx,
-                        const float *S, int lds, const float *Y, int ldy, int C, bool single_head, float *out, int ldo) {
+                        const float *S, int lds, const float *Y, int ldy, int C, bool single_head, float *out, int ldo, const float *Ls) {
   if (!pl.use) {
     launch_attn_apply(b_A.ptr<float>(), aoff, r, X, ldx, S, lds, Y, ldy, C, vd, single_head ? 1 : 0, out, ldo, st);
     return;
@@ -1095,6 +1122,7 @@ void Engine::attn_apply(const AttnPlan &pl, const StackW &s, const RaggedDesc &r
   a.mapsA = pl.mapsA; a.len = r.len; a.off = r.off; a.n_utt = r.n; a.single_head = single_head ? 1 : 0; a.C = C; a.dv = vd;
   a.Y = Y; a.ldy = ldy; a.out = out; a.ldo = ldo; a.split3 = split3 ? 1 : 0;
   a.tile_counter = next_tile_counter();
+  a.Ls = Ls; a.H = s.H;
   if (single_head) {
     launch_transpose_v(X, ldx, S, lds, C, r, pl.dw_tile_off, pl.dw_tiles, pl.vt_offh, pl.VTh, split3 ? pl.VThlo : nullptr, st);
     a.mapsV = pl.mapsVh; a.mapsVlo = pl.mapsVhlo; a.tile_off = pl.tile_offh; a.n_tiles = pl.n_tilesh;
@@ -1136,20 +1164,23 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   // attention weights (computed once per layer from the layer input)
   gemm(src, D, w.attn_in_w, w.attn_in_b, nullptr, 0, proj, pw, M, pw, D, ACT_NONE);
   gemm(b_pe.ptr<float>(), pos_dim, w.pos_w, nullptr, nullptr, 0, pp, H * pd, 2 * Lmax - 1, H * pd, pos_dim, ACT_NONE);
-  if (pl.use && attn_weights_tc_supported(qd, pd) && !getenv("B200ASR_ATTN_SIMT"))
-    launch_attn_weights_tc(proj, pw, M, pp, r, aoff, pl.tile_off12, pl.n_tiles12, H, A, precision == 0, st, next_tile_counter());
-  else
+  float *Ls = nullptr;
+  if (pl.use && attn_weights_tc_supported(qd, pd) && !getenv("B200ASR_ATTN_SIMT")) {
+    if (!exact_softmax) Ls = b_ls.get<float>((size_t)M * H);
+    launch_attn_weights_tc(proj, pw, M, pp, r, aoff, pl.tile_off12, pl.n_tiles12, H, A, precision == 0, st, next_tile_counter(), Ls, sm_flag);
+  } else {
     launch_attn_weights(proj, pw, pp, r, aoff, H, qd, pd, A, st);
+  }
   // feed_forward1
   feed_forward(w, 0, src, src, w1, M, D, proj);
   // nonlin attention (head 0)
   gemm(w1, D, w.nl_in_w, w.nl_in_b, nullptr, 0, proj, 3 * h, M, 3 * h, D, ACT_NONE);
-  attn_apply(pl, s, r, aoff, proj + h, 3 * h, proj, 3 * h, proj + 2 * h, 3 * h, h, true, hid, h);
+  attn_apply(pl, s, r, aoff, proj + h, 3 * h, proj, 3 * h, proj + 2 * h, 3 * h, h, true, hid, h, Ls);
   gemm(hid, h, w.nl_out_w, w.nl_out_b, w1, D, w1, D, M, D, h, ACT_NONE);
   for (int j = 0; j < 2; ++j) {
     // self attention j
     gemm(w1, D, w.sa_in_w[j], w.sa_in_b[j], nullptr, 0, proj, H * vd, M, H * vd, D, ACT_NONE);
-    attn_apply(pl, s, r, aoff, proj, H * vd, nullptr, 0, nullptr, 0, H * vd, false, hid, H * vd);
+    attn_apply(pl, s, r, aoff, proj, H * vd, nullptr, 0, nullptr, 0, H * vd, false, hid, H * vd, Ls);
     gemm(hid, H * vd, w.sa_out_w[j], w.sa_out_b[j], w1, D, w1, D, M, D, H * vd, ACT_NONE);
     // conv module j
     gemm(w1, D, w.cv_in_w[j], w.cv_in_b[j], nullptr, 0, proj, 2 * D, M, 2 * D, D, ACT_NONE);
@@ -1311,6 +1342,7 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, DevBuf
   launch_concat_downsample2(pieces.data(), (int)pieces.size(), d_down[1], Mr[1], out_dim, W("encoder.downsample_output.bias"), cat, st);
   gemm(cat, out_dim, W("encoder.encoder_proj.weight"), W("encoder.encoder_proj.bias"), nullptr, 0, enc, join_dim, Mr[1], join_dim,
        out_dim, ACT_NONE);
+  if (!exact_softmax) CUDA_CHECK(cudaMemcpyAsync(sm_flag_host, sm_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   // the descriptor vectors uploaded asynchronously above stay alive until the next pass (no synchronisation here)
   keep(std::move(foff)); keep(std::move(c0off)); keep(std::move(c1off)); keep(std::move(Tclamped)); keep(std::move(dwt));
   for (auto &v : aoffs) keep(std::move(v));
@@ -1556,6 +1588,10 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
     for (int g = 0; g < G; ++g) CUDA_CHECK(cudaStreamWaitEvent(st, lanes[g].s1, 0));
   CUDA_CHECK(cudaEventRecord(ev[3], st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (softmax_overflowed()) {   // rare: repeat the pass with the exact two-pass softmax
+    decode_pcm_device(d_pcm, h_soff, h_len, n, Tp, d_featin, h_foff, forced_groups);
+    return;
+  }
   for (int g = 0; g < G; ++g) search_print_prof(lane(g).search);
   n_groups_last = G;
   tm.fbank = tm.encoder = 0;
@@ -2036,9 +2072,14 @@ int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, co
   e->gemm_flops = 0; e->gemm_launches = 0; e->gemm_ev_used = 0;
   e->host_keep.clear();
   e->reset_tile_counters();
-  e->run_encoder(d_feats, T, e->b_enc, &d_enc, &Tp);
-  CUDA_CHECK(cudaMemcpyAsync(out, d_enc, (size_t)totp * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
-  CUDA_CHECK(cudaStreamSynchronize(e->st));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    e->run_encoder(d_feats, T, e->b_enc, &d_enc, &Tp);
+    CUDA_CHECK(cudaMemcpyAsync(out, d_enc, (size_t)totp * e->join_dim * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+    CUDA_CHECK(cudaStreamSynchronize(e->st));
+    if (!e->softmax_overflowed()) break;     // else: once more with the exact two-pass softmax
+    e->host_keep.clear();
+    e->reset_tile_counters();
+  }
   return (int32_t)totp;
   API_CATCH(-1)
 }

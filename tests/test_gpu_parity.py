@@ -107,6 +107,45 @@ def test_encoder_68m_matches_oracle(m68, n):
         assert feats.shape[0] == 3000 and got.shape == (748, 512)
 
 
+def test_softmax_single_pass_two_pass_and_retry(model_dirs, monkeypatch):
+    """Attention weights are written in one pass (shift = the row's diagonal score, unnormalised, consumers divide by the row
+    sum); the exact two-pass kernel stays behind B200ASR_SOFTMAX_2PASS=1 and is what a pass is repeated with when a row sum
+    leaves the safe range. All three routes against the oracle, the retry route bit-equal to the two-pass one."""
+    from sherpa_vietnamese_asr_b200 import synth
+    cfg, paths, d = model_dirs("zipformer-30m", 30)
+    audio = synth.speech_like(16000 * 7 + 31, 4242)
+    rec1 = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+    feats, got1, want = _encoder_taps_check(cfg, paths, rec1, audio, 1e-4)
+    monkeypatch.setenv("B200ASR_SOFTMAX_2PASS", "1")
+    rec2 = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+    monkeypatch.delenv("B200ASR_SOFTMAX_2PASS")
+    _, got2, _ = _encoder_taps_check(cfg, paths, rec2, audio, 1e-4)
+    assert rel_err(got1, got2) <= 2e-5
+    rec3 = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+    monkeypatch.setenv("B200ASR_DBG_FORCE_SOFTMAX_RETRY", "1")
+    got3 = rec3.encoder([feats])[0]
+    monkeypatch.delenv("B200ASR_DBG_FORCE_SOFTMAX_RETRY")
+    np.testing.assert_array_equal(got3, got2)
+    np.testing.assert_array_equal(rec3.encoder([feats])[0], got2)        # the recognizer stays on the exact kernel
+    # a ragged batch through the decode path (the retry there repeats the whole pass)
+    rec4 = _gpu_rec(paths, decoding_method="modified_beam_search", max_active_paths=4)
+    utts = [synth.speech_like(n, 900 + i) for i, n in enumerate([16000 * 3, 16000 * 5 + 7, 9000])]
+
+    def decode(rec):
+        ss = []
+        for a in utts:
+            s = rec.create_stream()
+            s.accept_waveform(16000, a)
+            ss.append(s)
+        rec.decode_streams(ss)
+        return [s.result.token_ids for s in ss]
+    want_tokens = decode(rec1)
+    monkeypatch.setenv("B200ASR_DBG_FORCE_SOFTMAX_RETRY", "1")
+    assert decode(rec4) == want_tokens
+    monkeypatch.delenv("B200ASR_DBG_FORCE_SOFTMAX_RETRY")
+    assert decode(rec2) == want_tokens
+
+
 def test_c2_slice_68m_streams_token_exact(m68):
     """BASELINE config C2 on the model it names: the first 20 segments of bench.py's workload (ragged, 1-30 s) through
     create_stream / accept_waveform / decode_streams, token- and frame-exact against the oracle run segment by segment."""
