@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const float *__restric
     float v = 0.f;
     if (j < Tk && c < C) {
       v = X[(rbase + j) * ldx + c];
-      if (S) v *= tanhf(S[(rbase + j) * lds + c]);
+      if (S) v *= tanh_sfu(S[(rbase + j) * lds + c]);
     }
     tile[r][tx] = v;
   }

@@ -41,6 +41,19 @@ __device__ __forceinline__ void split_pair_f16(float x0, float x1, uint32_t &hi,
   const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
 }
+// SFU forms of the activations' transcendentals (ex2 / lg2 / rcp .approx.ftz: one MUFU each, no denormal fix-up code around
+// them). softplus: the 1 + t rounding bounds the absolute error at ~1e-7, fp32 noise on the O(1) Swoosh output; denormal
+// exponentials flush to 0 where 1 + t = 1 anyway. sigmoid: 2 ulp. Measured in the kernels that use them: a third of the
+// epilogue instructions of the Swoosh GEMMs and over half of glu_dwconv's were expf / log1pf / division sequences.
+__device__ __forceinline__ float sfu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float softplus_sfu(float x) {
+  return fmaf(sfu_lg2(1.0f + sfu_ex2(-fabsf(x) * 1.4426950408889634f)), 0.6931471805599453f, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float sigmoid_sfu(float x) { return sfu_rcp(1.0f + sfu_ex2(-x * 1.4426950408889634f)); }
+// tanh = 1 - 2 / (1 + e^(2x)): absolute error ~1e-7 (saturates correctly: e^(2x) -> inf gives 1, -> 0 gives -1)
+__device__ __forceinline__ float tanh_sfu(float x) { return fmaf(-2.0f, sfu_rcp(1.0f + sfu_ex2(x * 2.8853900817779268f)), 1.0f); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>

@@ -18,9 +18,9 @@ namespace b200asr {
 
 namespace {
 
-__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float softplus_f(float x) { return softplus_sfu(x); }
 __device__ __forceinline__ float swoosh_r(float v) { return softplus_f(v - 1.0f) - 0.08f * v - 0.313261687f; }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return sigmoid_sfu(x); }
 
 // ------------------------------------------------------------------ Conv2dSubsampling (App. B.2)
 // last u with off[u] <= row (off ascending, off[n] = total)

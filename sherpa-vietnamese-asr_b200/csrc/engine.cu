@@ -1291,10 +1291,25 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, DevBuf
   launch_embed_im2col2(c1, d_c1off, rd[0].off, n, M1, pw1, st);   // pw1 buffer doubles as the im2col scratch (288 <= 384)
   gemm(pw1, 288, w_conv2, W("encoder.embed.conv2.bias"), nullptr, 0, c2, 128, M1 * 19, 128, 288, ACT_SWOOSH_R);
   launch_embed_dw7(c2, rd[0], d_dwt, dwt[n], w_dw7, W("encoder.embed.convnext.dw.bias"), dw, st);
-  gemm(dw, 128, W("encoder.embed.convnext.pw1.weight"), W("encoder.embed.convnext.pw1.bias"), nullptr, 0, pw1, 384, M1 * 19, 384, 128,
-       ACT_SWOOSH_L);
-  gemm(pw1, 384, W("encoder.embed.convnext.pw2.weight"), W("encoder.embed.convnext.pw2.bias"), c2, 128, cn, 128, M1 * 19, 128, 384,
-       ACT_NONE);
+  {
+    // ConvNeXt pointwise pair over T1 * 19 rows: the 384-wide hidden tensor (4.2 GB on the bench batch) is three times the size
+    // of its input and output, and both GEMMs are HBM-bound (K = 128 / N = 128). Walking the rows in chunks whose hidden block
+    // stays in L2 keeps it out of HBM (B200ASR_EMBED_CHUNK_MB, 0 = one pass).
+    static const long long chunk_mb = getenv("B200ASR_EMBED_CHUNK_MB") ? atoll(getenv("B200ASR_EMBED_CHUNK_MB")) : 0;
+    const long long rows_all = (long long)M1 * 19;
+    long long rows_c = rows_all;
+    if (chunk_mb > 0) {
+      rows_c = std::max<long long>(128 * 148, ((chunk_mb << 20) / (384 * 4)) / (128 * 148) * (128 * 148));
+      if (rows_c * 5 / 4 >= rows_all) rows_c = rows_all;
+    }
+    const float *w1 = W("encoder.embed.convnext.pw1.weight"), *b1 = W("encoder.embed.convnext.pw1.bias");
+    const float *w2 = W("encoder.embed.convnext.pw2.weight"), *b2 = W("encoder.embed.convnext.pw2.bias");
+    for (long long m0 = 0; m0 < rows_all; m0 += rows_c) {
+      const int mc = (int)std::min<long long>(rows_c, rows_all - m0);
+      gemm(dw + m0 * 128, 128, w1, b1, nullptr, 0, pw1, 384, mc, 384, 128, ACT_SWOOSH_L);
+      gemm(pw1, 384, w2, b2, c2 + m0 * 128, 128, cn + m0 * 128, 128, mc, 128, 384, ACT_NONE);
+    }
+  }
   gemm(cn, 2432, w_out, W("encoder.embed.out.bias"), nullptr, 0, dw, D0, M1, D0, 2432, ACT_NONE);   // dw reused as scratch
   launch_biasnorm(dw, M1, D0, W("encoder.embed.out_norm.bias"), W("encoder.embed.out_norm.log_scale"), x0, st);
 

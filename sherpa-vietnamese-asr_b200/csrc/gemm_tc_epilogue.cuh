@@ -8,7 +8,7 @@
 namespace b200asr {
 namespace tc {
 
-__device__ __forceinline__ float softplus_f(float x) { return fmaxf(x, 0.f) + __logf(1.0f + __expf(-fabsf(x))); }
+__device__ __forceinline__ float softplus_f(float x) { return softplus_sfu(x); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_SWOOSH_L) return softplus_f(v - 4.0f) - 0.08f * v - 0.035f;
   if (act == ACT_SWOOSH_R) return softplus_f(v - 1.0f) - 0.08f * v - 0.313261687f;
@@ -82,10 +82,9 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
       if (n0 + c0 >= p.N) continue;                      // warp-uniform
-      if (p.acc_scale != 0.f && p.acc_scale != 1.0f) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * p.acc_scale);
-      }
+      // the accumulator scale (a power of two, so the product is exact) rides in the FMA that adds the bias: same bits as
+      // scaling first, one instruction less per element
+      const float asc = (p.acc_scale != 0.f) ? p.acc_scale : 1.0f;
       const int mrow0 = m0 + q * 32;
       if constexpr (EPI > 0) {
         const int nbase = n0 + c0;
@@ -96,8 +95,8 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 bq = first_chunk ? bias_pf[j4] : __ldg(b4 + j4);
-            const float x0 = __uint_as_float(r[4 * j4]) + bq.x, x1 = __uint_as_float(r[4 * j4 + 1]) + bq.y;
-            const float x2 = __uint_as_float(r[4 * j4 + 2]) + bq.z, x3 = __uint_as_float(r[4 * j4 + 3]) + bq.w;
+            const float x0 = fmaf(__uint_as_float(r[4 * j4]), asc, bq.x), x1 = fmaf(__uint_as_float(r[4 * j4 + 1]), asc, bq.y);
+            const float x2 = fmaf(__uint_as_float(r[4 * j4 + 2]), asc, bq.z), x3 = fmaf(__uint_as_float(r[4 * j4 + 3]), asc, bq.w);
             r[4 * j4] = __float_as_uint(x0); r[4 * j4 + 1] = __float_as_uint(x1);
             r[4 * j4 + 2] = __float_as_uint(x2); r[4 * j4 + 3] = __float_as_uint(x3);
             mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
@@ -106,7 +105,7 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = nbase + j;
-            const float x = n < p.N ? __uint_as_float(r[j]) + __ldg(p.bias + n) : -INFINITY;
+            const float x = n < p.N ? fmaf(__uint_as_float(r[j]), asc, __ldg(p.bias + n)) : -INFINITY;
             r[j] = __float_as_uint(x);
             mx = fmaxf(mx, x);
           }
@@ -151,7 +150,8 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
         }
       }
       if (EPI > 0 && p.C == nullptr) continue;               // records only: the selection never reads the logits
-      const float *bias_late = EPI > 0 ? nullptr : p.bias;   // the joiner epilogue has already added it
+      const float *bias_late = EPI > 0 ? nullptr : p.bias;   // the joiner epilogue has already added it (and scaled)
+      const float sc_late = EPI > 0 ? 1.0f : asc;
       __syncwarp();
 #pragma unroll
       for (int k4 = 0; k4 < 8; ++k4)                      // row = lane; 128-bit stores, conflict-free per quarter warp
@@ -178,8 +178,8 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
           const int rr = rsub + 4 * it, m = mrow0 + rr;
           if (nv && m < p.M) {
             float4 v = lds128(stg + (uint32_t)(rr * 32 + (((lane & 7) ^ (rr & 7)) << 2)) * 4u);
-            v.x = apply_act(v.x + bv.x, kAct) + res[it].x; v.y = apply_act(v.y + bv.y, kAct) + res[it].y;
-            v.z = apply_act(v.z + bv.z, kAct) + res[it].z; v.w = apply_act(v.w + bv.w, kAct) + res[it].w;
+            v.x = apply_act(fmaf(v.x, sc_late, bv.x), kAct) + res[it].x; v.y = apply_act(fmaf(v.y, sc_late, bv.y), kAct) + res[it].y;
+            v.z = apply_act(fmaf(v.z, sc_late, bv.z), kAct) + res[it].z; v.w = apply_act(fmaf(v.w, sc_late, bv.w), kAct) + res[it].w;
             *reinterpret_cast<float4 *>(p.C + (long long)m * p.ldc + n) = v;
           }
         }
@@ -193,7 +193,7 @@ __device__ __forceinline__ void tc_epilogue_warps(const TcParams &p, uint32_t tm
           const int m = mrow0 + rr;
           if (nv && m < p.M) {
             const float4 v4 = lds128(stg + (uint32_t)(rr * 32 + (((lane >> 2) ^ (rr & 7)) << 2)) * 4u);
-            float v = ((lane & 3) == 0 ? v4.x : (lane & 3) == 1 ? v4.y : (lane & 3) == 2 ? v4.z : v4.w) + bs;
+            float v = fmaf((lane & 3) == 0 ? v4.x : (lane & 3) == 1 ? v4.y : (lane & 3) == 2 ? v4.z : v4.w, sc_late, bs);
             const float rv = p.R ? p.R[(long long)m * p.ldr + n] : 0.f;
             v = apply_act(v, kAct) + rv;
             p.C[(long long)m * p.ldc + n] = v;

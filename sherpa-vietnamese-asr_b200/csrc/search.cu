@@ -499,6 +499,17 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
     }
     sh.n_new = n_new;
     sh.n_nodes = n_nodes;
+    if (d.prof && blockIdx.x == 0) {   // how often a frame only extends hypotheses with blank (what a speculative next frame could use)
+      bool all_blank = true;
+      for (int r = 0; r < k; ++r) {
+        const unsigned long long key = sh.win[r];
+        if (key == 0ULL) break;
+        const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
+        if (idx - (idx / V) * V != m.blank_id) all_blank = false;
+      }
+      if (all_blank) atomicAdd((unsigned long long *)&d.prof[5], 1ULL);
+      if (n_nodes == 0) atomicAdd((unsigned long long *)&d.prof[6], 1ULL);
+    }
     d.node_count[s] = node_count;
     d.hyp_count[(cur ^ 1) * d.n + s] = n_new;
     // rows of the new beam whose decoder output has to be recomputed before the next joiner step, and the per-row
@@ -1243,7 +1254,7 @@ void search_print_prof(SearchState *S) {
     CUDA_CHECK(cudaMemcpy(h, S->d_prof, sizeof h, cudaMemcpyDeviceToHost));
     cudaFree(S->d_prof); S->d_prof = nullptr;
     const int max_len = S->prof_steps;
-    const char *names[8] = {"load", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "-", "-", "decoder pre-activation"};
+    const char *names[8] = {"load", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "all-blank frames", "frames without a new token", "decoder pre-activation"};
     fprintf(stderr, "[b200asr search prof] CTA0 cycles over %d steps:", max_len);
     for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f/step", names[i], (double)h[i] / std::max(max_len, 1));
     fprintf(stderr, "\n");

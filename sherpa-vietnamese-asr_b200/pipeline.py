@@ -107,14 +107,14 @@ def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments
                       rover_recognizer=None, hotword_phrases: Sequence[str] = (), rank: int = 0, world_size: int = 1,
                       max_batch_seconds: float = 3000.0, decode_chunks=None, gather=None, vad_prob_fn: Optional[vad.ProbFn] = None,
                       skip_preprocessing: bool = False, rms_normalize: bool = False, work_queue=None, prefetch: int = 8,
-                      stats: Optional[dict] = None, vad_prob_fns: Optional[Sequence[Optional[vad.ProbFn]]] = None):
+                      stats: Optional[dict] = None, vad_prob_fns: Optional[Sequence[Optional[vad.ProbFn]]] = None, planners: int = 2):
     """Many recordings at once (BASELINE config C5: a 10 h corpus of 15-minute files), every rank pulling from one queue.
 
     * Queue: recordings, longest first. `work_queue.next()` hands each one out exactly once - LocalWorkQueue inside a
       process, StoreWorkQueue across the ranks of a torchrun job (default when world_size > 1 and torch.distributed is
       initialised; without it the recordings are dealt statically by duration, sharding.partition_by_duration).
-    * Producer thread (host): pull -> prepare_recording (VAD, preprocessing, 5 s merge) -> speech concatenation and chunk
-      plan (energy scan on the GPU), up to `prefetch` recordings ahead of the decoder.
+    * `planners` producer threads (host): pull -> prepare_recording (VAD, preprocessing, 5 s merge) -> speech concatenation and
+      chunk plan (energy scan on the GPU), together up to `prefetch` recordings ahead of the decoder.
     * Consumer (this thread): takes a round of up to `prefetch` planned recordings (while it decodes, the producer plans the
       next round), pools their chunks ACROSS recordings into
       length-sorted batches of up to `max_batch_seconds` (the search's frame loop costs the same whether a batch holds 30
@@ -169,52 +169,86 @@ def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments
             ready.put(e)
         ready.put(done)
 
-    th = threading.Thread(target=producer, daemon=True)
-    th.start()
+    planners = max(1, int(planners))
+    ths = [threading.Thread(target=producer, daemon=True) for _ in range(planners)]
+    for th in ths:
+        th.start()
     local: Dict[int, dict] = {}
     st = {"recordings": 0, "batches": 0, "chunks": 0, "idle_s": 0.0, "decode_s": 0.0}
-    finished = False
-    while not finished:
-        items = []
-        while len(items) < max(1, prefetch) and not finished:     # a round = up to `prefetch` planned recordings
+    is_rover = rover_recognizer is not None
+
+    # Finisher thread: word times back to each recording, overlap stitch, suspect flags, filler removal of a decoded round,
+    # while this thread already decodes the next round (the GPU would otherwise idle through the host-only tail of every round).
+    to_finish: "_queue.Queue" = _queue.Queue(maxsize=2)
+    finish_error: List[BaseException] = []
+
+    def finisher():
+        while True:
+            job = to_finish.get()
+            if job is done:
+                return
+            if finish_error:
+                continue                      # drain: the consumer must never block on a dead finisher
+            try:
+                items, decoded = job
+                for i, audio, probs, err, vs, rp in items:
+                    k = len(rp.plan)
+                    per_chunk = [decoded["a"][(i, c)] for c in range(k)]
+                    per_rover = [decoded["b"][(i, c)] for c in range(k)] if is_rover else None
+                    res = chunking.finish_recording(rp, per_chunk, per_rover, hotword_phrases)
+                    words, text = postprocess.finish_transcript(res["words"], audio, is_rover=is_rover, vad_probs=probs)
+                    local[i] = {"words": words, "text": text, "chunk_plan": res["chunk_plan"], "vad_segments": vs, "vad_error": err}
+            except BaseException as e:  # noqa: BLE001   surfaces in the consumer
+                finish_error.append(e)
+
+    fin = threading.Thread(target=finisher, daemon=True)
+    fin.start()
+    finished, live = False, planners
+    try:
+        while not finished:
+            items = []
+            while len(items) < max(1, prefetch) and not finished:     # a round = up to `prefetch` planned recordings
+                t0 = time.perf_counter()
+                it = ready.get()
+                st["idle_s"] += time.perf_counter() - t0
+                if it is done:
+                    live -= 1
+                    finished = live == 0
+                elif isinstance(it, BaseException):
+                    raise it
+                else:
+                    items.append(it)
+            if finish_error:
+                raise finish_error[0]
+            if not items:
+                continue
+            plans = {i: rp for i, _, _, _, _, rp in items}
+            pool = [(i, k) for i in plans for k in range(len(plans[i].plan))]                 # (recording, chunk)
+            lengths = [plans[i].plan[k][1] - plans[i].plan[k][0] for i, k in pool]
+            decoded: Dict[str, dict] = {"a": {}, "b": {}}
             t0 = time.perf_counter()
-            it = ready.get()
-            st["idle_s"] += time.perf_counter() - t0
-            if it is done:
-                finished = True
-            elif isinstance(it, BaseException):
-                raise it
-            else:
-                items.append(it)
-        if not items:
-            continue
-        plans = {i: rp for i, _, _, _, _, rp in items}
-        pool = [(i, k) for i in plans for k in range(len(plans[i].plan))]                 # (recording, chunk)
-        lengths = [plans[i].plan[k][1] - plans[i].plan[k][0] for i, k in pool]
-        decoded: Dict[str, dict] = {"a": {}, "b": {}}
-        t0 = time.perf_counter()
-        for batch in sharding.batches_by_length(range(len(pool)), lengths, max_batch_seconds):
-            audio_b = [plans[pool[j][0]].chunks[pool[j][1]] for j in batch]
-            offs_b = [plans[pool[j][0]].offsets[pool[j][1]] for j in batch]
-            feats = recognizer.engine.fbank_batch(audio_b) if shared_fbank else None
-            kw = {"precomputed_features": feats} if feats is not None else {}
-            for j, words in zip(batch, _dc(recognizer, audio_b, offs_b, **kw)):
-                decoded["a"][pool[j]] = words
-            if rover_recognizer is not None:
-                for j, words in zip(batch, _dc(rover_recognizer, audio_b, offs_b, **kw)):
-                    decoded["b"][pool[j]] = words
-            st["batches"] += 1
-            st["chunks"] += len(batch)
-        st["decode_s"] += time.perf_counter() - t0
-        for i, audio, probs, err, vs, rp in items:
-            k = len(rp.plan)
-            per_chunk = [decoded["a"][(i, c)] for c in range(k)]
-            per_rover = [decoded["b"][(i, c)] for c in range(k)] if rover_recognizer is not None else None
-            res = chunking.finish_recording(rp, per_chunk, per_rover, hotword_phrases)
-            words, text = postprocess.finish_transcript(res["words"], audio, is_rover=rover_recognizer is not None, vad_probs=probs)
-            local[i] = {"words": words, "text": text, "chunk_plan": res["chunk_plan"], "vad_segments": vs, "vad_error": err}
-            st["recordings"] += 1
-    th.join()
+            for batch in sharding.batches_by_length(range(len(pool)), lengths, max_batch_seconds):
+                audio_b = [plans[pool[j][0]].chunks[pool[j][1]] for j in batch]
+                offs_b = [plans[pool[j][0]].offsets[pool[j][1]] for j in batch]
+                feats = recognizer.engine.fbank_batch(audio_b) if shared_fbank else None
+                kw = {"precomputed_features": feats} if feats is not None else {}
+                for j, words in zip(batch, _dc(recognizer, audio_b, offs_b, **kw)):
+                    decoded["a"][pool[j]] = words
+                if rover_recognizer is not None:
+                    for j, words in zip(batch, _dc(rover_recognizer, audio_b, offs_b, **kw)):
+                        decoded["b"][pool[j]] = words
+                st["batches"] += 1
+                st["chunks"] += len(batch)
+            st["decode_s"] += time.perf_counter() - t0
+            st["recordings"] += len(items)
+            to_finish.put((items, decoded))
+    finally:
+        to_finish.put(done)
+        fin.join()
+    if finish_error:
+        raise finish_error[0]
+    for th in ths:
+        th.join()
     if stats is not None:
         stats.update(st)
     if world_size == 1:
