@@ -402,6 +402,12 @@ struct SelShared {
   NewNode nodes[kMaxBeam];
   int chg_pos[kMaxBeam];
   int slot_of[kMaxBeam];        // winner r -> slot in the new beam, -1 if it merged into an earlier one (decoder-table mode)
+  // the k winners expanded in parallel (lane r of warp 0): the hypothesis it would become, its arena node, parent slot
+  HypSlot cand[kMaxBeam];
+  ArenaNode cand_node[kMaxBeam];
+  int cand_hi[kMaxBeam];        // parent slot, -1 = no winner r
+  int rep[kMaxBeam];            // slot q of the new beam -> the winner that opened it
+  int node_of[kMaxBeam];        // winner r -> arena index of its new node (non-blank winners that open a slot)
   float rstats[kMaxBeam][4];   // per-row token statistics when they come from the partial records
   int n_new, n_nodes;
   int node_count0;             // arena fill of this utterance, fetched at kernel start (off the serial section)
@@ -440,75 +446,98 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
       }
     }
   }
-  if (tid == 0) {
-    int n_new = 0, n_nodes = 0;
-    int node_count = sh.node_count0;
-    for (int r = 0; r < kMaxBeam; ++r) sh.slot_of[r] = -1;
-    for (int r = 0; r < k; ++r) {
-      const unsigned long long key = sh.win[r];
-      if (key == 0ULL) break;
-      const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
-      const float lp32 = unord_f32((unsigned)(key >> 32));
-      const int hi = idx / V, tok = idx - hi * V;
-      const HypSlot &p = sh.old_[hi];
-      HypSlot c;
-      c.score = (double)lp32;
-      bool is_blank = (tok == m.blank_id);
-      if (is_blank) {
-        c.hash = p.hash; c.node = p.node; c.len = p.len; c.ctx = p.ctx; c.y0 = p.y0; c.y1 = p.y1; c.dec_src = hi;
-      } else {
-        c.hash = mix_hash(p.hash, tok);
-        c.len = p.len + 1; c.ctx = p.ctx; c.y0 = p.y1; c.y1 = tok; c.dec_src = -1; c.node = -1;
-        if (has_graph && !greedy && tok != m.unk_id) {
-          int nxt;
-          c.score += cg_forward_one_step(g, p.ctx, tok, &nxt);
-          c.ctx = nxt;
-        }
-      }
-      if (greedy) c.score = 0.0;
-      // dedup against already inserted hypotheses (same token sequence)
-      int dup = -1;
-      for (int q = 0; q < n_new && dup < 0; ++q) {
-        if (sh.new_[q].len != c.len || sh.new_[q].hash != c.hash) continue;
-        if (is_blank) {
-          if (same_chain(arena, sh.new_[q].node, p.node)) dup = q;
+  // Expansion in two halves. Everything that depends on one winner only - key decode, the integer division, hash, hotword
+  // arc, float64 score, the arena node's fields - is computed by lane r of warp 0 for all k winners at once; what depends on the
+  // ORDER of the winners (:1109-1140: dedup against the hypotheses already inserted, log-add merge, slot and arena numbering)
+  // stays one thread's serial loop, which is then a few compares and struct copies per winner.
+  const long long _tA = (d.prof && blockIdx.x == 0 && tid == 0) ? clock64() : 0;
+  if (warp == 0) {
+    if (lane < kMaxBeam) {
+      int hi = -1;
+      const unsigned long long key = lane < k ? sh.win[lane] : 0ULL;
+      if (key != 0ULL) {
+        const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
+        const float lp32 = unord_f32((unsigned)(key >> 32));
+        hi = idx / V;
+        const int tok = idx - hi * V;
+        const HypSlot &p = sh.old_[hi];
+        HypSlot c;
+        c.score = (double)lp32;
+        if (tok == m.blank_id) {
+          c.hash = p.hash; c.node = p.node; c.len = p.len; c.ctx = p.ctx; c.y0 = p.y0; c.y1 = p.y1; c.dec_src = hi;
         } else {
-          const int qn = sh.new_[q].node;
-          if (qn >= 0 && arena[qn].token == tok && same_chain(arena, arena[qn].parent, p.node)) dup = q;
+          c.hash = mix_hash(p.hash, tok);
+          c.len = p.len + 1; c.ctx = p.ctx; c.y0 = p.y1; c.y1 = tok; c.dec_src = -1; c.node = -1;
+          if (has_graph && !greedy && tok != m.unk_id) {
+            int nxt;
+            c.score += cg_forward_one_step(g, p.ctx, tok, &nxt);
+            c.ctx = nxt;
+          }
         }
-      }
-      if (dup >= 0) {
-        sh.new_[dup].score = log_add_d(sh.new_[dup].score, c.score);
-        continue;
-      }
-      if (!is_blank) {
-        const int ai = node_count++;
+        if (greedy) c.score = 0.0;
         ArenaNode nd;
         nd.parent = p.node; nd.token = tok; nd.frame = t;
         nd.tok_lp = (float)((double)lp32 - (greedy ? 0.0 : p.score));   // (:1121)
         if (rows) { nd.stats[0] = nd.stats[1] = nd.stats[2] = nd.stats[3] = 0.f; }
         else { nd.stats[0] = sh.rstats[hi][0]; nd.stats[1] = sh.rstats[hi][1]; nd.stats[2] = sh.rstats[hi][2]; nd.stats[3] = sh.rstats[hi][3]; }
-        arena[ai] = nd;
-        c.node = ai;
+        sh.cand[lane] = c;
+        sh.cand_node[lane] = nd;
+      }
+      sh.cand_hi[lane] = hi;
+      sh.slot_of[lane] = -1;
+    }
+    __syncwarp();
+  }
+  if (tid == 0) {
+    const long long _tB = (d.prof && blockIdx.x == 0) ? clock64() : 0;
+    int n_new = 0, n_nodes = 0, n_dup = 0;
+    int node_count = sh.node_count0;
+    for (int r = 0; r < k; ++r) {
+      const int hi = sh.cand_hi[r];
+      if (hi < 0) break;
+      const int len_r = sh.cand[r].len;
+      const unsigned long long hash_r = sh.cand[r].hash;
+      const int tok_r = sh.cand_node[r].token, pn_r = sh.cand_node[r].parent;
+      const bool blank_r = (tok_r == m.blank_id);
+      // dedup against the hypotheses already inserted (same token sequence). A slot's sequence is its opener's: the parent's
+      // chain, plus the new token unless the opener was a blank extension - compared without the arena node that is written
+      // only after this loop (same comparisons as walking it: core/asr_engine.py:1126-1134 compares the token tuples).
+      int dup = -1;
+      for (int q = 0; q < n_new && dup < 0; ++q) {
+        const int rq = sh.rep[q];
+        if (sh.cand[rq].len != len_r || sh.cand[rq].hash != hash_r) continue;
+        const int tok_q = sh.cand_node[rq].token, pn_q = sh.cand_node[rq].parent;
+        const bool blank_q = (tok_q == m.blank_id);
+        bool same;
+        if (blank_q == blank_r) same = (blank_r || tok_q == tok_r) && same_chain(arena, pn_q, pn_r);
+        else if (blank_r) same = pn_r >= 0 && arena[pn_r].token == tok_q && same_chain(arena, pn_q, arena[pn_r].parent);
+        else same = pn_q >= 0 && arena[pn_q].token == tok_r && same_chain(arena, arena[pn_q].parent, pn_r);
+        if (same) dup = q;
+      }
+      if (dup >= 0) {
+        const int rq = sh.rep[dup];
+        sh.cand[rq].score = log_add_d(sh.cand[rq].score, sh.cand[r].score);
+        ++n_dup;
+        continue;
+      }
+      sh.rep[n_new] = r;
+      sh.slot_of[r] = n_new;
+      if (!blank_r) {
+        const int ai = node_count++;
+        sh.node_of[r] = ai;
         sh.nodes[n_nodes].arena_idx = ai;
         sh.nodes[n_nodes].row = hi;
         ++n_nodes;
       }
-      sh.slot_of[r] = n_new;
-      sh.new_[n_new++] = c;
+      ++n_new;
     }
     sh.n_new = n_new;
     sh.n_nodes = n_nodes;
-    if (d.prof && blockIdx.x == 0) {   // how often a frame only extends hypotheses with blank (what a speculative next frame could use)
-      bool all_blank = true;
-      for (int r = 0; r < k; ++r) {
-        const unsigned long long key = sh.win[r];
-        if (key == 0ULL) break;
-        const int idx = (int)(~(unsigned)(key & 0xffffffffULL));
-        if (idx - (idx / V) * V != m.blank_id) all_blank = false;
-      }
-      if (all_blank) atomicAdd((unsigned long long *)&d.prof[5], 1ULL);
-      if (n_nodes == 0) atomicAdd((unsigned long long *)&d.prof[6], 1ULL);
+    if (d.prof && blockIdx.x == 0) {   // CTA 0: merges per step, cycles of the parallel and of the serial half
+      const long long now = clock64();
+      atomicAdd((unsigned long long *)&d.prof[5], (unsigned long long)n_dup);
+      atomicAdd((unsigned long long *)&d.prof[6], (unsigned long long)(_tB - _tA));
+      atomicAdd((unsigned long long *)&d.prof[7], (unsigned long long)(now - _tB));
     }
     d.node_count[s] = node_count;
     d.hyp_count[(cur ^ 1) * d.n + s] = n_new;
@@ -519,13 +548,13 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
       int n_chg = 0;
       for (int q = 0; q < n_new; ++q) {
         sh.chg_pos[q] = -1;
-        if (more && sh.new_[q].dec_src < 0) sh.chg_pos[q] = n_chg++;
+        if (more && sh.cand[sh.rep[q]].dec_src < 0) sh.chg_pos[q] = n_chg++;   // (new_ is filled after this block)
       }
       const int enc_next = (int)d.enc_off[s] + t + 1;
       int2 *rdesc = d.rowdesc + (size_t)((t + 1) & 1) * d.n * d.beam + (size_t)s * d.beam;
       for (int q = 0; q < d.beam; ++q) {
         int src = -2;
-        if (more && q < n_new) src = sh.new_[q].dec_src < 0 ? -1 : s * d.beam + sh.new_[q].dec_src;
+        if (more && q < n_new) src = sh.cand[sh.rep[q]].dec_src < 0 ? -1 : s * d.beam + sh.cand[sh.rep[q]].dec_src;
         rdesc[q] = make_int2(src, enc_next);
       }
       if (n_chg > 0) {
@@ -534,6 +563,18 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
         for (int q = 0; q < n_new; ++q)
           if (sh.chg_pos[q] >= 0) list[base + sh.chg_pos[q]] = make_int2(s * d.beam + q, enc_next);
       }
+    }
+  }
+  if (warp == 0) {
+    // the structs move in parallel: winner r that opened slot q becomes new_[q]; its arena node goes out
+    __syncwarp();
+    if (lane < k && sh.cand_hi[lane] >= 0 && sh.slot_of[lane] >= 0) {
+      HypSlot c = sh.cand[lane];
+      if (sh.cand_node[lane].token != m.blank_id) {
+        c.node = sh.node_of[lane];
+        arena[c.node] = sh.cand_node[lane];
+      }
+      sh.new_[sh.slot_of[lane]] = c;
     }
   }
   __syncthreads();
@@ -614,10 +655,19 @@ __device__ void finish_step(const SearchModel &m, const SearchDev &d, const Cont
           make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f));
     }
   }
-  SEL_PROF(7);
 }
 
-// block-wide top-k over per-thread descending candidate lists loc[KB] (0 = empty): per warp KB shuffle rounds, then
+// warp-wide maximum of 64-bit keys with two 32-bit hardware reductions (redux.sync) instead of five rounds of 64-bit shuffles:
+// first the high words, then the low words of the lanes that hold the maximal high word. Keys are unique (they carry the flat
+// index), 0 = empty.
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
+// block-wide top-k over per-thread descending candidate lists loc[KB] (0 = empty): per warp KB reduction rounds, then
 // warp 0 merges the 8 x KB survivors. Two barriers in total. Results in sh.win[0..k).
 template <int KB>
 __device__ void block_topk(unsigned long long (&loc)[KB], int k, SelShared &sh, unsigned long long *s_wk /* [8*KB] */) {
@@ -632,12 +682,7 @@ __device__ void block_topk(unsigned long long (&loc)[KB], int k, SelShared &sh, 
     unsigned long long best = 0ULL;
 #pragma unroll
     for (int i = 0; i < KB; ++i) if (i == head) best = loc[i];
-    unsigned long long wb = best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
-      wb = other > wb ? other : wb;
-    }
+    const unsigned long long wb = warp_max_u64(best);
     if (best == wb && wb != 0ULL) ++head;
     if (lane == 0) s_wk[warp * KB + round] = wb;
   }
@@ -652,12 +697,7 @@ __device__ void block_topk(unsigned long long (&loc)[KB], int k, SelShared &sh, 
       unsigned long long best = 0ULL;
 #pragma unroll
       for (int j = 0; j < PER; ++j) best = c[j] > best ? c[j] : best;
-      unsigned long long wb = best;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, wb, o);
-        wb = other > wb ? other : wb;
-      }
+      const unsigned long long wb = warp_max_u64(best);
       if (wb != 0ULL) {
 #pragma unroll
         for (int j = 0; j < PER; ++j) if (c[j] == wb) c[j] = 0ULL;   // keys are unique (they carry the flat index)
@@ -1254,7 +1294,7 @@ void search_print_prof(SearchState *S) {
     CUDA_CHECK(cudaMemcpy(h, S->d_prof, sizeof h, cudaMemcpyDeviceToHost));
     cudaFree(S->d_prof); S->d_prof = nullptr;
     const int max_len = S->prof_steps;
-    const char *names[8] = {"load", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "all-blank frames", "frames without a new token", "decoder pre-activation"};
+    const char *names[8] = {"load", "logsumexp", "top-k", "expand/dedup", "stats+writeback", "merges (count)", "expansion: parallel half", "expansion: serial half"};
     fprintf(stderr, "[b200asr search prof] CTA0 cycles over %d steps:", max_len);
     for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f/step", names[i], (double)h[i] / std::max(max_len, 1));
     fprintf(stderr, "\n");
