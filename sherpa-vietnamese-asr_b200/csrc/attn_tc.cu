@@ -3,8 +3,8 @@
 // heads; nonlin_attention: head-0 weights x (x * tanh(s)), then * y) - /root/reference core/asr_engine.py:1047,
 // architecture per SURVEY.md App. B.3.
 //
-// One group per utterance (ragged batch): the attention weights A[u], block-tiled by attn_weights_tc.cu ([head][row tile of
-// 128][column block of 32] contiguous 16 KB blocks, described to TMA as a [blocks * 128, 32] matrix), are the K-major "A operand"; V is transposed once per call into VT[u] = [C][Tk4] so it is
+// One group per utterance (ragged batch): the attention weights A[u] = [H][Tk][Tk4] (Tk4 = Tk rounded up to 4 so a
+// row pitch is TMA-legal) are the K-major "A operand"; V is transposed once per call into VT[u] = [C][Tk4] so it is
 // a K-major "B operand" (the transpose kernel also applies x * tanh(s) for nonlin-attention and emits the low part
 // of the 3xTF32 split). Per-utterance tensor maps live in global memory; a persistent CTA walks tiles
 // (utterance, head | column tile, 128 query rows), the K loop runs over the keys in blocks of 32.
@@ -35,13 +35,10 @@ struct AttnTcParams {
   const float *Y; int ldy;
   float *out; int ldo;
   int *tile_counter;       // dynamic tile scheduling (tc_common.cuh); null = static
-  int dbg;                 // timing experiments only (B200ASR_DBG_ATTN; results wrong): 1 no MMAs, 2 no split arithmetic, 4 no V loads, 8 no A
-                           // loads, 16 no proxy fence. Measured (C2): none of them is the kernel's pace alone - MMAs ~2.2 ms, split ~1,
-                           // A loads ~1.4 of the 7 ms; the rest is the per-stage hand-over skeleton and the per-tile epilogue
   const float *Ls; int H;  // unnormalised weights (single-pass attn_weights): output row i of head h is divided by Ls[row, h]
 };
 
-struct TileInfo { int u, a_row0, v_row0, m_row0, col0, ncols, nk, Tk; };   // a_row0: map row of the tile's first column block
+struct TileInfo { int u, a_row0, v_row0, m_row0, col0, ncols, nk, Tk; };
 
 template <int BN>
 __device__ __forceinline__ TileInfo decode_tile(const AttnTcParams &p, int tile) {
@@ -55,15 +52,15 @@ __device__ __forceinline__ TileInfo decode_tile(const AttnTcParams &p, int tile)
   t.Tk = __ldg(p.len + lo);
   const int mt = (t.Tk + TBM - 1) / TBM;
   const int lt = tile - __ldg(p.tile_off + lo);
-  t.nk = (t.Tk + TBK - 1) / TBK;                       // = column blocks per row tile
   if (!p.single_head) {
     const int h = lt / mt, mi = lt - h * mt;
-    t.m_row0 = mi * TBM; t.a_row0 = (h * mt + mi) * t.nk * TBM; t.v_row0 = h * p.dv; t.col0 = h * p.dv; t.ncols = p.dv;
+    t.m_row0 = mi * TBM; t.a_row0 = h * t.Tk + t.m_row0; t.v_row0 = h * p.dv; t.col0 = h * p.dv; t.ncols = p.dv;
   } else {
     const int nt = (p.C + BN - 1) / BN;
     const int mi = lt / nt, ni = lt - mi * nt;
-    t.m_row0 = mi * TBM; t.a_row0 = mi * t.nk * TBM; t.v_row0 = ni * BN; t.col0 = ni * BN; t.ncols = min(BN, p.C - t.col0);
+    t.m_row0 = mi * TBM; t.a_row0 = t.m_row0; t.v_row0 = ni * BN; t.col0 = ni * BN; t.ncols = min(BN, p.C - t.col0);
   }
+  t.nk = (t.Tk + TBK - 1) / TBK;
   return t;
 }
 
@@ -130,11 +127,10 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
           const int s = it % kNS;
           const uint32_t ph = (it / kNS) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          const bool no_v = (p.dbg & 4) != 0, no_a = (p.dbg & 8) != 0;
-          mbar_expect_tx(&full_bar[s], (no_a ? 0 : kABytes) + (no_v ? 0 : kVBytes * (SPLIT3 ? 2 : 1)));
-          if (!no_a) tma_load_2d(ma, &full_bar[s], sA + s * kABytes, 0, t.a_row0 + kb * TBM);     // block kb of this row tile: 16 KB contiguous
-          if (!no_v) tma_load_2d(mv, &full_bar[s], sV + s * kVStride, kb * TBK, t.v_row0);
-          if constexpr (SPLIT3) if (!no_v) tma_load_2d(mvl, &full_bar[s], sVlo + s * kVStride, kb * TBK, t.v_row0);
+          mbar_expect_tx(&full_bar[s], kABytes + kVBytes * (SPLIT3 ? 2 : 1));
+          tma_load_2d(ma, &full_bar[s], sA + s * kABytes, kb * TBK, t.a_row0);
+          tma_load_2d(mv, &full_bar[s], sV + s * kVStride, kb * TBK, t.v_row0);
+          if constexpr (SPLIT3) tma_load_2d(mvl, &full_bar[s], sVlo + s * kVStride, kb * TBK, t.v_row0);
         }
       }
     }
@@ -157,9 +153,7 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t da = make_smem_desc(smem_u32(sA + s * kABytes));
           const uint64_t dv = make_smem_desc(smem_u32(sV + s * kVStride));
-          if (p.dbg & 1) {
-            if (kb == 0) umma_tf32(tmem_d, da, dv, idesc, 0u);
-          } else if constexpr (SPLIT3) {
+          if constexpr (SPLIT3) {
             const uint64_t dal = make_smem_desc(smem_u32(sAlo + s * kABytes));
             const uint64_t dvl = make_smem_desc(smem_u32(sVlo + s * kVStride));
 #pragma unroll
@@ -240,7 +234,7 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
           mbar_wait(&full_bar[s], ph);
           const uint32_t a4 = smem_u32(sA + s * kABytes), al4 = smem_u32(sAlo + s * kABytes);
 #pragma unroll 8
-          for (int i = tix; i < ((p.dbg & 2) ? 0 : kABytes / 16); i += 128) {
+          for (int i = tix; i < kABytes / 16; i += 128) {
             const float4 v = lds128(a4 + i * 16);
             float4 l;
             l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -249,7 +243,7 @@ __global__ void __launch_bounds__(SPLIT3 ? 320 : 192, 1) attn_apply_tcgen05_kern
             l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
             sts128(al4 + i * 16, l);
           }
-          if (!(p.dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
         }
       }
@@ -342,8 +336,6 @@ void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st) {
   p.tile_off = a.tile_off; p.len = a.len; p.off = a.off; p.n_utt = a.n_utt; p.n_tiles = a.n_tiles;
   p.single_head = a.single_head; p.C = a.C; p.dv = a.dv; p.Y = a.Y; p.ldy = a.ldy; p.out = a.out; p.ldo = a.ldo;
   p.tile_counter = a.tile_counter; p.Ls = a.Ls; p.H = a.H;
-  static const int dbg = getenv("B200ASR_DBG_ATTN") ? atoi(getenv("B200ASR_DBG_ATTN")) : 0;
-  p.dbg = dbg;
   const unsigned grid = (unsigned)std::min(a.n_tiles, persistent_grid_limit(n_sms));
   if (a.single_head) {
     if (a.split3) attn_apply_tcgen05_kernel<64, true><<<grid, 320, attn_smem(64, true), st>>>(p);
@@ -359,16 +351,6 @@ void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st) {
 
 // Host-side plan for one stack of one batch: per-utterance tensor maps + tile offsets, uploaded once and reused
 // by every layer of the stack (the A / VT buffers do not move between layers).
-// maps of the block-tiled attention weights: utterance u is a [H * nIT * nJB * 128, 32] matrix with 128-byte rows
-void attn_tc_encode_tiled_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int H) {
-  CUtensorMap *m = reinterpret_cast<CUtensorMap *>(h_maps);
-  for (int u = 0; u < n; ++u) {
-    const int Tk = std::max(len[u], 1);
-    const long long blocks = (long long)H * ((Tk + 127) / 128) * ((Tk + 31) / 32);
-    make_map_uncached(&m[u], base + elem_off[u], (int)(blocks * 128), 32, 32, 128);
-  }
-}
-
 void attn_tc_encode_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int rows_mult,
                          int rows_fixed, int box_rows) {
   CUtensorMap *m = reinterpret_cast<CUtensorMap *>(h_maps);

@@ -20,12 +20,6 @@
 // overflows only if some score exceeds the diagonal one by more than ~80; a row sum that is not finite or beyond 1e36 raises a
 // device flag and the engine repeats the pass with the exact two-pass kernel (and keeps it for that recognizer).
 //
-// A leaves this kernel BLOCK-TILED (the tensor-core consumers of attn_tc.cu read it the same way): per utterance and head,
-// row tiles of 128 queries x column blocks of 32 keys, each block a contiguous [128][32] fp32 array (16 KB) at
-// ((h * nIT + it) * nJB + jb) * 4096, nIT = ceil(Tk / 128), nJB = ceil(Tk / 32). An epilogue warp (32 rows x 32 columns) then
-// writes 4 KB of consecutive memory instead of 32 rows a whole matrix row apart, and a consumer's TMA box is one contiguous
-// 16 KB read instead of 128 separate 128-byte segments. Keys past Tk inside the last block are written as zeros.
-//
 // Warp roles (704 threads): warps 0..15 epilogue (TMEM lane quarter = warp % 4, 32-column group = warp / 4),
 // warp 16 TMA producer, warp 17 TMEM allocator + MMA issuer, warps 18..21 hi/lo operand splitter (3xTF32 mode).
 #include <algorithm>
@@ -201,9 +195,8 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
       const bool row_ok = i < t.Tk;
       float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row_ok) pi = __ldg(reinterpret_cast<const float4 *>(p.proj + (t.row0 + i) * p.ldp + 2 * p.H * 32 + t.h * 4));
-      const int nJB = (t.Tk + 31) >> 5;
-      // row il of the blocks (h, it = i0 / 128, jb): jb-th block of this row tile starts at atile + jb * 4096
-      float *atile = p.A + __ldg(p.aoff + t.u) + ((long long)(t.h * t.nkt + t.i0 / TBM) * nJB) * 4096 + il * 32;
+      const int Tk4 = (t.Tk + 3) & ~3;
+      float *arow = p.A + __ldg(p.aoff + t.u) + ((long long)t.h * t.Tk + i) * Tk4;
       float m = -INFINITY, l = 0.f, inv = 0.f;
       constexpr float kLog2e = 1.4426950408889634f;
       if constexpr (ONEPASS) {
@@ -261,7 +254,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
             if constexpr (ONEPASS) {
               const float mb = m * kLog2e;
               float add0 = 0.f, add1 = 0.f;
-              float *dst = atile + (long long)(kt * 4 + cg) * 4096;
+              float *dst = arow + j0;
               if (nvalid == 32) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -276,9 +269,9 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
               } else {
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {
-                  const float e = ex2f(fmaf(__uint_as_float(r[jj]), kLog2e, -mb));   // -inf past the keys: 0 (written: the block is read whole)
+                  const float e = ex2f(fmaf(__uint_as_float(r[jj]), kLog2e, -mb));   // -inf past the keys: 0
                   add0 += e;
-                  if (row_ok) dst[jj] = e;
+                  if (row_ok && jj < nvalid) dst[jj] = e;
                 }
               }
               l += add0 + add1;
@@ -297,7 +290,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
               l = l * ex2f((m - nm) * kLog2e) + (add0 + add1);   // m = -inf on the first block: ex2(-inf) = 0
               m = nm;
             } else if (row_ok) {
-              float *dst = atile + (long long)(kt * 4 + cg) * 4096;
+              float *dst = arow + j0;
               const float mb = m * kLog2e;
               if (nvalid == 32) {
 #pragma unroll
@@ -312,7 +305,7 @@ attn_weights_tcgen05_kernel(const __grid_constant__ CUtensorMap map_proj, const 
               } else {
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj)
-                  dst[jj] = ex2f(fmaf(__uint_as_float(r[jj]), kLog2e, -mb)) * inv;     // -inf past the keys: 0
+                  if (jj < nvalid) dst[jj] = ex2f(fmaf(__uint_as_float(r[jj]), kLog2e, -mb)) * inv;
               }
             }
           }

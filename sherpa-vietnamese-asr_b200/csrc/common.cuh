@@ -206,14 +206,6 @@ void launch_transpose_v(const float *X, int ldx, const float *S, int lds, int C,
 void launch_attn_apply_tc(const AttnTcLaunch &a, cudaStream_t st);
 void attn_tc_encode_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int rows_mult,
                          int rows_fixed, int box_rows);
-void attn_tc_encode_tiled_maps(void *h_maps, int n, const float *base, const long long *elem_off, const int *len, int H);
-// elements of one utterance's attention weights: the larger of the row-major form (CUDA-core kernels: H * Tk * Tk4) and the
-// block-tiled form of the tensor-core kernels (H * ceil(Tk/128) * ceil(Tk/32) blocks of 128 x 32)
-inline long long attn_weights_elems(int H, int Tk) {
-  const long long row_major = (long long)H * Tk * ((Tk + 3) & ~3);
-  const long long tiled = (long long)H * ((Tk + 127) / 128) * ((Tk + 31) / 32) * 4096;
-  return row_major > tiled ? row_major : tiled;
-}
 // conv module middle: h [M, 2D] -> out [M, D] = SwooshR(dwconv_k(x * sigmoid(s)) + b); tile_off = cumulative
 // ceil(len / 128) per utterance
 void launch_glu_dwconv(const float *h, const RaggedDesc &r, const int *tile_off, int n_tiles, int D, int k, const float *w,

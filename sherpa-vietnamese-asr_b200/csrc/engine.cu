@@ -1068,8 +1068,6 @@ void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const long l
 void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const std::vector<long long> &aoff_host) {
   *pl = AttnPlan{};
   if (precision == 2 || n <= 0) return;   // CUDA-core mode keeps the CUDA-core attention kernels
-  // the tensor-core pair shares the block-tiled layout of the weights, the CUDA-core pair the row-major one: both or neither
-  if (getenv("B200ASR_ATTN_SIMT") || !attn_weights_tc_supported(qd, pd)) return;
   const int H = s.H, C12 = H * vd, hid = (3 * s.D) / 4;
   const std::vector<int> &len = h_len[q];
   std::vector<long long> vt12(n + 1, 0), vth(n + 1, 0);
@@ -1091,7 +1089,7 @@ void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const 
   // tensor maps (128 bytes each): A, V12, V12lo, Vh, Vhlo
   unsigned char *hm = const_cast<unsigned char *>(keep(std::vector<unsigned char>((size_t)5 * n * 128 + 64)));
   unsigned char *hp = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hm) + 63) & ~uintptr_t(63));
-  attn_tc_encode_tiled_maps(hp + 0 * (size_t)n * 128, n, b_A.ptr<float>(), aoff_host.data(), len.data(), H);
+  attn_tc_encode_maps(hp + 0 * (size_t)n * 128, n, b_A.ptr<float>(), aoff_host.data(), len.data(), H, 0, 128);
   attn_tc_encode_maps(hp + 1 * (size_t)n * 128, n, pl->VT12, vt12.data(), len.data(), 0, C12, 16);
   attn_tc_encode_maps(hp + 2 * (size_t)n * 128, n, split3 ? pl->VT12lo : pl->VT12, vt12.data(), len.data(), 0, C12, 16);
   attn_tc_encode_maps(hp + 3 * (size_t)n * 128, n, pl->VTh, vth.data(), len.data(), 0, hid, 64);
@@ -1167,7 +1165,7 @@ void Engine::run_layer(const StackW &s, const LayerW &w, float *src, const Ragge
   gemm(src, D, w.attn_in_w, w.attn_in_b, nullptr, 0, proj, pw, M, pw, D, ACT_NONE);
   gemm(b_pe.ptr<float>(), pos_dim, w.pos_w, nullptr, nullptr, 0, pp, H * pd, 2 * Lmax - 1, H * pd, pos_dim, ACT_NONE);
   float *Ls = nullptr;
-  if (pl.use) {
+  if (pl.use && attn_weights_tc_supported(qd, pd) && !getenv("B200ASR_ATTN_SIMT")) {
     if (!exact_softmax) Ls = b_ls.get<float>((size_t)M * H);
     launch_attn_weights_tc(proj, pw, M, pp, r, aoff, pl.tile_off12, pl.n_tiles12, H, A, precision == 0, st, next_tile_counter(), Ls, sm_flag);
   } else {
@@ -1264,7 +1262,7 @@ void Engine::run_encoder(const float *d_feats, const std::vector<int> &T, DevBuf
   for (size_t i = 0; i < ns; ++i) {
     const int q = rate_idx(stacks[i].ds);
     for (int u = 0; u < n; ++u)
-      aoffs[i][u + 1] = aoffs[i][u] + attn_weights_elems(stacks[i].H, h_len[q][u]);
+      aoffs[i][u + 1] = aoffs[i][u] + (long long)stacks[i].H * h_len[q][u] * ((h_len[q][u] + 3) & ~3);
     maxA = std::max(maxA, aoffs[i][n]);
   }
   long long *d_aoff = b_aoff.get<long long>(ns * (n + 1));
