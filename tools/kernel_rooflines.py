@@ -88,10 +88,23 @@ def main():
         a = fl_gemm / 1e12 / (t * 1e-6)
         print(f"| `gemm_tf32_tcgen05_kernel` (encoder Linears, 3xTF32) | {c} | {t / 1e3:.2f} | tensor | {fl_gemm / 1e12:.2f} TFLOP (x3 MMAs issued) | "
               f"{a:.0f} TFLOP/s | {a / tf:.3f} (x3 = {3 * a / tf:.3f} of the BF16 peak in issued MMA FLOPs) |")
+    c = t = 0
+    for pre in ("gemm_f16_tcgen05_kernel<128, 0", "gemm_f16_tcgen05_kernel<64, 0", "gemm_f16_tcgen05_kernel<128, -", "gemm_f16_tcgen05_kernel<64, -"):
+        cc, tt = fam(pre)
+        c, t = c + cc, t + tt
+    if c:
+        a = fl_gemm / 1e12 / (t * 1e-6)
+        print(f"| `gemm_f16_tcgen05_kernel` (encoder Linears, fp16 hi/lo operand split) | {c} | {t / 1e3:.2f} | tensor | {fl_gemm / 1e12:.2f} TFLOP (x3 MMAs issued) | "
+              f"{a:.0f} TFLOP/s | {a / tf:.3f} (x3 = {3 * a / tf:.3f} of the BF16 peak in issued MMA FLOPs) |")
     c, t = fam("attn_weights_tcgen05_kernel")
     if c:
         print(f"| `attn_weights_tcgen05_kernel` (as FLOPs) | {c} | {t / 1e3:.2f} | tensor | {fl_aw / 1e12:.3f} TFLOP | {fl_aw / 1e12 / (t * 1e-6):.1f} TFLOP/s | "
               f"{fl_aw / 1e12 / (t * 1e-6) / tf:.4f} (epilogue-bound: K = 32) |")
+    js, jt = fam("joiner_f16ss_tcgen05_kernel")
+    if js:
+        st = fam("select_partials_kernel")[1]
+        print(f"| search step: `joiner_f16ss` GEMM / `select_partials` (decoder table: no decoder kernel) | {js} steps | {(jt + st) / 1e3:.2f} | latency | "
+              f"{jt / js:.1f} / {st / js:.1f} us per frame step (cold cache; 21 us per step live) | - | - |")
     steps = agg.get("decoder_joinin_kernel", [0, 0])[0]
     if steps:
         tj = fam("gemm_tf32_tcgen05_kernel<64, 1, 4")[1] + fam("gemm_tf32_tcgen05_kernel<128, 1, 4")[1]
