@@ -218,8 +218,12 @@ class ParallelCopy {
     int ranks = 1;
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
     const int share = std::max(1, hw / ranks);
-    int n = std::min(7, share - 1);                        // helpers besides the calling thread: copies come in short bursts, so a
-                                                           // rank may use its whole share of the cores for them
+    // helpers besides the calling thread. A rank's kernel-launch thread must never wait for a core (the search issues a launch
+    // every ~11 us), and a feeder thread usually runs accept_waveform beside it; so helpers take at most half of the rank's share
+    // of the cores minus those two, and none at all when the share is small (8 ranks on 32 cores: measured, 40 runnable threads
+    // on 32 cores stretched the device-timed step by 7 % and the accept loop fourfold; one copying thread per rank hides
+    // under the decode of the previous batch anyway)
+    int n = share >= 8 ? std::min(7, share / 2 - 1) : 0;
     if (const char *e = getenv("B200ASR_COPY_THREADS")) n = atoi(e) - 1;
     n_workers_ = std::max(0, std::min(n, share > 1 ? share - 1 : 0));
     for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this, i] { worker(i + 1); });
