@@ -156,18 +156,28 @@ def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments
     ready: "_queue.Queue" = _queue.Queue(maxsize=prefetch)
     done = object()
 
+    stop = threading.Event()          # set when the consumer leaves early (an error): planners stop pulling and never block
+
+    def hand_over(item):
+        while not stop.is_set():
+            try:
+                ready.put(item, timeout=0.2)
+                return
+            except _queue.Full:
+                continue
+
     def producer():
         try:
-            while True:
+            while not stop.is_set():
                 i = work_queue.next()
                 if i is None:
                     break
                 pf = vad_prob_fns[i] if vad_prob_fns is not None else vad_prob_fn      # per-recording VAD, or one for all
                 audio, vs, probs, err = prepare_recording(recordings[i], pf, segs[i], skip_preprocessing, rms_normalize, device_id)
-                ready.put((i, audio, probs, err, vs, chunking.plan_recording(audio, vs or (), device_id)))
+                hand_over((i, audio, probs, err, vs, chunking.plan_recording(audio, vs or (), device_id)))
         except BaseException as e:  # noqa: BLE001   surfaces in the consumer
-            ready.put(e)
-        ready.put(done)
+            hand_over(e)
+        hand_over(done)
 
     planners = max(1, int(planners))
     ths = [threading.Thread(target=producer, daemon=True) for _ in range(planners)]
@@ -243,6 +253,7 @@ def transcribe_corpus(recognizer, recordings: Sequence[np.ndarray], vad_segments
             st["recordings"] += len(items)
             to_finish.put((items, decoded))
     finally:
+        stop.set()
         to_finish.put(done)
         fin.join()
     if finish_error:

@@ -143,6 +143,43 @@ def test_transcribe_corpus_pools_chunks_across_recordings_and_ranks():
     assert all(p for p in parts) and set(parts[0]) | set(parts[1]) == set(range(len(recs))) and not set(parts[0]) & set(parts[1])
 
 
+def test_corpus_threads_do_not_change_results_and_surface_errors(monkeypatch):
+    """transcribe_corpus runs planner threads ahead of the decoder and a finisher thread behind it (the GPU decodes the next
+    round during the host-only tail of the last one): the thread counts change nothing in the output, and an exception in
+    either side reaches the caller instead of hanging the queues."""
+    import pytest
+    recs = [cc.silence_audio(60 + i, sec) for i, sec in enumerate([40.0, 75.0, 9.0, 33.0, 61.0, 20.0])]
+    base = pipeline.transcribe_corpus(None, recs, max_batch_seconds=90.0, decode_chunks=_fake_decode, planners=1, prefetch=2)
+    for planners, prefetch in ((3, 2), (2, 8), (4, 1)):
+        got = pipeline.transcribe_corpus(None, recs, max_batch_seconds=90.0, decode_chunks=_fake_decode, planners=planners, prefetch=prefetch)
+        assert [g["text"] for g in got] == [g["text"] for g in base]
+        assert [g["chunk_plan"] for g in got] == [g["chunk_plan"] for g in base]
+        assert [[(w["text"], w["start"], w["end"]) for w in g["words"]] for g in got] == \
+               [[(w["text"], w["start"], w["end"]) for w in g["words"]] for g in base]
+    stats = {}
+    pipeline.transcribe_corpus(None, recs, max_batch_seconds=90.0, decode_chunks=_fake_decode, stats=stats)
+    assert stats["recordings"] == len(recs) and stats["chunks"] == sum(len(g["chunk_plan"]) for g in base)
+
+    real_finish = postprocess.finish_transcript
+    calls = []
+
+    def failing_finish(*a, **k):
+        calls.append(1)
+        if len(calls) == 3:
+            raise RuntimeError("finisher failed")
+        return real_finish(*a, **k)
+    monkeypatch.setattr(postprocess, "finish_transcript", failing_finish)
+    with pytest.raises(RuntimeError, match="finisher failed"):
+        pipeline.transcribe_corpus(None, recs, max_batch_seconds=90.0, decode_chunks=_fake_decode, prefetch=2)
+    monkeypatch.setattr(postprocess, "finish_transcript", real_finish)
+
+    def failing_plan(*a, **k):
+        raise ValueError("planner failed")
+    monkeypatch.setattr(chunking, "plan_recording", failing_plan)
+    with pytest.raises(ValueError, match="planner failed"):
+        pipeline.transcribe_corpus(None, recs, max_batch_seconds=90.0, decode_chunks=_fake_decode)
+
+
 def test_corpus_of_one_equals_transcribe_recording_with_vad():
     """Both entry points share prepare_recording (VAD -> preprocess_audio -> 5 s merge, core/asr_engine.py:2076-2128): with the
     same VAD input - a probability function, or given segments - they build the same speech concatenation, chunk plan, words and
