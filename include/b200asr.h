@@ -252,6 +252,10 @@ B200ASR_API int32_t B200AsrLastPassTokens(const B200AsrOfflineRecognizer *r, int
  * n_groups, the sum of the groups' search times and each one's (ms, lane_ms8[8]), and the device->host result bytes. */
 B200ASR_API int32_t B200AsrLastPipelineStats(const B200AsrOfflineRecognizer *r, int32_t *n_groups, float *search_busy_ms,
                                              float *lane_ms8, int64_t *d2h_bytes);
+/* Timeline of the last pass: for each of its groups (chained batches / length-sorted groups) four device times in ms from the
+ * start of the pass - encoder begin, encoder end, search begin, search end (CUDA events on the streams they ran on): the
+ * search of group g beside the encoder of group g + 1. t_ms holds 4 * max_groups floats; returns the number of groups. */
+B200ASR_API int32_t B200AsrLastPipelineTimeline(const B200AsrOfflineRecognizer *r, float *t_ms, int32_t max_groups);
 /* Per-stage device times (ms, CUDA events on the engine's stream) of the last decode / staged run:
  * out[0]=fbank, [1]=encoder, [2]=search, [3]=total, [4]=H2D, [5]=D2H; and kernel launch count. */
 B200ASR_API int32_t B200AsrLastTimings(const B200AsrOfflineRecognizer *r, float *out6, int64_t *n_launches);

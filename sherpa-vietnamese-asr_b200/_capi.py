@@ -98,6 +98,7 @@ SYMBOLS = {
     "B200AsrReleaseBatch": (C.c_int32, [_P, C.c_int32]),
     "B200AsrLastPassTokens": (C.c_int32, [_P, C.c_int32, _I32, _I32, C.c_int32]),
     "B200AsrLastPipelineStats": (C.c_int32, [_P, _I32, _F, _F, _I64]),
+    "B200AsrLastPipelineTimeline": (C.c_int32, [_P, _F, C.c_int32]),
     "B200AsrLastTimings": (C.c_int32, [_P, _F, _I64]),
     "B200AsrLastGemmStats": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _I64]),
     "B200AsrLastGemmBytes": (C.c_double, [_P]),

@@ -185,6 +185,22 @@ class PinnedPool {
 // accept_waveform is a host memcpy of the caller's samples into pinned memory; one core moves ~8 GB/s, so a 256-stream
 // batch (180 MB) spends >20 ms there. Large copies are split over a few helper threads that keep spinning for a short
 // while after a job (an accept loop issues the next one within microseconds) and otherwise sleep on a condition variable.
+// Helper threads a rank may start for a short burst of independent host work (beside the calling thread): half of its share of
+// the cores (affinity- and torchrun-aware), at most 7, none when the share is below 4.
+static int host_helper_threads() {
+  static const int n = [] {
+    int hw = (int)std::thread::hardware_concurrency();
+    cpu_set_t cs;
+    if (sched_getaffinity(0, sizeof cs, &cs) == 0 && CPU_COUNT(&cs) > 0) hw = std::min(hw > 0 ? hw : CPU_COUNT(&cs), CPU_COUNT(&cs));
+    int ranks = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    const int share = std::max(1, hw / ranks);
+    if (const char *e = getenv("B200ASR_PLAN_THREADS")) return std::max(0, atoi(e) - 1);
+    return share >= 4 ? std::min(7, share / 2 - 1) : 0;
+  }();
+  return n;
+}
+
 class ParallelCopy {
  public:
   static ParallelCopy &get() { static ParallelCopy p; return p; }
@@ -461,7 +477,26 @@ struct Engine {
   cudaEvent_t ev_part = nullptr;
   void ensure_partition();
   int n_groups_last = 1;
+  // Pinned staging for host->device descriptor uploads larger than the driver's inline limit (the per-stack tensor maps, 160 KB
+  // for 256 utterances): from PAGEABLE memory such a cudaMemcpyAsync first waits for the stream to drain, which tied the host to
+  // the GPU at every stack boundary (26 ms of "host time" per encoder) and, in chained passes, held back the launch sequence of
+  // the previous batch's search until the next encoder had all but finished. Bump-allocated, reset when a pass starts.
+  unsigned char *pin_arena = nullptr;
+  size_t pin_cap = 0, pin_used = 0;
+  unsigned char *pinned_scratch(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (!pin_arena) {
+      pin_cap = (size_t)32 << 20;
+      if (cudaHostAlloc(reinterpret_cast<void **>(&pin_arena), pin_cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); pin_arena = nullptr; pin_cap = 0; }
+    }
+    if (!pin_arena || pin_used + bytes > pin_cap) return nullptr;     // caller falls back to pageable memory
+    unsigned char *p = pin_arena + pin_used;
+    pin_used += bytes;
+    return p;
+  }
+  double hp_gemm = 0, hp_plan = 0, hp_attn = 0;   // B200ASR_HOST_PROF: host time inside gemm(), build_attn_plan(), attention launches
   float search_busy_ms = 0, lane_ms[kMaxLanes] = {0};
+  float lane_t[kMaxLanes][4] = {{0}};   // last pass, ms from its start: encoder begin / end, search begin / end of each group
   std::vector<int> lane_of, idx_of;   // last pass: utterance -> (lane, index inside the lane's group)
   double kappa = 50.0;                // search ms per second of utterance length / encoder ms per audio-second (adapted per pass)
   long long d2h_bytes_last = 0;
@@ -597,6 +632,7 @@ struct Stream {
 };
 
 Engine::~Engine() {
+  if (pin_arena) cudaFreeHost(pin_arena);
   if (sm_flag) cudaFree(sm_flag);
   if (sm_flag_host) cudaFreeHost(sm_flag_host);
   for (auto &kv : tensors) if (kv.second.dev) cudaFree(kv.second.dev);
@@ -998,6 +1034,9 @@ void Engine::set_graph(const int32_t *tokens, const int32_t *offsets, const floa
 
 void Engine::gemm(const float *A, int lda, const float *Wt, const float *bias, const float *R, int ldr, float *C, int ldc, int M,
                   int N, int K, int act) {
+  static const bool hprof = getenv("B200ASR_HOST_PROF") != nullptr;
+  struct Tm { double *acc; std::chrono::steady_clock::time_point t0; ~Tm() { if (acc) *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } };
+  Tm _tm{hprof ? &hp_gemm : nullptr, std::chrono::steady_clock::now()};
   GemmArgs g{};
   g.A = A; g.lda = lda; g.W = Wt; g.bias = bias; g.R = R; g.ldr = ldr; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.act = act;
   // programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch) runs on SMs
@@ -1070,6 +1109,9 @@ void Engine::run_fbank(const float *d_pcm, const long long *d_soff, const long l
 
 // ------------------------------------------------------------------ encoder
 void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const std::vector<long long> &aoff_host) {
+  static const bool hprof = getenv("B200ASR_HOST_PROF") != nullptr;
+  struct Tm { double *acc; std::chrono::steady_clock::time_point t0; ~Tm() { if (acc) *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); } };
+  Tm _tm{hprof ? &hp_plan : nullptr, std::chrono::steady_clock::now()};
   *pl = AttnPlan{};
   if (precision == 2 || n <= 0) return;   // CUDA-core mode keeps the CUDA-core attention kernels
   const int H = s.H, C12 = H * vd, hid = (3 * s.D) / 4;
@@ -1091,13 +1133,45 @@ void Engine::build_attn_plan(AttnPlan *pl, const StackW &s, int q, int n, const 
     pl->VThlo = b_vthlo.get<float>((size_t)std::max<long long>(vth[n], 4));
   }
   // tensor maps (128 bytes each): A, V12, V12lo, Vh, Vhlo
-  unsigned char *hm = const_cast<unsigned char *>(keep(std::vector<unsigned char>((size_t)5 * n * 128 + 64)));
-  unsigned char *hp = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hm) + 63) & ~uintptr_t(63));
-  attn_tc_encode_maps(hp + 0 * (size_t)n * 128, n, b_A.ptr<float>(), aoff_host.data(), len.data(), H, 0, 128);
-  attn_tc_encode_maps(hp + 1 * (size_t)n * 128, n, pl->VT12, vt12.data(), len.data(), 0, C12, 16);
-  attn_tc_encode_maps(hp + 2 * (size_t)n * 128, n, split3 ? pl->VT12lo : pl->VT12, vt12.data(), len.data(), 0, C12, 16);
-  attn_tc_encode_maps(hp + 3 * (size_t)n * 128, n, pl->VTh, vth.data(), len.data(), 0, hid, 64);
-  attn_tc_encode_maps(hp + 4 * (size_t)n * 128, n, split3 ? pl->VThlo : pl->VTh, vth.data(), len.data(), 0, hid, 64);
+  unsigned char *hp = pinned_scratch((size_t)5 * n * 128);
+  if (!hp) {
+    unsigned char *hm = const_cast<unsigned char *>(keep(std::vector<unsigned char>((size_t)5 * n * 128 + 64)));
+    hp = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(hm) + 63) & ~uintptr_t(63));
+  }
+  // 5 n driver calls (cuTensorMapEncodeTiled, ~3 us each): 26 of the 27 ms of host time one encoder pass of the bench batch took
+  // were these, which in chained passes delayed the launch sequence of the previous batch's search by as much. The encodes
+  // are independent host work, so they are dealt in blocks of 32 utterances to a few threads.
+  {
+    struct Job { int which, u0, u1; };
+    std::vector<Job> jobs;
+    for (int w = 0; w < 5; ++w)
+      for (int u0 = 0; u0 < n; u0 += 32) jobs.push_back(Job{w, u0, std::min(n, u0 + 32)});
+    const float *bases[5] = {b_A.ptr<float>(), pl->VT12, split3 ? pl->VT12lo : pl->VT12, pl->VTh, split3 ? pl->VThlo : pl->VTh};
+    const long long *offs[5] = {aoff_host.data(), vt12.data(), vt12.data(), vth.data(), vth.data()};
+    const int rows_mult[5] = {H, 0, 0, 0, 0}, rows_fixed[5] = {0, C12, C12, hid, hid}, box_rows[5] = {128, 16, 16, 64, 64};
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    auto work = [&] {
+      try {
+        CUDA_CHECK(cudaSetDevice(device));     // the driver call wants this device's context current in the calling thread
+        for (size_t j = next.fetch_add(1); j < jobs.size(); j = next.fetch_add(1)) {
+          const Job &jb = jobs[j];
+          attn_tc_encode_maps(hp + ((size_t)jb.which * n + jb.u0) * 128, jb.u1 - jb.u0, bases[jb.which], offs[jb.which] + jb.u0,
+                              len.data() + jb.u0, rows_mult[jb.which], rows_fixed[jb.which], box_rows[jb.which]);
+        }
+      } catch (...) {
+        std::lock_guard<std::mutex> lk(err_mu);
+        if (!err) err = std::current_exception();
+      }
+    };
+    const int helpers = std::min<int>(host_helper_threads(), (int)jobs.size() / 4);
+    std::vector<std::thread> ths;
+    for (int i = 0; i < helpers; ++i) ths.emplace_back(work);
+    work();
+    for (auto &t : ths) t.join();
+    if (err) std::rethrow_exception(err);
+  }
   unsigned char *dm = b_maps.get<unsigned char>((size_t)5 * n * 128);
   CUDA_CHECK(cudaMemcpyAsync(dm, hp, (size_t)5 * n * 128, cudaMemcpyHostToDevice, st));
   const int nt12 = t12[n], nth = th[n];
@@ -1521,6 +1595,7 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
   gemm_flops = 0; gemm_bytes = 0; gemm_launches = 0; gemm_ev_used = 0;
   const long long l0 = g_launches;
   host_keep.clear();   // every entry point returns synchronised, so the previous pass has consumed its uploads
+  pin_used = 0;
   reset_tile_counters();
   const std::vector<std::vector<int>> groups = forced_groups ? *forced_groups : plan_groups(h_len);
   const int G = (int)groups.size();
@@ -1592,11 +1667,20 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
                  max_active_paths, blank_penalty, ss);
     CUDA_CHECK(cudaEventRecord(l.s1, ss));
   };
-  issue_encoder(0);
+  static const bool issue_prof = getenv("B200ASR_HOST_PROF") != nullptr;
+  auto timed = [&](const char *what, int g, auto &&fn) {
+    if (!issue_prof) { fn(); return; }
+    const auto t0 = std::chrono::steady_clock::now();
+    fn();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[b200asr host prof] issue %s(%d): %.2f ms of host time (gemm() %.2f, attention plans %.2f)\n", what, g, ms, hp_gemm, hp_plan);
+    hp_gemm = hp_plan = 0;
+  };
+  timed("encoder", 0, [&] { issue_encoder(0); });
   if (no_overlap) for (int g = 1; g < G; ++g) issue_encoder(g);
   for (int g = 0; g < G; ++g) {
-    if (g + 1 < G && !no_overlap) issue_encoder(g + 1);
-    issue_search(g);
+    if (g + 1 < G && !no_overlap) timed("encoder", g + 1, [&] { issue_encoder(g + 1); });
+    timed("search", g, [&] { issue_search(g); });
   }
   if (st != st_main) {   // back to the main stream, after the partition's last encoder
     CUDA_CHECK(cudaEventRecord(ev_part, st));
@@ -1624,6 +1708,8 @@ void Engine::decode_pcm_device(const float *d_pcm, const std::vector<long long> 
     cudaEventElapsedTime(&b, l.f1, l.e1);
     cudaEventElapsedTime(&c, l.s0, l.s1);
     tm.fbank += a; tm.encoder += b; search_busy_ms += c; lane_ms[g] = c;
+    cudaEventElapsedTime(&lane_t[g][0], ev[0], l.f0); cudaEventElapsedTime(&lane_t[g][1], ev[0], l.e1);
+    cudaEventElapsedTime(&lane_t[g][2], ev[0], l.s0); cudaEventElapsedTime(&lane_t[g][3], ev[0], l.s1);
     d2h_bytes_last += search_result_bytes(l.search);
     if (l.steps > 0) { steps_ms += c; steps_len += l.steps / 25.0; }
   }
@@ -2090,6 +2176,7 @@ int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, co
   std::vector<int> Tp;
   e->gemm_flops = 0; e->gemm_launches = 0; e->gemm_ev_used = 0;
   e->host_keep.clear();
+  e->pin_used = 0;
   e->reset_tile_counters();
   for (int attempt = 0; attempt < 2; ++attempt) {
     e->run_encoder(d_feats, T, e->b_enc, &d_enc, &Tp);
@@ -2097,6 +2184,7 @@ int32_t B200AsrEncoder(const B200AsrOfflineRecognizer *r, const float *feats, co
     CUDA_CHECK(cudaStreamSynchronize(e->st));
     if (!e->softmax_overflowed()) break;     // else: once more with the exact two-pass softmax
     e->host_keep.clear();
+    e->pin_used = 0;
     e->reset_tile_counters();
   }
   return (int32_t)totp;
@@ -2380,6 +2468,14 @@ int32_t B200AsrLastPipelineStats(const B200AsrOfflineRecognizer *r, int32_t *n_g
   if (lane_ms8) for (int i = 0; i < kMaxLanes; ++i) lane_ms8[i] = i < e.n_groups_last ? e.lane_ms[i] : 0.f;
   if (d2h_bytes) *d2h_bytes = e.d2h_bytes_last;
   return 0;
+}
+
+int32_t B200AsrLastPipelineTimeline(const B200AsrOfflineRecognizer *r, float *t_ms, int32_t max_groups) {
+  if (!r || !t_ms) return -1;
+  const Engine &e = r->eng;
+  const int n = std::min<int>(e.n_groups_last, max_groups);
+  for (int g = 0; g < n; ++g) for (int k = 0; k < 4; ++k) t_ms[g * 4 + k] = e.lane_t[g][k];
+  return n;
 }
 
 int32_t B200AsrReleaseBatch(const B200AsrOfflineRecognizer *r, int32_t handle) {

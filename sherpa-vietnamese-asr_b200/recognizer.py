@@ -485,6 +485,12 @@ class OfflineRecognizer:
         return {"groups": ng.value, "search_busy_ms": busy.value, "lane_ms": [lanes[i] for i in range(ng.value)],
                 "d2h_bytes": d2h.value}
 
+    def last_pipeline_timeline(self):
+        """Per group of the last pass: (encoder begin, encoder end, search begin, search end) in device ms from the pass start."""
+        t = (C.c_float * 32)()
+        n = _capi.lib().B200AsrLastPipelineTimeline(self._h, t, 8)
+        return [tuple(round(t[g * 4 + k], 3) for k in range(4)) for g in range(max(n, 0))]
+
     def run_staged_chained(self, handle: int, reps: int):
         """`reps` (<= 8) passes over a staged batch back to back, each pass's search beside the next pass's encoder.
         Returns (token counts of the last pass, device ms for all passes)."""

@@ -25,6 +25,16 @@ if chain > 1:     # `chain` passes issued back to back: search of pass k beside 
     for i in range(n):
         ntok, ms = rec.run_staged_chained(h, chain)
         print(f"chained x{chain}: {ms:.2f} ms total, {ms / chain:.2f} ms per pass", rec.last_pipeline_stats(), "tokens", int(ntok.sum()), flush=True)
+        if i == n - 1:      # text timeline: one row per batch, '=' encoder, '#' search, 1 column = 2 ms
+            tl = rec.last_pipeline_timeline()
+            print("timeline (device ms from the start of the call; batch: encoder begin-end | search begin-end)")
+            for g, (a, b, c, d) in enumerate(tl):
+                row = [" "] * (int(ms / 2) + 2)
+                for x in range(int(a / 2), int(b / 2) + 1):
+                    row[x] = "="
+                for x in range(int(c / 2), int(d / 2) + 1):
+                    row[x] = "#" if row[x] == " " else "%"
+                print(f"  batch {g}: {a:7.2f}-{b:7.2f} | {c:7.2f}-{d:7.2f}  " + "".join(row))
     sys.exit(0)
 tot = []
 prof = os.environ.get("PROFILE_LAST") is not None      # ncu --profile-from-start off: only the last pass is captured
