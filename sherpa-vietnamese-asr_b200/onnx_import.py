@@ -260,6 +260,23 @@ def named_parameters(model: dict) -> Tuple[Dict[str, np.ndarray], List[str]]:
         if module:
             params[module + ".weight"] = np.ascontiguousarray(inits[w[0]].T)      # [in, out] -> [out, in]
             placed.add(w[0])
+    # Linear layers on 2-D inputs are exported as Gemm(A, B, C): B anonymous -> the module comes from the named bias C (or the
+    # node name); whether B is [out, in] (transB = 1, the usual export) or [in, out] is read off the bias length
+    for nd in nodes:
+        if nd["op_type"] != "Gemm" or len(nd["inputs"]) < 2:
+            continue
+        b = nd["inputs"][1]
+        if b not in inits or b in params or inits[b].ndim != 2:
+            continue
+        c = nd["inputs"][2] if len(nd["inputs"]) > 2 else None
+        module = c[: -len(".bias")] if c in params and c.endswith(".bias") else (_module_of_node(nd["name"]) if nd["name"] else None)
+        if not module:
+            continue
+        w = inits[b]
+        if c in params and w.shape[0] != params[c].shape[0] and w.shape[1] == params[c].shape[0]:
+            w = w.T
+        params[module + ".weight"] = np.ascontiguousarray(w)
+        placed.add(b)
     unplaced = [n for n, a in inits.items() if n not in params and n not in placed and getattr(a, "ndim", 0) >= 2]
     return params, unplaced
 

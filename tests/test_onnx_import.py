@@ -66,7 +66,11 @@ def _write_part(path, W, part):
             inits[anon] = np.ascontiguousarray(a.T)
             module = ip[: -len(".weight")]
             has_bias = (cn[: -len("weight")] + "bias") in W
-            if has_bias and k % 2:          # half of the biased Linears: anonymous node name, found through the Add's bias
+            if has_bias and part != "encoder":     # Linear on 2-D inputs: Gemm(A, B [out, in] or [in, out], C = named bias)
+                if part == "decoder":
+                    inits[anon] = np.ascontiguousarray(a)                      # transB = 1 form
+                nodes.append({"op_type": "Gemm", "name": f"Gemm_{k}", "inputs": [f"x{k}", anon, module + ".bias"], "outputs": [f"y{k}"]})
+            elif has_bias and k % 2:        # half of the biased Linears: anonymous node name, found through the Add's bias
                 nodes.append({"op_type": "MatMul", "name": f"MatMul_{k}", "inputs": [f"x{k}", anon], "outputs": [f"mm{k}"]})
                 nodes.append({"op_type": "Add", "name": f"Add_{k}", "inputs": [module + ".bias", f"mm{k}"], "outputs": [f"y{k}"]})
             else:
