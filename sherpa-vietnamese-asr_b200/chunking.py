@@ -20,6 +20,7 @@ against golden vectors produced by them).
 from __future__ import annotations
 
 import bisect
+import functools
 import math
 import re
 import unicodedata
@@ -172,6 +173,13 @@ def normalize_word_for_overlap(word: str) -> str:
     return re.sub(r"[^\w]", "", word, flags=re.UNICODE)
 
 
+@functools.lru_cache(maxsize=1 << 16)
+def _fuzzy_match(w1: str, w2: str, threshold: float) -> bool:
+    m = SequenceMatcher(None, w1, w2)
+    # difflib's two upper bounds on ratio() first: most word pairs of an overlap window are unrelated
+    return m.real_quick_ratio() >= threshold and m.quick_ratio() >= threshold and m.ratio() >= threshold
+
+
 def words_match(w1: str, w2: str, threshold: float = FUZZY_MATCH_THRESHOLD) -> bool:
     if w1 == w2:
         return True
@@ -179,9 +187,7 @@ def words_match(w1: str, w2: str, threshold: float = FUZZY_MATCH_THRESHOLD) -> b
         return False
     if len(w1) > 2 and len(w2) > 2 and (w1 in w2 or w2 in w1):
         return True
-    m = SequenceMatcher(None, w1, w2)
-    # difflib's two upper bounds on ratio() first: most word pairs of an overlap window are unrelated
-    return m.real_quick_ratio() >= threshold and m.quick_ratio() >= threshold and m.ratio() >= threshold
+    return _fuzzy_match(w1, w2, threshold)      # speech repeats its words: the same pairs come back in every overlap window
 
 
 def _mean_prob(words: Sequence[dict]) -> float:
